@@ -1,0 +1,784 @@
+// api.cu -- kmeans_cuda() / knn_cuda(): the drop-in C ABI of include/kmcuda.h.
+//
+// Role of the reference's kmcuda.cc (argument validation kmcuda.cc:19-61, device mask -> device list
+// :63-137, allocation + ingest :139-170, centroid initialisation :189-400, driver :402-531, k-NN
+// driver :572-730) and of the host halves of kmeans.cu (Lloyd loop :934-1026, Yinyang loop
+// :1028-1263).  Differences by design: samples are range-partitioned across the GPUs in
+// the mask instead of replicated; no transpose; the per-iteration exchange is ONE NCCL all-reduce of
+// the [K][D] partial sums + [K] counts instead of 5-6 rounds of peer copies; centroid update is a
+// deterministic sort + segmented compensated sum instead of one thread per centroid.
+#include <nccl.h>
+
+#include <algorithm>
+#include <cinttypes>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <vector>
+
+#include "kmcuda.h"
+#include "shard.h"
+
+namespace kmb {
+
+static const float kYinyangGroupTolerance = 0.02f;      // reference kmeans.cu:27
+static const float kYinyangDraftReassignments = 0.11f;  // reference kmeans.cu:28
+static const float kYinyangRefreshEpsilon = 1e-4f;      // reference kmeans.cu:29
+
+struct Dev {
+  int dev = 0;
+  cudaStream_t st = nullptr;
+  uint32_t off = 0, len = 0;
+  std::unique_ptr<Shard> shard;
+  DevBuf<float> X, C, sums, dists;
+  DevBuf<uint32_t> assign, prev, ccounts, counts, d_changed;
+  DevBuf<double> d_dsum;
+  ncclComm_t comm = nullptr;
+};
+
+// equal split of `amount` rows over the devices, chunk starts aligned to 512 bytes without
+// breaking rows (same rule as the reference's distribute(), private.h:240-273)
+static std::vector<std::pair<uint32_t, uint32_t>> split_rows(uint32_t amount, uint32_t row_bytes,
+                                                             size_t ndev) {
+  std::vector<std::pair<uint32_t, uint32_t>> res;
+  if (ndev == 0) return res;
+  if (ndev == 1) {
+    res.emplace_back(0, amount);
+    return res;
+  }
+  uint32_t a = row_bytes, b = 512, gcd = 0;
+  for (;;) {
+    if (a == 0) { gcd = b; break; }
+    b %= a;
+    if (b == 0) { gcd = a; break; }
+    a %= b;
+  }
+  uint32_t stride = 512 / gcd, offset = 0;
+  for (size_t i = 0; i + 1 < ndev; i++) {
+    float step = (amount - offset + .0f) / (ndev - i);
+    uint32_t len = static_cast<uint32_t>(roundf(step / stride)) * stride;
+    len = std::min(len, amount - offset);
+    res.emplace_back(offset, len);
+    offset += len;
+  }
+  res.emplace_back(offset, amount - offset);
+  return res;
+}
+
+static KMCUDAResult list_devices(uint32_t device, int verbosity, std::vector<int>* devs) {
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return kmcudaNoSuchDevice;
+  if (count < 32 && device > (1u << count)) return kmcudaNoSuchDevice;  // kmcuda.cc:40-44
+  if (device == 0) device = count >= 32 ? 0xFFFFFFFFu : (1u << count) - 1;
+  for (int dev = 0; device; dev++, device >>= 1) {
+    if (!(device & 1)) continue;
+    if (dev >= count || cudaSetDevice(dev) != cudaSuccess) {
+      KMB_INFO("failed to cudaSetDevice(%d)\n", dev);
+      continue;
+    }
+    cudaDeviceProp props;
+    if (cudaGetDeviceProperties(&props, dev) != cudaSuccess) continue;
+    if (props.major < 10) {
+      KMB_INFO("compute capability mismatch for device %d: this build targets sm_100a, have %d.%d\n",
+               dev, props.major, props.minor);
+      continue;
+    }
+    devs->push_back(dev);
+  }
+  return devs->empty() ? kmcudaNoSuchDevice : kmcudaSuccess;
+}
+
+static void enable_p2p(const std::vector<int>& devs, int extra, int verbosity) {
+  std::vector<int> all(devs);
+  if (extra >= 0 && std::find(all.begin(), all.end(), extra) == all.end()) all.push_back(extra);
+  if (all.size() < 2) return;
+  for (int d1 : all) {
+    cudaSetDevice(d1);
+    for (int d2 : all) {
+      if (d1 == d2) continue;
+      int access = 0;
+      cudaDeviceCanAccessPeer(&access, d1, d2);
+      if (!access) {
+        KMB_INFO("warning: p2p %d <-> %d is impossible\n", d1, d2);
+        continue;
+      }
+      cudaError_t e = cudaDeviceEnablePeerAccess(d2, 0);
+      if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+      else if (e != cudaSuccess) KMB_INFO("warning: failed to enable p2p on gpu #%d: %s\n", d1, cudaGetErrorString(e));
+    }
+  }
+}
+
+class Job {
+ public:
+  Job(int metric, uint32_t N, int D, uint32_t K, int verbosity)
+      : metric(metric), N(N), D(D), K(K), verbosity(verbosity) {}
+  ~Job() {
+    for (auto& d : devs) {
+      cudaSetDevice(d.dev);
+      if (d.comm) ncclCommDestroy(d.comm);
+      d.shard.reset();
+      if (d.st) cudaStreamDestroy(d.st);
+    }
+  }
+
+  const int metric;
+  const uint32_t N;
+  const int D;
+  const uint32_t K;
+  const int verbosity;
+  std::vector<Dev> devs;
+
+  KMCUDAResult setup(const std::vector<int>& dev_ids, bool alloc_samples);
+  KMCUDAResult ingest(const float* samples, int device_ptrs, bool fp16x2);
+  KMCUDAResult sync_all();
+  KMCUDAResult set_centroids_from_host(const float* hostC);
+  KMCUDAResult fetch_row(uint32_t idx, float* host_row);
+  KMCUDAResult init_centroids(KMCUDAInitMethod method, const void* init_params, uint32_t seed,
+                              int device_ptrs, bool fp16x2, const float* user_centroids);
+  KMCUDAResult init_random();
+  KMCUDAResult init_plusplus();
+  KMCUDAResult assign_pass(uint32_t* changed);
+  KMCUDAResult update();
+  KMCUDAResult lloyd(float tolerance, int* iter_out, uint32_t* changed_out);
+  KMCUDAResult yinyang(float tolerance, uint32_t G);
+  KMCUDAResult group_centroids(uint32_t G, std::vector<uint32_t>* groups);
+  KMCUDAResult average_distance(float* out);
+};
+
+KMCUDAResult Job::setup(const std::vector<int>& dev_ids, bool alloc_samples) {
+  auto plan = split_rows(N, static_cast<uint32_t>(D) * sizeof(float), dev_ids.size());
+  devs.resize(dev_ids.size());
+  for (size_t i = 0; i < dev_ids.size(); i++) {
+    Dev& d = devs[i];
+    d.dev = dev_ids[i];
+    d.off = plan[i].first;
+    d.len = plan[i].second;
+    KMB_CU(cudaSetDevice(d.dev), kmcudaNoSuchDevice);
+    KMB_CU(cudaStreamCreateWithFlags(&d.st, cudaStreamNonBlocking), kmcudaRuntimeError);
+    if (alloc_samples) KMB_CU(d.X.alloc(static_cast<size_t>(d.len) * D), kmcudaMemoryAllocationFailure);
+    KMB_CU(d.C.alloc(static_cast<size_t>(K) * D), kmcudaMemoryAllocationFailure);
+    KMB_CU(d.sums.alloc(static_cast<size_t>(K) * D), kmcudaMemoryAllocationFailure);
+    KMB_CU(d.assign.alloc(d.len), kmcudaMemoryAllocationFailure);
+    KMB_CU(d.prev.alloc(d.len), kmcudaMemoryAllocationFailure);
+    KMB_CU(d.ccounts.alloc(K), kmcudaMemoryAllocationFailure);
+    KMB_CU(d.counts.alloc(K), kmcudaMemoryAllocationFailure);
+    KMB_CU(d.d_changed.alloc(1), kmcudaMemoryAllocationFailure);
+    KMB_CU(d.d_dsum.alloc(1), kmcudaMemoryAllocationFailure);
+    d.shard.reset(new Shard(metric, d.dev, d.len, D, K, verbosity));
+    KMB_RET(d.shard->create(true));
+  }
+  if (devs.size() > 1) {
+    std::vector<ncclComm_t> comms(devs.size());
+    ncclResult_t r = ncclCommInitAll(comms.data(), static_cast<int>(devs.size()), dev_ids.data());
+    if (r != ncclSuccess) {
+      KMB_INFO("ncclCommInitAll failed: %s\n", ncclGetErrorString(r));
+      return kmcudaRuntimeError;
+    }
+    for (size_t i = 0; i < devs.size(); i++) devs[i].comm = comms[i];
+  }
+  if (verbosity > 1) {
+    printf("plans: [");
+    for (size_t i = 0; i < devs.size(); i++) printf("%s(%" PRIu32 ", %" PRIu32 ")", i ? ", " : "", devs[i].off, devs[i].len);
+    printf("]\n");
+  }
+  return kmcudaSuccess;
+}
+
+KMCUDAResult Job::sync_all() {
+  for (auto& d : devs) {
+    KMB_CU(cudaSetDevice(d.dev), kmcudaRuntimeError);
+    KMB_CU(cudaStreamSynchronize(d.st), kmcudaRuntimeError);
+  }
+  return kmcudaSuccess;
+}
+
+// samples: [N][D] fp32, or [N][D/2] half2 when fp16x2 (D is already the real dimension here)
+KMCUDAResult Job::ingest(const float* samples, int device_ptrs, bool fp16x2) {
+  const size_t elem = fp16x2 ? 2 : 4;
+  for (auto& d : devs) {
+    KMB_CU(cudaSetDevice(d.dev), kmcudaRuntimeError);
+    const size_t count = static_cast<size_t>(d.len) * D;
+    const char* src = reinterpret_cast<const char*>(samples) + static_cast<size_t>(d.off) * D * elem;
+    if (!fp16x2) {
+      if (device_ptrs < 0) {
+        KMB_CU(cudaMemcpyAsync(d.X.get(), src, count * 4, cudaMemcpyHostToDevice, d.st), kmcudaMemoryCopyError);
+      } else if (device_ptrs == d.dev) {
+        d.X.borrow(const_cast<float*>(reinterpret_cast<const float*>(src)));  // work in place, read-only
+      } else {
+        KMB_CU(cudaMemcpyPeerAsync(d.X.get(), d.dev, src, device_ptrs, count * 4, d.st), kmcudaMemoryCopyError);
+      }
+    } else {
+      DevBuf<char> tmp;
+      const void* hsrc = src;
+      if (!(device_ptrs >= 0 && device_ptrs == d.dev)) {
+        KMB_CU(tmp.alloc(count * 2), kmcudaMemoryAllocationFailure);
+        if (device_ptrs < 0)
+          KMB_CU(cudaMemcpyAsync(tmp.get(), src, count * 2, cudaMemcpyHostToDevice, d.st), kmcudaMemoryCopyError);
+        else
+          KMB_CU(cudaMemcpyPeerAsync(tmp.get(), d.dev, src, device_ptrs, count * 2, d.st), kmcudaMemoryCopyError);
+        hsrc = tmp.get();
+      }
+      KMB_CU(launch_half_to_float(hsrc, d.X.get(), count, d.st), kmcudaRuntimeError);
+      KMB_CU(cudaStreamSynchronize(d.st), kmcudaMemoryCopyError);  // tmp dies here
+    }
+  }
+  return sync_all();
+}
+
+KMCUDAResult Job::set_centroids_from_host(const float* hostC) {
+  for (auto& d : devs) {
+    KMB_CU(cudaSetDevice(d.dev), kmcudaRuntimeError);
+    KMB_CU(cudaMemcpyAsync(d.C.get(), hostC, sizeof(float) * static_cast<size_t>(K) * D,
+                           cudaMemcpyHostToDevice, d.st), kmcudaMemoryCopyError);
+  }
+  return sync_all();
+}
+
+KMCUDAResult Job::fetch_row(uint32_t idx, float* host_row) {
+  for (auto& d : devs) {
+    if (idx >= d.off && idx < d.off + d.len) {
+      KMB_CU(cudaSetDevice(d.dev), kmcudaRuntimeError);
+      KMB_CU(cudaMemcpy(host_row, d.X.get() + static_cast<size_t>(idx - d.off) * D, sizeof(float) * D,
+                        cudaMemcpyDeviceToHost), kmcudaMemoryCopyError);
+      return kmcudaSuccess;
+    }
+  }
+  return kmcudaRuntimeError;
+}
+
+// K distinct random samples; same host RNG walk as the reference (kmcuda.cc:245-260):
+// identity permutation shuffled with rand() the way libstdc++'s std::random_shuffle does.
+KMCUDAResult Job::init_random() {
+  KMB_INFO("randomly picking initial centroids...\n");
+  std::vector<uint32_t> chosen(N);
+  for (uint32_t s = 0; s < N; s++) chosen[s] = s;
+  for (uint32_t i = 1; i < N; i++) {
+    uint32_t j = static_cast<uint32_t>(rand() % (static_cast<int64_t>(i) + 1));
+    if (i != j) std::swap(chosen[i], chosen[j]);
+  }
+  std::vector<float> hostC(static_cast<size_t>(K) * D);
+  for (uint32_t c = 0; c < K; c++) KMB_RET(fetch_row(chosen[c], hostC.data() + static_cast<size_t>(c) * D));
+  return set_centroids_from_host(hostC.data());
+}
+
+// k-means++ driven by the host RNG: reference kmcuda.cc:262-333 + kernel kmeans.cu:42-67
+KMCUDAResult Job::init_plusplus() {
+  std::vector<float> hostC(static_cast<size_t>(K) * D);
+  std::vector<float> host_dists(N);
+  uint32_t first_index;
+  float smoke = NAN;
+  do {
+    first_index = rand() % N;
+    std::vector<float> row(D);
+    KMB_RET(fetch_row(first_index, row.data()));
+    smoke = row[0];
+    if (smoke == smoke) memcpy(hostC.data(), row.data(), sizeof(float) * D);
+  } while (smoke != smoke);
+  KMB_INFO("performing kmeans++...\n");
+  for (auto& d : devs) {
+    KMB_CU(cudaSetDevice(d.dev), kmcudaRuntimeError);
+    KMB_CU(d.dists.alloc(d.len), kmcudaMemoryAllocationFailure);
+  }
+  for (uint32_t i = 1; i < K; i++) {
+    if (verbosity > 1 || (verbosity > 0 && (K < 100 || i % (K / 100) == 0))) {
+      printf("\rstep %d", i);
+      fflush(stdout);
+    }
+    double dist_sum = 0;
+    for (auto& d : devs) {
+      KMB_CU(cudaSetDevice(d.dev), kmcudaRuntimeError);
+      float* cdst = d.C.get() + static_cast<size_t>(i - 1) * D;
+      KMB_CU(cudaMemcpyAsync(cdst, hostC.data() + static_cast<size_t>(i - 1) * D, sizeof(float) * D,
+                             cudaMemcpyHostToDevice, d.st), kmcudaMemoryCopyError);
+      KMB_CU(cudaMemsetAsync(d.d_dsum.get(), 0, sizeof(double), d.st), kmcudaRuntimeError);
+      KMB_CU(launch_plusplus_step(metric, d.X, d.len, D, cdst, i == 1, d.dists, d.d_dsum, d.st), kmcudaRuntimeError);
+      KMB_CU(cudaMemcpyAsync(host_dists.data() + d.off, d.dists.get(), sizeof(float) * d.len,
+                             cudaMemcpyDeviceToHost, d.st), kmcudaMemoryCopyError);
+    }
+    for (auto& d : devs) {
+      double part = 0;
+      KMB_CU(cudaSetDevice(d.dev), kmcudaRuntimeError);
+      KMB_CU(cudaMemcpyAsync(&part, d.d_dsum.get(), sizeof(double), cudaMemcpyDeviceToHost, d.st), kmcudaMemoryCopyError);
+      KMB_CU(cudaStreamSynchronize(d.st), kmcudaRuntimeError);
+      dist_sum += part;
+    }
+    if (dist_sum != dist_sum) KMB_INFO("\ninternal bug inside kmeans_init_centroids: dist_sum is NaN\n");
+    double choice = ((rand() + .0) / RAND_MAX);
+    uint32_t choice_approx = static_cast<uint32_t>(choice * N);
+    double choice_sum = choice * dist_sum;
+    uint32_t j;
+    if (choice_approx < 100) {
+      double s2 = 0;
+      for (j = 0; j < N && s2 < choice_sum; j++) s2 += host_dists[j];
+    } else {
+      double s2 = 0;
+      for (uint32_t t = 0; t < choice_approx; t++) s2 += host_dists[t];
+      if (s2 < choice_sum) {
+        for (j = choice_approx; j < N && s2 < choice_sum; j++) s2 += host_dists[j];
+      } else {
+        for (j = choice_approx; j > 1 && s2 >= choice_sum; j--) s2 -= host_dists[j];
+        j++;
+      }
+    }
+    if (j == 0 || j > N) {
+      KMB_INFO("\ninternal bug in kmeans_init_centroids: j = %" PRIu32 "\n", j);
+      j = std::min(std::max(j, 1u), N);
+    }
+    KMB_RET(fetch_row(j - 1, hostC.data() + static_cast<size_t>(i) * D));
+  }
+  for (auto& d : devs) d.dists.release();
+  return set_centroids_from_host(hostC.data());
+}
+
+KMCUDAResult Job::init_centroids(KMCUDAInitMethod method, const void* init_params, uint32_t seed,
+                                 int device_ptrs, bool fp16x2, const float* user_centroids) {
+  if (metric == 1 && !fp16x2) {  // three probe samples must be unit length (kmcuda.cc:195-219)
+    std::vector<float> row(D);
+    for (uint32_t s : {0u, N / 2, N - 1}) {
+      KMB_RET(fetch_row(s, row.data()));
+      double norm = 0;
+      for (int f = 0; f < D; f++) norm += row[f] * row[f];
+      const float high = 1.00001, low = 0.99999;
+      if (norm > high || norm < low) {
+        KMB_INFO("error: angular distance: samples[%" PRIu32 "] has L2 norm = %f which is outside [%f, %f]\n",
+                 s, norm, low, high);
+        return kmcudaInvalidArguments;
+      }
+    }
+  }
+  srand(seed);
+  switch (method) {
+    case kmcudaInitMethodImport: {
+      const size_t count = static_cast<size_t>(K) * D;
+      for (auto& d : devs) {
+        KMB_CU(cudaSetDevice(d.dev), kmcudaRuntimeError);
+        if (!fp16x2) {
+          if (device_ptrs < 0)
+            KMB_CU(cudaMemcpyAsync(d.C.get(), user_centroids, count * 4, cudaMemcpyHostToDevice, d.st), kmcudaMemoryCopyError);
+          else
+            KMB_CU(cudaMemcpyPeerAsync(d.C.get(), d.dev, user_centroids, device_ptrs, count * 4, d.st), kmcudaMemoryCopyError);
+        } else {
+          DevBuf<char> tmp;
+          KMB_CU(tmp.alloc(count * 2), kmcudaMemoryAllocationFailure);
+          if (device_ptrs < 0)
+            KMB_CU(cudaMemcpyAsync(tmp.get(), user_centroids, count * 2, cudaMemcpyHostToDevice, d.st), kmcudaMemoryCopyError);
+          else
+            KMB_CU(cudaMemcpyPeerAsync(tmp.get(), d.dev, user_centroids, device_ptrs, count * 2, d.st), kmcudaMemoryCopyError);
+          KMB_CU(launch_half_to_float(tmp.get(), d.C.get(), count, d.st), kmcudaRuntimeError);
+          KMB_CU(cudaStreamSynchronize(d.st), kmcudaMemoryCopyError);
+        }
+      }
+      KMB_RET(sync_all());
+      break;
+    }
+    case kmcudaInitMethodRandom:
+      KMB_RET(init_random());
+      break;
+    case kmcudaInitMethodPlusPlus:
+      KMB_RET(init_plusplus());
+      break;
+    case kmcudaInitMethodAFKMC2:
+      (void)init_params;
+      KMB_INFO("afkmc2 initialisation is not built into this library yet (use k-means++ / random / import)\n");
+      return kmcudaInvalidArguments;
+    default:
+      return kmcudaInvalidArguments;
+  }
+  KMB_INFO("\rdone            \n");
+  return kmcudaSuccess;
+}
+
+// one assignment pass over every shard; *changed = total reassignments
+KMCUDAResult Job::assign_pass(uint32_t* changed) {
+  for (auto& d : devs) {
+    KMB_CU(cudaSetDevice(d.dev), kmcudaRuntimeError);
+    KMB_CU(cudaMemsetAsync(d.d_changed.get(), 0, sizeof(uint32_t), d.st), kmcudaRuntimeError);
+    KMB_RET(d.shard->assign(d.len, d.X, d.C, d.assign, d.prev, d.d_changed, d.st));
+  }
+  uint32_t total = 0;
+  for (auto& d : devs) {
+    uint32_t mine = 0;
+    KMB_CU(cudaSetDevice(d.dev), kmcudaRuntimeError);
+    KMB_CU(cudaMemcpyAsync(&mine, d.d_changed.get(), sizeof(mine), cudaMemcpyDeviceToHost, d.st), kmcudaMemoryCopyError);
+    KMB_CU(cudaStreamSynchronize(d.st), kmcudaRuntimeError);
+    total += mine;
+  }
+  *changed = total;
+  return kmcudaSuccess;
+}
+
+// centroid update: shard partial sums -> NCCL all-reduce (sum) -> normalise on every GPU
+KMCUDAResult Job::update() {
+  for (auto& d : devs) {
+    KMB_CU(cudaSetDevice(d.dev), kmcudaRuntimeError);
+    KMB_RET(d.shard->partial_sums(d.len, d.X, d.assign, d.sums, d.counts, d.st));
+  }
+  if (devs.size() > 1) {
+    ncclGroupStart();
+    for (auto& d : devs) {
+      ncclAllReduce(d.sums.get(), d.sums.get(), static_cast<size_t>(K) * D, ncclFloat32, ncclSum, d.comm, d.st);
+      ncclAllReduce(d.counts.get(), d.counts.get(), K, ncclUint32, ncclSum, d.comm, d.st);
+    }
+    ncclResult_t r = ncclGroupEnd();
+    if (r != ncclSuccess) {
+      KMB_INFO("ncclAllReduce failed: %s\n", ncclGetErrorString(r));
+      return kmcudaRuntimeError;
+    }
+  }
+  for (auto& d : devs) {
+    KMB_CU(cudaSetDevice(d.dev), kmcudaRuntimeError);
+    KMB_RET(d.shard->finish_update(d.sums, d.counts, d.C, d.ccounts, d.st));
+  }
+  return kmcudaSuccess;
+}
+
+// reference kmeans_cuda_lloyd, kmeans.cu:934-1026 (resume == false)
+KMCUDAResult Job::lloyd(float tolerance, int* iter_out, uint32_t* changed_out) {
+  for (auto& d : devs) {
+    KMB_CU(cudaSetDevice(d.dev), kmcudaRuntimeError);
+    KMB_CU(cudaMemsetAsync(d.ccounts.get(), 0, sizeof(uint32_t) * K, d.st), kmcudaRuntimeError);
+    KMB_CU(cudaMemsetAsync(d.assign.get(), 0xff, sizeof(uint32_t) * d.len, d.st), kmcudaRuntimeError);
+    KMB_CU(cudaMemsetAsync(d.prev.get(), 0xff, sizeof(uint32_t) * d.len, d.st), kmcudaRuntimeError);
+  }
+  for (int iter = 1;; iter++) {
+    uint32_t changed = 0;
+    KMB_RET(assign_pass(&changed));
+    KMB_INFO("iteration %d: %" PRIu32 " reassignments\n", iter, changed);
+    if (iter_out) *iter_out = iter;
+    if (changed_out) *changed_out = changed;
+    if (changed <= tolerance * N) return kmcudaSuccess;  // float compare, kmeans.cu:707
+    KMB_RET(update());
+  }
+}
+
+// Yinyang groups = k-means (k-means++ with srand(0), Lloyd to 2 %) over the K centroids,
+// reference kmeans.cu:1061-1094.  Runs on the first device, result broadcast by the caller.
+KMCUDAResult Job::group_centroids(uint32_t G, std::vector<uint32_t>* groups) {
+  Job sub(metric, K, D, G, verbosity);
+  std::vector<int> one{devs[0].dev};
+  KMB_RET(sub.setup(one, false));
+  sub.devs[0].X.borrow(devs[0].C.get());
+  srand(0);
+  KMB_RET(sub.init_plusplus());
+  KMB_INFO("\rdone            \n");
+  KMB_RET(sub.lloyd(kYinyangGroupTolerance, nullptr, nullptr));
+  groups->resize(K);
+  KMB_CU(cudaSetDevice(devs[0].dev), kmcudaRuntimeError);
+  KMB_CU(cudaMemcpy(groups->data(), sub.devs[0].assign.get(), sizeof(uint32_t) * K, cudaMemcpyDeviceToHost),
+         kmcudaMemoryCopyError);
+  return kmcudaSuccess;
+}
+
+// reference kmeans_cuda_yy, kmeans.cu:1028-1263
+KMCUDAResult Job::yinyang(float tolerance, uint32_t G) {
+  if (G == 0 || kYinyangDraftReassignments <= tolerance) {
+    if (verbosity > 0) {
+      if (G == 0) printf("too few clusters for this yinyang_t => Lloyd\n");
+      else printf("tolerance is too high (>= %.2f) => Lloyd\n", kYinyangDraftReassignments);
+    }
+    return lloyd(tolerance, nullptr, nullptr);
+  }
+  KMB_INFO("running Lloyd until reassignments drop below %" PRIu32 "\n",
+           static_cast<uint32_t>(kYinyangDraftReassignments * N));
+  int iter = 0;
+  uint32_t changed = 0;
+  KMB_RET(lloyd(kYinyangDraftReassignments, &iter, &changed));
+  if (changed <= tolerance * N) return kmcudaSuccess;
+  std::vector<uint32_t> groups;
+  KMB_RET(group_centroids(G, &groups));
+  for (auto& d : devs) {
+    KMB_RET(d.shard->enable_yinyang(G));
+    KMB_CU(cudaSetDevice(d.dev), kmcudaRuntimeError);
+    KMB_CU(cudaMemcpyAsync(d.shard->groups.get(), groups.data(), sizeof(uint32_t) * K, cudaMemcpyHostToDevice, d.st),
+           kmcudaMemoryCopyError);
+    KMB_CU(cudaMemsetAsync(d.d_changed.get(), 0, sizeof(uint32_t), d.st), kmcudaRuntimeError);
+  }
+  KMB_RET(sync_all());
+  bool refresh = true;
+  for (;; iter++) {
+    if (!refresh) {
+      uint32_t total_changed = 0, total_passed = 0;
+      for (auto& d : devs) {
+        uint32_t c = 0, p = 0;
+        KMB_CU(cudaSetDevice(d.dev), kmcudaRuntimeError);
+        KMB_CU(cudaMemcpyAsync(&c, d.d_changed.get(), 4, cudaMemcpyDeviceToHost, d.st), kmcudaMemoryCopyError);
+        KMB_CU(cudaMemcpyAsync(&p, d.shard->d_npassed.get(), 4, cudaMemcpyDeviceToHost, d.st), kmcudaMemoryCopyError);
+        KMB_CU(cudaStreamSynchronize(d.st), kmcudaRuntimeError);
+        total_changed += c;
+        total_passed += p;
+      }
+      KMB_INFO("iteration %d: %" PRIu32 " reassignments\n", iter, total_changed);
+      if (total_changed <= tolerance * N) return kmcudaSuccess;
+      for (auto& d : devs) {
+        KMB_CU(cudaSetDevice(d.dev), kmcudaRuntimeError);
+        KMB_CU(cudaMemsetAsync(d.d_changed.get(), 0, sizeof(uint32_t), d.st), kmcudaRuntimeError);
+      }
+      KMB_DEBUG("passed number: %" PRIu32 "\n", total_passed);
+      if (1.f - (total_passed + 0.f) / N < kYinyangRefreshEpsilon) refresh = true;
+    }
+    if (refresh) {
+      KMB_INFO("refreshing Yinyang bounds...\n");
+      for (auto& d : devs) {
+        KMB_CU(cudaSetDevice(d.dev), kmcudaRuntimeError);
+        KMB_CU(launch_yy_init(metric, d.X, d.C, d.len, D, K, G, d.assign, d.shard->groups, d.shard->bounds, d.st),
+               kmcudaRuntimeError);
+      }
+      refresh = false;
+    }
+    for (auto& d : devs) {
+      KMB_CU(cudaSetDevice(d.dev), kmcudaRuntimeError);
+      KMB_CU(cudaMemcpyAsync(d.shard->oldC.get(), d.C.get(), sizeof(float) * static_cast<size_t>(K) * D,
+                             cudaMemcpyDeviceToDevice, d.st), kmcudaMemoryCopyError);
+    }
+    KMB_RET(update());
+    for (auto& d : devs) {
+      Shard* s = d.shard.get();
+      KMB_CU(cudaSetDevice(d.dev), kmcudaRuntimeError);
+      KMB_CU(launch_yy_drifts(metric, d.C, s->oldC, K, D, G, s->groups, s->drift, s->maxdrift, d.st), kmcudaRuntimeError);
+      KMB_CU(cudaMemsetAsync(s->d_npassed.get(), 0, sizeof(uint32_t), d.st), kmcudaRuntimeError);
+      KMB_CU(launch_yy_global_filter(metric, d.X, d.C, d.len, D, G, s->drift, s->maxdrift, d.assign, d.prev,
+                                     s->bounds, s->passed, s->d_npassed, d.st), kmcudaRuntimeError);
+      KMB_CU(launch_yy_local_filter(metric, d.X, d.C, d.len, D, K, G, s->groups, s->drift, s->maxdrift,
+                                    s->passed, s->d_npassed, d.assign, s->bounds, d.d_changed, d.st),
+             kmcudaRuntimeError);
+    }
+  }
+}
+
+KMCUDAResult Job::average_distance(float* out) {
+  KMB_INFO("calculating the average distance...\n");
+  double sum = 0;
+  for (auto& d : devs) {
+    KMB_CU(cudaSetDevice(d.dev), kmcudaRuntimeError);
+    KMB_CU(cudaMemsetAsync(d.d_dsum.get(), 0, sizeof(double), d.st), kmcudaRuntimeError);
+    KMB_CU(launch_average_distance(metric, d.X, d.C, d.len, D, d.assign, d.d_dsum, d.st), kmcudaRuntimeError);
+  }
+  for (auto& d : devs) {
+    double part = 0;
+    KMB_CU(cudaSetDevice(d.dev), kmcudaRuntimeError);
+    KMB_CU(cudaMemcpyAsync(&part, d.d_dsum.get(), sizeof(double), cudaMemcpyDeviceToHost, d.st), kmcudaMemoryCopyError);
+    KMB_CU(cudaStreamSynchronize(d.st), kmcudaRuntimeError);
+    sum += part;
+  }
+  *out = static_cast<float>(sum / N);
+  return kmcudaSuccess;
+}
+
+static KMCUDAResult print_memory_stats(const std::vector<int>& devs) {
+  for (int dev : devs) {
+    cudaSetDevice(dev);
+    size_t free_bytes, total_bytes;
+    if (cudaMemGetInfo(&free_bytes, &total_bytes) != cudaSuccess) return kmcudaRuntimeError;
+    printf("GPU #%d memory: used %zu bytes (%.1f%%), free %zu bytes, total %zu bytes\n", dev,
+           total_bytes - free_bytes, (total_bytes - free_bytes) * 100.0 / total_bytes, free_bytes, total_bytes);
+  }
+  return kmcudaSuccess;
+}
+
+}  // namespace kmb
+
+using namespace kmb;
+
+extern "C" {
+
+KMCUDAResult kmeans_cuda(KMCUDAInitMethod init, const void* init_params, float tolerance,
+                         float yinyang_t, KMCUDADistanceMetric metric, uint32_t samples_size,
+                         uint16_t features_size, uint32_t clusters_size, uint32_t seed,
+                         uint32_t device, int32_t device_ptrs, int32_t fp16x2, int32_t verbosity,
+                         const float* samples, float* centroids, uint32_t* assignments,
+                         float* average_distance) {
+  KMB_DEBUG("arguments: %d %p %.3f %.2f %d %" PRIu32 " %" PRIu16 " %" PRIu32 " %" PRIu32 " %" PRIu32
+            " %d %" PRIi32 " %p %p %p %p\n", init, init_params, tolerance, yinyang_t, metric, samples_size,
+            features_size, clusters_size, seed, device, fp16x2, verbosity, samples, centroids, assignments,
+            average_distance);
+  // argument validation: reference check_kmeans_args, kmcuda.cc:19-61
+  if (clusters_size < 2 || clusters_size == UINT32_MAX) return kmcudaInvalidArguments;
+  if (features_size == 0) return kmcudaInvalidArguments;
+  if (samples_size < clusters_size) return kmcudaInvalidArguments;
+  {
+    int count = 0;
+    cudaGetDeviceCount(&count);
+    if (count < 32 && device > (1u << count)) return kmcudaNoSuchDevice;
+  }
+  if (samples == nullptr || centroids == nullptr || assignments == nullptr) return kmcudaInvalidArguments;
+  if (!(tolerance >= 0 && tolerance <= 1)) return kmcudaInvalidArguments;
+  if (!(yinyang_t >= 0 && yinyang_t <= 0.5)) return kmcudaInvalidArguments;
+  if (static_cast<uint64_t>(features_size) * (fp16x2 ? 2 : 1) > 65535u) return kmcudaInvalidArguments;
+  KMB_INFO("reassignments threshold: %" PRIu32 "\n", static_cast<uint32_t>(tolerance * samples_size));
+  const uint32_t yy_groups_size = static_cast<uint32_t>(yinyang_t * clusters_size);
+  KMB_DEBUG("yinyang groups: %" PRIu32 "\n", yy_groups_size);
+  std::vector<int> dev_ids;
+  KMB_RET(list_devices(device, verbosity, &dev_ids));
+  enable_p2p(dev_ids, device_ptrs, verbosity);
+  const int m = metric == kmcudaDistanceMetricCosine ? 1 : 0;
+  const int D = static_cast<int>(features_size) * (fp16x2 ? 2 : 1);
+  Job job(m, samples_size, D, clusters_size, verbosity);
+  KMB_RET(job.setup(dev_ids, true));
+  KMB_RET(job.ingest(samples, device_ptrs, fp16x2 != 0));
+  if (verbosity > 1) KMB_RET(print_memory_stats(dev_ids));
+  KMB_RET(job.init_centroids(init, init_params, seed, device_ptrs, fp16x2 != 0, centroids));
+  KMB_RET(job.yinyang(tolerance, yy_groups_size));
+  if (average_distance) KMB_RET(job.average_distance(average_distance));
+  // copy-out: centroids from the first device (identical everywhere), assignment slices from each shard
+  const size_t ccount = static_cast<size_t>(clusters_size) * D;
+  {
+    Dev& d0 = job.devs[0];
+    KMB_CU(cudaSetDevice(d0.dev), kmcudaRuntimeError);
+    const void* csrc = d0.C.get();
+    DevBuf<char> tmp;
+    if (fp16x2) {
+      KMB_CU(tmp.alloc(ccount * 2), kmcudaMemoryAllocationFailure);
+      KMB_CU(launch_float_to_half(d0.C.get(), tmp.get(), ccount, d0.st), kmcudaRuntimeError);
+      csrc = tmp.get();
+    }
+    const size_t cbytes = ccount * (fp16x2 ? 2 : 4);
+    if (device_ptrs < 0)
+      KMB_CU(cudaMemcpyAsync(centroids, csrc, cbytes, cudaMemcpyDeviceToHost, d0.st), kmcudaMemoryCopyError);
+    else
+      KMB_CU(cudaMemcpyPeerAsync(centroids, device_ptrs, csrc, d0.dev, cbytes, d0.st), kmcudaMemoryCopyError);
+    KMB_CU(cudaStreamSynchronize(d0.st), kmcudaMemoryCopyError);
+  }
+  for (auto& d : job.devs) {
+    KMB_CU(cudaSetDevice(d.dev), kmcudaRuntimeError);
+    if (device_ptrs < 0)
+      KMB_CU(cudaMemcpyAsync(assignments + d.off, d.assign.get(), sizeof(uint32_t) * d.len,
+                             cudaMemcpyDeviceToHost, d.st), kmcudaMemoryCopyError);
+    else
+      KMB_CU(cudaMemcpyPeerAsync(assignments + d.off, device_ptrs, d.assign.get(), d.dev,
+                                 sizeof(uint32_t) * d.len, d.st), kmcudaMemoryCopyError);
+  }
+  KMB_RET(job.sync_all());
+  KMB_DEBUG("return kmcudaSuccess\n");
+  return kmcudaSuccess;
+}
+
+KMCUDAResult knn_cuda(uint16_t k, KMCUDADistanceMetric metric, uint32_t samples_size,
+                      uint16_t features_size, uint32_t clusters_size, uint32_t device,
+                      int32_t device_ptrs, int32_t fp16x2, int32_t verbosity, const float* samples,
+                      const float* centroids, const uint32_t* assignments, uint32_t* neighbors) {
+  KMB_DEBUG("arguments: %" PRIu16 " %d %" PRIu32 " %" PRIu16 " %" PRIu32 " %" PRIu32 " %" PRIi32 " %" PRIi32
+            " %" PRIi32 " %p %p %p %p\n", k, metric, samples_size, features_size, clusters_size, device,
+            device_ptrs, fp16x2, verbosity, samples, centroids, assignments, neighbors);
+  // reference check_knn_args, kmcuda.cc:537-570 (the reference computes but ignores the verdict,
+  // kmcuda.cc:583-584; here invalid arguments are rejected)
+  if (k == 0) return kmcudaInvalidArguments;
+  if (clusters_size < 2 || clusters_size == UINT32_MAX) return kmcudaInvalidArguments;
+  if (features_size == 0) return kmcudaInvalidArguments;
+  if (samples_size < clusters_size) return kmcudaInvalidArguments;
+  if (samples == nullptr || centroids == nullptr || assignments == nullptr || neighbors == nullptr)
+    return kmcudaInvalidArguments;
+  if (static_cast<uint64_t>(features_size) * (fp16x2 ? 2 : 1) > 65535u) return kmcudaInvalidArguments;
+  std::vector<int> dev_ids;
+  KMB_RET(list_devices(device, verbosity, &dev_ids));
+  enable_p2p(dev_ids, device_ptrs, verbosity);
+  const int m = metric == kmcudaDistanceMetricCosine ? 1 : 0;
+  const int D = static_cast<int>(features_size) * (fp16x2 ? 2 : 1);
+  const uint32_t N = samples_size, K = clusters_size;
+  auto plan = split_rows(N, static_cast<uint32_t>(D) * sizeof(float), dev_ids.size());
+  unsigned long long total_pairs = 0;
+  struct KDev {
+    DevBuf<float> X, C, cd, radii, heap;
+    DevBuf<uint32_t> assign, inv_keys, iota, inv, off, counts, neigh;
+    DevBuf<char> cub;
+    DevBuf<unsigned long long> pairs;
+    cudaStream_t st = nullptr;
+  };
+  std::vector<std::unique_ptr<KDev>> kd;
+  auto cleanup = [&]() {
+    for (size_t i = 0; i < kd.size(); i++) {
+      cudaSetDevice(dev_ids[i]);
+      if (kd[i]->st) cudaStreamDestroy(kd[i]->st);
+    }
+  };
+  // every device gets the whole sample matrix (candidates can live anywhere), its slice of queries
+  for (size_t i = 0; i < dev_ids.size(); i++) {
+    kd.emplace_back(new KDev);
+    KDev& d = *kd.back();
+    const int dev = dev_ids[i];
+    const uint32_t qlen = plan[i].second;
+#define KNN_CU(call, code) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { KMB_INFO("%s:%d -> %s\n", __FILE__, __LINE__, cudaGetErrorString(e__)); cleanup(); return code; } } while (false)
+    KNN_CU(cudaSetDevice(dev), kmcudaNoSuchDevice);
+    KNN_CU(cudaStreamCreateWithFlags(&d.st, cudaStreamNonBlocking), kmcudaRuntimeError);
+    const size_t xcount = static_cast<size_t>(N) * D, ccount = static_cast<size_t>(K) * D;
+    auto load = [&](DevBuf<float>& dst, const float* src, size_t count) -> cudaError_t {
+      cudaError_t e;
+      if (!fp16x2) {
+        if (device_ptrs >= 0 && device_ptrs == dev) { dst.borrow(const_cast<float*>(src)); return cudaSuccess; }
+        if ((e = dst.alloc(count)) != cudaSuccess) return e;
+        if (device_ptrs < 0) return cudaMemcpyAsync(dst.get(), src, count * 4, cudaMemcpyHostToDevice, d.st);
+        return cudaMemcpyPeerAsync(dst.get(), dev, src, device_ptrs, count * 4, d.st);
+      }
+      if ((e = dst.alloc(count)) != cudaSuccess) return e;
+      DevBuf<char> tmp;
+      const void* hsrc = src;
+      if (!(device_ptrs >= 0 && device_ptrs == dev)) {
+        if ((e = tmp.alloc(count * 2)) != cudaSuccess) return e;
+        e = device_ptrs < 0 ? cudaMemcpyAsync(tmp.get(), src, count * 2, cudaMemcpyHostToDevice, d.st)
+                            : cudaMemcpyPeerAsync(tmp.get(), dev, src, device_ptrs, count * 2, d.st);
+        if (e != cudaSuccess) return e;
+        hsrc = tmp.get();
+      }
+      if ((e = launch_half_to_float(hsrc, dst.get(), count, d.st)) != cudaSuccess) return e;
+      return cudaStreamSynchronize(d.st);
+    };
+    KNN_CU(load(d.X, samples, xcount), kmcudaMemoryCopyError);
+    KNN_CU(load(d.C, centroids, ccount), kmcudaMemoryCopyError);
+    if (device_ptrs >= 0 && device_ptrs == dev) {
+      d.assign.borrow(const_cast<uint32_t*>(assignments));
+    } else {
+      KNN_CU(d.assign.alloc(N), kmcudaMemoryAllocationFailure);
+      if (device_ptrs < 0) KNN_CU(cudaMemcpyAsync(d.assign.get(), assignments, 4ull * N, cudaMemcpyHostToDevice, d.st), kmcudaMemoryCopyError);
+      else KNN_CU(cudaMemcpyPeerAsync(d.assign.get(), dev, assignments, device_ptrs, 4ull * N, d.st), kmcudaMemoryCopyError);
+    }
+    KNN_CU(d.inv_keys.alloc(N), kmcudaMemoryAllocationFailure);
+    KNN_CU(d.iota.alloc(N), kmcudaMemoryAllocationFailure);
+    KNN_CU(d.inv.alloc(N), kmcudaMemoryAllocationFailure);
+    KNN_CU(d.off.alloc(static_cast<size_t>(K) + 1), kmcudaMemoryAllocationFailure);
+    KNN_CU(d.counts.alloc(K), kmcudaMemoryAllocationFailure);
+    KNN_CU(d.cd.alloc(static_cast<size_t>(K) * K), kmcudaMemoryAllocationFailure);
+    KNN_CU(d.radii.alloc(K), kmcudaMemoryAllocationFailure);
+    KNN_CU(d.heap.alloc(static_cast<size_t>(qlen) * 2 * k), kmcudaMemoryAllocationFailure);
+    KNN_CU(d.neigh.alloc(static_cast<size_t>(qlen) * k), kmcudaMemoryAllocationFailure);
+    KNN_CU(d.pairs.alloc(1), kmcudaMemoryAllocationFailure);
+    KNN_CU(cudaMemsetAsync(d.pairs.get(), 0, sizeof(unsigned long long), d.st), kmcudaRuntimeError);
+    // inverse assignments (reference: host std::sort of (assignment, index) tuples, kmcuda.cc:648-691):
+    // stable device radix sort + binary-searched CSR offsets
+    if (i == 0) KMB_INFO("initializing the inverse assignments...\n");
+    UpdateWorkspace ws;
+    ws.cub_tmp_bytes = update_cub_bytes(N);
+    KNN_CU(d.cub.alloc(ws.cub_tmp_bytes), kmcudaMemoryAllocationFailure);
+    ws.cub_tmp = d.cub.get();
+    KNN_CU(launch_knn_inverse(d.assign, N, K, d.iota, d.inv_keys, d.inv, d.off, d.counts, ws, d.st), kmcudaRuntimeError);
+    KNN_CU(launch_knn_radii(m, d.X, d.C, N, D, K, d.assign, d.radii, d.st), kmcudaRuntimeError);
+    KNN_CU(launch_knn_centroid_distances(m, d.C, K, D, d.cd, d.st), kmcudaRuntimeError);
+    KNN_CU(launch_knn_search(m, k, d.X, d.C, N, D, K, plan[i].first, qlen, d.assign, d.inv, d.off, d.cd,
+                             d.radii, d.heap, d.neigh, d.pairs, d.st), kmcudaRuntimeError);
+  }
+  for (size_t i = 0; i < dev_ids.size(); i++) {
+    KDev& d = *kd[i];
+    const int dev = dev_ids[i];
+    const uint32_t qoff = plan[i].first, qlen = plan[i].second;
+    KNN_CU(cudaSetDevice(dev), kmcudaRuntimeError);
+    if (device_ptrs < 0)
+      KNN_CU(cudaMemcpyAsync(neighbors + static_cast<size_t>(qoff) * k, d.neigh.get(),
+                             sizeof(uint32_t) * static_cast<size_t>(qlen) * k, cudaMemcpyDeviceToHost, d.st),
+             kmcudaMemoryCopyError);
+    else
+      KNN_CU(cudaMemcpyPeerAsync(neighbors + static_cast<size_t>(qoff) * k, device_ptrs, d.neigh.get(), dev,
+                                 sizeof(uint32_t) * static_cast<size_t>(qlen) * k, d.st), kmcudaMemoryCopyError);
+    unsigned long long p = 0;
+    KNN_CU(cudaMemcpyAsync(&p, d.pairs.get(), sizeof(p), cudaMemcpyDeviceToHost, d.st), kmcudaMemoryCopyError);
+    KNN_CU(cudaStreamSynchronize(d.st), kmcudaRuntimeError);
+    total_pairs += p;
+  }
+#undef KNN_CU
+  cleanup();
+  KMB_INFO("calculated %f of all the distances\n",
+           static_cast<double>(total_pairs) / (static_cast<double>(N) * N));  // reference knn.cu:530
+  KMB_DEBUG("return kmcudaSuccess\n");
+  return kmcudaSuccess;
+}
+
+}  // extern "C"

@@ -1,0 +1,765 @@
+// assign_tc.cu -- the B200 hot path: samples x centroids L2 ranking as a dense fp16 contraction on
+// tcgen05 tensor cores, fused with a per-sample candidate filter; the exact fp32 re-check
+// (simt_kernels.cu) then makes the final, reference-identical decision.
+//
+// What the reference does here: kmeans_assign_lloyd (reference src/kmeans.cu:293-364) -- one CUDA
+// thread per sample, N*K*D Kahan-compensated round-down FMAs on the FP32 pipe.
+//
+// What this file does instead, per persistent CTA (one per SM) and per tile of 128 samples:
+//   converter warps : ld.global.nc fp32 rows -> *s (power of two) -> fp16 -> 128B-swizzled K-major
+//                     A tile in shared memory; per row ||x~||, ||x - x~|| for the error bound
+//   TMA warp        : streams the fp16 centroid table (B operand, 256 centroids x 64 features per
+//                     stage, 128B swizzle) + the per-tile bias block through an mbarrier ring
+//   MMA thread      : tcgen05.mma kind::f16, M=128 N=256 K=16, fp32 accumulators double-buffered
+//                     in TMEM (2 x 256 columns); one extra K=16 step adds -||c||^2/2 (three fp16
+//                     terms against constant ones) so that acc = x.c - ||c||^2/2
+//   epilogue warps  : tcgen05.ld 32 columns at a time; running row maximum M; every column whose
+//                     value is within `margin` of M is recorded (bit mask per 32-column chunk);
+//                     margin is a rigorous bound on |approx - exact| derived from the actual
+//                     rounding residuals (Cauchy-Schwarz), so the reference's fp32 winner is
+//                     guaranteed to be among the recorded candidates.
+//   rows with one candidate are final; rows with several go to the exact re-check queue; rows with
+//   non-finite data or too many candidates go to the exact full pass.  Assignments are therefore
+//   bit-identical to the reference kernel's, ties included.
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include <cstdio>
+#include <cstring>
+
+#include "exact.cuh"
+#include "kernels.h"
+#include "sm100_ptx.cuh"
+
+namespace kmb {
+
+namespace tc {
+constexpr int TM = 128;                 // samples per tile (UMMA M)
+constexpr int TN = 256;                 // centroids per n-tile (UMMA N)
+constexpr int KB = 64;                  // fp16 elements per K-block = one 128-byte swizzle row
+constexpr int MAX_NKB = 4;              // D <= 256
+constexpr int B_STAGES = 3;
+constexpr int A_KB_BYTES = TM * 128;    // 16 KiB
+constexpr int B_STAGE_BYTES = TN * 128; // 32 KiB
+constexpr int AUG_A_BYTES = TM * 32;    // 4 KiB  (K=16 fp16, no swizzle)
+constexpr int AUG_B_BYTES = TN * 32;    // 8 KiB
+constexpr int LIST_LEN = 12;            // chunk entries per epilogue thread
+constexpr int N_CONV_WARPS = 4;
+constexpr int N_EPI_WARPS = 8;
+constexpr int FIRST_CONV_WARP = 2;
+constexpr int FIRST_EPI_WARP = 6;
+constexpr int N_THREADS = (FIRST_EPI_WARP + N_EPI_WARPS) * 32;  // 448
+constexpr int MAX_CAND = 16;            // candidates per row before falling back to the full exact pass
+constexpr uint32_t TMEM_COLS = 512;
+
+// counters[] slots
+enum { CNT_PAIRS = 0, CNT_ROWQ = 1, CNT_OVF = 2, CNT_ERR = 3, CNT_N = 4 };
+
+struct Stats {       // written by the centroid prep kernels, read by the main kernel
+  float scale;       // s = 2^k applied to samples and centroids before fp16 rounding
+  float cmax;        // max_c ||s*c||  (finite centroids)
+  float dcmax;       // max_c ||s*c - fp16(s*c)||
+  uint32_t csq_max_bits;
+};
+
+struct SmemLayout {  // byte offsets from the 1024-aligned dynamic smem base
+  uint32_t a, b, aug_a, aug_b, list_cm, list_mask, list_g, norms, fin, bars, tmem_slot, total;
+};
+
+__host__ __device__ inline SmemLayout smem_layout(int nkb) {
+  SmemLayout L;
+  uint32_t o = 0;
+  L.a = o; o += nkb * A_KB_BYTES;
+  L.b = o; o += B_STAGES * B_STAGE_BYTES;
+  L.aug_a = o; o += AUG_A_BYTES;
+  L.aug_b = o; o += 2 * AUG_B_BYTES;
+  L.list_cm = o; o += LIST_LEN * 256 * 4;
+  L.list_mask = o; o += LIST_LEN * 256 * 4;
+  L.list_g = o; o += LIST_LEN * 256 * 2;
+  L.norms = o; o += 2 * 2 * TM * 4;   // [parity][x|d][row]
+  L.fin = o; o += 256 * 4 * 3;        // M, cnt, flags of the 256 epilogue threads
+  L.bars = o; o += 64 * 8;
+  L.tmem_slot = o; o += 16;
+  L.total = o;
+  return L;
+}
+
+// barrier indices inside the bars[] array
+__host__ __device__ constexpr int BAR_B_FULL(int s) { return s; }
+__host__ __device__ constexpr int BAR_B_EMPTY(int s) { return B_STAGES + s; }
+__host__ __device__ constexpr int BAR_AUG_FULL(int s) { return 2 * B_STAGES + s; }
+__host__ __device__ constexpr int BAR_AUG_EMPTY(int s) { return 2 * B_STAGES + 2 + s; }
+__host__ __device__ constexpr int BAR_A_FULL(int kb) { return 2 * B_STAGES + 4 + kb; }
+__host__ __device__ constexpr int BAR_A_EMPTY(int kb) { return 2 * B_STAGES + 4 + MAX_NKB + kb; }
+__host__ __device__ constexpr int BAR_ACC_FULL(int b) { return 2 * B_STAGES + 4 + 2 * MAX_NKB + b; }
+__host__ __device__ constexpr int BAR_ACC_EMPTY(int b) { return 2 * B_STAGES + 6 + 2 * MAX_NKB + b; }
+
+struct Params {
+  const float* X;            // [n][D] fp32 row-major
+  uint32_t n;
+  int D;
+  uint32_t K;
+  int nkb;                   // K-blocks of 64 features
+  int nt;                    // n-tiles of 256 centroids
+  uint32_t ntiles;           // sample tiles
+  const __half* aug_blob;    // [nt][AUG_B_BYTES] in the shared-memory byte layout
+  const Stats* stats;
+  uint32_t* result;          // [n]
+  uint32_t* pair_row;        // re-check queue: (row, candidate) pairs
+  uint32_t* pair_cand;
+  uint32_t max_pairs;
+  uint32_t* rowq;            // [3*i]: row, first pair, pair count
+  uint32_t* ovf_rows;        // rows for the full exact pass
+  uint32_t* counters;        // CNT_*
+  int aug_swap;              // debug: swap LBO/SBO of the no-swizzle descriptors
+  float* dbg_scores;         // optional [ntiles*128][nt*256] dump of the approximate scores
+};
+
+// ---------------------------------------------------------------------------------------------------
+// centroid preparation: scale, fp16 table (zero padded to [nt*256][nkb*64]), bias blobs, statistics
+// ---------------------------------------------------------------------------------------------------
+__global__ void tc_prep_stats_kernel(const float* __restrict__ csq, uint32_t K, Stats* __restrict__ st) {
+  // max finite ||c||^2 (positive floats order like unsigned ints)
+  uint32_t best = 0;
+  for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < K; c += gridDim.x * blockDim.x) {
+    float v = csq[c];
+    if (v == v && v < 3.0e38f) best = max(best, __float_as_uint(fmaxf(v, 0.f)));
+  }
+  for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(&st->csq_max_bits, best);
+}
+
+__global__ void tc_prep_scale_kernel(Stats* __restrict__ st) {
+  float cmax = __fsqrt_ru(__uint_as_float(st->csq_max_bits));
+  float s = 1.f;
+  if (cmax > 0.f && cmax < 3.0e38f) {
+    int e;
+    frexpf(cmax, &e);          // cmax = m * 2^e, m in [0.5, 1)
+    s = ldexpf(1.f, 6 - e);    // s*cmax in [32, 64)
+  }
+  st->scale = s;
+  st->cmax = cmax * s * 1.001f;
+  st->dcmax = 0.f;
+}
+
+// one warp per centroid row (including the zero padding rows up to nt*256)
+__global__ void tc_prep_table_kernel(const float* __restrict__ C, const float* __restrict__ csq,
+                                     uint32_t K, int D, int nkb, int nt, __half* __restrict__ table,
+                                     __half* __restrict__ aug_blob, Stats* __restrict__ st) {
+  const uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rows_pad = static_cast<uint32_t>(nt) * TN;
+  if (row >= rows_pad) return;
+  const int Dp = nkb * KB;
+  const float s = st->scale;
+  bool finite = row < K;
+  if (finite) {
+    float q = csq[row];
+    finite = (q == q) && q < 3.0e38f;
+    for (int f = lane; f < D; f += 32) {
+      float v = C[static_cast<size_t>(row) * D + f];
+      if (!(fabsf(v) < 3.0e38f)) finite = false;
+    }
+    finite = __all_sync(0xffffffffu, finite);
+  }
+  float d2 = 0.f;
+  for (int f = lane; f < Dp; f += 32) {
+    float v = (finite && f < D) ? C[static_cast<size_t>(row) * D + f] * s : 0.f;
+    __half h = __float2half_rn(v);
+    float r = v - __half2float(h);
+    d2 = fmaf(r, r, d2);
+    table[static_cast<size_t>(row) * Dp + f] = h;
+  }
+  for (int o = 16; o > 0; o >>= 1) d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+  if (lane == 0) {
+    if (finite) atomicMax(reinterpret_cast<uint32_t*>(&st->dcmax), __float_as_uint(__fsqrt_ru(d2) * 1.0001f));
+    // bias: three fp16 terms of -(s^2 ||c||^2 / 2); invalid / padded centroids get -65504
+    __half b[3];
+    if (finite) {
+      float h = -0.5f * s * s * csq[row];
+      b[0] = __float2half_rn(h);
+      float r1 = h - __half2float(b[0]);
+      b[1] = __float2half_rn(r1);
+      float r2 = r1 - __half2float(b[1]);
+      b[2] = __float2half_rn(r2);
+    } else {
+      b[0] = __float2half_rn(-65504.f);
+      b[1] = b[2] = __float2half_rn(0.f);
+    }
+    // shared-memory layout of the K=16 no-swizzle block: core matrix = 8 rows x 16 bytes contiguous,
+    // 8-row groups 128 bytes apart, second K half TN*16 bytes further
+    const uint32_t t = row / TN, r = row % TN;
+    __half* blob = aug_blob + static_cast<size_t>(t) * (AUG_B_BYTES / 2);
+    for (int k = 0; k < 16; k++) {
+      int j = k >> 3, e = k & 7;
+      blob[(j * (TN * 16) + (r >> 3) * 128 + (r & 7) * 16) / 2 + e] = k < 3 ? b[k] : __float2half_rn(0.f);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// the main kernel
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void note_timeout(uint32_t* counters, int where) {
+  atomicMax(&counters[CNT_ERR], 0x1000u + where);
+}
+
+__global__ void __launch_bounds__(N_THREADS, 1)
+tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const SmemLayout L = smem_layout(p.nkb);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L.tmem_slot);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nkb = p.nkb, nt = p.nt;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmap_b);
+    for (int s = 0; s < B_STAGES; s++) {
+      ptx::mbar_init(&bars[BAR_B_FULL(s)], 1);
+      ptx::mbar_init(&bars[BAR_B_EMPTY(s)], 1);
+    }
+    for (int s = 0; s < 2; s++) {
+      ptx::mbar_init(&bars[BAR_AUG_FULL(s)], 1);
+      ptx::mbar_init(&bars[BAR_AUG_EMPTY(s)], 1);
+      ptx::mbar_init(&bars[BAR_ACC_FULL(s)], 1);
+      ptx::mbar_init(&bars[BAR_ACC_EMPTY(s)], N_EPI_WARPS);
+    }
+    for (int kb = 0; kb < MAX_NKB; kb++) {
+      ptx::mbar_init(&bars[BAR_A_FULL(kb)], N_CONV_WARPS);
+      ptx::mbar_init(&bars[BAR_A_EMPTY(kb)], 1);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) ptx::tmem_alloc(tmem_slot, TMEM_COLS);
+  // constant A-side bias block: ones in the first three K positions of every row
+  for (int i = threadIdx.x; i < TM * 16; i += N_THREADS) {
+    int r = i >> 4, k = i & 15;
+    int j = k >> 3, e = k & 7;
+    reinterpret_cast<__half*>(smem + L.aug_a)[(j * (TM * 16) + (r >> 3) * 128 + (r & 7) * 16) / 2 + e] =
+        __float2half_rn(k < 3 ? 1.f : 0.f);
+  }
+  ptx::fence_proxy_async_smem();
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================ TMA producer (B operand) ================================
+    if (lane == 0) {
+      uint32_t pc = 0, ac = 0;
+      for (uint32_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+        for (int n = 0; n < nt; n++) {
+          for (int kb = 0; kb < nkb; kb++, pc++) {
+            const int s = pc % B_STAGES;
+            const uint32_t ph = (pc / B_STAGES) & 1;
+            if (!ptx::mbar_wait(&bars[BAR_B_EMPTY(s)], ph ^ 1, p.counters + CNT_ERR)) note_timeout(p.counters, 1);
+            ptx::mbar_arrive_expect_tx(&bars[BAR_B_FULL(s)], B_STAGE_BYTES);
+            ptx::tma_load_2d(smem + L.b + s * B_STAGE_BYTES, &tmap_b, kb * KB, n * TN, &bars[BAR_B_FULL(s)]);
+          }
+          const int as = ac & 1;
+          const uint32_t aph = (ac >> 1) & 1;
+          if (!ptx::mbar_wait(&bars[BAR_AUG_EMPTY(as)], aph ^ 1, p.counters + CNT_ERR)) note_timeout(p.counters, 2);
+          ptx::mbar_arrive_expect_tx(&bars[BAR_AUG_FULL(as)], AUG_B_BYTES);
+          ptx::bulk_load(smem + L.aug_b + as * AUG_B_BYTES,
+                         reinterpret_cast<const uint8_t*>(p.aug_blob) + static_cast<size_t>(n) * AUG_B_BYTES,
+                         AUG_B_BYTES, &bars[BAR_AUG_FULL(as)]);
+          ac++;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    if (lane == 0) {
+      const uint32_t idesc = ptx::make_idesc_f16(TM, TN);
+      const uint32_t a_base = ptx::smem_u32(smem + L.a), b_base = ptx::smem_u32(smem + L.b);
+      const uint32_t auga = ptx::smem_u32(smem + L.aug_a), augb = ptx::smem_u32(smem + L.aug_b);
+      const uint32_t aug_lbo_a = p.aug_swap ? 128 : TM * 16, aug_sbo_a = p.aug_swap ? TM * 16 : 128;
+      const uint32_t aug_lbo_b = p.aug_swap ? 128 : TN * 16, aug_sbo_b = p.aug_swap ? TN * 16 : 128;
+      uint32_t pc = 0, ac = 0, it = 0;
+      for (uint32_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, it++) {
+        for (int n = 0; n < nt; n++, ac++) {
+          const int buf = ac & 1;
+          const uint32_t aph = (ac >> 1) & 1;
+          if (!ptx::mbar_wait(&bars[BAR_ACC_EMPTY(buf)], aph ^ 1, p.counters + CNT_ERR)) note_timeout(p.counters, 3);
+          ptx::tc_fence_after();
+          const uint32_t d_tmem = tmem_base + buf * TN;
+          for (int kb = 0; kb < nkb; kb++, pc++) {
+            const int s = pc % B_STAGES;
+            const uint32_t ph = (pc / B_STAGES) & 1;
+            if (n == 0 && !ptx::mbar_wait(&bars[BAR_A_FULL(kb)], it & 1, p.counters + CNT_ERR)) note_timeout(p.counters, 4);
+            if (!ptx::mbar_wait(&bars[BAR_B_FULL(s)], ph, p.counters + CNT_ERR)) note_timeout(p.counters, 5);
+            ptx::tc_fence_after();
+#pragma unroll
+            for (int ks = 0; ks < KB / 16; ks++) {
+              uint64_t ad = ptx::make_smem_desc(a_base + kb * A_KB_BYTES + ks * 32, 16, 1024, 2);
+              uint64_t bd = ptx::make_smem_desc(b_base + s * B_STAGE_BYTES + ks * 32, 16, 1024, 2);
+              ptx::umma_f16(d_tmem, ad, bd, idesc, (kb | ks) ? 1u : 0u);
+            }
+            ptx::umma_commit(&bars[BAR_B_EMPTY(s)]);
+            if (n == nt - 1) ptx::umma_commit(&bars[BAR_A_EMPTY(kb)]);
+          }
+          // bias step: acc += ones(128x16) * bias(256x16)^T  (no-swizzle K-major blocks)
+          if (!ptx::mbar_wait(&bars[BAR_AUG_FULL(buf)], aph, p.counters + CNT_ERR)) note_timeout(p.counters, 6);
+          ptx::tc_fence_after();
+          {
+            uint64_t ad = ptx::make_smem_desc(auga, aug_lbo_a, aug_sbo_a, 0);
+            uint64_t bd = ptx::make_smem_desc(augb + buf * AUG_B_BYTES, aug_lbo_b, aug_sbo_b, 0);
+            ptx::umma_f16(d_tmem, ad, bd, idesc, 1u);
+          }
+          ptx::umma_commit(&bars[BAR_AUG_EMPTY(buf)]);
+          ptx::umma_commit(&bars[BAR_ACC_FULL(buf)]);
+        }
+      }
+    }
+  } else if (warp < FIRST_EPI_WARP) {
+    // ================================ converters (A operand) ================================
+    const int cw = warp - FIRST_CONV_WARP;  // rows [32cw, 32cw+32)
+    const int r4 = lane >> 3, j = lane & 7;
+    const float s = p.stats->scale;
+    uint32_t it = 0;
+    for (uint32_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, it++) {
+      float nx[8], nd[8];
+#pragma unroll
+      for (int i = 0; i < 8; i++) nx[i] = nd[i] = 0.f;
+      for (int kb = 0; kb < nkb; kb++) {
+        // issue all global loads of this K-block before waiting for the slot
+        float4 v[8][2];
+        const int f0 = kb * KB + j * 8;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          const int row = cw * 32 + i * 4 + r4;
+          const uint64_t grow = static_cast<uint64_t>(tile) * TM + row;
+          if (grow < p.n && f0 < p.D) {
+            const float* src = p.X + grow * p.D + f0;
+            v[i][0] = ptx::ldg_nc_f4(src);
+            v[i][1] = ptx::ldg_nc_f4(src + 4);
+          } else {
+            v[i][0] = v[i][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+        if (!ptx::mbar_wait(&bars[BAR_A_EMPTY(kb)], (it & 1) ^ 1, p.counters + CNT_ERR)) note_timeout(p.counters, 7);
+        uint8_t* a_kb = smem + L.a + kb * A_KB_BYTES;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          const int row = cw * 32 + i * 4 + r4;
+          float x[8] = {v[i][0].x, v[i][0].y, v[i][0].z, v[i][0].w, v[i][1].x, v[i][1].y, v[i][1].z, v[i][1].w};
+          __half2 h[4];
+#pragma unroll
+          for (int e = 0; e < 4; e++) {
+            float a = x[2 * e] * s, b = x[2 * e + 1] * s;
+            h[e] = __floats2half2_rn(a, b);
+            float2 back = __half22float2(h[e]);
+            float da = a - back.x, db = b - back.y;
+            nx[i] = fmaf(back.x, back.x, nx[i]);
+            nx[i] = fmaf(back.y, back.y, nx[i]);
+            nd[i] = fmaf(da, da, nd[i]);
+            nd[i] = fmaf(db, db, nd[i]);
+          }
+          uint4 packed;
+          packed.x = *reinterpret_cast<uint32_t*>(&h[0]);
+          packed.y = *reinterpret_cast<uint32_t*>(&h[1]);
+          packed.z = *reinterpret_cast<uint32_t*>(&h[2]);
+          packed.w = *reinterpret_cast<uint32_t*>(&h[3]);
+          *reinterpret_cast<uint4*>(a_kb + row * 128 + ((j ^ (row & 7)) << 4)) = packed;
+        }
+        if (kb == nkb - 1) {
+          // per-row norms of this tile (8 lanes share a row)
+          float* norms = reinterpret_cast<float*>(smem + L.norms) + (it & 1) * 2 * TM;
+#pragma unroll
+          for (int i = 0; i < 8; i++) {
+            float a = nx[i], b = nd[i];
+            a += __shfl_xor_sync(0xffffffffu, a, 1); b += __shfl_xor_sync(0xffffffffu, b, 1);
+            a += __shfl_xor_sync(0xffffffffu, a, 2); b += __shfl_xor_sync(0xffffffffu, b, 2);
+            a += __shfl_xor_sync(0xffffffffu, a, 4); b += __shfl_xor_sync(0xffffffffu, b, 4);
+            if (j == 0) {
+              const int row = cw * 32 + i * 4 + r4;
+              norms[row] = a;
+              norms[TM + row] = b;
+            }
+          }
+        }
+        ptx::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&bars[BAR_A_FULL(kb)]);
+      }
+    }
+  } else {
+    // ================================ epilogue ================================
+    const int e = warp - FIRST_EPI_WARP;       // 0..7
+    const int q = warp & 3;                    // TMEM lane quarter this warp may access
+    const int h = e >> 2;                      // column half of every 256-column accumulator
+    const int row = q * 32 + lane;
+    const int slot = h * TM + row;             // 0..255
+    float* list_cm = reinterpret_cast<float*>(smem + L.list_cm);
+    uint32_t* list_mask = reinterpret_cast<uint32_t*>(smem + L.list_mask);
+    uint16_t* list_g = reinterpret_cast<uint16_t*>(smem + L.list_g);
+    float* fin_m = reinterpret_cast<float*>(smem + L.fin);
+    uint32_t* fin_cnt = reinterpret_cast<uint32_t*>(smem + L.fin) + 256;
+    uint32_t* fin_flag = reinterpret_cast<uint32_t*>(smem + L.fin) + 512;
+    const float cmax = p.stats->cmax, dcmax = p.stats->dcmax;
+    uint32_t ac = 0, it = 0;
+    for (uint32_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, it++) {
+      float M = -INFINITY, margin = 0.f;
+      uint32_t cnt = 0, flags = 0;
+      for (int n = 0; n < nt; n++, ac++) {
+        const int buf = ac & 1;
+        const uint32_t aph = (ac >> 1) & 1;
+        if (!ptx::mbar_wait(&bars[BAR_ACC_FULL(buf)], aph, p.counters + CNT_ERR)) note_timeout(p.counters, 8);
+        ptx::tc_fence_after();
+        if (n == 0) {
+          const float* norms = reinterpret_cast<const float*>(smem + L.norms) + (it & 1) * 2 * TM;
+          // rigorous bound on |acc - (s^2 x.c - s^2||c||^2/2)| (see header): Cauchy-Schwarz on the
+          // actual rounding residuals + accumulation + the reference's own rounding slack
+          const float nx = __fsqrt_ru(norms[row]) * 1.0001f, nd = __fsqrt_ru(norms[TM + row]) * 1.0001f;
+          const float xn = nx + nd;
+          float E = nx * dcmax + nd * cmax + nd * dcmax;
+          E += static_cast<float>(p.nkb * KB + 16) * 2.4e-7f * nx * cmax;   // fp32 accumulation in the tensor core
+          E += 2.0e-6f * (cmax * cmax + xn * cmax);                        // reference Kahan/rd rounding, bias split
+          margin = 2.f * E * 1.001f + 1e-30f;
+          if (!(margin < 1.0e30f)) flags |= 1u;                            // NaN / Inf somewhere in the row
+        }
+        for (int c = 0; c < 4; c++) {
+          uint32_t r[32];
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * TN + h * 128 + c * 32;
+          ptx::tmem_ld_32x32(taddr, r);
+          ptx::tmem_ld_wait();
+          if (p.dbg_scores) {
+            const uint64_t grow = static_cast<uint64_t>(tile) * TM + row;
+            float* dst = p.dbg_scores + grow * (static_cast<uint64_t>(nt) * TN) + n * TN + h * 128 + c * 32;
+            for (int jj = 0; jj < 32; jj++) dst[jj] = __uint_as_float(r[jj]);
+          }
+          float cm = __uint_as_float(r[0]);
+#pragma unroll
+          for (int jj = 1; jj < 32; jj++) cm = fmaxf(cm, __uint_as_float(r[jj]));
+          M = fmaxf(M, cm);
+          const float thr = M - margin;
+          uint32_t mask = 0;
+#pragma unroll
+          for (int jj = 0; jj < 32; jj++)
+            if (__uint_as_float(r[jj]) >= thr) mask |= (1u << jj);
+          if (mask) {
+            if (cnt < LIST_LEN) {
+              list_cm[cnt * 256 + slot] = cm;
+              list_mask[cnt * 256 + slot] = mask;
+              list_g[cnt * 256 + slot] = static_cast<uint16_t>(n * 8 + h * 4 + c);
+              cnt++;
+            } else {
+              flags |= 2u;
+            }
+          }
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&bars[BAR_ACC_EMPTY(buf)]);
+      }
+      // merge the two column halves of every row and emit
+      fin_m[slot] = M;
+      fin_cnt[slot] = cnt;
+      fin_flag[slot] = flags;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (h == 0) {
+        const uint64_t grow = static_cast<uint64_t>(tile) * TM + row;
+        if (grow < p.n) {
+          const float Mf = fmaxf(M, fin_m[TM + row]);
+          const float thr = Mf - margin;
+          uint32_t fl = flags | fin_flag[TM + row];
+          uint32_t cand[MAX_CAND];
+          uint32_t total = 0;
+          for (int hh = 0; hh < 2; hh++) {
+            const int sl = hh * TM + row;
+            const uint32_t c2 = fin_cnt[sl];
+            for (uint32_t i = 0; i < c2; i++) {
+              if (!(list_cm[i * 256 + sl] >= thr)) continue;
+              uint32_t m = list_mask[i * 256 + sl];
+              const uint32_t g = list_g[i * 256 + sl];
+              while (m) {
+                const int b = __ffs(m) - 1;
+                m &= m - 1;
+                const uint32_t col = g * 32 + b;
+                if (col < p.K) {
+                  if (total < MAX_CAND) cand[total] = col;
+                  total++;
+                }
+              }
+            }
+          }
+          if (fl || total > MAX_CAND) {
+            p.ovf_rows[atomicAdd(&p.counters[CNT_OVF], 1u)] = static_cast<uint32_t>(grow);
+          } else if (total == 1) {
+            p.result[grow] = cand[0];
+          } else if (total == 0) {
+            p.result[grow] = kUntouched;  // every score NaN: nothing wins (reference kmeans.cu:349-353)
+          } else {
+            const uint32_t base = atomicAdd(&p.counters[CNT_PAIRS], total);
+            if (base + total <= p.max_pairs) {
+              for (uint32_t i = 0; i < total; i++) {
+                p.pair_row[base + i] = static_cast<uint32_t>(grow);
+                p.pair_cand[base + i] = cand[i];
+              }
+              const uint32_t rq = atomicAdd(&p.counters[CNT_ROWQ], 1u);
+              p.rowq[3 * rq] = static_cast<uint32_t>(grow);
+              p.rowq[3 * rq + 1] = base;
+              p.rowq[3 * rq + 2] = total;
+            } else {
+              p.ovf_rows[atomicAdd(&p.counters[CNT_OVF], 1u)] = static_cast<uint32_t>(grow);
+            }
+          }
+        }
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+    }
+  }
+  // teardown
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+}  // namespace tc
+
+// ---------------------------------------------------------------------------------------------------
+// exact re-check of (row, candidate) pairs + per-row reduction
+// ---------------------------------------------------------------------------------------------------
+template <int METRIC>
+__global__ void __launch_bounds__(128)
+recheck_pairs_kernel(const float* __restrict__ X, const float* __restrict__ C,
+                     const float* __restrict__ csq, int D, const uint32_t* __restrict__ pair_row,
+                     const uint32_t* __restrict__ pair_cand, const uint32_t* __restrict__ d_npairs,
+                     uint32_t max_pairs, uint32_t n, uint32_t K, float* __restrict__ pair_score) {
+  __shared__ float sX[32 * 129];
+  __shared__ float sC[128 * 33];
+  const uint32_t np = min(*d_npairs, max_pairs);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (uint32_t tile0 = blockIdx.x * 128; tile0 < np; tile0 += gridDim.x * 128) {
+    const uint32_t pidx = tile0 + threadIdx.x;
+    const bool active = pidx < np;
+    Kahan k;
+    for (int f0 = 0; f0 < D; f0 += 32) {
+      const int fl = min(32, D - f0);
+      __syncthreads();
+      for (int i = 0; i < 32; i++) {
+        const uint32_t pi = tile0 + warp * 32 + i;
+        if (pi < np && lane < fl) {
+          // (slots past the last complete row group may hold stale data: stay in bounds)
+          const uint32_t r = min(pair_row[pi], n - 1), c = min(pair_cand[pi], K - 1);
+          sX[lane * 129 + warp * 32 + i] = X[static_cast<size_t>(r) * D + f0 + lane];
+          sC[(warp * 32 + i) * 33 + lane] = C[static_cast<size_t>(c) * D + f0 + lane];
+        }
+      }
+      __syncthreads();
+      if (active)
+        for (int f = 0; f < fl; f++) k.mac(sX[f * 129 + threadIdx.x], sC[threadIdx.x * 33 + f]);
+    }
+    if (active) pair_score[pidx] = lloyd_score<METRIC>(k.sum, csq[min(pair_cand[pidx], K - 1)]);
+  }
+}
+
+__global__ void recheck_reduce_kernel(const uint32_t* __restrict__ rowq, const uint32_t* __restrict__ d_nrowq,
+                                      const uint32_t* __restrict__ pair_cand,
+                                      const float* __restrict__ pair_score, uint32_t* __restrict__ result) {
+  const uint32_t nq = *d_nrowq;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nq; i += gridDim.x * blockDim.x) {
+    const uint32_t row = rowq[3 * i], base = rowq[3 * i + 1], cnt = rowq[3 * i + 2];
+    float best = FLT_MAX;
+    uint32_t arg = UINT32_MAX;
+    for (uint32_t j = 0; j < cnt; j++) {
+      const float sc = pair_score[base + j];
+      const uint32_t c = pair_cand[base + j];
+      // strict '<' in ascending centroid order == lowest index among equal scores
+      if (sc < best || (sc == best && c < arg)) {
+        best = sc;
+        arg = c;
+      }
+    }
+    result[row] = (arg == UINT32_MAX) ? kUntouched : arg;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+struct TcPlan {
+  int metric, D, device, nkb, nt;
+  uint32_t K, max_n, max_pairs;
+  __half* table = nullptr;
+  __half* aug_blob = nullptr;
+  tc::Stats* stats = nullptr;
+  uint32_t *pair_row = nullptr, *pair_cand = nullptr, *rowq = nullptr, *ovf_rows = nullptr, *counters = nullptr;
+  float* pair_score = nullptr;
+  uint32_t* h_counters = nullptr;  // pinned
+  CUtensorMap tmap;
+  int num_sms = 148;
+  size_t smem_bytes = 0;
+  int aug_swap = 0;
+  float* dbg_scores = nullptr;
+};
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+bool tc_supported(int metric, uint32_t n, int D, uint32_t K) {
+  if (metric != 0) return false;                       // cosine: next round
+  if (D < 8 || D % 8 != 0 || D > tc::MAX_NKB * tc::KB) return false;
+  if (K < 2 || K > 65535u * 32u) return false;
+  if (n == 0) return false;
+  return true;
+}
+
+void tc_plan_destroy(TcPlan* p) {
+  if (!p) return;
+  cudaFree(p->table);
+  cudaFree(p->aug_blob);
+  cudaFree(p->stats);
+  cudaFree(p->pair_row);
+  cudaFree(p->pair_cand);
+  cudaFree(p->pair_score);
+  cudaFree(p->rowq);
+  cudaFree(p->ovf_rows);
+  cudaFree(p->counters);
+  cudaFree(p->dbg_scores);
+  if (p->h_counters) cudaFreeHost(p->h_counters);
+  delete p;
+}
+
+cudaError_t tc_plan_create(TcPlan** out, int metric, uint32_t max_n, int D, uint32_t K, int device) {
+  using namespace tc;
+  TcPlan* p = new TcPlan;
+  p->metric = metric;
+  p->D = D;
+  p->K = K;
+  p->device = device;
+  p->max_n = max_n;
+  p->nkb = (D + KB - 1) / KB;
+  p->nt = static_cast<int>((K + TN - 1) / TN);
+  p->max_pairs = max_n < (1u << 30) ? 2 * max_n + 1024 : 0xFFFFFFF0u;
+  const char* sw = getenv("KMCUDA_B200_AUG_SWAP");
+  p->aug_swap = (sw && sw[0] == '1') ? 1 : 0;
+  cudaError_t e;
+#define TC_TRY(x) do { e = (x); if (e != cudaSuccess) { tc_plan_destroy(p); return e; } } while (0)
+  cudaDeviceProp prop;
+  TC_TRY(cudaGetDeviceProperties(&prop, device));
+  p->num_sms = prop.multiProcessorCount;
+  const size_t rows_pad = static_cast<size_t>(p->nt) * TN;
+  TC_TRY(cudaMalloc(&p->table, rows_pad * p->nkb * KB * sizeof(__half)));
+  TC_TRY(cudaMalloc(&p->aug_blob, static_cast<size_t>(p->nt) * AUG_B_BYTES));
+  TC_TRY(cudaMalloc(&p->stats, sizeof(Stats)));
+  TC_TRY(cudaMalloc(&p->pair_row, sizeof(uint32_t) * p->max_pairs));
+  TC_TRY(cudaMalloc(&p->pair_cand, sizeof(uint32_t) * p->max_pairs));
+  TC_TRY(cudaMalloc(&p->pair_score, sizeof(float) * p->max_pairs));
+  TC_TRY(cudaMalloc(&p->rowq, sizeof(uint32_t) * 3 * static_cast<size_t>(max_n)));
+  TC_TRY(cudaMalloc(&p->ovf_rows, sizeof(uint32_t) * static_cast<size_t>(max_n)));
+  TC_TRY(cudaMalloc(&p->counters, sizeof(uint32_t) * CNT_N));
+  TC_TRY(cudaMallocHost(&p->h_counters, sizeof(uint32_t) * CNT_N));
+  memset(p->h_counters, 0, sizeof(uint32_t) * CNT_N);
+  const char* dbg = getenv("KMCUDA_B200_DUMP_SCORES");
+  if (dbg && dbg[0] == '1') {
+    size_t tiles = (static_cast<size_t>(max_n) + TM - 1) / TM;
+    TC_TRY(cudaMalloc(&p->dbg_scores, tiles * TM * rows_pad * sizeof(float)));
+  }
+  // tensor map over the fp16 centroid table [rows_pad][nkb*64], box 64 x 256, 128-byte swizzle
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) { tc_plan_destroy(p); return cudaErrorNotSupported; }
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(p->nkb * KB), static_cast<cuuint64_t>(rows_pad)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(p->nkb * KB) * sizeof(__half)};
+  cuuint32_t box[2] = {KB, TN};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult cr = enc(&p->tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, p->table, gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) { tc_plan_destroy(p); return cudaErrorInvalidValue; }
+  p->smem_bytes = smem_layout(p->nkb).total + 1024;
+  TC_TRY(cudaFuncSetAttribute(tc_assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              static_cast<int>(p->smem_bytes)));
+#undef TC_TRY
+  *out = p;
+  return cudaSuccess;
+}
+
+cudaError_t tc_assign(TcPlan* p, const float* X, const float* C, const float* csq, uint32_t n,
+                      uint32_t* result, cudaStream_t st) {
+  using namespace tc;
+  if (n > p->max_n) return cudaErrorInvalidValue;
+  if (reinterpret_cast<uintptr_t>(X) & 15) return cudaErrorMisalignedAddress;
+  cudaError_t e;
+  if ((e = cudaMemsetAsync(p->counters, 0, sizeof(uint32_t) * CNT_N, st)) != cudaSuccess) return e;
+  if ((e = cudaMemsetAsync(p->stats, 0, sizeof(Stats), st)) != cudaSuccess) return e;
+  tc_prep_stats_kernel<<<8, 256, 0, st>>>(csq, p->K, p->stats);
+  tc_prep_scale_kernel<<<1, 1, 0, st>>>(p->stats);
+  const uint32_t rows_pad = static_cast<uint32_t>(p->nt) * TN;
+  tc_prep_table_kernel<<<(rows_pad * 32 + 255) / 256, 256, 0, st>>>(C, csq, p->K, p->D, p->nkb, p->nt, p->table,
+                                                                    p->aug_blob, p->stats);
+  Params prm;
+  prm.X = X;
+  prm.n = n;
+  prm.D = p->D;
+  prm.K = p->K;
+  prm.nkb = p->nkb;
+  prm.nt = p->nt;
+  prm.ntiles = (n + TM - 1) / TM;
+  prm.aug_blob = p->aug_blob;
+  prm.stats = p->stats;
+  prm.result = result;
+  prm.pair_row = p->pair_row;
+  prm.pair_cand = p->pair_cand;
+  prm.max_pairs = p->max_pairs;
+  prm.rowq = p->rowq;
+  prm.ovf_rows = p->ovf_rows;
+  prm.counters = p->counters;
+  prm.aug_swap = p->aug_swap;
+  prm.dbg_scores = p->dbg_scores;
+  const unsigned grid = min(static_cast<uint32_t>(p->num_sms), prm.ntiles);
+  tc_assign_kernel<<<grid, N_THREADS, p->smem_bytes, st>>>(p->tmap, prm);
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  // exact re-check of the multi-candidate rows, then the rows that need the full exact pass
+  const unsigned rgrid = p->num_sms * 4;
+  recheck_pairs_kernel<0><<<rgrid, 128, 0, st>>>(X, C, csq, p->D, p->pair_row, p->pair_cand,
+                                                 p->counters + CNT_PAIRS, p->max_pairs, n, p->K, p->pair_score);
+  recheck_reduce_kernel<<<p->num_sms * 2, 256, 0, st>>>(p->rowq, p->counters + CNT_ROWQ, p->pair_cand,
+                                                        p->pair_score, result);
+  if ((e = launch_assign_exact(p->metric, X, C, csq, n, p->D, p->K, p->ovf_rows, p->counters + CNT_OVF, result,
+                               st)) != cudaSuccess)
+    return e;
+  return cudaMemcpyAsync(p->h_counters, p->counters, sizeof(uint32_t) * CNT_N, cudaMemcpyDeviceToHost, st);
+}
+
+// valid after the stream has been synchronised
+void tc_last_stats(TcPlan* p, uint32_t* n_recheck, uint32_t* n_overflow) {
+  *n_recheck = p->h_counters[tc::CNT_ROWQ];
+  *n_overflow = p->h_counters[tc::CNT_OVF];
+}
+
+uint32_t tc_last_error(TcPlan* p) { return p->h_counters[tc::CNT_ERR]; }
+const float* tc_debug_scores(TcPlan* p, size_t* row_stride) {
+  *row_stride = static_cast<size_t>(p->nt) * tc::TN;
+  return p->dbg_scores;
+}
+void tc_debug_stats(TcPlan* p, float* out4) {
+  tc::Stats st;
+  cudaMemcpy(&st, p->stats, sizeof(st), cudaMemcpyDeviceToHost);
+  out4[0] = st.scale;
+  out4[1] = st.cmax;
+  out4[2] = st.dcmax;
+  out4[3] = __builtin_bit_cast(float, st.csq_max_bits);
+}
+
+}  // namespace kmb

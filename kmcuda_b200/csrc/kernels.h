@@ -1,0 +1,111 @@
+// kernels.h -- host-callable launchers of the device code (one CUDA stream per device context).
+//
+// Two families:
+//   * exact kernels (simt_kernels.cu, knn_kernels.cu): bit-for-bit the reference's fp32 arithmetic
+//     (exact.cuh); they make every decision that leaves the library.
+//   * the tensor-core filter (assign_tc.cu): tcgen05 fp16 distance GEMM that proposes, per sample,
+//     the short list of centroids the exact re-check has to look at.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace kmb {
+
+constexpr uint32_t kUntouched = 0xFFFFFFFEu;  // "no centroid won": leave the assignment alone
+constexpr int kMaxCand = 4;                   // candidates carried per re-check queue entry
+
+// ---- exact Lloyd assignment (all K centroids), optional row list -------------------------------
+// result[i] = argmin (strict <, ascending index), K for "insane" rows, kUntouched if nothing wins.
+// rows == nullptr: rows 0..n-1; else the n row ids in rows[] (device), results still indexed by row.
+cudaError_t launch_csqr(int metric, const float* C, uint32_t K, int D, float* csq, cudaStream_t st);
+cudaError_t launch_assign_exact(int metric, const float* X, const float* C, const float* csq,
+                                uint32_t n, int D, uint32_t K, const uint32_t* rows,
+                                const uint32_t* d_nrows, uint32_t* result, cudaStream_t st);
+
+// ---- exact re-check of short candidate lists produced by the tensor-core filter ----------------
+// queue entry q: row = qrow[q], candidates qcand[q*kMaxCand .. +kMaxCand) (ascending, UINT32_MAX pad)
+cudaError_t launch_recheck(int metric, const float* X, const float* C, const float* csq, int D,
+                           const uint32_t* qrow, const uint32_t* qcand, const uint32_t* d_nq,
+                           uint32_t max_q, uint32_t* result, cudaStream_t st);
+
+// prev[i]=assign[i]; assign[i]=result[i] unless kUntouched; *changed += #(assign changed)
+cudaError_t launch_finalize_assign(uint32_t n, const uint32_t* result, uint32_t* assign,
+                                   uint32_t* prev, uint32_t* d_changed, cudaStream_t st);
+
+// ---- centroid update ----------------------------------------------------------------------------
+// Deterministic: stable radix sort of (assignment, index), then per-cluster Kahan sums in index order.
+struct UpdateWorkspace {
+  uint32_t *keys_in = nullptr, *keys_out = nullptr, *vals_in = nullptr, *vals_out = nullptr;
+  uint32_t* offsets = nullptr;   // [K+1]
+  float* partial = nullptr;      // [K][kSplits][D]
+  void* cub_tmp = nullptr;
+  size_t cub_tmp_bytes = 0;
+};
+constexpr int kUpdateSplits = 8;
+size_t update_cub_bytes(uint32_t n);
+// sums[K][D] (fp32) and counts[K] (uint32) of this shard's samples
+cudaError_t launch_partial_sums(const float* X, uint32_t n, int D, uint32_t K, const uint32_t* assign,
+                                UpdateWorkspace& ws, float* sums, uint32_t* counts, cudaStream_t st);
+// C = sums/count (L2, NaN for empty) or sums/||sums|| (cosine); ccounts = counts
+cudaError_t launch_normalize(int metric, const float* sums, const uint32_t* counts, uint32_t K, int D,
+                             float* C, uint32_t* ccounts, cudaStream_t st);
+
+// ---- Yinyang -------------------------------------------------------------------------------------
+// bounds layout [(G+1)][n]: row 0 = upper bound, row 1+g = lower bound of group g
+cudaError_t launch_yy_init(int metric, const float* X, const float* C, uint32_t n, int D, uint32_t K,
+                           uint32_t G, const uint32_t* assign, const uint32_t* groups, float* bounds,
+                           cudaStream_t st);
+cudaError_t launch_yy_drifts(int metric, const float* Cnew, const float* Cold, uint32_t K, int D,
+                             uint32_t G, const uint32_t* groups, float* drift, float* maxdrift,
+                             cudaStream_t st);
+cudaError_t launch_yy_global_filter(int metric, const float* X, const float* C, uint32_t n, int D,
+                                    uint32_t G, const float* drift, const float* maxdrift,
+                                    const uint32_t* assign, uint32_t* prev, float* bounds,
+                                    uint32_t* passed, uint32_t* d_npassed, cudaStream_t st);
+cudaError_t launch_yy_local_filter(int metric, const float* X, const float* C, uint32_t n, int D,
+                                   uint32_t K, uint32_t G, const uint32_t* groups, const float* drift,
+                                   const float* maxdrift, const uint32_t* passed,
+                                   const uint32_t* d_npassed, uint32_t* assign, float* bounds,
+                                   uint32_t* d_changed, cudaStream_t st);
+
+// ---- misc ------------------------------------------------------------------------------------------
+cudaError_t launch_average_distance(int metric, const float* X, const float* C, uint32_t n, int D,
+                                    const uint32_t* assign, double* d_sum, cudaStream_t st);
+cudaError_t launch_plusplus_step(int metric, const float* X, uint32_t n, int D, const float* centroid,
+                                 int first, float* dists, double* d_sum, cudaStream_t st);
+cudaError_t launch_half_to_float(const void* src, float* dst, size_t n, cudaStream_t st);
+cudaError_t launch_float_to_half(const float* src, void* dst, size_t n, cudaStream_t st);
+cudaError_t launch_fill_u32(uint32_t* p, uint32_t v, size_t n, cudaStream_t st);
+
+// ---- k-NN ------------------------------------------------------------------------------------------
+// inverse assignments: inv[] = sample ids sorted by (cluster, id), off[K+1] = CSR offsets
+cudaError_t launch_knn_inverse(const uint32_t* assign, uint32_t n, uint32_t K, uint32_t* iota,
+                               uint32_t* keys_out, uint32_t* inv, uint32_t* off, uint32_t* counts,
+                               UpdateWorkspace& ws, cudaStream_t st);
+cudaError_t launch_knn_radii(int metric, const float* X, const float* C, uint32_t n, int D, uint32_t K,
+                             const uint32_t* assign, float* radii, cudaStream_t st);
+cudaError_t launch_knn_centroid_distances(int metric, const float* C, uint32_t K, int D, float* cd,
+                                          cudaStream_t st);
+cudaError_t launch_knn_search(int metric, int k, const float* X, const float* C, uint32_t N, int D,
+                              uint32_t K, uint32_t q_offset, uint32_t q_length, const uint32_t* assign,
+                              const uint32_t* inv, const uint32_t* inv_off, const float* cd,
+                              const float* radii, float* heap_scratch, uint32_t* neighbors,
+                              unsigned long long* d_pairs, cudaStream_t st);
+
+// ---- tensor-core filter (assign_tc.cu) -----------------------------------------------------------
+struct TcPlan;  // opaque; owns the fp16 centroid table, tensor maps, queues
+bool tc_supported(int metric, uint32_t n, int D, uint32_t K);
+cudaError_t tc_plan_create(TcPlan** plan, int metric, uint32_t max_n, int D, uint32_t K, int device);
+void tc_plan_destroy(TcPlan* plan);
+// one full assignment pass: result[i] as launch_assign_exact would produce it
+cudaError_t tc_assign(TcPlan* plan, const float* X, const float* C, const float* csq, uint32_t n,
+                      uint32_t* result, cudaStream_t st);
+// statistics of the last pass (for logging / bench): queue length and overflow rows
+void tc_last_stats(TcPlan* plan, uint32_t* n_recheck, uint32_t* n_overflow);
+// 0 = clean; 0x1000+site = a pipeline wait timed out at `site` (results of that pass are invalid)
+uint32_t tc_last_error(TcPlan* plan);
+// diagnostics (KMCUDA_B200_DUMP_SCORES=1): approximate scores [tiles*128][nt*256], prep statistics
+const float* tc_debug_scores(TcPlan* plan, size_t* row_stride);
+void tc_debug_stats(TcPlan* plan, float* out4);
+
+}  // namespace kmb

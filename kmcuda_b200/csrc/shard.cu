@@ -1,0 +1,212 @@
+// shard.cu -- per-GPU hot-path steps + the shard-level C ABI (include/kmcuda_b200.h).
+#include "shard.h"
+
+#include <cstdlib>
+#include <new>
+
+#include "kmcuda_b200.h"
+
+namespace kmb {
+
+Shard::~Shard() {
+  cudaSetDevice(device);
+  if (tc) tc_plan_destroy(tc);
+}
+
+KMCUDAResult Shard::create(bool with_update) {
+  KMB_CU(cudaSetDevice(device), kmcudaNoSuchDevice);
+  const char* fe = getenv("KMCUDA_B200_FORCE_EXACT");
+  force_exact = fe && fe[0] == '1';
+  KMB_CU(csq.alloc(K), kmcudaMemoryAllocationFailure);
+  KMB_CU(result.alloc(max_n), kmcudaMemoryAllocationFailure);
+  if (with_update) {
+    KMB_CU(ws_keys_out.alloc(max_n), kmcudaMemoryAllocationFailure);
+    KMB_CU(ws_vals_in.alloc(max_n), kmcudaMemoryAllocationFailure);
+    KMB_CU(ws_vals_out.alloc(max_n), kmcudaMemoryAllocationFailure);
+    KMB_CU(ws_offsets.alloc(static_cast<size_t>(K) + 1), kmcudaMemoryAllocationFailure);
+    KMB_CU(ws_partial.alloc(static_cast<size_t>(K) * kUpdateSplits * D), kmcudaMemoryAllocationFailure);
+    ws.cub_tmp_bytes = update_cub_bytes(max_n);
+    KMB_CU(ws_cub.alloc(ws.cub_tmp_bytes), kmcudaMemoryAllocationFailure);
+    ws.keys_out = ws_keys_out;
+    ws.vals_in = ws_vals_in;
+    ws.vals_out = ws_vals_out;
+    ws.offsets = ws_offsets;
+    ws.partial = ws_partial;
+    ws.cub_tmp = ws_cub.get();
+  }
+  if (!force_exact && tc_supported(metric, max_n, D, K)) {
+    cudaError_t e = tc_plan_create(&tc, metric, max_n, D, K, device);
+    if (e != cudaSuccess) {
+      // No silent fallback: a shape the tensor-core path claims must get the tensor-core path.
+      KMB_INFO("tensor-core plan creation failed: %s\n", cudaGetErrorString(e));
+      tc = nullptr;
+      return e == cudaErrorMemoryAllocation ? kmcudaMemoryAllocationFailure : kmcudaRuntimeError;
+    }
+  }
+  return kmcudaSuccess;
+}
+
+KMCUDAResult Shard::enable_yinyang(uint32_t groups_size) {
+  KMB_CU(cudaSetDevice(device), kmcudaNoSuchDevice);
+  G = groups_size;
+  KMB_CU(bounds.alloc(static_cast<size_t>(max_n) * (G + 1)), kmcudaMemoryAllocationFailure);
+  KMB_CU(drift.alloc(K), kmcudaMemoryAllocationFailure);
+  KMB_CU(maxdrift.alloc(G), kmcudaMemoryAllocationFailure);
+  KMB_CU(oldC.alloc(static_cast<size_t>(K) * D), kmcudaMemoryAllocationFailure);
+  KMB_CU(passed.alloc(max_n), kmcudaMemoryAllocationFailure);
+  KMB_CU(groups.alloc(K), kmcudaMemoryAllocationFailure);
+  KMB_CU(d_npassed.alloc(1), kmcudaMemoryAllocationFailure);
+  return kmcudaSuccess;
+}
+
+KMCUDAResult Shard::assign(uint32_t n, const float* X, const float* C, uint32_t* assignments,
+                           uint32_t* prev, uint32_t* d_changed, cudaStream_t st) {
+  if (n > max_n) return kmcudaInvalidArguments;
+  KMB_CU(launch_csqr(metric, C, K, D, csq, st), kmcudaRuntimeError);
+  last_tc = false;
+  if (tc && n > 0) {
+    KMB_CU(tc_assign(tc, X, C, csq, n, result, st), kmcudaRuntimeError);
+    last_tc = true;
+  } else {
+    KMB_CU(launch_assign_exact(metric, X, C, csq, n, D, K, nullptr, nullptr, result, st),
+           kmcudaRuntimeError);
+  }
+  KMB_CU(launch_finalize_assign(n, result, assignments, prev, d_changed, st), kmcudaRuntimeError);
+  return kmcudaSuccess;
+}
+
+KMCUDAResult Shard::partial_sums(uint32_t n, const float* X, const uint32_t* assignments, float* sums,
+                                 uint32_t* counts, cudaStream_t st) {
+  if (n > max_n || ws.cub_tmp == nullptr) return kmcudaInvalidArguments;
+  KMB_CU(launch_partial_sums(X, n, D, K, assignments, ws, sums, counts, st), kmcudaRuntimeError);
+  return kmcudaSuccess;
+}
+
+KMCUDAResult Shard::finish_update(const float* sums, const uint32_t* counts, float* C,
+                                  uint32_t* ccounts, cudaStream_t st) {
+  KMB_CU(launch_normalize(metric, sums, counts, K, D, C, ccounts, st), kmcudaRuntimeError);
+  return kmcudaSuccess;
+}
+
+}  // namespace kmb
+
+// ---------------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------------
+struct kmcuda_b200_shard {
+  kmb::Shard* impl;
+};
+
+extern "C" {
+
+KMCUDAResult kmcuda_b200_shard_create(kmcuda_b200_shard** shard, KMCUDADistanceMetric metric,
+                                      uint32_t max_samples, uint16_t features_size,
+                                      uint32_t clusters_size, int32_t verbosity) {
+  if (!shard || features_size == 0 || clusters_size < 2 || clusters_size == UINT32_MAX)
+    return kmcudaInvalidArguments;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return kmcudaNoSuchDevice;
+  auto* impl = new (std::nothrow) kmb::Shard(metric == kmcudaDistanceMetricCosine ? 1 : 0, dev,
+                                             max_samples, features_size, clusters_size, verbosity);
+  if (!impl) return kmcudaMemoryAllocationFailure;
+  KMCUDAResult r = impl->create(true);
+  if (r != kmcudaSuccess) {
+    delete impl;
+    return r;
+  }
+  *shard = new kmcuda_b200_shard{impl};
+  return kmcudaSuccess;
+}
+
+void kmcuda_b200_shard_destroy(kmcuda_b200_shard* shard) {
+  if (!shard) return;
+  delete shard->impl;
+  delete shard;
+}
+
+KMCUDAResult kmcuda_b200_assign(kmcuda_b200_shard* shard, uint32_t samples_size, const float* samples,
+                                const float* centroids, uint32_t* assignments,
+                                uint32_t* assignments_prev, uint32_t* changed, void* stream) {
+  if (!shard || !samples || !centroids || !assignments || !assignments_prev || !changed)
+    return kmcudaInvalidArguments;
+  return shard->impl->assign(samples_size, samples, centroids, assignments, assignments_prev, changed,
+                             static_cast<cudaStream_t>(stream));
+}
+
+int32_t kmcuda_b200_last_pass_info(kmcuda_b200_shard* shard, uint32_t* rechecked, uint32_t* overflowed) {
+  if (!shard) return 0;
+  kmb::Shard* s = shard->impl;
+  if (s->last_tc && s->tc) kmb::tc_last_stats(s->tc, &s->last_rechecked, &s->last_overflowed);
+  else s->last_rechecked = s->last_overflowed = 0;
+  if (rechecked) *rechecked = s->last_rechecked;
+  if (overflowed) *overflowed = s->last_overflowed;
+  return s->last_tc ? 1 : 0;
+}
+
+KMCUDAResult kmcuda_b200_partial_sums(kmcuda_b200_shard* shard, uint32_t samples_size,
+                                      const float* samples, const uint32_t* assignments, float* sums,
+                                      uint32_t* counts, void* stream) {
+  if (!shard || !samples || !assignments || !sums || !counts) return kmcudaInvalidArguments;
+  return shard->impl->partial_sums(samples_size, samples, assignments, sums, counts,
+                                   static_cast<cudaStream_t>(stream));
+}
+
+KMCUDAResult kmcuda_b200_finish_update(kmcuda_b200_shard* shard, const float* sums,
+                                       const uint32_t* counts, float* centroids, uint32_t* ccounts,
+                                       void* stream) {
+  if (!shard || !sums || !counts || !centroids || !ccounts) return kmcudaInvalidArguments;
+  return shard->impl->finish_update(sums, counts, centroids, ccounts, static_cast<cudaStream_t>(stream));
+}
+
+// ---- diagnostics (used by tests; not part of the drop-in surface) ----
+// returns the pipeline error word of the last tensor-core pass (0 = clean); call after a sync
+uint32_t kmcuda_b200_debug_last_error(kmcuda_b200_shard* shard) {
+  if (!shard || !shard->impl->tc) return 0;
+  return kmb::tc_last_error(shard->impl->tc);
+}
+// copies rows x cols of the dumped approximate scores (KMCUDA_B200_DUMP_SCORES=1) to host memory
+int32_t kmcuda_b200_debug_scores(kmcuda_b200_shard* shard, float* host_out, uint32_t rows, uint32_t cols) {
+  if (!shard || !shard->impl->tc) return -1;
+  size_t stride = 0;
+  const float* src = kmb::tc_debug_scores(shard->impl->tc, &stride);
+  if (!src || cols > stride) return -2;
+  return cudaMemcpy2D(host_out, cols * sizeof(float), src, stride * sizeof(float), cols * sizeof(float), rows,
+                      cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -3;
+}
+int32_t kmcuda_b200_debug_stats(kmcuda_b200_shard* shard, float* out4) {
+  if (!shard || !shard->impl->tc) return -1;
+  kmb::tc_debug_stats(shard->impl->tc, out4);
+  return 0;
+}
+
+KMCUDAResult kmcuda_b200_device_malloc(int32_t device, uint64_t bytes, void** ptr) {
+  if (!ptr) return kmcudaInvalidArguments;
+  if (cudaSetDevice(device) != cudaSuccess) return kmcudaNoSuchDevice;
+  return cudaMalloc(ptr, bytes ? bytes : 1) == cudaSuccess ? kmcudaSuccess : kmcudaMemoryAllocationFailure;
+}
+
+KMCUDAResult kmcuda_b200_device_free(int32_t device, void* ptr) {
+  if (cudaSetDevice(device) != cudaSuccess) return kmcudaNoSuchDevice;
+  return cudaFree(ptr) == cudaSuccess ? kmcudaSuccess : kmcudaRuntimeError;
+}
+
+KMCUDAResult kmcuda_b200_device_memcpy(int32_t device, void* dst, const void* src, uint64_t bytes,
+                                       int32_t direction) {
+  if (cudaSetDevice(device) != cudaSuccess) return kmcudaNoSuchDevice;
+  cudaMemcpyKind kind = direction == 1 ? cudaMemcpyHostToDevice
+                        : direction == 2 ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+  return cudaMemcpy(dst, src, bytes, kind) == cudaSuccess ? kmcudaSuccess : kmcudaMemoryCopyError;
+}
+
+KMCUDAResult kmcuda_b200_device_synchronize(int32_t device) {
+  if (cudaSetDevice(device) != cudaSuccess) return kmcudaNoSuchDevice;
+  return cudaDeviceSynchronize() == cudaSuccess ? kmcudaSuccess : kmcudaRuntimeError;
+}
+
+int32_t kmcuda_b200_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+}  // extern "C"

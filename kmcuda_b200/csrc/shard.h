@@ -1,0 +1,131 @@
+// shard.h -- one GPU's share of a clustering job: device buffers + the hot-path steps.
+//
+// The reference replicates the whole sample matrix on every GPU and splits only the kernel launch
+// ranges (kmcuda.cc:139-170, private.h:240-273).  Here a Shard owns just its range of samples and a
+// full copy of the (small) centroid table; the caller all-reduces the partial sums between
+// partial_sums() and finish_update().
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <vector>
+
+#include "kernels.h"
+#include "kmcuda.h"
+
+namespace kmb {
+
+#define KMB_INFO(...) do { if (verbosity > 0) { printf(__VA_ARGS__); } } while (false)
+#define KMB_DEBUG(...) do { if (verbosity > 1) { printf(__VA_ARGS__); } } while (false)
+
+// CUDA call -> KMCUDAResult, logging like the reference's CUCH (private.h:39-48)
+#define KMB_CU(call, code)                                                          \
+  do {                                                                              \
+    cudaError_t kmb_err__ = (call);                                                 \
+    if (kmb_err__ != cudaSuccess) {                                                 \
+      KMB_DEBUG("%s\n", #call);                                                     \
+      KMB_INFO("%s:%d -> %s\n", __FILE__, __LINE__, cudaGetErrorString(kmb_err__)); \
+      return code;                                                                  \
+    }                                                                               \
+  } while (false)
+
+#define KMB_RET(call)                            \
+  do {                                           \
+    KMCUDAResult kmb_res__ = (call);             \
+    if (kmb_res__ != kmcudaSuccess) return kmb_res__; \
+  } while (false)
+
+// cudaMalloc'ed buffer that frees itself; `borrow` wraps a caller-owned pointer (wrappers.h:16-21)
+template <typename T>
+class DevBuf {
+ public:
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  DevBuf(DevBuf&& o) noexcept : p_(o.p_), owned_(o.owned_) {
+    o.p_ = nullptr;
+    o.owned_ = false;
+  }
+  DevBuf& operator=(DevBuf&& o) noexcept {
+    if (this != &o) {
+      release();
+      p_ = o.p_;
+      owned_ = o.owned_;
+      o.p_ = nullptr;
+      o.owned_ = false;
+    }
+    return *this;
+  }
+  ~DevBuf() { release(); }
+  cudaError_t alloc(size_t n) {
+    release();
+    if (n == 0) n = 1;
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&p_), n * sizeof(T));
+    owned_ = (e == cudaSuccess);
+    if (!owned_) p_ = nullptr;
+    return e;
+  }
+  void borrow(T* p) {
+    release();
+    p_ = p;
+    owned_ = false;
+  }
+  void release() {
+    if (owned_ && p_) cudaFree(p_);
+    p_ = nullptr;
+    owned_ = false;
+  }
+  T* get() const { return p_; }
+  operator T*() const { return p_; }
+
+ private:
+  T* p_ = nullptr;
+  bool owned_ = false;
+};
+
+class Shard {
+ public:
+  Shard(int metric, int device, uint32_t max_n, int D, uint32_t K, int verbosity)
+      : metric(metric), device(device), max_n(max_n), D(D), K(K), verbosity(verbosity) {}
+  ~Shard();
+  Shard(const Shard&) = delete;
+
+  KMCUDAResult create(bool with_update);
+  KMCUDAResult enable_yinyang(uint32_t G);
+
+  // hot path
+  KMCUDAResult assign(uint32_t n, const float* X, const float* C, uint32_t* assignments,
+                      uint32_t* prev, uint32_t* d_changed, cudaStream_t st);
+  KMCUDAResult partial_sums(uint32_t n, const float* X, const uint32_t* assignments, float* sums,
+                            uint32_t* counts, cudaStream_t st);
+  KMCUDAResult finish_update(const float* sums, const uint32_t* counts, float* C, uint32_t* ccounts,
+                             cudaStream_t st);
+
+  const int metric, device;
+  const uint32_t max_n;
+  const int D;
+  const uint32_t K;
+  const int verbosity;
+
+  bool last_tc = false;
+  uint32_t last_rechecked = 0, last_overflowed = 0;
+  bool force_exact = false;  // KMCUDA_B200_FORCE_EXACT=1 (debug / parity tests)
+
+  // scratch
+  DevBuf<float> csq;
+  DevBuf<uint32_t> result;
+  UpdateWorkspace ws;
+  DevBuf<uint32_t> ws_keys_out, ws_vals_in, ws_vals_out, ws_offsets;
+  DevBuf<float> ws_partial;
+  DevBuf<char> ws_cub;
+  TcPlan* tc = nullptr;
+
+  // Yinyang state (per shard)
+  uint32_t G = 0;
+  DevBuf<float> bounds, drift, maxdrift, oldC;
+  DevBuf<uint32_t> passed, groups;
+  DevBuf<uint32_t> d_npassed;
+};
+
+}  // namespace kmb

@@ -1,0 +1,688 @@
+// simt_kernels.cu -- exact (reference-arithmetic) CUDA-core kernels.
+//
+// Everything here consumes the caller's row-major [N][D] layout directly (the reference first
+// transposes to feature-major through a managed staging copy, transpose.cu:83-117; that component
+// does not exist here).  Sample tiles are staged through padded shared memory so that the
+// sequential Kahan chains of exact.cuh read conflict-free, and centroid features are warp-uniform
+// broadcast loads.
+#include <cub/device/device_radix_sort.cuh>
+
+#include "exact.cuh"
+#include "kernels.h"
+
+namespace kmb {
+
+static inline unsigned cdiv(size_t a, size_t b) { return static_cast<unsigned>((a + b - 1) / b); }
+
+// ------------------------------------------------------------------------------------------------
+// ||c||^2 table (reference computes it per CTA per chunk, kmeans.cu:322-323)
+// ------------------------------------------------------------------------------------------------
+template <int METRIC>
+__global__ void csqr_kernel(const float* __restrict__ C, uint32_t K, int D, float* __restrict__ csq) {
+  uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= K) return;
+  csq[c] = csqr_exact<METRIC>(C + static_cast<size_t>(c) * D, D);
+}
+
+cudaError_t launch_csqr(int metric, const float* C, uint32_t K, int D, float* csq, cudaStream_t st) {
+  if (metric == 1) csqr_kernel<1><<<cdiv(K, 128), 128, 0, st>>>(C, K, D, csq);
+  else csqr_kernel<0><<<cdiv(K, 128), 128, 0, st>>>(C, K, D, csq);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Exact pass over ALL K centroids.  MODE 0: Lloyd argmin (reference kmeans.cu:293-364).
+// MODE 1: Yinyang bounds refresh (reference kmeans.cu:431-485).
+// One thread per sample, 4 independent Kahan chains (4 centroids) in flight per thread.
+// ------------------------------------------------------------------------------------------------
+template <int METRIC, int MODE>
+__global__ void __launch_bounds__(128)
+exact_pass_kernel(const float* __restrict__ X, const float* __restrict__ C,
+                  const float* __restrict__ csq, uint32_t n, int D, uint32_t K,
+                  const uint32_t* __restrict__ rows, const uint32_t* __restrict__ d_nrows,
+                  uint32_t* __restrict__ result, int use_smem,
+                  // MODE 1 only
+                  uint32_t G, const uint32_t* __restrict__ assign,
+                  const uint32_t* __restrict__ groups, float* __restrict__ bounds) {
+  extern __shared__ float sX[];
+  const int BS = blockDim.x;
+  const uint32_t nrows = d_nrows ? *d_nrows : n;
+  for (uint32_t tile0 = blockIdx.x * BS; tile0 < nrows; tile0 += gridDim.x * BS) {
+    const uint32_t slot = tile0 + threadIdx.x;
+    const bool active = slot < nrows;
+    const uint32_t row = active ? (rows ? rows[slot] : slot) : 0;
+    const float* xs;
+    int xstride;
+    if (use_smem) {
+      __syncthreads();
+      const int cnt = min(static_cast<uint32_t>(BS), nrows - tile0);
+      for (int e = threadIdx.x; e < cnt * D; e += BS) {
+        int s = e / D, f = e - s * D;
+        uint32_t r = rows ? rows[tile0 + s] : tile0 + s;
+        sX[f * (BS + 1) + s] = X[static_cast<size_t>(r) * D + f];
+      }
+      __syncthreads();
+      xs = sX + threadIdx.x;
+      xstride = BS + 1;
+    } else {
+      xs = X + static_cast<size_t>(row) * D;
+      xstride = 1;
+    }
+    if (!active) continue;
+    if (MODE == 0) {
+      float x0 = xs[0];
+      if (x0 != x0) {  // "insane" sample: first feature NaN (kmeans.cu:312,355)
+        result[row] = K;
+        continue;
+      }
+    }
+    float best = FLT_MAX;
+    uint32_t arg = UINT32_MAX;
+    uint32_t mine = 0;
+    if (MODE == 1) {
+      mine = assign[row];
+      for (uint32_t g = 0; g <= G; g++) bounds[static_cast<size_t>(n) * g + row] = FLT_MAX;
+    }
+    for (uint32_t c0 = 0; c0 < K; c0 += 4) {
+      const float* cp[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) cp[j] = C + static_cast<size_t>(min(c0 + j, K - 1)) * D;
+      Kahan k[4];
+      for (int f = 0; f < D; f++) {
+        float x = xs[f * xstride];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          float cv = __ldg(cp[j] + f);
+          if (MODE == 1 && METRIC == 0) k[j].sqdiff(x, cv);
+          else k[j].mac(x, cv);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        uint32_t c = c0 + j;
+        if (c >= K) break;
+        if (MODE == 0) {
+          float score = lloyd_score<METRIC>(k[j].sum, csq[c]);
+          if (score < best) {
+            best = score;
+            arg = c;
+          }
+        } else {
+          uint32_t g = groups[c];
+          if (g >= G) continue;  // NaN centroid (kmeans.cu:464-468)
+          float dist = finalize_distance<METRIC>(k[j].sum);
+          if (c != mine) {
+            size_t gi = static_cast<size_t>(n) * (1 + g) + row;
+            if (dist < bounds[gi]) bounds[gi] = dist;
+          } else {
+            bounds[row] = dist;
+          }
+        }
+      }
+    }
+    if (MODE == 0) result[row] = (arg == UINT32_MAX) ? kUntouched : arg;
+  }
+}
+
+struct ExactCfg {
+  int bs, use_smem;
+  size_t smem;
+};
+static ExactCfg exact_cfg(int D) {
+  const size_t limit = 200 * 1024;
+  for (int bs : {128, 64, 32}) {
+    size_t need = static_cast<size_t>(bs + 1) * D * sizeof(float);
+    if (need <= limit) return {bs, 1, need};
+  }
+  return {128, 0, 0};
+}
+
+template <int METRIC, int MODE>
+static cudaError_t launch_exact_pass(const float* X, const float* C, const float* csq, uint32_t n,
+                                     int D, uint32_t K, const uint32_t* rows,
+                                     const uint32_t* d_nrows, uint32_t* result, uint32_t G,
+                                     const uint32_t* assign, const uint32_t* groups, float* bounds,
+                                     cudaStream_t st) {
+  ExactCfg cfg = exact_cfg(D);
+  auto kern = exact_pass_kernel<METRIC, MODE>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(cfg.smem));
+  if (e != cudaSuccess) return e;
+  unsigned grid = d_nrows ? 148 * 4 : cdiv(n, cfg.bs);
+  if (grid == 0) return cudaSuccess;
+  kern<<<grid, cfg.bs, cfg.smem, st>>>(X, C, csq, n, D, K, rows, d_nrows, result, cfg.use_smem, G,
+                                       assign, groups, bounds);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_assign_exact(int metric, const float* X, const float* C, const float* csq,
+                                uint32_t n, int D, uint32_t K, const uint32_t* rows,
+                                const uint32_t* d_nrows, uint32_t* result, cudaStream_t st) {
+  if (metric == 1)
+    return launch_exact_pass<1, 0>(X, C, csq, n, D, K, rows, d_nrows, result, 0, nullptr, nullptr,
+                                   nullptr, st);
+  return launch_exact_pass<0, 0>(X, C, csq, n, D, K, rows, d_nrows, result, 0, nullptr, nullptr,
+                                 nullptr, st);
+}
+
+cudaError_t launch_yy_init(int metric, const float* X, const float* C, uint32_t n, int D, uint32_t K,
+                           uint32_t G, const uint32_t* assign, const uint32_t* groups, float* bounds,
+                           cudaStream_t st) {
+  if (metric == 1)
+    return launch_exact_pass<1, 1>(X, C, nullptr, n, D, K, nullptr, nullptr, nullptr, G, assign,
+                                   groups, bounds, st);
+  return launch_exact_pass<0, 1>(X, C, nullptr, n, D, K, nullptr, nullptr, nullptr, G, assign, groups,
+                                 bounds, st);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Exact re-check of the short candidate lists emitted by the tensor-core filter.
+// 128 queue entries per CTA, features streamed through shared memory 32 at a time (coalesced
+// 128-byte row segments), Kahan state of the <=4 candidate chains lives in registers.
+// ------------------------------------------------------------------------------------------------
+template <int METRIC>
+__global__ void __launch_bounds__(128)
+recheck_kernel(const float* __restrict__ X, const float* __restrict__ C,
+               const float* __restrict__ csq, int D, const uint32_t* __restrict__ qrow,
+               const uint32_t* __restrict__ qcand, const uint32_t* __restrict__ d_nq, uint32_t max_q,
+               uint32_t* __restrict__ result) {
+  __shared__ float sXc[32 * 129];
+  extern __shared__ float sCc[];  // [kMaxCand*128][33]
+  const uint32_t nq = min(*d_nq, max_q);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (uint32_t tile0 = blockIdx.x * 128; tile0 < nq; tile0 += gridDim.x * 128) {
+    const uint32_t e = tile0 + threadIdx.x;
+    const bool active = e < nq;
+    uint32_t cand[kMaxCand];
+#pragma unroll
+    for (int j = 0; j < kMaxCand; j++) cand[j] = active ? qcand[static_cast<size_t>(e) * kMaxCand + j] : UINT32_MAX;
+    Kahan k[kMaxCand];
+    for (int f0 = 0; f0 < D; f0 += 32) {
+      const int fl = min(32, D - f0);
+      __syncthreads();
+      for (int i = 0; i < 32; i++) {  // sample chunk: warp w stages entries 32w..32w+31
+        uint32_t ent = tile0 + warp * 32 + i;
+        if (ent < nq && lane < fl) {
+          uint32_t r = qrow[ent];
+          sXc[lane * 129 + warp * 32 + i] = X[static_cast<size_t>(r) * D + f0 + lane];
+        }
+      }
+      for (int i = 0; i < kMaxCand * 32; i++) {  // candidate centroid chunks
+        int rowid = warp * (kMaxCand * 32) + i;   // = j*128 + entry
+        int j = rowid >> 7, ent_l = rowid & 127;
+        uint32_t ent = tile0 + ent_l;
+        if (ent < nq && lane < fl) {
+          uint32_t c = qcand[static_cast<size_t>(ent) * kMaxCand + j];
+          if (c != UINT32_MAX) sCc[rowid * 33 + lane] = C[static_cast<size_t>(c) * D + f0 + lane];
+        }
+      }
+      __syncthreads();
+      if (active) {
+        for (int f = 0; f < fl; f++) {
+          float x = sXc[f * 129 + threadIdx.x];
+#pragma unroll
+          for (int j = 0; j < kMaxCand; j++)
+            if (cand[j] != UINT32_MAX) k[j].mac(x, sCc[(j * 128 + threadIdx.x) * 33 + f]);
+        }
+      }
+    }
+    if (active) {
+      float best = FLT_MAX;
+      uint32_t arg = UINT32_MAX;
+#pragma unroll
+      for (int j = 0; j < kMaxCand; j++) {
+        if (cand[j] == UINT32_MAX) continue;
+        float score = lloyd_score<METRIC>(k[j].sum, csq[cand[j]]);
+        if (score < best) {
+          best = score;
+          arg = cand[j];
+        }
+      }
+      result[qrow[e]] = (arg == UINT32_MAX) ? kUntouched : arg;
+    }
+  }
+}
+
+cudaError_t launch_recheck(int metric, const float* X, const float* C, const float* csq, int D,
+                           const uint32_t* qrow, const uint32_t* qcand, const uint32_t* d_nq,
+                           uint32_t max_q, uint32_t* result, cudaStream_t st) {
+  size_t smem = static_cast<size_t>(kMaxCand) * 128 * 33 * sizeof(float);
+  unsigned grid = 148 * 2;
+  if (max_q == 0) return cudaSuccess;
+  grid = min(grid, cdiv(max_q, 128));
+  cudaError_t e;
+  if (metric == 1) {
+    e = cudaFuncSetAttribute(recheck_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    recheck_kernel<1><<<grid, 128, smem, st>>>(X, C, csq, D, qrow, qcand, d_nq, max_q, result);
+  } else {
+    e = cudaFuncSetAttribute(recheck_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    recheck_kernel<0><<<grid, 128, smem, st>>>(X, C, csq, D, qrow, qcand, d_nq, max_q, result);
+  }
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// prev/assign bookkeeping + reassignment counter (reference kmeans.cu:358-363)
+// ------------------------------------------------------------------------------------------------
+__global__ void finalize_assign_kernel(uint32_t n, const uint32_t* __restrict__ result,
+                                       uint32_t* __restrict__ assign, uint32_t* __restrict__ prev,
+                                       uint32_t* __restrict__ d_changed) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  int changed = 0;
+  if (i < n) {
+    uint32_t r = result[i];
+    if (r != kUntouched) {
+      uint32_t a = assign[i];
+      prev[i] = a;
+      if (a != r) {
+        assign[i] = r;
+        changed = 1;
+      }
+    }
+  }
+  unsigned mask = __ballot_sync(0xffffffffu, changed);
+  if ((threadIdx.x & 31) == 0 && mask) atomicAdd(d_changed, __popc(mask));
+}
+
+cudaError_t launch_finalize_assign(uint32_t n, const uint32_t* result, uint32_t* assign,
+                                   uint32_t* prev, uint32_t* d_changed, cudaStream_t st) {
+  if (n == 0) return cudaSuccess;
+  finalize_assign_kernel<<<cdiv(n, 256), 256, 0, st>>>(n, result, assign, prev, d_changed);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Centroid update.  The reference updates incrementally with one thread per centroid scanning all
+// N assignments (kmeans.cu:366-429); here: stable radix sort by cluster, per-cluster compensated
+// sums in sample-index order (deterministic), all-reduce across shards by the caller, normalise.
+// ------------------------------------------------------------------------------------------------
+__global__ void iota_kernel(uint32_t* p, uint32_t n) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = i;
+}
+
+__global__ void segment_offsets_kernel(const uint32_t* __restrict__ keys, uint32_t n, uint32_t K,
+                                       uint32_t* __restrict__ offsets, uint32_t* __restrict__ counts) {
+  uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c > K) return;
+  uint32_t lo = 0, hi = n;  // first position with key >= c
+  while (lo < hi) {
+    uint32_t mid = lo + (hi - lo) / 2;
+    if (keys[mid] < c) lo = mid + 1;
+    else hi = mid;
+  }
+  offsets[c] = lo;
+  if (c < K) {
+    uint32_t lo2 = lo, hi2 = n;  // first position with key >= c+1
+    while (lo2 < hi2) {
+      uint32_t mid = lo2 + (hi2 - lo2) / 2;
+      if (keys[mid] < c + 1) lo2 = mid + 1;
+      else hi2 = mid;
+    }
+    counts[c] = lo2 - lo;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+cluster_sums_kernel(const float* __restrict__ X, int D, const uint32_t* __restrict__ idx,
+                    const uint32_t* __restrict__ offsets, float* __restrict__ partial) {
+  const uint32_t c = blockIdx.x, s = blockIdx.y;
+  const uint32_t beg = offsets[c], end = offsets[c + 1];
+  const uint32_t len = end - beg, per = (len + kUpdateSplits - 1) / kUpdateSplits;
+  const uint32_t b = min(end, beg + s * per), e = min(end, b + per);
+  for (int f = threadIdx.x; f < D; f += blockDim.x) {
+    float sum = 0.f, comp = 0.f;
+    uint32_t j = b;
+    for (; j + 4 <= e; j += 4) {
+      uint32_t i0 = idx[j], i1 = idx[j + 1], i2 = idx[j + 2], i3 = idx[j + 3];
+      float v0 = X[static_cast<size_t>(i0) * D + f], v1 = X[static_cast<size_t>(i1) * D + f];
+      float v2 = X[static_cast<size_t>(i2) * D + f], v3 = X[static_cast<size_t>(i3) * D + f];
+      float y, t;
+      y = v0 - comp; t = sum + y; comp = (t - sum) - y; sum = t;
+      y = v1 - comp; t = sum + y; comp = (t - sum) - y; sum = t;
+      y = v2 - comp; t = sum + y; comp = (t - sum) - y; sum = t;
+      y = v3 - comp; t = sum + y; comp = (t - sum) - y; sum = t;
+    }
+    for (; j < e; j++) {
+      float v = X[static_cast<size_t>(idx[j]) * D + f];
+      float y = v - comp, t = sum + y;
+      comp = (t - sum) - y;
+      sum = t;
+    }
+    partial[(static_cast<size_t>(c) * kUpdateSplits + s) * D + f] = sum;
+  }
+}
+
+__global__ void combine_partials_kernel(const float* __restrict__ partial, uint32_t K, int D,
+                                        float* __restrict__ sums) {
+  size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<size_t>(K) * D) return;
+  uint32_t c = i / D;
+  int f = i - static_cast<size_t>(c) * D;
+  float sum = 0.f, comp = 0.f;
+  for (int s = 0; s < kUpdateSplits; s++) {
+    float v = partial[(static_cast<size_t>(c) * kUpdateSplits + s) * D + f];
+    float y = v - comp, t = sum + y;
+    comp = (t - sum) - y;
+    sum = t;
+  }
+  sums[i] = sum;
+}
+
+size_t update_cub_bytes(uint32_t n) {
+  size_t bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr,
+                                  (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)n, 0, 32);
+  return bytes;
+}
+
+cudaError_t launch_partial_sums(const float* X, uint32_t n, int D, uint32_t K, const uint32_t* assign,
+                                UpdateWorkspace& ws, float* sums, uint32_t* counts, cudaStream_t st) {
+  if (n == 0) {
+    cudaMemsetAsync(sums, 0, sizeof(float) * static_cast<size_t>(K) * D, st);
+    cudaMemsetAsync(counts, 0, sizeof(uint32_t) * K, st);
+    return cudaGetLastError();
+  }
+  iota_kernel<<<cdiv(n, 256), 256, 0, st>>>(ws.vals_in, n);
+  int bits = 1;
+  while ((1ull << bits) <= K) bits++;  // keys are in [0, K] (K = "insane")
+  size_t bytes = ws.cub_tmp_bytes;
+  cudaError_t e = cub::DeviceRadixSort::SortPairs(ws.cub_tmp, bytes, assign, ws.keys_out, ws.vals_in,
+                                                  ws.vals_out, (int)n, 0, bits, st);
+  if (e != cudaSuccess) return e;
+  segment_offsets_kernel<<<cdiv(K + 1, 128), 128, 0, st>>>(ws.keys_out, n, K, ws.offsets, counts);
+  cluster_sums_kernel<<<dim3(K, kUpdateSplits), 256, 0, st>>>(X, D, ws.vals_out, ws.offsets, ws.partial);
+  combine_partials_kernel<<<cdiv(static_cast<size_t>(K) * D, 256), 256, 0, st>>>(ws.partial, K, D, sums);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_knn_inverse(const uint32_t* assign, uint32_t n, uint32_t K, uint32_t* iota,
+                               uint32_t* keys_out, uint32_t* inv, uint32_t* off, uint32_t* counts,
+                               UpdateWorkspace& ws, cudaStream_t st) {
+  iota_kernel<<<cdiv(n, 256), 256, 0, st>>>(iota, n);
+  int bits = 1;
+  while ((1ull << bits) <= K) bits++;
+  size_t bytes = ws.cub_tmp_bytes;
+  cudaError_t e = cub::DeviceRadixSort::SortPairs(ws.cub_tmp, bytes, assign, keys_out, iota, inv, (int)n, 0,
+                                                  bits, st);
+  if (e != cudaSuccess) return e;
+  segment_offsets_kernel<<<cdiv(K + 1, 128), 128, 0, st>>>(keys_out, n, K, off, counts);
+  return cudaGetLastError();
+}
+
+// reference metric_abstraction.h:138-144 (L2: multiply by __frcp_rn(count)) and :255-272 (cosine)
+template <int METRIC>
+__global__ void normalize_kernel(const float* __restrict__ sums, const uint32_t* __restrict__ counts,
+                                 uint32_t K, int D, float* __restrict__ C,
+                                 uint32_t* __restrict__ ccounts) {
+  uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= K) return;
+  const float* s = sums + static_cast<size_t>(c) * D;
+  float* o = C + static_cast<size_t>(c) * D;
+  uint32_t cnt = counts[c];
+  float scale;
+  if (METRIC == 1) {
+    Kahan k;
+    for (int f = 0; f < D; f++) k.mac(s[f], s[f]);
+    scale = __frcp_rn(__fsqrt_rn(k.sum));
+  } else {
+    scale = __frcp_rn(static_cast<float>(cnt));
+  }
+  for (int f = 0; f < D; f++) o[f] = s[f] * scale;
+  ccounts[c] = cnt;
+}
+
+cudaError_t launch_normalize(int metric, const float* sums, const uint32_t* counts, uint32_t K, int D,
+                             float* C, uint32_t* ccounts, cudaStream_t st) {
+  if (metric == 1) normalize_kernel<1><<<cdiv(K, 64), 64, 0, st>>>(sums, counts, K, D, C, ccounts);
+  else normalize_kernel<0><<<cdiv(K, 64), 64, 0, st>>>(sums, counts, K, D, C, ccounts);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Yinyang bound maintenance (reference kmeans.cu:487-672), exact arithmetic, row-major samples.
+// ------------------------------------------------------------------------------------------------
+template <int METRIC>
+__global__ void yy_drifts_kernel(const float* __restrict__ Cnew, const float* __restrict__ Cold,
+                                 uint32_t K, int D, float* __restrict__ drift) {
+  uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= K) return;
+  drift[c] = distance_exact<METRIC>(Cnew + static_cast<size_t>(c) * D, Cold + static_cast<size_t>(c) * D, D);
+}
+
+__global__ void yy_group_max_kernel(const float* __restrict__ drift, const uint32_t* __restrict__ groups,
+                                    uint32_t K, uint32_t G, float* __restrict__ maxdrift) {
+  uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= G) return;
+  float m = -FLT_MAX;
+  for (uint32_t c = 0; c < K; c++)
+    if (groups[c] == g) {
+      float d = drift[c];
+      if (m < d) m = d;
+    }
+  maxdrift[g] = m;
+}
+
+cudaError_t launch_yy_drifts(int metric, const float* Cnew, const float* Cold, uint32_t K, int D,
+                             uint32_t G, const uint32_t* groups, float* drift, float* maxdrift,
+                             cudaStream_t st) {
+  if (metric == 1) yy_drifts_kernel<1><<<cdiv(K, 64), 64, 0, st>>>(Cnew, Cold, K, D, drift);
+  else yy_drifts_kernel<0><<<cdiv(K, 64), 64, 0, st>>>(Cnew, Cold, K, D, drift);
+  yy_group_max_kernel<<<cdiv(G, 64), 64, 0, st>>>(drift, groups, K, G, maxdrift);
+  return cudaGetLastError();
+}
+
+template <int METRIC>
+__global__ void yy_global_filter_kernel(const float* __restrict__ X, const float* __restrict__ C,
+                                        uint32_t n, int D, uint32_t G,
+                                        const float* __restrict__ drift,
+                                        const float* __restrict__ maxdrift,
+                                        const uint32_t* __restrict__ assign,
+                                        uint32_t* __restrict__ prev, float* __restrict__ bounds,
+                                        uint32_t* __restrict__ passed, uint32_t* __restrict__ d_npassed) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  bool pass = false;
+  if (i < n) {
+    uint32_t a = assign[i];
+    prev[i] = a;
+    float ub = bounds[i] + drift[a];
+    float minlb = FLT_MAX;
+    for (uint32_t g = 0; g < G; g++) {
+      size_t gi = static_cast<size_t>(n) * (1 + g) + i;
+      float lb = bounds[gi] - maxdrift[g];
+      bounds[gi] = lb;
+      if (lb < minlb) minlb = lb;
+    }
+    if (minlb >= ub) {
+      bounds[i] = ub;
+    } else {
+      ub = distance_exact<METRIC>(X + static_cast<size_t>(i) * D, C + static_cast<size_t>(a) * D, D);
+      bounds[i] = ub;
+      pass = !(minlb >= ub);
+    }
+  }
+  unsigned mask = __ballot_sync(0xffffffffu, pass);
+  if (mask) {
+    int lane = threadIdx.x & 31, leader = __ffs(mask) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(d_npassed, __popc(mask));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (pass) passed[base + __popc(mask & ((1u << lane) - 1))] = i;
+  }
+}
+
+cudaError_t launch_yy_global_filter(int metric, const float* X, const float* C, uint32_t n, int D,
+                                    uint32_t G, const float* drift, const float* maxdrift,
+                                    const uint32_t* assign, uint32_t* prev, float* bounds,
+                                    uint32_t* passed, uint32_t* d_npassed, cudaStream_t st) {
+  if (n == 0) return cudaSuccess;
+  if (metric == 1)
+    yy_global_filter_kernel<1><<<cdiv(n, 256), 256, 0, st>>>(X, C, n, D, G, drift, maxdrift, assign, prev,
+                                                            bounds, passed, d_npassed);
+  else
+    yy_global_filter_kernel<0><<<cdiv(n, 256), 256, 0, st>>>(X, C, n, D, G, drift, maxdrift, assign, prev,
+                                                            bounds, passed, d_npassed);
+  return cudaGetLastError();
+}
+
+template <int METRIC>
+__global__ void yy_local_filter_kernel(const float* __restrict__ X, const float* __restrict__ C,
+                                       uint32_t n, int D, uint32_t K, uint32_t G,
+                                       const uint32_t* __restrict__ groups,
+                                       const float* __restrict__ drift,
+                                       const float* __restrict__ maxdrift,
+                                       const uint32_t* __restrict__ passed,
+                                       const uint32_t* __restrict__ d_npassed,
+                                       uint32_t* __restrict__ assign, float* __restrict__ bounds,
+                                       uint32_t* __restrict__ d_changed) {
+  const uint32_t np = *d_npassed;
+  int changed = 0;
+  for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < np; p += gridDim.x * blockDim.x) {
+    const uint32_t i = passed[p];
+    const float ub = bounds[i];
+    const uint32_t a = assign[i];
+    float mn = ub, sec = FLT_MAX;
+    uint32_t near = a;
+    const float* x = X + static_cast<size_t>(i) * D;
+    for (uint32_t c = 0; c < K; c++) {
+      if (c == a) continue;
+      uint32_t g = groups[c];
+      if (g >= G) continue;
+      float lb = bounds[static_cast<size_t>(n) * (1 + g) + i];
+      if (lb >= ub) {
+        if (lb < sec) sec = lb;
+        continue;
+      }
+      lb += maxdrift[g] - drift[c];
+      if (sec < lb) continue;
+      float d = distance_exact<METRIC>(x, C + static_cast<size_t>(c) * D, D);
+      if (d < mn) {
+        sec = mn;
+        mn = d;
+        near = c;
+      } else if (d < sec) {
+        sec = d;
+      }
+    }
+    uint32_t ng = groups[near], pg = groups[a];
+    bounds[static_cast<size_t>(n) * (1 + ng) + i] = sec;
+    if (ng != pg) {
+      size_t gi = static_cast<size_t>(n) * (1 + pg) + i;
+      if (bounds[gi] > ub) bounds[gi] = ub;
+    }
+    bounds[i] = mn;
+    if (near != a) {
+      assign[i] = near;
+      changed++;
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) changed += __shfl_down_sync(0xffffffffu, changed, o);
+  if ((threadIdx.x & 31) == 0 && changed) atomicAdd(d_changed, changed);
+}
+
+cudaError_t launch_yy_local_filter(int metric, const float* X, const float* C, uint32_t n, int D,
+                                   uint32_t K, uint32_t G, const uint32_t* groups, const float* drift,
+                                   const float* maxdrift, const uint32_t* passed,
+                                   const uint32_t* d_npassed, uint32_t* assign, float* bounds,
+                                   uint32_t* d_changed, cudaStream_t st) {
+  if (n == 0) return cudaSuccess;
+  unsigned grid = min(cdiv(n, 128), 148u * 16u);
+  if (metric == 1)
+    yy_local_filter_kernel<1><<<grid, 128, 0, st>>>(X, C, n, D, K, G, groups, drift, maxdrift, passed,
+                                                    d_npassed, assign, bounds, d_changed);
+  else
+    yy_local_filter_kernel<0><<<grid, 128, 0, st>>>(X, C, n, D, K, G, groups, drift, maxdrift, passed,
+                                                    d_npassed, assign, bounds, d_changed);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// average distance (kmeans.cu:674-691) and the k-means++ distance step (kmeans.cu:42-67)
+// ------------------------------------------------------------------------------------------------
+template <int METRIC>
+__global__ void average_distance_kernel(const float* __restrict__ X, const float* __restrict__ C,
+                                        uint32_t n, int D, const uint32_t* __restrict__ assign,
+                                        double* __restrict__ d_sum) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  float dist = 0.f;
+  if (i < n)
+    dist = distance_exact<METRIC>(X + static_cast<size_t>(i) * D, C + static_cast<size_t>(assign[i]) * D, D);
+  for (int o = 16; o > 0; o >>= 1) dist += __shfl_down_sync(0xffffffffu, dist, o);
+  if ((threadIdx.x & 31) == 0) atomicAdd(d_sum, static_cast<double>(dist));
+}
+
+cudaError_t launch_average_distance(int metric, const float* X, const float* C, uint32_t n, int D,
+                                    const uint32_t* assign, double* d_sum, cudaStream_t st) {
+  if (n == 0) return cudaSuccess;
+  if (metric == 1) average_distance_kernel<1><<<cdiv(n, 256), 256, 0, st>>>(X, C, n, D, assign, d_sum);
+  else average_distance_kernel<0><<<cdiv(n, 256), 256, 0, st>>>(X, C, n, D, assign, d_sum);
+  return cudaGetLastError();
+}
+
+template <int METRIC>
+__global__ void plusplus_kernel(const float* __restrict__ X, uint32_t n, int D,
+                                const float* __restrict__ centroid, int first,
+                                float* __restrict__ dists, double* __restrict__ d_sum) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  float dist = 0.f;
+  if (i < n) {
+    const float* x = X + static_cast<size_t>(i) * D;
+    if (x[0] == x[0]) dist = distance_exact<METRIC>(x, centroid, D);
+    float prev;
+    if (first || dist < (prev = dists[i])) dists[i] = dist;
+    else dist = prev;
+  }
+  for (int o = 16; o > 0; o >>= 1) dist += __shfl_down_sync(0xffffffffu, dist, o);
+  if ((threadIdx.x & 31) == 0) atomicAdd(d_sum, static_cast<double>(dist));
+}
+
+cudaError_t launch_plusplus_step(int metric, const float* X, uint32_t n, int D, const float* centroid,
+                                 int first, float* dists, double* d_sum, cudaStream_t st) {
+  if (n == 0) return cudaSuccess;
+  if (metric == 1) plusplus_kernel<1><<<cdiv(n, 256), 256, 0, st>>>(X, n, D, centroid, first, dists, d_sum);
+  else plusplus_kernel<0><<<cdiv(n, 256), 256, 0, st>>>(X, n, D, centroid, first, dists, d_sum);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// fp16x2 ingest / egress (exact widening; centroids narrowed round-to-nearest on the way out)
+// ------------------------------------------------------------------------------------------------
+}  // namespace kmb
+#include <cuda_fp16.h>
+namespace kmb {
+
+__global__ void half_to_float_kernel(const __half* __restrict__ src, float* __restrict__ dst, size_t n) {
+  size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (; i < n; i += stride) dst[i] = __half2float(src[i]);
+}
+__global__ void float_to_half_kernel(const float* __restrict__ src, __half* __restrict__ dst, size_t n) {
+  size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (; i < n; i += stride) dst[i] = __float2half_rn(src[i]);
+}
+__global__ void fill_u32_kernel(uint32_t* p, uint32_t v, size_t n) {
+  size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (; i < n; i += stride) p[i] = v;
+}
+
+cudaError_t launch_half_to_float(const void* src, float* dst, size_t n, cudaStream_t st) {
+  if (!n) return cudaSuccess;
+  half_to_float_kernel<<<min(cdiv(n, 256), 148u * 32u), 256, 0, st>>>(static_cast<const __half*>(src), dst, n);
+  return cudaGetLastError();
+}
+cudaError_t launch_float_to_half(const float* src, void* dst, size_t n, cudaStream_t st) {
+  if (!n) return cudaSuccess;
+  float_to_half_kernel<<<min(cdiv(n, 256), 148u * 32u), 256, 0, st>>>(src, static_cast<__half*>(dst), n);
+  return cudaGetLastError();
+}
+cudaError_t launch_fill_u32(uint32_t* p, uint32_t v, size_t n, cudaStream_t st) {
+  if (!n) return cudaSuccess;
+  fill_u32_kernel<<<min(cdiv(n, 256), 148u * 32u), 256, 0, st>>>(p, v, n);
+  return cudaGetLastError();
+}
+
+}  // namespace kmb

@@ -1,0 +1,122 @@
+"""Python mirror of the shard-level C ABI (include/kmcuda_b200.h) over torch device tensors.
+
+torch is plumbing here: it owns device memory and streams (and, in bench.py / multi-process jobs,
+the NCCL communicator).  Every computation goes through libKMCUDA.so.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib, _raise_for
+
+_lib.kmcuda_b200_shard_create.restype = ctypes.c_int
+_lib.kmcuda_b200_shard_create.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.c_uint32,
+                                          ctypes.c_uint16, ctypes.c_uint32, ctypes.c_int32]
+_lib.kmcuda_b200_shard_destroy.restype = None
+_lib.kmcuda_b200_shard_destroy.argtypes = [ctypes.c_void_p]
+_lib.kmcuda_b200_assign.restype = ctypes.c_int
+_lib.kmcuda_b200_assign.argtypes = [ctypes.c_void_p, ctypes.c_uint32] + [ctypes.c_void_p] * 6
+_lib.kmcuda_b200_last_pass_info.restype = ctypes.c_int32
+_lib.kmcuda_b200_last_pass_info.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint32),
+                                            ctypes.POINTER(ctypes.c_uint32)]
+_lib.kmcuda_b200_partial_sums.restype = ctypes.c_int
+_lib.kmcuda_b200_partial_sums.argtypes = [ctypes.c_void_p, ctypes.c_uint32] + [ctypes.c_void_p] * 5
+_lib.kmcuda_b200_finish_update.restype = ctypes.c_int
+_lib.kmcuda_b200_finish_update.argtypes = [ctypes.c_void_p] + [ctypes.c_void_p] * 5
+_lib.kmcuda_b200_debug_last_error.restype = ctypes.c_uint32
+_lib.kmcuda_b200_debug_last_error.argtypes = [ctypes.c_void_p]
+_lib.kmcuda_b200_debug_scores.restype = ctypes.c_int32
+_lib.kmcuda_b200_debug_scores.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32]
+_lib.kmcuda_b200_debug_stats.restype = ctypes.c_int32
+_lib.kmcuda_b200_debug_stats.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+
+
+def _stream_ptr():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t, dtype):
+    assert t.is_cuda and t.is_contiguous() and t.dtype == dtype, (t.device, t.dtype, t.is_contiguous())
+    return ctypes.c_void_p(t.data_ptr())
+
+
+class Shard:
+    """One GPU's share of a clustering job (the current torch CUDA device at construction)."""
+
+    def __init__(self, max_samples, features, clusters, metric="L2", verbosity=0):
+        self.device = torch.cuda.current_device()
+        self.n, self.D, self.K = int(max_samples), int(features), int(clusters)
+        self.metric = 1 if metric in ("cos", "cosine", "angular") else 0
+        h = ctypes.c_void_p()
+        _raise_for(_lib.kmcuda_b200_shard_create(ctypes.byref(h), self.metric, self.n, self.D, self.K,
+                                                 int(verbosity)), "kmcuda_b200_shard_create")
+        self._h = h
+
+    def close(self):
+        if self._h:
+            _lib.kmcuda_b200_shard_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def assign(self, X, C, assignments, prev, changed):
+        """One assignment pass, enqueued on the current torch stream (no host sync)."""
+        _raise_for(_lib.kmcuda_b200_assign(self._h, X.shape[0], _ptr(X, torch.float32), _ptr(C, torch.float32),
+                                           _ptr(assignments, torch.int32), _ptr(prev, torch.int32),
+                                           _ptr(changed, torch.int32), _stream_ptr()), "kmcuda_b200_assign")
+
+    def last_pass_info(self):
+        """(used_tensor_cores, rows_rechecked, rows_overflowed) of the last pass; sync first."""
+        a, b = ctypes.c_uint32(0), ctypes.c_uint32(0)
+        tc = _lib.kmcuda_b200_last_pass_info(self._h, ctypes.byref(a), ctypes.byref(b))
+        return bool(tc), a.value, b.value
+
+    def last_error(self):
+        return int(_lib.kmcuda_b200_debug_last_error(self._h))
+
+    def partial_sums(self, X, assignments, sums, counts):
+        _raise_for(_lib.kmcuda_b200_partial_sums(self._h, X.shape[0], _ptr(X, torch.float32),
+                                                 _ptr(assignments, torch.int32), _ptr(sums, torch.float32),
+                                                 _ptr(counts, torch.int32), _stream_ptr()),
+                   "kmcuda_b200_partial_sums")
+
+    def finish_update(self, sums, counts, C, ccounts):
+        _raise_for(_lib.kmcuda_b200_finish_update(self._h, _ptr(sums, torch.float32), _ptr(counts, torch.int32),
+                                                  _ptr(C, torch.float32), _ptr(ccounts, torch.int32),
+                                                  _stream_ptr()), "kmcuda_b200_finish_update")
+
+    # diagnostics
+    def debug_scores(self, rows, cols):
+        out = np.empty((rows, cols), np.float32)
+        rc = _lib.kmcuda_b200_debug_scores(self._h, out.ctypes.data, rows, cols)
+        if rc != 0:
+            raise RuntimeError("debug scores unavailable (%d); set KMCUDA_B200_DUMP_SCORES=1" % rc)
+        return out
+
+    def debug_stats(self):
+        out = np.zeros(4, np.float32)
+        if _lib.kmcuda_b200_debug_stats(self._h, out.ctypes.data) != 0:
+            return None
+        return {"scale": float(out[0]), "cmax": float(out[1]), "dcmax": float(out[2])}
+
+
+def assign_once(X, C, metric="L2", assignments=None):
+    """Convenience: one pass over torch tensors; returns (assignments, prev, changed, info)."""
+    n = X.shape[0]
+    sh = Shard(n, X.shape[1], C.shape[0], metric)
+    a = torch.full((n,), -1, dtype=torch.int32, device=X.device) if assignments is None else assignments
+    prev = torch.full((n,), -1, dtype=torch.int32, device=X.device)
+    changed = torch.zeros(1, dtype=torch.int32, device=X.device)
+    sh.assign(X, C, a, prev, changed)
+    torch.cuda.synchronize()
+    info = sh.last_pass_info()
+    err = sh.last_error()
+    sh.close()
+    if err:
+        raise RuntimeError("tensor-core pipeline error 0x%x" % err)
+    return a, prev, int(changed.item()), info
