@@ -48,6 +48,10 @@ KMCUDAResult kmcuda_b200_assign(kmcuda_b200_shard *shard, uint32_t samples_size,
  * kernel; also reports how many samples needed the re-check / the full exact fallback. */
 int32_t kmcuda_b200_last_pass_info(kmcuda_b200_shard *shard, uint32_t *rechecked, uint32_t *overflowed);
 
+/* Device time in ms (CUDA events on `stream`) of the tensor-core kernel in the most recent passes,
+ * oldest first (up to 64 are kept); returns the number written.  Synchronise the stream first. */
+int32_t kmcuda_b200_kernel_times(kmcuda_b200_shard *shard, float *ms_out, int32_t max_out);
+
 /* sums [K][D] fp32 and counts [K] uint32 of the shard (to be all-reduced by the caller). */
 KMCUDAResult kmcuda_b200_partial_sums(kmcuda_b200_shard *shard, uint32_t samples_size,
                                       const float *samples, const uint32_t *assignments, float *sums,

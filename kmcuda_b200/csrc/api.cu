@@ -7,7 +7,8 @@
 // the mask instead of replicated; no transpose; the per-iteration exchange is ONE NCCL all-reduce of
 // the [K][D] partial sums + [K] counts instead of 5-6 rounds of peer copies; centroid update is a
 // deterministic sort + segmented compensated sum instead of one thread per centroid.
-#include <nccl.h>
+#include <dlfcn.h>
+#include <nccl.h>  // types and enums only: NCCL is bound at run time, see NcclApi below
 
 #include <algorithm>
 #include <cinttypes>
@@ -25,6 +26,41 @@ namespace kmb {
 static const float kYinyangGroupTolerance = 0.02f;      // reference kmeans.cu:27
 static const float kYinyangDraftReassignments = 0.11f;  // reference kmeans.cu:28
 static const float kYinyangRefreshEpsilon = 1e-4f;      // reference kmeans.cu:29
+
+// NCCL is resolved lazily with dlopen the first time a job spans more than one GPU.  Linking it
+// would either pin a second libnccl.so.2 into processes that also import torch (which ships its own,
+// newer NCCL under the same soname) or, linked statically, add ~400 MB to the library.
+struct NcclApi {
+  ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool ok = false;
+};
+
+static const NcclApi& nccl_api() {
+  static NcclApi api;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_LOCAL);  // already in the process?
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_LOCAL);
+    if (h) {
+      api.CommInitAll = reinterpret_cast<decltype(api.CommInitAll)>(dlsym(h, "ncclCommInitAll"));
+      api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(dlsym(h, "ncclCommDestroy"));
+      api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(dlsym(h, "ncclAllReduce"));
+      api.GroupStart = reinterpret_cast<decltype(api.GroupStart)>(dlsym(h, "ncclGroupStart"));
+      api.GroupEnd = reinterpret_cast<decltype(api.GroupEnd)>(dlsym(h, "ncclGroupEnd"));
+      api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(dlsym(h, "ncclGetErrorString"));
+      api.ok = api.CommInitAll && api.CommDestroy && api.AllReduce && api.GroupStart && api.GroupEnd &&
+               api.GetErrorString;
+    }
+  }
+  return api;
+}
 
 struct Dev {
   int dev = 0;
@@ -117,7 +153,7 @@ class Job {
   ~Job() {
     for (auto& d : devs) {
       cudaSetDevice(d.dev);
-      if (d.comm) ncclCommDestroy(d.comm);
+      if (d.comm) nccl_api().CommDestroy(d.comm);
       d.shard.reset();
       if (d.st) cudaStreamDestroy(d.st);
     }
@@ -170,10 +206,14 @@ KMCUDAResult Job::setup(const std::vector<int>& dev_ids, bool alloc_samples) {
     KMB_RET(d.shard->create(true));
   }
   if (devs.size() > 1) {
+    if (!nccl_api().ok) {
+      KMB_INFO("multi-GPU jobs need NCCL (libnccl.so.2), which could not be loaded\n");
+      return kmcudaRuntimeError;
+    }
     std::vector<ncclComm_t> comms(devs.size());
-    ncclResult_t r = ncclCommInitAll(comms.data(), static_cast<int>(devs.size()), dev_ids.data());
+    ncclResult_t r = nccl_api().CommInitAll(comms.data(), static_cast<int>(devs.size()), dev_ids.data());
     if (r != ncclSuccess) {
-      KMB_INFO("ncclCommInitAll failed: %s\n", ncclGetErrorString(r));
+      KMB_INFO("ncclCommInitAll failed: %s\n", nccl_api().GetErrorString(r));
       return kmcudaRuntimeError;
     }
     for (size_t i = 0; i < devs.size(); i++) devs[i].comm = comms[i];
@@ -416,14 +456,15 @@ KMCUDAResult Job::update() {
     KMB_RET(d.shard->partial_sums(d.len, d.X, d.assign, d.sums, d.counts, d.st));
   }
   if (devs.size() > 1) {
-    ncclGroupStart();
+    const NcclApi& nc = nccl_api();
+    nc.GroupStart();
     for (auto& d : devs) {
-      ncclAllReduce(d.sums.get(), d.sums.get(), static_cast<size_t>(K) * D, ncclFloat32, ncclSum, d.comm, d.st);
-      ncclAllReduce(d.counts.get(), d.counts.get(), K, ncclUint32, ncclSum, d.comm, d.st);
+      nc.AllReduce(d.sums.get(), d.sums.get(), static_cast<size_t>(K) * D, ncclFloat32, ncclSum, d.comm, d.st);
+      nc.AllReduce(d.counts.get(), d.counts.get(), K, ncclUint32, ncclSum, d.comm, d.st);
     }
-    ncclResult_t r = ncclGroupEnd();
+    ncclResult_t r = nc.GroupEnd();
     if (r != ncclSuccess) {
-      KMB_INFO("ncclAllReduce failed: %s\n", ncclGetErrorString(r));
+      KMB_INFO("ncclAllReduce failed: %s\n", nc.GetErrorString(r));
       return kmcudaRuntimeError;
     }
   }

@@ -598,6 +598,10 @@ struct TcPlan {
   size_t smem_bytes = 0;
   int aug_swap = 0;
   float* dbg_scores = nullptr;
+  // CUDA-event pairs around the main kernel of the most recent passes (bench.py roofline)
+  static constexpr int kEvRing = 64;
+  cudaEvent_t ev0[kEvRing] = {}, ev1[kEvRing] = {};
+  uint64_t passes = 0;
 };
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -638,6 +642,10 @@ void tc_plan_destroy(TcPlan* p) {
   cudaFree(p->counters);
   cudaFree(p->dbg_scores);
   if (p->h_counters) cudaFreeHost(p->h_counters);
+  for (int i = 0; i < TcPlan::kEvRing; i++) {
+    if (p->ev0[i]) cudaEventDestroy(p->ev0[i]);
+    if (p->ev1[i]) cudaEventDestroy(p->ev1[i]);
+  }
   delete p;
 }
 
@@ -687,6 +695,10 @@ cudaError_t tc_plan_create(TcPlan** out, int metric, uint32_t max_n, int D, uint
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (cr != CUDA_SUCCESS) { tc_plan_destroy(p); return cudaErrorInvalidValue; }
+  for (int i = 0; i < TcPlan::kEvRing; i++) {
+    TC_TRY(cudaEventCreate(&p->ev0[i]));
+    TC_TRY(cudaEventCreate(&p->ev1[i]));
+  }
   p->smem_bytes = smem_layout(p->nkb).total + 1024;
   TC_TRY(cudaFuncSetAttribute(tc_assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               static_cast<int>(p->smem_bytes)));
@@ -728,7 +740,11 @@ cudaError_t tc_assign(TcPlan* p, const float* X, const float* C, const float* cs
   prm.aug_swap = p->aug_swap;
   prm.dbg_scores = p->dbg_scores;
   const unsigned grid = min(static_cast<uint32_t>(p->num_sms), prm.ntiles);
+  const int slot = static_cast<int>(p->passes % TcPlan::kEvRing);
+  cudaEventRecord(p->ev0[slot], st);
   tc_assign_kernel<<<grid, N_THREADS, p->smem_bytes, st>>>(p->tmap, prm);
+  cudaEventRecord(p->ev1[slot], st);
+  p->passes++;
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   // exact re-check of the multi-candidate rows, then the rows that need the full exact pass
   const unsigned rgrid = p->num_sms * 4;
@@ -749,6 +765,19 @@ void tc_last_stats(TcPlan* p, uint32_t* n_recheck, uint32_t* n_overflow) {
 }
 
 uint32_t tc_last_error(TcPlan* p) { return p->h_counters[tc::CNT_ERR]; }
+
+// device time (ms) of the main kernel in the most recent passes, oldest first; call after a sync
+int tc_kernel_times(TcPlan* p, float* ms_out, int max_out) {
+  const uint64_t have = p->passes < static_cast<uint64_t>(TcPlan::kEvRing) ? p->passes : TcPlan::kEvRing;
+  const int n = static_cast<int>(have < static_cast<uint64_t>(max_out) ? have : max_out);
+  for (int i = 0; i < n; i++) {
+    const int slot = static_cast<int>((p->passes - n + i) % TcPlan::kEvRing);
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, p->ev0[slot], p->ev1[slot]) != cudaSuccess) ms = -1.f;
+    ms_out[i] = ms;
+  }
+  return n;
+}
 const float* tc_debug_scores(TcPlan* p, size_t* row_stride) {
   *row_stride = static_cast<size_t>(p->nt) * tc::TN;
   return p->dbg_scores;

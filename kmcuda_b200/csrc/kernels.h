@@ -104,6 +104,7 @@ cudaError_t tc_assign(TcPlan* plan, const float* X, const float* C, const float*
 void tc_last_stats(TcPlan* plan, uint32_t* n_recheck, uint32_t* n_overflow);
 // 0 = clean; 0x1000+site = a pipeline wait timed out at `site` (results of that pass are invalid)
 uint32_t tc_last_error(TcPlan* plan);
+int tc_kernel_times(TcPlan* plan, float* ms_out, int max_out);
 // diagnostics (KMCUDA_B200_DUMP_SCORES=1): approximate scores [tiles*128][nt*256], prep statistics
 const float* tc_debug_scores(TcPlan* plan, size_t* row_stride);
 void tc_debug_stats(TcPlan* plan, float* out4);

@@ -173,6 +173,12 @@ int32_t kmcuda_b200_debug_scores(kmcuda_b200_shard* shard, float* host_out, uint
   return cudaMemcpy2D(host_out, cols * sizeof(float), src, stride * sizeof(float), cols * sizeof(float), rows,
                       cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -3;
 }
+// device time (ms) of the tensor-core kernel in the most recent passes (CUDA events on the launching
+// stream), oldest first; returns how many were written.  Call after synchronising the stream.
+int32_t kmcuda_b200_kernel_times(kmcuda_b200_shard* shard, float* ms_out, int32_t max_out) {
+  if (!shard || !shard->impl->tc || !ms_out) return 0;
+  return kmb::tc_kernel_times(shard->impl->tc, ms_out, max_out);
+}
 int32_t kmcuda_b200_debug_stats(kmcuda_b200_shard* shard, float* out4) {
   if (!shard || !shard->impl->tc) return -1;
   kmb::tc_debug_stats(shard->impl->tc, out4);

@@ -14,6 +14,9 @@ namespace kmb {
 
 static inline unsigned cdiv(size_t a, size_t b) { return static_cast<unsigned>((a + b - 1) / b); }
 
+// row lists up to this length are handled one CTA per row (exact_rows_few_kernel)
+constexpr uint32_t kFewRows = 8192;
+
 // ------------------------------------------------------------------------------------------------
 // ||c||^2 table (reference computes it per CTA per chunk, kmeans.cu:322-323)
 // ------------------------------------------------------------------------------------------------
@@ -47,6 +50,7 @@ exact_pass_kernel(const float* __restrict__ X, const float* __restrict__ C,
   extern __shared__ float sX[];
   const int BS = blockDim.x;
   const uint32_t nrows = d_nrows ? *d_nrows : n;
+  if (MODE == 0 && d_nrows && nrows <= kFewRows) return;  // exact_rows_few_kernel handles short lists
   for (uint32_t tile0 = blockIdx.x * BS; tile0 < nrows; tile0 += gridDim.x * BS) {
     const uint32_t slot = tile0 + threadIdx.x;
     const bool active = slot < nrows;
@@ -124,6 +128,63 @@ exact_pass_kernel(const float* __restrict__ X, const float* __restrict__ C,
   }
 }
 
+// Row-list variant for FEW rows (the tensor-core filter's overflow list is normally a handful of rows
+// out of millions): one CTA per row, the K centroids spread over the 128 threads, so a single row does
+// not serialise K*D dependent operations on one thread.  Each thread scans its centroids in ascending
+// order with strict '<'; the block reduction breaks equal scores towards the lowest index, which is
+// exactly the reference's ascending strict-'<' scan (kmeans.cu:343-346).
+
+template <int METRIC>
+__global__ void __launch_bounds__(128)
+exact_rows_few_kernel(const float* __restrict__ X, const float* __restrict__ C,
+                      const float* __restrict__ csq, int D, uint32_t K,
+                      const uint32_t* __restrict__ rows, const uint32_t* __restrict__ d_nrows,
+                      uint32_t* __restrict__ result) {
+  extern __shared__ float sx[];
+  __shared__ float s_best[128];
+  __shared__ uint32_t s_arg[128];
+  const uint32_t nrows = *d_nrows;
+  if (nrows > kFewRows) return;  // the tiled kernel takes over
+  for (uint32_t e = blockIdx.x; e < nrows; e += gridDim.x) {
+    const uint32_t row = rows[e];
+    __syncthreads();
+    for (int f = threadIdx.x; f < D; f += 128) sx[f] = X[static_cast<size_t>(row) * D + f];
+    __syncthreads();
+    if (sx[0] != sx[0]) {
+      if (threadIdx.x == 0) result[row] = K;
+      continue;
+    }
+    float best = FLT_MAX;
+    uint32_t arg = UINT32_MAX;
+    for (uint32_t c = threadIdx.x; c < K; c += 128) {
+      const float* cp = C + static_cast<size_t>(c) * D;
+      Kahan k;
+      for (int f = 0; f < D; f++) k.mac(sx[f], __ldg(cp + f));
+      float score = lloyd_score<METRIC>(k.sum, csq[c]);
+      if (score < best) {
+        best = score;
+        arg = c;
+      }
+    }
+    s_best[threadIdx.x] = best;
+    s_arg[threadIdx.x] = arg;
+    __syncthreads();
+    for (int o = 64; o > 0; o >>= 1) {
+      if (threadIdx.x < o) {
+        float b2 = s_best[threadIdx.x + o];
+        uint32_t a2 = s_arg[threadIdx.x + o];
+        if (a2 != UINT32_MAX && (s_arg[threadIdx.x] == UINT32_MAX || b2 < s_best[threadIdx.x] ||
+                                 (b2 == s_best[threadIdx.x] && a2 < s_arg[threadIdx.x]))) {
+          s_best[threadIdx.x] = b2;
+          s_arg[threadIdx.x] = a2;
+        }
+      }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) result[row] = (s_arg[0] == UINT32_MAX) ? kUntouched : s_arg[0];
+  }
+}
+
 struct ExactCfg {
   int bs, use_smem;
   size_t smem;
@@ -158,6 +219,13 @@ static cudaError_t launch_exact_pass(const float* X, const float* C, const float
 cudaError_t launch_assign_exact(int metric, const float* X, const float* C, const float* csq,
                                 uint32_t n, int D, uint32_t K, const uint32_t* rows,
                                 const uint32_t* d_nrows, uint32_t* result, cudaStream_t st) {
+  if (d_nrows) {  // list mode: short lists go to the one-CTA-per-row kernel (decided on the device)
+    const size_t smem = sizeof(float) * D;
+    if (metric == 1) exact_rows_few_kernel<1><<<148 * 4, 128, smem, st>>>(X, C, csq, D, K, rows, d_nrows, result);
+    else exact_rows_few_kernel<0><<<148 * 4, 128, smem, st>>>(X, C, csq, D, K, rows, d_nrows, result);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
   if (metric == 1)
     return launch_exact_pass<1, 0>(X, C, csq, n, D, K, rows, d_nrows, result, 0, nullptr, nullptr,
                                    nullptr, st);

@@ -24,6 +24,8 @@ _lib.kmcuda_b200_partial_sums.restype = ctypes.c_int
 _lib.kmcuda_b200_partial_sums.argtypes = [ctypes.c_void_p, ctypes.c_uint32] + [ctypes.c_void_p] * 5
 _lib.kmcuda_b200_finish_update.restype = ctypes.c_int
 _lib.kmcuda_b200_finish_update.argtypes = [ctypes.c_void_p] + [ctypes.c_void_p] * 5
+_lib.kmcuda_b200_kernel_times.restype = ctypes.c_int32
+_lib.kmcuda_b200_kernel_times.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32]
 _lib.kmcuda_b200_debug_last_error.restype = ctypes.c_uint32
 _lib.kmcuda_b200_debug_last_error.argtypes = [ctypes.c_void_p]
 _lib.kmcuda_b200_debug_scores.restype = ctypes.c_int32
@@ -75,6 +77,12 @@ class Shard:
         a, b = ctypes.c_uint32(0), ctypes.c_uint32(0)
         tc = _lib.kmcuda_b200_last_pass_info(self._h, ctypes.byref(a), ctypes.byref(b))
         return bool(tc), a.value, b.value
+
+    def kernel_times(self, max_out=64):
+        """device ms of the tensor-core kernel in the most recent passes (sync first)"""
+        buf = np.zeros(max_out, np.float32)
+        n = _lib.kmcuda_b200_kernel_times(self._h, buf.ctypes.data, max_out)
+        return buf[:n].tolist()
 
     def last_error(self):
         return int(_lib.kmcuda_b200_debug_last_error(self._h))

@@ -1,0 +1,293 @@
+"""GPU parity tests (run on the B200 box: `pytest -m gpu`).  Everything goes through the C ABI of
+kmcuda_b200/libKMCUDA.so; the oracle (oracle/) and the rebuilt reference (oracle/_ref) are checkers only.
+
+Bars: bit-exact for assignments / neighbour indices (the tensor-core filter + exact re-check is
+designed to be bit-identical to the reference kernel, ties included; cosine and k-NN distance ties are
+exempt as in the reference's own suite); centroids within 1e-5 relative (fp32)."""
+import ctypes
+import os
+import sys
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+
+import cases  # noqa: E402
+from oracle import oracle as O  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+IMPORT = 3
+GOLDEN = np.load(os.path.join(HERE, "golden", "golden.npz"))
+
+
+@pytest.fixture(scope="module")
+def km():
+    import torch
+    assert torch.cuda.is_available()
+    import kmcuda_b200
+    return kmcuda_b200
+
+
+@pytest.fixture(scope="module")
+def ours(km):
+    return O.load_c_api(km.LIB_PATH)
+
+
+@pytest.fixture(scope="module")
+def ref():
+    if not O.reference_available():
+        pytest.skip("oracle/_ref/libKMCUDA.so not built")
+    return O.reference_lib()
+
+
+def c_kmeans(lib, X, C0, tol, yy, metric=0, verbosity=0, init=IMPORT, seed=3):
+    X = np.ascontiguousarray(X)
+    N, D = X.shape
+    K = C0.shape[0] if hasattr(C0, "shape") else int(C0)
+    C = np.array(C0, copy=True, order="C") if hasattr(C0, "shape") else np.zeros((K, D), np.float32)
+    A = np.zeros(N, np.uint32)
+    m = ctypes.c_uint32(0)
+    rc = lib.kmeans_cuda(init, ctypes.byref(m), tol, yy, metric, N, D, K, seed, 1, -1, 0, verbosity,
+                         X.ctypes.data, C.ctypes.data, A.ctypes.data, None)
+    assert rc == 0, rc
+    return C, A
+
+
+def one_pass(lib, X, C0, metric=0):
+    return c_kmeans(lib, X, C0, 1.0, 0.0, metric)[1]
+
+
+def test_oracle_matches_reference(ref):
+    """pins the CPU oracle against the UNMODIFIED reference kernels running on this GPU"""
+    for name in ["uniform_3000x256_k1024", "ragged_4097x100_k33", "blobs_13000x2_k50", "wide_range_2000x32_k16",
+                 "dupes_1024x64_k64"]:
+        X, C = cases.make_assign_case(*cases.ASSIGN_CASES[name])
+        assert np.array_equal(one_pass(ref, X, C), GOLDEN["assign/" + name]), name
+
+
+@pytest.mark.parametrize("name", sorted(cases.ASSIGN_CASES))
+@pytest.mark.parametrize("force_exact", ["0", "1"])
+def test_assign_matches_golden(ours, name, force_exact, monkeypatch):
+    """one assignment pass (tolerance=1 trick, reference src/test.py:512-519) == golden, bit for bit;
+    force_exact=0 takes the tcgen05 filter + re-check wherever the shape allows it"""
+    monkeypatch.setenv("KMCUDA_B200_FORCE_EXACT", force_exact)
+    X, C = cases.make_assign_case(*cases.ASSIGN_CASES[name])
+    got = one_pass(ours, X, C)
+    exp = GOLDEN["assign/" + name]
+    assert np.array_equal(got, exp), "%s: %d mismatches" % (name, int((got != exp).sum()))
+
+
+def _shard_pass(X, C, assign=None):
+    import torch
+    from kmcuda_b200.shard import assign_once
+    a, prev, changed, info = assign_once(torch.from_numpy(X).cuda(), torch.from_numpy(C).cuda(),
+                                         assignments=None if assign is None else torch.from_numpy(
+                                             assign.astype(np.int32)).cuda())
+    return a.cpu().numpy().astype(np.uint32), prev.cpu().numpy().astype(np.uint32), changed, info
+
+
+def test_tensor_core_path_runs_and_matches_reference_100k(ref):
+    """C1-sized pass: the tcgen05 path must be the one that runs, and equal the reference kernel"""
+    rng = np.random.default_rng(777)
+    X = rng.random((100000, 256), dtype=np.float32)
+    C = X[rng.choice(len(X), 1024, replace=False)].copy()
+    a, prev, changed, info = _shard_pass(X, C)
+    assert info[0], "tensor-core path not taken"
+    exp = one_pass(ref, X, C)
+    assert np.array_equal(a, exp), int((a != exp).sum())
+    assert changed == len(X) and (prev == 0xFFFFFFFF).all()
+    # idempotence: a second pass from the result changes nothing
+    a2, prev2, changed2, _ = _shard_pass(X, C, assign=a)
+    assert changed2 == 0 and np.array_equal(a2, a) and np.array_equal(prev2, a)
+
+
+def test_edge_cases_nan_ragged_ties(ours, ref):
+    rng = np.random.default_rng(11)
+    X = rng.random((1000, 64), dtype=np.float32)
+    C = X[rng.choice(1000, 37, replace=False)].copy()
+    X[5, 0] = np.nan            # "insane" row -> K
+    X[77, 13] = np.nan          # NaN elsewhere -> nothing wins
+    X[200] = 1e30               # overflows the fp16 filter -> exact fallback
+    C[3] = np.nan               # NaN centroid never wins
+    C[10] = C[4]                # duplicate centroid -> lowest index
+    X[300] = C[4]
+    got = one_pass(ours, X, C)
+    exp = one_pass(ref, X, C)
+    keep = np.ones(len(X), bool)
+    keep[77] = False            # left untouched by both (contents of the output buffer are unspecified)
+    assert np.array_equal(got[keep], exp[keep])
+    assert got[5] == 37 and got[300] == 4 and not (got[keep] == 3).any() and not (got[keep] == 10).any()
+
+
+def test_headline_size_properties(km):
+    """8M x 256 @ 1024 (BASELINE config 2): size-independent properties + exact spot check"""
+    import torch
+    from kmcuda_b200.shard import Shard
+    n, d, k = 8000000, 256, 1024
+    g = torch.Generator(device="cuda").manual_seed(777)
+    X = torch.rand((n, d), generator=g, device="cuda", dtype=torch.float32)
+    C = X[torch.randperm(n, generator=g, device="cuda")[:k]].contiguous()
+    sh = Shard(n, d, k)
+    a = torch.full((n,), -1, dtype=torch.int32, device="cuda")
+    prev = torch.full((n,), -1, dtype=torch.int32, device="cuda")
+    ch = torch.zeros(1, dtype=torch.int32, device="cuda")
+    sh.assign(X, C, a, prev, ch)
+    torch.cuda.synchronize()
+    assert sh.last_error() == 0 and sh.last_pass_info()[0]
+    assert int(ch.item()) == n and int(a.min()) >= 0 and int(a.max()) < k
+    # the chosen centroid is at least as close (fp64) as any other, up to fp32 rounding, on a sample
+    idx = torch.randperm(n, generator=g, device="cuda")[:20000]
+    xs = X[idx].double()
+    d2 = (C.double() ** 2).sum(1)[None, :] - 2 * xs @ C.double().T
+    best = d2.min(1).values
+    mine = d2.gather(1, a[idx].long()[:, None])[:, 0]
+    assert float((mine - best).max()) <= 1e-4
+    # rows whose source IS a centroid must map to it
+    ch.zero_()
+    sh.assign(X, C, a, prev, ch)
+    torch.cuda.synchronize()
+    assert int(ch.item()) == 0          # idempotent
+    # bit-exact against the exact SIMT kernel of this library on the sample
+    os.environ["KMCUDA_B200_FORCE_EXACT"] = "1"
+    try:
+        she = Shard(20000, d, k)
+        ae = torch.full((20000,), -1, dtype=torch.int32, device="cuda")
+        pe = torch.full((20000,), -1, dtype=torch.int32, device="cuda")
+        she.assign(X[idx].contiguous(), C, ae, pe, ch)
+        torch.cuda.synchronize()
+        assert not she.last_pass_info()[0]
+        assert bool((ae == a[idx]).all().item())
+    finally:
+        os.environ.pop("KMCUDA_B200_FORCE_EXACT", None)
+
+
+def test_update_matches_oracle():
+    import torch
+    from kmcuda_b200.shard import Shard
+    rng = np.random.default_rng(5)
+    X = rng.random((20000, 64), dtype=np.float32)
+    C0 = X[:100].copy()
+    a, prev, _ = O.assign_lloyd(X, C0)
+    Cexp, cnt = O.adjust(X, C0, prev, a, np.zeros(100, np.uint32))
+    sh = Shard(len(X), 64, 100)
+    Xt, at = torch.from_numpy(X).cuda(), torch.from_numpy(a.astype(np.int32)).cuda()
+    sums = torch.zeros((100, 64), device="cuda")
+    counts = torch.zeros(100, dtype=torch.int32, device="cuda")
+    Ct = torch.zeros((100, 64), device="cuda")
+    cc = torch.zeros(100, dtype=torch.int32, device="cuda")
+    sh.partial_sums(Xt, at, sums, counts)
+    sh.finish_update(sums, counts, Ct, cc)
+    torch.cuda.synchronize()
+    assert np.array_equal(cc.cpu().numpy().astype(np.uint32), cnt)
+    np.testing.assert_allclose(Ct.cpu().numpy(), Cexp, rtol=1e-5)   # tolerance of north_star: 1e-5 relative
+
+
+def _validate(X, centroids, assignments, tolerance):
+    """reference src/test.py:176-183: one more sklearn Lloyd step changes < tolerance of the labels"""
+    d = ((X[:, None, :].astype(np.float64) - centroids[None].astype(np.float64)) ** 2).sum(-1)
+    assert (d.argmin(1) != assignments).mean() < tolerance
+
+
+@pytest.mark.parametrize("init,yy", [("random", 0.0), ("k-means++", 0.0), ("k-means++", 0.1)])
+def test_kmeans_python_surface_validates(km, init, yy, capfd):
+    """reference src/test.py:207-233 (random Lloyd / kmeans++ Lloyd / kmeans++ Yinyang)"""
+    X = cases.blobs()
+    cent, asg = km.kmeans_cuda(X, 50, init=init, device=1, verbosity=2, seed=3, tolerance=0.01, yinyang_t=yy)
+    out = capfd.readouterr().out
+    iters = sum(1 for line in out.split("\n") if line.startswith("iteration"))
+    assert iters >= 2
+    assert cent.shape == (50, 2) and asg.shape == (13000,) and asg.dtype == np.uint32
+    assert not np.isnan(cent).any()
+    _validate(X, cent, asg, 0.01)
+
+
+def test_kmeans_runs_match_reference_trajectory(ours, ref):
+    """same imported centroids -> same assignments as the reference library after a whole run"""
+    X = cases.blobs()
+    rng = np.random.default_rng(1)
+    C0 = X[rng.choice(len(X), 50, replace=False)].copy()
+    for yy in (0.0, 0.1):
+        C1, A1 = c_kmeans(ours, X, C0, 0.01, yy)
+        C2, A2 = c_kmeans(ref, X, C0, 0.01, yy)
+        assert (A1 == A2).mean() > 0.99
+        ok = ~np.isnan(C2).any(1)
+        np.testing.assert_allclose(C1[ok], C2[ok], rtol=0, atol=2e-2)
+
+
+def test_fp16_and_average_distance(km):
+    X = cases.blobs()
+    c32, a32, avg = km.kmeans_cuda(X, 50, init="k-means++", device=1, seed=3, tolerance=0.01, yinyang_t=0,
+                                   average_distance=True)
+    dists = np.linalg.norm(X - c32[a32], axis=1)
+    assert abs(avg - dists.mean()) < 1e-5
+    c16, a16 = km.kmeans_cuda(X.astype(np.float16), 50, init="k-means++", device=1, seed=3, tolerance=0.01,
+                              yinyang_t=0)
+    assert c16.dtype == np.float16 and c16.shape == (50, 2)
+    _validate(X.astype(np.float16).astype(np.float32), c16.astype(np.float32), a16, 0.02)
+
+
+def test_cosine_lloyd(km):
+    rng = np.random.default_rng(3)
+    X = rng.standard_normal((5000, 32)).astype(np.float32)
+    X /= np.linalg.norm(X, axis=1, keepdims=True)
+    cent, asg = km.kmeans_cuda(X, 20, init="random", metric="cos", device=1, seed=3, yinyang_t=0, tolerance=0.01)
+    norms = np.linalg.norm(cent, axis=1)
+    assert ((norms > 0.9999) & (norms < 1.0001)).all()          # reference src/test.py:437-440
+    assert ((X @ cent.T).argmax(1) != asg).mean() < 0.02
+    with pytest.raises(ValueError):                               # un-normalised samples are rejected
+        km.kmeans_cuda(X * 2, 20, metric="cos", device=1)
+
+
+def test_knn_matches_sklearn_exactly(km):
+    """reference src/test.py:598-606: k=10 on the blobs must equal sklearn's neighbours"""
+    X = cases.blobs()
+    cent, asg = km.kmeans_cuda(X, 50, init="k-means++", device=1, seed=777, yinyang_t=0)
+    nb = km.knn_cuda(10, X, cent, asg, device=1, verbosity=1)
+    exp = GOLDEN["knn/blobs_k10"]
+    assert nb.shape == exp.shape
+    diff = nb != exp
+    if diff.any():   # only exact distance ties may differ
+        rows = np.unique(np.argwhere(diff)[:, 0])
+        for r in rows:
+            dg = np.linalg.norm(X[nb[r]].astype(np.float64) - X[r], axis=1)
+            de = np.linalg.norm(X[exp[r]].astype(np.float64) - X[r], axis=1)
+            assert np.allclose(dg, de, atol=1e-7)
+    assert diff.mean() < 1e-3
+
+
+def test_knn_matches_reference(ours, ref):
+    rng = np.random.default_rng(9)
+    X = rng.random((20000, 48), dtype=np.float32)
+    C0 = X[rng.choice(len(X), 200, replace=False)].copy()
+    C, A = c_kmeans(ref, X, C0, 0.05, 0.0)
+    k = 10
+    outs = []
+    for lib in (ours, ref):
+        out = np.zeros((len(X), k), np.uint32)
+        rc = lib.knn_cuda(k, 0, len(X), 48, 200, 1, -1, 0, 0, X.ctypes.data, C.ctypes.data, A.ctypes.data,
+                          out.ctypes.data)
+        assert rc == 0
+        outs.append(out)
+    assert (outs[0] != outs[1]).mean() < 1e-4
+
+
+def test_device_pointer_api(km):
+    """reference src/test.py:348-372: raw device pointers in, raw device pointers out; samples untouched"""
+    import torch
+    X = cases.blobs()
+    Xt = torch.from_numpy(X).cuda()
+    before = Xt.clone()
+    cptr, aptr = km.kmeans_cuda((Xt.data_ptr(), 0, X.shape), 50, init="k-means++", device=1, seed=3,
+                                tolerance=0.01, yinyang_t=0)
+    assert isinstance(cptr, int) and isinstance(aptr, int)
+    cent = np.empty((50, 2), np.float32)
+    asg = np.empty(13000, np.uint32)
+    km._cuda_memcpy_d2h(0, cent.ctypes.data, cptr, cent.nbytes)
+    km._cuda_memcpy_d2h(0, asg.ctypes.data, aptr, asg.nbytes)
+    km._cuda_free(0, cptr)
+    km._cuda_free(0, aptr)
+    assert torch.equal(Xt, before)
+    _validate(X, cent, asg, 0.01)
