@@ -44,11 +44,11 @@ constexpr int B_STAGE_BYTES = TN * 128; // 32 KiB
 constexpr int AUG_A_BYTES = TM * 32;    // 4 KiB  (K=16 fp16, no swizzle)
 constexpr int AUG_B_BYTES = TN * 32;    // 8 KiB
 constexpr int LIST_LEN = 12;            // chunk entries per epilogue thread
-constexpr int N_CONV_WARPS = 4;
+constexpr int N_CONV_WARPS = 8;
 constexpr int N_EPI_WARPS = 8;
 constexpr int FIRST_CONV_WARP = 2;
-constexpr int FIRST_EPI_WARP = 6;
-constexpr int N_THREADS = (FIRST_EPI_WARP + N_EPI_WARPS) * 32;  // 448
+constexpr int FIRST_EPI_WARP = FIRST_CONV_WARP + N_CONV_WARPS;  // 10
+constexpr int N_THREADS = (FIRST_EPI_WARP + N_EPI_WARPS) * 32;  // 576
 constexpr int MAX_CAND = 16;            // candidates per row before falling back to the full exact pass
 constexpr uint32_t TMEM_COLS = 512;
 
@@ -204,7 +204,7 @@ __device__ __forceinline__ void note_timeout(uint32_t* counters, int where) {
   atomicMax(&counters[CNT_ERR], 0x1000u + where);
 }
 
-__global__ void __launch_bounds__(N_THREADS, 1)
+__global__ void __maxnreg__(112)
 tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -316,74 +316,92 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p) {
     }
   } else if (warp < FIRST_EPI_WARP) {
     // ================================ converters (A operand) ================================
-    const int cw = warp - FIRST_CONV_WARP;  // rows [32cw, 32cw+32)
+    // 8 warps x 16 rows.  Global loads are software-pipelined two K-blocks deep in registers (the loads of
+    // item i+2 are issued as soon as item i has been written), so the fp32 rows of the next tile are already
+    // on chip when the MMA warp releases the A slots -- there is no load latency on the tile boundary.
+    const int cw = warp - FIRST_CONV_WARP;  // rows [16cw, 16cw+16)
     const int r4 = lane >> 3, j = lane & 7;
     const float s = p.stats->scale;
-    uint32_t it = 0;
-    for (uint32_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, it++) {
-      float nx[8], nd[8];
+    const uint32_t my_tiles = (p.ntiles > blockIdx.x) ? (p.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const uint32_t total = my_tiles * static_cast<uint32_t>(nkb);
+    float nx[4] = {0.f, 0.f, 0.f, 0.f}, nd[4] = {0.f, 0.f, 0.f, 0.f};
+
+    auto load_item = [&](float4 (&v)[4][2], uint32_t item) {
+      const uint32_t ti = item / nkb;
+      const int kb = static_cast<int>(item - ti * nkb);
+      const uint64_t tile = blockIdx.x + static_cast<uint64_t>(ti) * gridDim.x;
+      const int f0 = kb * KB + j * 8;
 #pragma unroll
-      for (int i = 0; i < 8; i++) nx[i] = nd[i] = 0.f;
-      for (int kb = 0; kb < nkb; kb++) {
-        // issue all global loads of this K-block before waiting for the slot
-        float4 v[8][2];
-        const int f0 = kb * KB + j * 8;
-#pragma unroll
-        for (int i = 0; i < 8; i++) {
-          const int row = cw * 32 + i * 4 + r4;
-          const uint64_t grow = static_cast<uint64_t>(tile) * TM + row;
-          if (grow < p.n && f0 < p.D) {
-            const float* src = p.X + grow * p.D + f0;
-            v[i][0] = ptx::ldg_nc_f4(src);
-            v[i][1] = ptx::ldg_nc_f4(src + 4);
-          } else {
-            v[i][0] = v[i][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-          }
+      for (int i = 0; i < 4; i++) {
+        const uint64_t grow = tile * TM + cw * 16 + i * 4 + r4;
+        if (grow < p.n && f0 < p.D) {
+          const float* src = p.X + grow * p.D + f0;
+          v[i][0] = ptx::ldg_nc_f4(src);
+          v[i][1] = ptx::ldg_nc_f4(src + 4);
+        } else {
+          v[i][0] = v[i][1] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        if (!ptx::mbar_wait(&bars[BAR_A_EMPTY(kb)], (it & 1) ^ 1, p.counters + CNT_ERR)) note_timeout(p.counters, 7);
-        uint8_t* a_kb = smem + L.a + kb * A_KB_BYTES;
+      }
+    };
+    auto store_item = [&](float4 (&v)[4][2], uint32_t item) {
+      const uint32_t ti = item / nkb;
+      const int kb = static_cast<int>(item - ti * nkb);
+      if (!ptx::mbar_wait(&bars[BAR_A_EMPTY(kb)], (ti & 1) ^ 1, p.counters + CNT_ERR)) note_timeout(p.counters, 7);
+      uint8_t* a_kb = smem + L.a + kb * A_KB_BYTES;
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-          const int row = cw * 32 + i * 4 + r4;
-          float x[8] = {v[i][0].x, v[i][0].y, v[i][0].z, v[i][0].w, v[i][1].x, v[i][1].y, v[i][1].z, v[i][1].w};
-          __half2 h[4];
+      for (int i = 0; i < 4; i++) {
+        const int row = cw * 16 + i * 4 + r4;
+        float x[8] = {v[i][0].x, v[i][0].y, v[i][0].z, v[i][0].w, v[i][1].x, v[i][1].y, v[i][1].z, v[i][1].w};
+        __half2 h[4];
 #pragma unroll
-          for (int e = 0; e < 4; e++) {
-            float a = x[2 * e] * s, b = x[2 * e + 1] * s;
-            h[e] = __floats2half2_rn(a, b);
-            float2 back = __half22float2(h[e]);
-            float da = a - back.x, db = b - back.y;
-            nx[i] = fmaf(back.x, back.x, nx[i]);
-            nx[i] = fmaf(back.y, back.y, nx[i]);
-            nd[i] = fmaf(da, da, nd[i]);
-            nd[i] = fmaf(db, db, nd[i]);
-          }
-          uint4 packed;
-          packed.x = *reinterpret_cast<uint32_t*>(&h[0]);
-          packed.y = *reinterpret_cast<uint32_t*>(&h[1]);
-          packed.z = *reinterpret_cast<uint32_t*>(&h[2]);
-          packed.w = *reinterpret_cast<uint32_t*>(&h[3]);
-          *reinterpret_cast<uint4*>(a_kb + row * 128 + ((j ^ (row & 7)) << 4)) = packed;
+        for (int e = 0; e < 4; e++) {
+          float a = x[2 * e] * s, b = x[2 * e + 1] * s;
+          h[e] = __floats2half2_rn(a, b);
+          float2 back = __half22float2(h[e]);
+          float da = a - back.x, db = b - back.y;
+          nx[i] = fmaf(back.x, back.x, nx[i]);
+          nx[i] = fmaf(back.y, back.y, nx[i]);
+          nd[i] = fmaf(da, da, nd[i]);
+          nd[i] = fmaf(db, db, nd[i]);
         }
-        if (kb == nkb - 1) {
-          // per-row norms of this tile (8 lanes share a row)
-          float* norms = reinterpret_cast<float*>(smem + L.norms) + (it & 1) * 2 * TM;
+        uint4 packed;
+        packed.x = *reinterpret_cast<uint32_t*>(&h[0]);
+        packed.y = *reinterpret_cast<uint32_t*>(&h[1]);
+        packed.z = *reinterpret_cast<uint32_t*>(&h[2]);
+        packed.w = *reinterpret_cast<uint32_t*>(&h[3]);
+        *reinterpret_cast<uint4*>(a_kb + row * 128 + ((j ^ (row & 7)) << 4)) = packed;
+      }
+      if (kb == nkb - 1) {
+        // per-row norms of this tile (8 lanes share a row), then reset for the next tile
+        float* norms = reinterpret_cast<float*>(smem + L.norms) + (ti & 1) * 2 * TM;
 #pragma unroll
-          for (int i = 0; i < 8; i++) {
-            float a = nx[i], b = nd[i];
-            a += __shfl_xor_sync(0xffffffffu, a, 1); b += __shfl_xor_sync(0xffffffffu, b, 1);
-            a += __shfl_xor_sync(0xffffffffu, a, 2); b += __shfl_xor_sync(0xffffffffu, b, 2);
-            a += __shfl_xor_sync(0xffffffffu, a, 4); b += __shfl_xor_sync(0xffffffffu, b, 4);
-            if (j == 0) {
-              const int row = cw * 32 + i * 4 + r4;
-              norms[row] = a;
-              norms[TM + row] = b;
-            }
+        for (int i = 0; i < 4; i++) {
+          float a = nx[i], b = nd[i];
+          a += __shfl_xor_sync(0xffffffffu, a, 1); b += __shfl_xor_sync(0xffffffffu, b, 1);
+          a += __shfl_xor_sync(0xffffffffu, a, 2); b += __shfl_xor_sync(0xffffffffu, b, 2);
+          a += __shfl_xor_sync(0xffffffffu, a, 4); b += __shfl_xor_sync(0xffffffffu, b, 4);
+          if (j == 0) {
+            const int row = cw * 16 + i * 4 + r4;
+            norms[row] = a;
+            norms[TM + row] = b;
           }
+          nx[i] = nd[i] = 0.f;
         }
-        ptx::fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&bars[BAR_A_FULL(kb)]);
+      }
+      ptx::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&bars[BAR_A_FULL(kb)]);
+    };
+
+    float4 v0[4][2], v1[4][2];
+    if (total > 0) load_item(v0, 0);
+    if (total > 1) load_item(v1, 1);
+    for (uint32_t item = 0; item < total; item += 2) {
+      store_item(v0, item);
+      if (item + 2 < total) load_item(v0, item + 2);
+      if (item + 1 < total) {
+        store_item(v1, item + 1);
+        if (item + 3 < total) load_item(v1, item + 3);
       }
     }
   } else {
@@ -532,31 +550,49 @@ recheck_pairs_kernel(const float* __restrict__ X, const float* __restrict__ C,
                      const float* __restrict__ csq, int D, const uint32_t* __restrict__ pair_row,
                      const uint32_t* __restrict__ pair_cand, const uint32_t* __restrict__ d_npairs,
                      uint32_t max_pairs, uint32_t n, uint32_t K, float* __restrict__ pair_score) {
-  __shared__ float sX[32 * 129];
-  __shared__ float sC[128 * 33];
+  // 128 (row, candidate) pairs per CTA; features stream through shared memory 32 at a time.
+  // Staging: every thread issues 16 independent 16-byte loads per chunk (8 lanes cover one 128-byte
+  // row segment), so the kernel runs at memory throughput rather than at load latency.
+  __shared__ float sX[32 * 129];     // [feature][pair]   (+1 padding: conflict-free both ways)
+  __shared__ float sC[128 * 33];     // [pair][feature]
+  __shared__ uint32_t s_row[128], s_cand[128];
   const uint32_t np = min(*d_npairs, max_pairs);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (uint32_t tile0 = blockIdx.x * 128; tile0 < np; tile0 += gridDim.x * 128) {
     const uint32_t pidx = tile0 + threadIdx.x;
     const bool active = pidx < np;
+    __syncthreads();
+    // (slots past the last complete row group may hold stale data: stay in bounds)
+    s_row[threadIdx.x] = active ? min(pair_row[pidx], n - 1) : 0;
+    s_cand[threadIdx.x] = active ? min(pair_cand[pidx], K - 1) : 0;
     Kahan k;
     for (int f0 = 0; f0 < D; f0 += 32) {
       const int fl = min(32, D - f0);
       __syncthreads();
-      for (int i = 0; i < 32; i++) {
-        const uint32_t pi = tile0 + warp * 32 + i;
-        if (pi < np && lane < fl) {
-          // (slots past the last complete row group may hold stale data: stay in bounds)
-          const uint32_t r = min(pair_row[pi], n - 1), c = min(pair_cand[pi], K - 1);
-          sX[lane * 129 + warp * 32 + i] = X[static_cast<size_t>(r) * D + f0 + lane];
-          sC[(warp * 32 + i) * 33 + lane] = C[static_cast<size_t>(c) * D + f0 + lane];
+      float4 v[16];
+#pragma unroll
+      for (int i = 0; i < 16; i++) {
+        const int idx = i * 128 + threadIdx.x;  // [which(1)][pair(7)][quad(3)]
+        const int q = idx & 7, e = (idx >> 3) & 127, which = idx >> 10;
+        const float* src = which ? C + static_cast<size_t>(s_cand[e]) * D : X + static_cast<size_t>(s_row[e]) * D;
+        v[i] = (q * 4 < fl) ? *reinterpret_cast<const float4*>(src + f0 + q * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int i = 0; i < 16; i++) {
+        const int idx = i * 128 + threadIdx.x;
+        const int q = idx & 7, e = (idx >> 3) & 127, which = idx >> 10;
+        if (which) {
+          float* d = sC + e * 33 + q * 4;
+          d[0] = v[i].x; d[1] = v[i].y; d[2] = v[i].z; d[3] = v[i].w;
+        } else {
+          float* d = sX + (q * 4) * 129 + e;
+          d[0] = v[i].x; d[129] = v[i].y; d[258] = v[i].z; d[387] = v[i].w;
         }
       }
       __syncthreads();
       if (active)
         for (int f = 0; f < fl; f++) k.mac(sX[f * 129 + threadIdx.x], sC[threadIdx.x * 33 + f]);
     }
-    if (active) pair_score[pidx] = lloyd_score<METRIC>(k.sum, csq[min(pair_cand[pidx], K - 1)]);
+    if (active) pair_score[pidx] = lloyd_score<METRIC>(k.sum, csq[s_cand[threadIdx.x]]);
   }
 }
 
