@@ -204,7 +204,7 @@ __device__ __forceinline__ void note_timeout(uint32_t* counters, int where) {
   atomicMax(&counters[CNT_ERR], 0x1000u + where);
 }
 
-__global__ void __maxnreg__(112)
+__global__ void __launch_bounds__(N_THREADS, 1)
 tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));

@@ -9,6 +9,7 @@
 
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include "kernels.h"
@@ -24,6 +25,8 @@ namespace kmb {
   do {                                                                              \
     cudaError_t kmb_err__ = (call);                                                 \
     if (kmb_err__ != cudaSuccess) {                                                 \
+      if (getenv("KMCUDA_B200_DEBUG"))                                              \
+        fprintf(stderr, "%s:%d %s -> %s\n", __FILE__, __LINE__, #call, cudaGetErrorString(kmb_err__)); \
       KMB_DEBUG("%s\n", #call);                                                     \
       KMB_INFO("%s:%d -> %s\n", __FILE__, __LINE__, cudaGetErrorString(kmb_err__)); \
       return code;                                                                  \
