@@ -1,18 +1,23 @@
 // assign_tc.cu -- the B200 hot path: samples x centroids L2 ranking as a dense fp16 contraction on
 // tcgen05 tensor cores, fused with a per-sample candidate filter; the exact fp32 re-check
-// (simt_kernels.cu) then makes the final, reference-identical decision.
+// (below + simt_kernels.cu) then makes the final, reference-identical decision.
 //
 // What the reference does here: kmeans_assign_lloyd (reference src/kmeans.cu:293-364) -- one CUDA
 // thread per sample, N*K*D Kahan-compensated round-down FMAs on the FP32 pipe.
 //
 // What this file does instead, per persistent CTA (one per SM) and per tile of 128 samples:
-//   converter warps : ld.global.nc fp32 rows -> *s (power of two) -> fp16 -> 128B-swizzled K-major
-//                     A tile in shared memory; per row ||x~||, ||x - x~|| for the error bound
-//   TMA warp        : streams the fp16 centroid table (B operand, 256 centroids x 64 features per
-//                     stage, 128B swizzle) + the per-tile bias block through an mbarrier ring
-//   MMA thread      : tcgen05.mma kind::f16, M=128 N=256 K=16, fp32 accumulators double-buffered
-//                     in TMEM (2 x 256 columns); one extra K=16 step adds -||c||^2/2 (three fp16
-//                     terms against constant ones) so that acc = x.c - ||c||^2/2
+//   X producer      : TMA (cp.async.bulk.tensor, 128B swizzle) streams the caller's fp32 rows, 32
+//                     features x 128 rows per stage, through a 4-deep mbarrier ring
+//   converter warps : one thread per sample row: LDS the fp32 stage -> *s (power of two) -> fp16 ->
+//                     tcgen05.st into TMEM, where the A operand lives double-buffered (so the next
+//                     tile is converted while the current one is multiplied); per row ||x~||,
+//                     ||x - x~|| are accumulated for the error bound
+//   B producer      : TMA streams the fp16 centroid table (128 centroids x 64 features per stage,
+//                     128B swizzle) + the per-n-tile bias block through mbarrier rings
+//   MMA thread      : tcgen05.mma kind::f16, A from TMEM, B from shared memory, M=128 N=128 K=16,
+//                     fp32 accumulators double-buffered in TMEM (2 x 128 columns); one extra K=16
+//                     step (A and B from shared memory) adds -||c||^2/2 as three fp16 terms against
+//                     constant ones, so acc = x.c - ||c||^2/2
 //   epilogue warps  : tcgen05.ld 32 columns at a time; running row maximum M; every column whose
 //                     value is within `margin` of M is recorded (bit mask per 32-column chunk);
 //                     margin is a rigorous bound on |approx - exact| derived from the actual
@@ -21,6 +26,9 @@
 //   rows with one candidate are final; rows with several go to the exact re-check queue; rows with
 //   non-finite data or too many candidates go to the exact full pass.  Assignments are therefore
 //   bit-identical to the reference kernel's, ties included.
+//
+// TMEM map (512 columns): [0,128) accumulator 0, [128,256) accumulator 1, [256,384) A buffer 0,
+// [384,512) A buffer 1 (128 rows x 256 fp16 = 128 lanes x 128 32-bit columns).
 #include <cuda.h>
 #include <cuda_fp16.h>
 
@@ -35,22 +43,25 @@ namespace kmb {
 
 namespace tc {
 constexpr int TM = 128;                 // samples per tile (UMMA M)
-constexpr int TN = 256;                 // centroids per n-tile (UMMA N)
-constexpr int KB = 64;                  // fp16 elements per K-block = one 128-byte swizzle row
-constexpr int MAX_NKB = 4;              // D <= 256
-constexpr int B_STAGES = 3;
-constexpr int A_KB_BYTES = TM * 128;    // 16 KiB
-constexpr int B_STAGE_BYTES = TN * 128; // 32 KiB
+constexpr int TN = 128;                 // centroids per n-tile (UMMA N)
+constexpr int KB = 64;                  // fp16 elements per K-block = one 128-byte swizzle row of B
+constexpr int MAX_NKB = 4;              // D <= 256 (A buffer = 32 TMEM columns per K-block)
+constexpr int X_STAGES = 4;             // fp32 sample stages: 32 features x 128 rows = 16 KiB
+constexpr int B_STAGES = 4;             // fp16 centroid stages: 64 features x 128 rows = 16 KiB
+constexpr int X_STAGE_BYTES = TM * 128;
+constexpr int B_STAGE_BYTES = TN * 128;
 constexpr int AUG_A_BYTES = TM * 32;    // 4 KiB  (K=16 fp16, no swizzle)
-constexpr int AUG_B_BYTES = TN * 32;    // 8 KiB
+constexpr int AUG_B_BYTES = TN * 32;    // 4 KiB
 constexpr int LIST_LEN = 12;            // chunk entries per epilogue thread
-constexpr int N_CONV_WARPS = 8;
+constexpr int WARP_B_PRODUCER = 0, WARP_MMA = 1, WARP_X_PRODUCER = 2;
+constexpr int FIRST_CONV_WARP = 4;      // 4 converter warps, warp % 4 = TMEM lane quarter
+constexpr int FIRST_EPI_WARP = 8;       // 8 epilogue warps
+constexpr int N_CONV_WARPS = 4;
 constexpr int N_EPI_WARPS = 8;
-constexpr int FIRST_CONV_WARP = 2;
-constexpr int FIRST_EPI_WARP = FIRST_CONV_WARP + N_CONV_WARPS;  // 10
-constexpr int N_THREADS = (FIRST_EPI_WARP + N_EPI_WARPS) * 32;  // 576
+constexpr int N_THREADS = (FIRST_EPI_WARP + N_EPI_WARPS) * 32;  // 512
 constexpr int MAX_CAND = 16;            // candidates per row before falling back to the full exact pass
 constexpr uint32_t TMEM_COLS = 512;
+constexpr uint32_t TMEM_ACC0 = 0, TMEM_A0 = 256;
 
 // counters[] slots
 enum { CNT_PAIRS = 0, CNT_ROWQ = 1, CNT_OVF = 2, CNT_ERR = 3, CNT_N = 4 };
@@ -63,13 +74,13 @@ struct Stats {       // written by the centroid prep kernels, read by the main k
 };
 
 struct SmemLayout {  // byte offsets from the 1024-aligned dynamic smem base
-  uint32_t a, b, aug_a, aug_b, list_cm, list_mask, list_g, norms, fin, bars, tmem_slot, total;
+  uint32_t x, b, aug_a, aug_b, list_cm, list_mask, list_g, norms, fin, bars, tmem_slot, total;
 };
 
-__host__ __device__ inline SmemLayout smem_layout(int nkb) {
+__host__ __device__ inline SmemLayout smem_layout() {
   SmemLayout L;
   uint32_t o = 0;
-  L.a = o; o += nkb * A_KB_BYTES;
+  L.x = o; o += X_STAGES * X_STAGE_BYTES;
   L.b = o; o += B_STAGES * B_STAGE_BYTES;
   L.aug_a = o; o += AUG_A_BYTES;
   L.aug_b = o; o += 2 * AUG_B_BYTES;
@@ -85,22 +96,27 @@ __host__ __device__ inline SmemLayout smem_layout(int nkb) {
 }
 
 // barrier indices inside the bars[] array
-__host__ __device__ constexpr int BAR_B_FULL(int s) { return s; }
-__host__ __device__ constexpr int BAR_B_EMPTY(int s) { return B_STAGES + s; }
-__host__ __device__ constexpr int BAR_AUG_FULL(int s) { return 2 * B_STAGES + s; }
-__host__ __device__ constexpr int BAR_AUG_EMPTY(int s) { return 2 * B_STAGES + 2 + s; }
-__host__ __device__ constexpr int BAR_A_FULL(int kb) { return 2 * B_STAGES + 4 + kb; }
-__host__ __device__ constexpr int BAR_A_EMPTY(int kb) { return 2 * B_STAGES + 4 + MAX_NKB + kb; }
-__host__ __device__ constexpr int BAR_ACC_FULL(int b) { return 2 * B_STAGES + 4 + 2 * MAX_NKB + b; }
-__host__ __device__ constexpr int BAR_ACC_EMPTY(int b) { return 2 * B_STAGES + 6 + 2 * MAX_NKB + b; }
+enum {
+  BAR_X_FULL = 0,                         // [X_STAGES]
+  BAR_X_EMPTY = BAR_X_FULL + X_STAGES,    // [X_STAGES]
+  BAR_B_FULL = BAR_X_EMPTY + X_STAGES,    // [B_STAGES]
+  BAR_B_EMPTY = BAR_B_FULL + B_STAGES,    // [B_STAGES]
+  BAR_AUG_FULL = BAR_B_EMPTY + B_STAGES,  // [2]
+  BAR_AUG_EMPTY = BAR_AUG_FULL + 2,       // [2]
+  BAR_A_FULL = BAR_AUG_EMPTY + 2,         // [2][MAX_NKB]
+  BAR_A_FREE = BAR_A_FULL + 2 * MAX_NKB,  // [2]
+  BAR_ACC_FULL = BAR_A_FREE + 2,          // [2]
+  BAR_ACC_EMPTY = BAR_ACC_FULL + 2,       // [2]
+  BAR_COUNT = BAR_ACC_EMPTY + 2
+};
+static_assert(BAR_COUNT <= 64, "barrier array too small");
 
 struct Params {
-  const float* X;            // [n][D] fp32 row-major
   uint32_t n;
   int D;
   uint32_t K;
   int nkb;                   // K-blocks of 64 features
-  int nt;                    // n-tiles of 256 centroids
+  int nt;                    // n-tiles of 128 centroids
   uint32_t ntiles;           // sample tiles
   const __half* aug_blob;    // [nt][AUG_B_BYTES] in the shared-memory byte layout
   const Stats* stats;
@@ -111,8 +127,7 @@ struct Params {
   uint32_t* rowq;            // [3*i]: row, first pair, pair count
   uint32_t* ovf_rows;        // rows for the full exact pass
   uint32_t* counters;        // CNT_*
-  int aug_swap;              // debug: swap LBO/SBO of the no-swizzle descriptors
-  float* dbg_scores;         // optional [ntiles*128][nt*256] dump of the approximate scores
+  float* dbg_scores;         // optional [ntiles*128][nt*128] dump of the approximate scores
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -203,12 +218,15 @@ __global__ void tc_prep_table_kernel(const float* __restrict__ C, const float* _
 __device__ __forceinline__ void note_timeout(uint32_t* counters, int where) {
   atomicMax(&counters[CNT_ERR], 0x1000u + where);
 }
+#define TC_WAIT(bar, parity, site) \
+  do { if (!ptx::mbar_wait(&bars[bar], (parity), p.counters + CNT_ERR)) note_timeout(p.counters, site); } while (0)
 
 __global__ void __launch_bounds__(N_THREADS, 1)
-tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p) {
+tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_x,
+                 const Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const SmemLayout L = smem_layout(p.nkb);
+  const SmemLayout L = smem_layout();
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L.tmem_slot);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -216,23 +234,26 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p) {
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmap_b);
+    ptx::prefetch_tmap(&tmap_x);
+    for (int s = 0; s < X_STAGES; s++) {
+      ptx::mbar_init(&bars[BAR_X_FULL + s], 1);
+      ptx::mbar_init(&bars[BAR_X_EMPTY + s], N_CONV_WARPS);
+    }
     for (int s = 0; s < B_STAGES; s++) {
-      ptx::mbar_init(&bars[BAR_B_FULL(s)], 1);
-      ptx::mbar_init(&bars[BAR_B_EMPTY(s)], 1);
+      ptx::mbar_init(&bars[BAR_B_FULL + s], 1);
+      ptx::mbar_init(&bars[BAR_B_EMPTY + s], 1);
     }
     for (int s = 0; s < 2; s++) {
-      ptx::mbar_init(&bars[BAR_AUG_FULL(s)], 1);
-      ptx::mbar_init(&bars[BAR_AUG_EMPTY(s)], 1);
-      ptx::mbar_init(&bars[BAR_ACC_FULL(s)], 1);
-      ptx::mbar_init(&bars[BAR_ACC_EMPTY(s)], N_EPI_WARPS);
-    }
-    for (int kb = 0; kb < MAX_NKB; kb++) {
-      ptx::mbar_init(&bars[BAR_A_FULL(kb)], N_CONV_WARPS);
-      ptx::mbar_init(&bars[BAR_A_EMPTY(kb)], 1);
+      ptx::mbar_init(&bars[BAR_AUG_FULL + s], 1);
+      ptx::mbar_init(&bars[BAR_AUG_EMPTY + s], 1);
+      ptx::mbar_init(&bars[BAR_ACC_FULL + s], 1);
+      ptx::mbar_init(&bars[BAR_ACC_EMPTY + s], N_EPI_WARPS);
+      ptx::mbar_init(&bars[BAR_A_FREE + s], 1);
+      for (int kb = 0; kb < MAX_NKB; kb++) ptx::mbar_init(&bars[BAR_A_FULL + s * MAX_NKB + kb], N_CONV_WARPS);
     }
     ptx::fence_mbar_init();
   }
-  if (warp == 1) ptx::tmem_alloc(tmem_slot, TMEM_COLS);
+  if (warp == WARP_MMA) ptx::tmem_alloc(tmem_slot, TMEM_COLS);
   // constant A-side bias block: ones in the first three K positions of every row
   for (int i = threadIdx.x; i < TM * 16; i += N_THREADS) {
     int r = i >> 4, k = i & 15;
@@ -246,8 +267,8 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p) {
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
-    // ================================ TMA producer (B operand) ================================
+  if (warp == WARP_B_PRODUCER) {
+    // ================================ TMA producer: centroid table + bias blocks ================================
     if (lane == 0) {
       uint32_t pc = 0, ac = 0;
       for (uint32_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
@@ -255,160 +276,133 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p) {
           for (int kb = 0; kb < nkb; kb++, pc++) {
             const int s = pc % B_STAGES;
             const uint32_t ph = (pc / B_STAGES) & 1;
-            if (!ptx::mbar_wait(&bars[BAR_B_EMPTY(s)], ph ^ 1, p.counters + CNT_ERR)) note_timeout(p.counters, 1);
-            ptx::mbar_arrive_expect_tx(&bars[BAR_B_FULL(s)], B_STAGE_BYTES);
-            ptx::tma_load_2d(smem + L.b + s * B_STAGE_BYTES, &tmap_b, kb * KB, n * TN, &bars[BAR_B_FULL(s)]);
+            TC_WAIT(BAR_B_EMPTY + s, ph ^ 1, 1);
+            ptx::mbar_arrive_expect_tx(&bars[BAR_B_FULL + s], B_STAGE_BYTES);
+            ptx::tma_load_2d(smem + L.b + s * B_STAGE_BYTES, &tmap_b, kb * KB, n * TN, &bars[BAR_B_FULL + s]);
           }
           const int as = ac & 1;
           const uint32_t aph = (ac >> 1) & 1;
-          if (!ptx::mbar_wait(&bars[BAR_AUG_EMPTY(as)], aph ^ 1, p.counters + CNT_ERR)) note_timeout(p.counters, 2);
-          ptx::mbar_arrive_expect_tx(&bars[BAR_AUG_FULL(as)], AUG_B_BYTES);
+          TC_WAIT(BAR_AUG_EMPTY + as, aph ^ 1, 2);
+          ptx::mbar_arrive_expect_tx(&bars[BAR_AUG_FULL + as], AUG_B_BYTES);
           ptx::bulk_load(smem + L.aug_b + as * AUG_B_BYTES,
                          reinterpret_cast<const uint8_t*>(p.aug_blob) + static_cast<size_t>(n) * AUG_B_BYTES,
-                         AUG_B_BYTES, &bars[BAR_AUG_FULL(as)]);
+                         AUG_B_BYTES, &bars[BAR_AUG_FULL + as]);
           ac++;
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == WARP_X_PRODUCER) {
+    // ================================ TMA producer: fp32 sample rows ================================
+    if (lane == 0) {
+      uint32_t xc = 0;
+      for (uint32_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+        for (int hs = 0; hs < 2 * nkb; hs++, xc++) {
+          const int s = xc % X_STAGES;
+          const uint32_t ph = (xc / X_STAGES) & 1;
+          TC_WAIT(BAR_X_EMPTY + s, ph ^ 1, 9);
+          ptx::mbar_arrive_expect_tx(&bars[BAR_X_FULL + s], X_STAGE_BYTES);
+          ptx::tma_load_2d(smem + L.x + s * X_STAGE_BYTES, &tmap_x, hs * 32, static_cast<int>(tile * TM),
+                           &bars[BAR_X_FULL + s]);
+        }
+      }
+    }
+  } else if (warp == WARP_MMA) {
     // ================================ MMA issuer ================================
     if (lane == 0) {
       const uint32_t idesc = ptx::make_idesc_f16(TM, TN);
-      const uint32_t a_base = ptx::smem_u32(smem + L.a), b_base = ptx::smem_u32(smem + L.b);
+      const uint32_t b_base = ptx::smem_u32(smem + L.b);
       const uint32_t auga = ptx::smem_u32(smem + L.aug_a), augb = ptx::smem_u32(smem + L.aug_b);
-      const uint32_t aug_lbo_a = p.aug_swap ? 128 : TM * 16, aug_sbo_a = p.aug_swap ? TM * 16 : 128;
-      const uint32_t aug_lbo_b = p.aug_swap ? 128 : TN * 16, aug_sbo_b = p.aug_swap ? TN * 16 : 128;
-      uint32_t pc = 0, ac = 0, it = 0;
-      for (uint32_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, it++) {
+      uint32_t pc = 0, ac = 0, ti = 0;
+      for (uint32_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ti++) {
+        const int abuf = ti & 1;
+        const uint32_t a_par = (ti >> 1) & 1;
+        const uint32_t a_tmem = tmem_base + TMEM_A0 + abuf * 128;
         for (int n = 0; n < nt; n++, ac++) {
           const int buf = ac & 1;
           const uint32_t aph = (ac >> 1) & 1;
-          if (!ptx::mbar_wait(&bars[BAR_ACC_EMPTY(buf)], aph ^ 1, p.counters + CNT_ERR)) note_timeout(p.counters, 3);
+          TC_WAIT(BAR_ACC_EMPTY + buf, aph ^ 1, 3);
           ptx::tc_fence_after();
-          const uint32_t d_tmem = tmem_base + buf * TN;
+          const uint32_t d_tmem = tmem_base + TMEM_ACC0 + buf * TN;
           for (int kb = 0; kb < nkb; kb++, pc++) {
             const int s = pc % B_STAGES;
             const uint32_t ph = (pc / B_STAGES) & 1;
-            if (n == 0 && !ptx::mbar_wait(&bars[BAR_A_FULL(kb)], it & 1, p.counters + CNT_ERR)) note_timeout(p.counters, 4);
-            if (!ptx::mbar_wait(&bars[BAR_B_FULL(s)], ph, p.counters + CNT_ERR)) note_timeout(p.counters, 5);
+            if (n == 0) TC_WAIT(BAR_A_FULL + abuf * MAX_NKB + kb, a_par, 4);
+            TC_WAIT(BAR_B_FULL + s, ph, 5);
             ptx::tc_fence_after();
 #pragma unroll
             for (int ks = 0; ks < KB / 16; ks++) {
-              uint64_t ad = ptx::make_smem_desc(a_base + kb * A_KB_BYTES + ks * 32, 16, 1024, 2);
               uint64_t bd = ptx::make_smem_desc(b_base + s * B_STAGE_BYTES + ks * 32, 16, 1024, 2);
-              ptx::umma_f16(d_tmem, ad, bd, idesc, (kb | ks) ? 1u : 0u);
+              ptx::umma_f16_ts(d_tmem, a_tmem + kb * 32 + ks * 8, bd, idesc, (kb | ks) ? 1u : 0u);
             }
-            ptx::umma_commit(&bars[BAR_B_EMPTY(s)]);
-            if (n == nt - 1) ptx::umma_commit(&bars[BAR_A_EMPTY(kb)]);
+            ptx::umma_commit(&bars[BAR_B_EMPTY + s]);
           }
-          // bias step: acc += ones(128x16) * bias(256x16)^T  (no-swizzle K-major blocks)
-          if (!ptx::mbar_wait(&bars[BAR_AUG_FULL(buf)], aph, p.counters + CNT_ERR)) note_timeout(p.counters, 6);
+          // bias step: acc += ones(128x16) * bias(128x16)^T  (both operands no-swizzle K-major smem blocks)
+          TC_WAIT(BAR_AUG_FULL + buf, aph, 6);
           ptx::tc_fence_after();
           {
-            uint64_t ad = ptx::make_smem_desc(auga, aug_lbo_a, aug_sbo_a, 0);
-            uint64_t bd = ptx::make_smem_desc(augb + buf * AUG_B_BYTES, aug_lbo_b, aug_sbo_b, 0);
+            uint64_t ad = ptx::make_smem_desc(auga, TM * 16, 128, 0);
+            uint64_t bd = ptx::make_smem_desc(augb + buf * AUG_B_BYTES, TN * 16, 128, 0);
             ptx::umma_f16(d_tmem, ad, bd, idesc, 1u);
           }
-          ptx::umma_commit(&bars[BAR_AUG_EMPTY(buf)]);
-          ptx::umma_commit(&bars[BAR_ACC_FULL(buf)]);
+          ptx::umma_commit(&bars[BAR_AUG_EMPTY + buf]);
+          ptx::umma_commit(&bars[BAR_ACC_FULL + buf]);
         }
+        ptx::umma_commit(&bars[BAR_A_FREE + abuf]);  // every MMA reading this A buffer has completed
       }
     }
-  } else if (warp < FIRST_EPI_WARP) {
-    // ================================ converters (A operand) ================================
-    // 8 warps x 16 rows.  Global loads are software-pipelined two K-blocks deep in registers (the loads of
-    // item i+2 are issued as soon as item i has been written), so the fp32 rows of the next tile are already
-    // on chip when the MMA warp releases the A slots -- there is no load latency on the tile boundary.
-    const int cw = warp - FIRST_CONV_WARP;  // rows [16cw, 16cw+16)
-    const int r4 = lane >> 3, j = lane & 7;
+  } else if (warp >= FIRST_CONV_WARP && warp < FIRST_EPI_WARP) {
+    // ================================ converters: fp32 smem stage -> fp16 A operand in TMEM ================================
+    const int q = warp & 3;                 // TMEM lane quarter
+    const int row = q * 32 + lane;          // this thread's sample row within the tile
     const float s = p.stats->scale;
-    const uint32_t my_tiles = (p.ntiles > blockIdx.x) ? (p.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    const uint32_t total = my_tiles * static_cast<uint32_t>(nkb);
-    float nx[4] = {0.f, 0.f, 0.f, 0.f}, nd[4] = {0.f, 0.f, 0.f, 0.f};
-
-    auto load_item = [&](float4 (&v)[4][2], uint32_t item) {
-      const uint32_t ti = item / nkb;
-      const int kb = static_cast<int>(item - ti * nkb);
-      const uint64_t tile = blockIdx.x + static_cast<uint64_t>(ti) * gridDim.x;
-      const int f0 = kb * KB + j * 8;
+    uint32_t xc = 0, ti = 0;
+    for (uint32_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ti++) {
+      const int abuf = ti & 1;
+      TC_WAIT(BAR_A_FREE + abuf, ((ti >> 1) & 1) ^ 1, 7);   // MMAs of tile ti-2 no longer read this buffer
+      ptx::tc_fence_after();
+      float nx = 0.f, nd = 0.f;
+      for (int kb = 0; kb < nkb; kb++) {
+        uint32_t pk[32];
 #pragma unroll
-      for (int i = 0; i < 4; i++) {
-        const uint64_t grow = tile * TM + cw * 16 + i * 4 + r4;
-        if (grow < p.n && f0 < p.D) {
-          const float* src = p.X + grow * p.D + f0;
-          v[i][0] = ptx::ldg_nc_f4(src);
-          v[i][1] = ptx::ldg_nc_f4(src + 4);
-        } else {
-          v[i][0] = v[i][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-      }
-    };
-    auto store_item = [&](float4 (&v)[4][2], uint32_t item) {
-      const uint32_t ti = item / nkb;
-      const int kb = static_cast<int>(item - ti * nkb);
-      if (!ptx::mbar_wait(&bars[BAR_A_EMPTY(kb)], (ti & 1) ^ 1, p.counters + CNT_ERR)) note_timeout(p.counters, 7);
-      uint8_t* a_kb = smem + L.a + kb * A_KB_BYTES;
+        for (int half = 0; half < 2; half++, xc++) {
+          const int st = xc % X_STAGES;
+          const uint32_t ph = (xc / X_STAGES) & 1;
+          TC_WAIT(BAR_X_FULL + st, ph, 10);
+          const uint8_t* xs = smem + L.x + st * X_STAGE_BYTES + row * 128;
 #pragma unroll
-      for (int i = 0; i < 4; i++) {
-        const int row = cw * 16 + i * 4 + r4;
-        float x[8] = {v[i][0].x, v[i][0].y, v[i][0].z, v[i][0].w, v[i][1].x, v[i][1].y, v[i][1].z, v[i][1].w};
-        __half2 h[4];
-#pragma unroll
-        for (int e = 0; e < 4; e++) {
-          float a = x[2 * e] * s, b = x[2 * e + 1] * s;
-          h[e] = __floats2half2_rn(a, b);
-          float2 back = __half22float2(h[e]);
-          float da = a - back.x, db = b - back.y;
-          nx[i] = fmaf(back.x, back.x, nx[i]);
-          nx[i] = fmaf(back.y, back.y, nx[i]);
-          nd[i] = fmaf(da, da, nd[i]);
-          nd[i] = fmaf(db, db, nd[i]);
-        }
-        uint4 packed;
-        packed.x = *reinterpret_cast<uint32_t*>(&h[0]);
-        packed.y = *reinterpret_cast<uint32_t*>(&h[1]);
-        packed.z = *reinterpret_cast<uint32_t*>(&h[2]);
-        packed.w = *reinterpret_cast<uint32_t*>(&h[3]);
-        *reinterpret_cast<uint4*>(a_kb + row * 128 + ((j ^ (row & 7)) << 4)) = packed;
-      }
-      if (kb == nkb - 1) {
-        // per-row norms of this tile (8 lanes share a row), then reset for the next tile
-        float* norms = reinterpret_cast<float*>(smem + L.norms) + (ti & 1) * 2 * TM;
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-          float a = nx[i], b = nd[i];
-          a += __shfl_xor_sync(0xffffffffu, a, 1); b += __shfl_xor_sync(0xffffffffu, b, 1);
-          a += __shfl_xor_sync(0xffffffffu, a, 2); b += __shfl_xor_sync(0xffffffffu, b, 2);
-          a += __shfl_xor_sync(0xffffffffu, a, 4); b += __shfl_xor_sync(0xffffffffu, b, 4);
-          if (j == 0) {
-            const int row = cw * 16 + i * 4 + r4;
-            norms[row] = a;
-            norms[TM + row] = b;
+          for (int c = 0; c < 8; c++) {
+            const float4 v = *reinterpret_cast<const float4*>(xs + ((c ^ (row & 7)) << 4));
+            const float a0 = v.x * s, a1 = v.y * s, a2 = v.z * s, a3 = v.w * s;
+            __half2 h0 = __floats2half2_rn(a0, a1), h1 = __floats2half2_rn(a2, a3);
+            const float2 b0 = __half22float2(h0), b1 = __half22float2(h1);
+            nx = fmaf(b0.x, b0.x, nx); nx = fmaf(b0.y, b0.y, nx);
+            nx = fmaf(b1.x, b1.x, nx); nx = fmaf(b1.y, b1.y, nx);
+            const float d0 = a0 - b0.x, d1 = a1 - b0.y, d2 = a2 - b1.x, d3 = a3 - b1.y;
+            nd = fmaf(d0, d0, nd); nd = fmaf(d1, d1, nd);
+            nd = fmaf(d2, d2, nd); nd = fmaf(d3, d3, nd);
+            pk[half * 16 + c * 2] = *reinterpret_cast<uint32_t*>(&h0);
+            pk[half * 16 + c * 2 + 1] = *reinterpret_cast<uint32_t*>(&h1);
           }
-          nx[i] = nd[i] = 0.f;
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&bars[BAR_X_EMPTY + st]);
         }
-      }
-      ptx::fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&bars[BAR_A_FULL(kb)]);
-    };
-
-    float4 v0[4][2], v1[4][2];
-    if (total > 0) load_item(v0, 0);
-    if (total > 1) load_item(v1, 1);
-    for (uint32_t item = 0; item < total; item += 2) {
-      store_item(v0, item);
-      if (item + 2 < total) load_item(v0, item + 2);
-      if (item + 1 < total) {
-        store_item(v1, item + 1);
-        if (item + 3 < total) load_item(v1, item + 3);
+        ptx::tmem_st_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + TMEM_A0 + abuf * 128 + kb * 32, pk);
+        ptx::tmem_st_wait();
+        if (kb == nkb - 1) {
+          float* norms = reinterpret_cast<float*>(smem + L.norms) + (ti & 1) * 2 * TM;
+          norms[row] = nx;
+          norms[TM + row] = nd;
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&bars[BAR_A_FULL + abuf * MAX_NKB + kb]);
       }
     }
-  } else {
+  } else if (warp >= FIRST_EPI_WARP) {
     // ================================ epilogue ================================
     const int e = warp - FIRST_EPI_WARP;       // 0..7
     const int q = warp & 3;                    // TMEM lane quarter this warp may access
-    const int h = e >> 2;                      // column half of every 256-column accumulator
+    const int h = e >> 2;                      // column half of every 128-column accumulator
     const int row = q * 32 + lane;
     const int slot = h * TM + row;             // 0..255
     float* list_cm = reinterpret_cast<float*>(smem + L.list_cm);
@@ -418,17 +412,17 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p) {
     uint32_t* fin_cnt = reinterpret_cast<uint32_t*>(smem + L.fin) + 256;
     uint32_t* fin_flag = reinterpret_cast<uint32_t*>(smem + L.fin) + 512;
     const float cmax = p.stats->cmax, dcmax = p.stats->dcmax;
-    uint32_t ac = 0, it = 0;
-    for (uint32_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, it++) {
+    uint32_t ac = 0, ti = 0;
+    for (uint32_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ti++) {
       float M = -INFINITY, margin = 0.f;
       uint32_t cnt = 0, flags = 0;
       for (int n = 0; n < nt; n++, ac++) {
         const int buf = ac & 1;
         const uint32_t aph = (ac >> 1) & 1;
-        if (!ptx::mbar_wait(&bars[BAR_ACC_FULL(buf)], aph, p.counters + CNT_ERR)) note_timeout(p.counters, 8);
+        TC_WAIT(BAR_ACC_FULL + buf, aph, 8);
         ptx::tc_fence_after();
         if (n == 0) {
-          const float* norms = reinterpret_cast<const float*>(smem + L.norms) + (it & 1) * 2 * TM;
+          const float* norms = reinterpret_cast<const float*>(smem + L.norms) + (ti & 1) * 2 * TM;
           // rigorous bound on |acc - (s^2 x.c - s^2||c||^2/2)| (see header): Cauchy-Schwarz on the
           // actual rounding residuals + accumulation + the reference's own rounding slack
           const float nx = __fsqrt_ru(norms[row]) * 1.0001f, nd = __fsqrt_ru(norms[TM + row]) * 1.0001f;
@@ -439,14 +433,15 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p) {
           margin = 2.f * E * 1.001f + 1e-30f;
           if (!(margin < 1.0e30f)) flags |= 1u;                            // NaN / Inf somewhere in the row
         }
-        for (int c = 0; c < 4; c++) {
+#pragma unroll 1
+        for (int c = 0; c < 2; c++) {
           uint32_t r[32];
-          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * TN + h * 128 + c * 32;
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + TMEM_ACC0 + buf * TN + h * 64 + c * 32;
           ptx::tmem_ld_32x32(taddr, r);
           ptx::tmem_ld_wait();
           if (p.dbg_scores) {
             const uint64_t grow = static_cast<uint64_t>(tile) * TM + row;
-            float* dst = p.dbg_scores + grow * (static_cast<uint64_t>(nt) * TN) + n * TN + h * 128 + c * 32;
+            float* dst = p.dbg_scores + grow * (static_cast<uint64_t>(nt) * TN) + n * TN + h * 64 + c * 32;
             for (int jj = 0; jj < 32; jj++) dst[jj] = __uint_as_float(r[jj]);
           }
           float cm = __uint_as_float(r[0]);
@@ -462,7 +457,7 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p) {
             if (cnt < LIST_LEN) {
               list_cm[cnt * 256 + slot] = cm;
               list_mask[cnt * 256 + slot] = mask;
-              list_g[cnt * 256 + slot] = static_cast<uint16_t>(n * 8 + h * 4 + c);
+              list_g[cnt * 256 + slot] = static_cast<uint16_t>(n * 4 + h * 2 + c);
               cnt++;
             } else {
               flags |= 2u;
@@ -471,7 +466,7 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p) {
         }
         ptx::tc_fence_before();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&bars[BAR_ACC_EMPTY(buf)]);
+        if (lane == 0) ptx::mbar_arrive(&bars[BAR_ACC_EMPTY + buf]);
       }
       // merge the two column halves of every row and emit
       fin_m[slot] = M;
@@ -533,7 +528,7 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p) {
   // teardown
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == WARP_MMA) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, TMEM_COLS);
   }
@@ -629,10 +624,9 @@ struct TcPlan {
   uint32_t *pair_row = nullptr, *pair_cand = nullptr, *rowq = nullptr, *ovf_rows = nullptr, *counters = nullptr;
   float* pair_score = nullptr;
   uint32_t* h_counters = nullptr;  // pinned
-  CUtensorMap tmap;
+  CUtensorMap tmap;     // fp16 centroid table
   int num_sms = 148;
   size_t smem_bytes = 0;
-  int aug_swap = 0;
   float* dbg_scores = nullptr;
   // CUDA-event pairs around the main kernel of the most recent passes (bench.py roofline)
   static constexpr int kEvRing = 64;
@@ -659,7 +653,7 @@ static EncodeTiledFn get_encode_fn() {
 
 bool tc_supported(int metric, uint32_t n, int D, uint32_t K) {
   if (metric != 0) return false;                       // cosine: next round
-  if (D < 8 || D % 8 != 0 || D > tc::MAX_NKB * tc::KB) return false;
+  if (D < 4 || D % 4 != 0 || D > tc::MAX_NKB * tc::KB) return false;   // TMA row pitch must be 16-byte aligned
   if (K < 2 || K > 65535u * 32u) return false;
   if (n == 0) return false;
   return true;
@@ -696,8 +690,6 @@ cudaError_t tc_plan_create(TcPlan** out, int metric, uint32_t max_n, int D, uint
   p->nkb = (D + KB - 1) / KB;
   p->nt = static_cast<int>((K + TN - 1) / TN);
   p->max_pairs = max_n < (1u << 30) ? 2 * max_n + 1024 : 0xFFFFFFF0u;
-  const char* sw = getenv("KMCUDA_B200_AUG_SWAP");
-  p->aug_swap = (sw && sw[0] == '1') ? 1 : 0;
   cudaError_t e;
 #define TC_TRY(x) do { e = (x); if (e != cudaSuccess) { tc_plan_destroy(p); return e; } } while (0)
   cudaDeviceProp prop;
@@ -735,7 +727,7 @@ cudaError_t tc_plan_create(TcPlan** out, int metric, uint32_t max_n, int D, uint
     TC_TRY(cudaEventCreate(&p->ev0[i]));
     TC_TRY(cudaEventCreate(&p->ev1[i]));
   }
-  p->smem_bytes = smem_layout(p->nkb).total + 1024;
+  p->smem_bytes = smem_layout().total + 1024;
   TC_TRY(cudaFuncSetAttribute(tc_assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               static_cast<int>(p->smem_bytes)));
 #undef TC_TRY
@@ -749,6 +741,21 @@ cudaError_t tc_assign(TcPlan* p, const float* X, const float* C, const float* cs
   if (n > p->max_n) return cudaErrorInvalidValue;
   if (reinterpret_cast<uintptr_t>(X) & 15) return cudaErrorMisalignedAddress;
   cudaError_t e;
+  // tensor map over the caller's fp32 samples [n][D]: box 32 features x 128 rows, 128-byte swizzle,
+  // out-of-range rows / features read as zero (ragged last tile, D not a multiple of 32)
+  CUtensorMap tmap_x;
+  {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) return cudaErrorNotSupported;
+    cuuint64_t gdim[2] = {static_cast<cuuint64_t>(p->D), static_cast<cuuint64_t>(n)};
+    cuuint64_t gstride[1] = {static_cast<cuuint64_t>(p->D) * sizeof(float)};
+    cuuint32_t box[2] = {32, TM};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult cr = enc(&tmap_x, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(X), gdim, gstride, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) return cudaErrorInvalidValue;
+  }
   if ((e = cudaMemsetAsync(p->counters, 0, sizeof(uint32_t) * CNT_N, st)) != cudaSuccess) return e;
   if ((e = cudaMemsetAsync(p->stats, 0, sizeof(Stats), st)) != cudaSuccess) return e;
   tc_prep_stats_kernel<<<8, 256, 0, st>>>(csq, p->K, p->stats);
@@ -757,7 +764,6 @@ cudaError_t tc_assign(TcPlan* p, const float* X, const float* C, const float* cs
   tc_prep_table_kernel<<<(rows_pad * 32 + 255) / 256, 256, 0, st>>>(C, csq, p->K, p->D, p->nkb, p->nt, p->table,
                                                                     p->aug_blob, p->stats);
   Params prm;
-  prm.X = X;
   prm.n = n;
   prm.D = p->D;
   prm.K = p->K;
@@ -773,12 +779,11 @@ cudaError_t tc_assign(TcPlan* p, const float* X, const float* C, const float* cs
   prm.rowq = p->rowq;
   prm.ovf_rows = p->ovf_rows;
   prm.counters = p->counters;
-  prm.aug_swap = p->aug_swap;
   prm.dbg_scores = p->dbg_scores;
   const unsigned grid = min(static_cast<uint32_t>(p->num_sms), prm.ntiles);
   const int slot = static_cast<int>(p->passes % TcPlan::kEvRing);
   cudaEventRecord(p->ev0[slot], st);
-  tc_assign_kernel<<<grid, N_THREADS, p->smem_bytes, st>>>(p->tmap, prm);
+  tc_assign_kernel<<<grid, N_THREADS, p->smem_bytes, st>>>(p->tmap, tmap_x, prm);
   cudaEventRecord(p->ev1[slot], st);
   p->passes++;
   if ((e = cudaGetLastError()) != cudaSuccess) return e;

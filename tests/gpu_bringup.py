@@ -109,7 +109,7 @@ def stage_tc_scores():
     os.environ["KMCUDA_B200_DUMP_SCORES"] = "1"
     try:
         for swap in ("0",):
-            os.environ["KMCUDA_B200_AUG_SWAP"] = swap
+            os.environ["KMCUDA_B200_PACK_SWAP"] = swap
             for (n, d, k) in [(128, 64, 256), (300, 64, 256), (512, 256, 1024), (700, 128, 300), (256, 72, 50)]:
                 X, C0 = data(n, d, k, seed=5)
                 Xt, Ct = torch.from_numpy(X).cuda(), torch.from_numpy(C0).cuda()
@@ -145,7 +145,7 @@ def stage_tc_scores():
                 sh.close()
     finally:
         os.environ.pop("KMCUDA_B200_DUMP_SCORES", None)
-        os.environ.pop("KMCUDA_B200_AUG_SWAP", None)
+        os.environ.pop("KMCUDA_B200_PACK_SWAP", None)
 
 
 def _time_assign(sh, Xt, Ct, iters=5):
