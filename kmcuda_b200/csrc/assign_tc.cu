@@ -58,7 +58,9 @@ constexpr int FIRST_CONV_WARP = 4;      // 4 converter warps, warp % 4 = TMEM la
 constexpr int FIRST_EPI_WARP = 8;       // 8 epilogue warps
 constexpr int N_CONV_WARPS = 4;
 constexpr int N_EPI_WARPS = 8;
-constexpr int N_THREADS = (FIRST_EPI_WARP + N_EPI_WARPS) * 32;  // 512
+constexpr int FIRST_EMIT_WARP = FIRST_EPI_WARP + N_EPI_WARPS;  // 16: 4 emitter warps (merge + global emission)
+constexpr int N_EMIT_WARPS = 4;
+constexpr int N_THREADS = (FIRST_EMIT_WARP + N_EMIT_WARPS) * 32;  // 640
 constexpr int MAX_CAND = 16;            // candidates per row before falling back to the full exact pass
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t TMEM_ACC0 = 0, TMEM_A0 = 256;
@@ -84,11 +86,11 @@ __host__ __device__ inline SmemLayout smem_layout() {
   L.b = o; o += B_STAGES * B_STAGE_BYTES;
   L.aug_a = o; o += AUG_A_BYTES;
   L.aug_b = o; o += 2 * AUG_B_BYTES;
-  L.list_cm = o; o += LIST_LEN * 256 * 4;
-  L.list_mask = o; o += LIST_LEN * 256 * 4;
-  L.list_g = o; o += LIST_LEN * 256 * 2;
+  L.list_cm = o; o += 2 * LIST_LEN * 256 * 4;    // [tile parity][entry][epilogue thread]
+  L.list_mask = o; o += 2 * LIST_LEN * 256 * 4;
+  L.list_g = o; o += 2 * LIST_LEN * 256 * 2;
   L.norms = o; o += 2 * 2 * TM * 4;   // [parity][x|d][row]
-  L.fin = o; o += 256 * 4 * 3;        // M, cnt, flags of the 256 epilogue threads
+  L.fin = o; o += 2 * 4 * 256 * 4;    // [tile parity][M|cnt|flags|margin][epilogue thread]
   L.bars = o; o += 64 * 8;
   L.tmem_slot = o; o += 16;
   L.total = o;
@@ -107,7 +109,9 @@ enum {
   BAR_A_FREE = BAR_A_FULL + 2 * MAX_NKB,  // [2]
   BAR_ACC_FULL = BAR_A_FREE + 2,          // [2]
   BAR_ACC_EMPTY = BAR_ACC_FULL + 2,       // [2]
-  BAR_COUNT = BAR_ACC_EMPTY + 2
+  BAR_EMIT_FULL = BAR_ACC_EMPTY + 2,      // [2] epilogue -> emitter (per tile parity)
+  BAR_EMIT_EMPTY = BAR_EMIT_FULL + 2,     // [2]
+  BAR_COUNT = BAR_EMIT_EMPTY + 2
 };
 static_assert(BAR_COUNT <= 64, "barrier array too small");
 
@@ -249,6 +253,8 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
       ptx::mbar_init(&bars[BAR_ACC_FULL + s], 1);
       ptx::mbar_init(&bars[BAR_ACC_EMPTY + s], N_EPI_WARPS);
       ptx::mbar_init(&bars[BAR_A_FREE + s], 1);
+      ptx::mbar_init(&bars[BAR_EMIT_FULL + s], N_EPI_WARPS);
+      ptx::mbar_init(&bars[BAR_EMIT_EMPTY + s], N_EMIT_WARPS);
       for (int kb = 0; kb < MAX_NKB; kb++) ptx::mbar_init(&bars[BAR_A_FULL + s * MAX_NKB + kb], N_CONV_WARPS);
     }
     ptx::fence_mbar_init();
@@ -308,46 +314,50 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
     }
   } else if (warp == WARP_MMA) {
     // ================================ MMA issuer ================================
-    if (lane == 0) {
-      const uint32_t idesc = ptx::make_idesc_f16(TM, TN);
-      const uint32_t b_base = ptx::smem_u32(smem + L.b);
-      const uint32_t auga = ptx::smem_u32(smem + L.aug_a), augb = ptx::smem_u32(smem + L.aug_b);
-      uint32_t pc = 0, ac = 0, ti = 0;
-      for (uint32_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ti++) {
-        const int abuf = ti & 1;
-        const uint32_t a_par = (ti >> 1) & 1;
-        const uint32_t a_tmem = tmem_base + TMEM_A0 + abuf * 128;
-        for (int n = 0; n < nt; n++, ac++) {
-          const int buf = ac & 1;
-          const uint32_t aph = (ac >> 1) & 1;
-          TC_WAIT(BAR_ACC_EMPTY + buf, aph ^ 1, 3);
+    // The whole warp runs the (warp-uniform) control flow so that addresses and descriptors stay in
+    // uniform registers; one elected lane issues the tcgen05 instructions.
+    const uint32_t idesc = ptx::make_idesc_f16(TM, TN);
+    const uint32_t b_base = ptx::smem_u32(smem + L.b);
+    const uint64_t aug_ad = ptx::make_smem_desc(ptx::smem_u32(smem + L.aug_a), TM * 16, 128, 0);
+    const uint32_t augb = ptx::smem_u32(smem + L.aug_b);
+    uint32_t pc = 0, ac = 0, ti = 0;
+    for (uint32_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ti++) {
+      const int abuf = ti & 1;
+      const uint32_t a_par = (ti >> 1) & 1;
+      const uint32_t a_tmem = tmem_base + TMEM_A0 + abuf * 128;
+      for (int n = 0; n < nt; n++, ac++) {
+        const int buf = ac & 1;
+        const uint32_t aph = (ac >> 1) & 1;
+        TC_WAIT(BAR_ACC_EMPTY + buf, aph ^ 1, 3);
+        const uint32_t d_tmem = tmem_base + TMEM_ACC0 + buf * TN;
+        for (int kb = 0; kb < nkb; kb++, pc++) {
+          const int s = pc % B_STAGES;
+          const uint32_t ph = (pc / B_STAGES) & 1;
+          if (n == 0) TC_WAIT(BAR_A_FULL + abuf * MAX_NKB + kb, a_par, 4);
+          TC_WAIT(BAR_B_FULL + s, ph, 5);
           ptx::tc_fence_after();
-          const uint32_t d_tmem = tmem_base + TMEM_ACC0 + buf * TN;
-          for (int kb = 0; kb < nkb; kb++, pc++) {
-            const int s = pc % B_STAGES;
-            const uint32_t ph = (pc / B_STAGES) & 1;
-            if (n == 0) TC_WAIT(BAR_A_FULL + abuf * MAX_NKB + kb, a_par, 4);
-            TC_WAIT(BAR_B_FULL + s, ph, 5);
-            ptx::tc_fence_after();
-#pragma unroll
-            for (int ks = 0; ks < KB / 16; ks++) {
-              uint64_t bd = ptx::make_smem_desc(b_base + s * B_STAGE_BYTES + ks * 32, 16, 1024, 2);
-              ptx::umma_f16_ts(d_tmem, a_tmem + kb * 32 + ks * 8, bd, idesc, (kb | ks) ? 1u : 0u);
-            }
+          if (ptx::elect_one()) {
+            const uint64_t bd0 = ptx::make_smem_desc(b_base + s * B_STAGE_BYTES, 16, 1024, 2);
+            const uint32_t at = a_tmem + kb * 32;
+            ptx::umma_f16_ts(d_tmem, at, bd0, idesc, kb ? 1u : 0u);
+            ptx::umma_f16_ts(d_tmem, at + 8, bd0 + 2, idesc, 1u);     // +32 bytes along K = +2 in the address field
+            ptx::umma_f16_ts(d_tmem, at + 16, bd0 + 4, idesc, 1u);
+            ptx::umma_f16_ts(d_tmem, at + 24, bd0 + 6, idesc, 1u);
             ptx::umma_commit(&bars[BAR_B_EMPTY + s]);
           }
-          // bias step: acc += ones(128x16) * bias(128x16)^T  (both operands no-swizzle K-major smem blocks)
-          TC_WAIT(BAR_AUG_FULL + buf, aph, 6);
-          ptx::tc_fence_after();
-          {
-            uint64_t ad = ptx::make_smem_desc(auga, TM * 16, 128, 0);
-            uint64_t bd = ptx::make_smem_desc(augb + buf * AUG_B_BYTES, TN * 16, 128, 0);
-            ptx::umma_f16(d_tmem, ad, bd, idesc, 1u);
-          }
+          __syncwarp();
+        }
+        // bias step: acc += ones(128x16) * bias(128x16)^T  (both operands no-swizzle K-major smem blocks)
+        TC_WAIT(BAR_AUG_FULL + buf, aph, 6);
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
+          const uint64_t bd = ptx::make_smem_desc(augb + buf * AUG_B_BYTES, TN * 16, 128, 0);
+          ptx::umma_f16(d_tmem, aug_ad, bd, idesc, 1u);
           ptx::umma_commit(&bars[BAR_AUG_EMPTY + buf]);
           ptx::umma_commit(&bars[BAR_ACC_FULL + buf]);
+          if (n == nt - 1) ptx::umma_commit(&bars[BAR_A_FREE + abuf]);  // every MMA reading this A buffer is done
         }
-        ptx::umma_commit(&bars[BAR_A_FREE + abuf]);  // every MMA reading this A buffer has completed
+        __syncwarp();
       }
     }
   } else if (warp >= FIRST_CONV_WARP && warp < FIRST_EPI_WARP) {
@@ -398,22 +408,23 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
         if (lane == 0) ptx::mbar_arrive(&bars[BAR_A_FULL + abuf * MAX_NKB + kb]);
       }
     }
-  } else if (warp >= FIRST_EPI_WARP) {
+  } else if (warp >= FIRST_EPI_WARP && warp < FIRST_EMIT_WARP) {
     // ================================ epilogue ================================
     const int e = warp - FIRST_EPI_WARP;       // 0..7
     const int q = warp & 3;                    // TMEM lane quarter this warp may access
     const int h = e >> 2;                      // column half of every 128-column accumulator
     const int row = q * 32 + lane;
     const int slot = h * TM + row;             // 0..255
-    float* list_cm = reinterpret_cast<float*>(smem + L.list_cm);
-    uint32_t* list_mask = reinterpret_cast<uint32_t*>(smem + L.list_mask);
-    uint16_t* list_g = reinterpret_cast<uint16_t*>(smem + L.list_g);
-    float* fin_m = reinterpret_cast<float*>(smem + L.fin);
-    uint32_t* fin_cnt = reinterpret_cast<uint32_t*>(smem + L.fin) + 256;
-    uint32_t* fin_flag = reinterpret_cast<uint32_t*>(smem + L.fin) + 512;
     const float cmax = p.stats->cmax, dcmax = p.stats->dcmax;
     uint32_t ac = 0, ti = 0;
     for (uint32_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ti++) {
+      const int par = ti & 1;
+      float* list_cm = reinterpret_cast<float*>(smem + L.list_cm) + par * LIST_LEN * 256;
+      uint32_t* list_mask = reinterpret_cast<uint32_t*>(smem + L.list_mask) + par * LIST_LEN * 256;
+      uint16_t* list_g = reinterpret_cast<uint16_t*>(smem + L.list_g) + par * LIST_LEN * 256;
+      float* fin = reinterpret_cast<float*>(smem + L.fin) + par * 4 * 256;
+      // the emitter warps must have consumed this parity's lists (tile ti-2)
+      TC_WAIT(BAR_EMIT_EMPTY + par, ((ti >> 1) & 1) ^ 1, 11);
       float M = -INFINITY, margin = 0.f;
       uint32_t cnt = 0, flags = 0;
       for (int n = 0; n < nt; n++, ac++) {
@@ -421,6 +432,11 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
         const uint32_t aph = (ac >> 1) & 1;
         TC_WAIT(BAR_ACC_FULL + buf, aph, 8);
         ptx::tc_fence_after();
+        // both 32-column chunks of this warp are fetched up front so that their dependency chains interleave
+        uint32_t r0[32], r1[32];
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + TMEM_ACC0 + buf * TN + h * 64;
+        ptx::tmem_ld_32x32(taddr, r0);
+        ptx::tmem_ld_32x32(taddr + 32, r1);
         if (n == 0) {
           const float* norms = reinterpret_cast<const float*>(smem + L.norms) + (ti & 1) * 2 * TM;
           // rigorous bound on |acc - (s^2 x.c - s^2||c||^2/2)| (see header): Cauchy-Schwarz on the
@@ -433,96 +449,151 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
           margin = 2.f * E * 1.001f + 1e-30f;
           if (!(margin < 1.0e30f)) flags |= 1u;                            // NaN / Inf somewhere in the row
         }
-#pragma unroll 1
-        for (int c = 0; c < 2; c++) {
-          uint32_t r[32];
-          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + TMEM_ACC0 + buf * TN + h * 64 + c * 32;
-          ptx::tmem_ld_32x32(taddr, r);
-          ptx::tmem_ld_wait();
-          if (p.dbg_scores) {
-            const uint64_t grow = static_cast<uint64_t>(tile) * TM + row;
-            float* dst = p.dbg_scores + grow * (static_cast<uint64_t>(nt) * TN) + n * TN + h * 64 + c * 32;
-            for (int jj = 0; jj < 32; jj++) dst[jj] = __uint_as_float(r[jj]);
-          }
-          float cm = __uint_as_float(r[0]);
-#pragma unroll
-          for (int jj = 1; jj < 32; jj++) cm = fmaxf(cm, __uint_as_float(r[jj]));
-          M = fmaxf(M, cm);
-          const float thr = M - margin;
-          uint32_t mask = 0;
-#pragma unroll
-          for (int jj = 0; jj < 32; jj++)
-            if (__uint_as_float(r[jj]) >= thr) mask |= (1u << jj);
-          if (mask) {
-            if (cnt < LIST_LEN) {
-              list_cm[cnt * 256 + slot] = cm;
-              list_mask[cnt * 256 + slot] = mask;
-              list_g[cnt * 256 + slot] = static_cast<uint16_t>(n * 4 + h * 2 + c);
-              cnt++;
-            } else {
-              flags |= 2u;
-            }
-          }
-        }
+        ptx::tmem_ld_wait();
+        // the accumulator values are in registers: hand the TMEM buffer back to the MMA warp right away
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&bars[BAR_ACC_EMPTY + buf]);
-      }
-      // merge the two column halves of every row and emit
-      fin_m[slot] = M;
-      fin_cnt[slot] = cnt;
-      fin_flag[slot] = flags;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (h == 0) {
-        const uint64_t grow = static_cast<uint64_t>(tile) * TM + row;
-        if (grow < p.n) {
-          const float Mf = fmaxf(M, fin_m[TM + row]);
-          const float thr = Mf - margin;
-          uint32_t fl = flags | fin_flag[TM + row];
-          uint32_t cand[MAX_CAND];
-          uint32_t total = 0;
-          for (int hh = 0; hh < 2; hh++) {
-            const int sl = hh * TM + row;
-            const uint32_t c2 = fin_cnt[sl];
-            for (uint32_t i = 0; i < c2; i++) {
-              if (!(list_cm[i * 256 + sl] >= thr)) continue;
-              uint32_t m = list_mask[i * 256 + sl];
-              const uint32_t g = list_g[i * 256 + sl];
-              while (m) {
-                const int b = __ffs(m) - 1;
-                m &= m - 1;
-                const uint32_t col = g * 32 + b;
-                if (col < p.K) {
-                  if (total < MAX_CAND) cand[total] = col;
-                  total++;
-                }
-              }
-            }
-          }
-          if (fl || total > MAX_CAND) {
-            p.ovf_rows[atomicAdd(&p.counters[CNT_OVF], 1u)] = static_cast<uint32_t>(grow);
-          } else if (total == 1) {
-            p.result[grow] = cand[0];
-          } else if (total == 0) {
-            p.result[grow] = kUntouched;  // every score NaN: nothing wins (reference kmeans.cu:349-353)
+        if (p.dbg_scores) {
+          const uint64_t grow = static_cast<uint64_t>(tile) * TM + row;
+          float* dst = p.dbg_scores + grow * (static_cast<uint64_t>(nt) * TN) + n * TN + h * 64;
+          for (int jj = 0; jj < 32; jj++) dst[jj] = __uint_as_float(r0[jj]);
+          for (int jj = 0; jj < 32; jj++) dst[32 + jj] = __uint_as_float(r1[jj]);
+        }
+        // chunk maxima as balanced trees (short dependency chains)
+        float t0[8], t1[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          t0[i] = fmaxf(fmaxf(__uint_as_float(r0[4 * i]), __uint_as_float(r0[4 * i + 1])),
+                        fmaxf(__uint_as_float(r0[4 * i + 2]), __uint_as_float(r0[4 * i + 3])));
+          t1[i] = fmaxf(fmaxf(__uint_as_float(r1[4 * i]), __uint_as_float(r1[4 * i + 1])),
+                        fmaxf(__uint_as_float(r1[4 * i + 2]), __uint_as_float(r1[4 * i + 3])));
+        }
+        const float cm0 = fmaxf(fmaxf(fmaxf(t0[0], t0[1]), fmaxf(t0[2], t0[3])), fmaxf(fmaxf(t0[4], t0[5]), fmaxf(t0[6], t0[7])));
+        const float cm1 = fmaxf(fmaxf(fmaxf(t1[0], t1[1]), fmaxf(t1[2], t1[3])), fmaxf(fmaxf(t1[4], t1[5]), fmaxf(t1[6], t1[7])));
+        M = fmaxf(M, fmaxf(cm0, cm1));
+        const float thr = M - margin;
+        // candidate masks: four independent partial masks per chunk
+        uint32_t m0[4] = {0, 0, 0, 0}, m1[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int jj = 0; jj < 32; jj++) {
+          if (__uint_as_float(r0[jj]) >= thr) m0[jj & 3] |= (1u << jj);
+          if (__uint_as_float(r1[jj]) >= thr) m1[jj & 3] |= (1u << jj);
+        }
+        const uint32_t mask0 = (m0[0] | m0[1]) | (m0[2] | m0[3]);
+        const uint32_t mask1 = (m1[0] | m1[1]) | (m1[2] | m1[3]);
+        if (mask0) {
+          if (cnt < LIST_LEN) {
+            list_cm[cnt * 256 + slot] = cm0;
+            list_mask[cnt * 256 + slot] = mask0;
+            list_g[cnt * 256 + slot] = static_cast<uint16_t>(n * 4 + h * 2);
+            cnt++;
           } else {
-            const uint32_t base = atomicAdd(&p.counters[CNT_PAIRS], total);
-            if (base + total <= p.max_pairs) {
-              for (uint32_t i = 0; i < total; i++) {
-                p.pair_row[base + i] = static_cast<uint32_t>(grow);
-                p.pair_cand[base + i] = cand[i];
+            flags |= 2u;
+          }
+        }
+        if (mask1) {
+          if (cnt < LIST_LEN) {
+            list_cm[cnt * 256 + slot] = cm1;
+            list_mask[cnt * 256 + slot] = mask1;
+            list_g[cnt * 256 + slot] = static_cast<uint16_t>(n * 4 + h * 2 + 1);
+            cnt++;
+          } else {
+            flags |= 2u;
+          }
+        }
+      }
+      // publish this half-row's state; the emitter warps merge the halves and write the results
+      fin[slot] = M;
+      reinterpret_cast<uint32_t*>(fin)[256 + slot] = cnt;
+      reinterpret_cast<uint32_t*>(fin)[512 + slot] = flags;
+      fin[768 + slot] = margin;
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&bars[BAR_EMIT_FULL + par]);
+    }
+  } else if (warp >= FIRST_EMIT_WARP) {
+    // ================================ emitters: merge column halves, write results / queues ================================
+    const int row = (warp - FIRST_EMIT_WARP) * 32 + lane;
+    uint32_t ti = 0;
+    for (uint32_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ti++) {
+      const int par = ti & 1;
+      const float* list_cm = reinterpret_cast<const float*>(smem + L.list_cm) + par * LIST_LEN * 256;
+      const uint32_t* list_mask = reinterpret_cast<const uint32_t*>(smem + L.list_mask) + par * LIST_LEN * 256;
+      const uint16_t* list_g = reinterpret_cast<const uint16_t*>(smem + L.list_g) + par * LIST_LEN * 256;
+      const float* fin = reinterpret_cast<const float*>(smem + L.fin) + par * 4 * 256;
+      const uint32_t* finu = reinterpret_cast<const uint32_t*>(fin);
+      TC_WAIT(BAR_EMIT_FULL + par, (ti >> 1) & 1, 12);
+      const uint64_t grow = static_cast<uint64_t>(tile) * TM + row;
+      uint32_t cand[MAX_CAND];
+      uint32_t total = 0, fl = 0;
+      const bool live = grow < p.n;
+      if (live) {
+        const float Mf = fmaxf(fin[row], fin[TM + row]);
+        const float thr = Mf - fin[768 + row];
+        fl = finu[512 + row] | finu[512 + TM + row];
+        for (int hh = 0; hh < 2; hh++) {
+          const int sl = hh * TM + row;
+          const uint32_t c2 = finu[256 + sl];
+          for (uint32_t i = 0; i < c2; i++) {
+            if (!(list_cm[i * 256 + sl] >= thr)) continue;
+            uint32_t m = list_mask[i * 256 + sl];
+            const uint32_t g = list_g[i * 256 + sl];
+            while (m) {
+              const int b = __ffs(m) - 1;
+              m &= m - 1;
+              const uint32_t col = g * 32 + b;
+              if (col < p.K) {
+                if (total < MAX_CAND) cand[total] = col;
+                total++;
               }
-              const uint32_t rq = atomicAdd(&p.counters[CNT_ROWQ], 1u);
-              p.rowq[3 * rq] = static_cast<uint32_t>(grow);
-              p.rowq[3 * rq + 1] = base;
-              p.rowq[3 * rq + 2] = total;
-            } else {
-              p.ovf_rows[atomicAdd(&p.counters[CNT_OVF], 1u)] = static_cast<uint32_t>(grow);
             }
           }
         }
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      // the lists of this parity are consumed: the epilogue may start tile ti+2
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&bars[BAR_EMIT_EMPTY + par]);
+      const bool overflow = live && (fl || total > MAX_CAND);
+      const bool multi = live && !overflow && total >= 2;
+      // warp-aggregated queue reservation: one atomic per warp for the pairs, one for the row queue
+      uint32_t want = multi ? total : 0, pre = want;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        uint32_t v = __shfl_up_sync(0xffffffffu, pre, o);
+        if (lane >= o) pre += v;
+      }
+      const uint32_t warp_total = __shfl_sync(0xffffffffu, pre, 31);
+      const unsigned mmask = __ballot_sync(0xffffffffu, multi);
+      uint32_t base = 0, rqbase = 0;
+      if (lane == 0 && warp_total) {
+        base = atomicAdd(&p.counters[CNT_PAIRS], warp_total);
+        rqbase = atomicAdd(&p.counters[CNT_ROWQ], static_cast<uint32_t>(__popc(mmask)));
+      }
+      base = __shfl_sync(0xffffffffu, base, 0) + (pre - want);
+      rqbase = __shfl_sync(0xffffffffu, rqbase, 0) + __popc(mmask & ((1u << lane) - 1));
+      if (live) {
+        if (overflow) {
+          p.ovf_rows[atomicAdd(&p.counters[CNT_OVF], 1u)] = static_cast<uint32_t>(grow);
+        } else if (total == 1) {
+          p.result[grow] = cand[0];
+        } else if (total == 0) {
+          p.result[grow] = kUntouched;  // every score NaN: nothing wins (reference kmeans.cu:349-353)
+        } else if (base + total <= p.max_pairs) {
+          for (uint32_t i = 0; i < total; i++) {
+            p.pair_row[base + i] = static_cast<uint32_t>(grow);
+            p.pair_cand[base + i] = cand[i];
+          }
+          p.rowq[3 * rqbase] = static_cast<uint32_t>(grow);
+          p.rowq[3 * rqbase + 1] = base;
+          p.rowq[3 * rqbase + 2] = total;
+        } else {
+          // queue full: the row goes to the full exact pass; its reserved row-queue slot is neutralised
+          p.rowq[3 * rqbase] = static_cast<uint32_t>(grow);
+          p.rowq[3 * rqbase + 1] = 0;
+          p.rowq[3 * rqbase + 2] = 0;
+          p.ovf_rows[atomicAdd(&p.counters[CNT_OVF], 1u)] = static_cast<uint32_t>(grow);
+        }
+      }
     }
   }
   // teardown
@@ -597,6 +668,7 @@ __global__ void recheck_reduce_kernel(const uint32_t* __restrict__ rowq, const u
   const uint32_t nq = *d_nrowq;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nq; i += gridDim.x * blockDim.x) {
     const uint32_t row = rowq[3 * i], base = rowq[3 * i + 1], cnt = rowq[3 * i + 2];
+    if (cnt == 0) continue;  // neutralised slot (pair queue was full; the row is on the overflow list)
     float best = FLT_MAX;
     uint32_t arg = UINT32_MAX;
     for (uint32_t j = 0; j < cnt; j++) {
