@@ -47,9 +47,10 @@ constexpr int TN = 128;                 // centroids per n-tile (UMMA N)
 constexpr int KB = 64;                  // fp16 elements per K-block = one 128-byte swizzle row of B
 constexpr int MAX_NKB = 4;              // D <= 256 (A buffer = 32 TMEM columns per K-block)
 constexpr int X_STAGES = 4;             // fp32 sample stages: 32 features x 128 rows = 16 KiB
-constexpr int B_STAGES = 4;             // fp16 centroid stages: 64 features x 128 rows = 16 KiB
+constexpr int B_STAGES = 2;             // fp16 centroid stages: up to 2 K-blocks (128 features) x 128 rows = 32 KiB
 constexpr int X_STAGE_BYTES = TM * 128;
-constexpr int B_STAGE_BYTES = TN * 128;
+constexpr int B_KB_BYTES = TN * 128;     // one K-block of the centroid tile: 16 KiB
+constexpr int B_STAGE_BYTES = 2 * B_KB_BYTES;
 constexpr int AUG_A_BYTES = TM * 32;    // 4 KiB  (K=16 fp16, no swizzle)
 constexpr int AUG_B_BYTES = TN * 32;    // 4 KiB
 constexpr int LIST_LEN = 12;            // chunk entries per epilogue thread
@@ -225,6 +226,7 @@ __device__ __forceinline__ void note_timeout(uint32_t* counters, int where) {
 #define TC_WAIT(bar, parity, site) \
   do { if (!ptx::mbar_wait(&bars[bar], (parity), p.counters + CNT_ERR)) note_timeout(p.counters, site); } while (0)
 
+template <int NKB>   // K-blocks of 64 features (compile-time: the MMA issue loop must be branch- and address-arithmetic-free)
 __global__ void __launch_bounds__(N_THREADS, 1)
 tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_x,
                  const Params p) {
@@ -234,7 +236,9 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L.tmem_slot);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nkb = p.nkb, nt = p.nt;
+  constexpr int nkb = NKB;
+  constexpr int SPN = (NKB + 1) / 2;   // B stages per n-tile
+  const int nt = p.nt;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmap_b);
@@ -279,12 +283,16 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
       uint32_t pc = 0, ac = 0;
       for (uint32_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
         for (int n = 0; n < nt; n++) {
-          for (int kb = 0; kb < nkb; kb++, pc++) {
+#pragma unroll
+          for (int st = 0; st < SPN; st++, pc++) {
             const int s = pc % B_STAGES;
             const uint32_t ph = (pc / B_STAGES) & 1;
+            const int nk = (2 * st + 1 < NKB) ? 2 : 1;   // K-blocks in this stage
             TC_WAIT(BAR_B_EMPTY + s, ph ^ 1, 1);
-            ptx::mbar_arrive_expect_tx(&bars[BAR_B_FULL + s], B_STAGE_BYTES);
-            ptx::tma_load_2d(smem + L.b + s * B_STAGE_BYTES, &tmap_b, kb * KB, n * TN, &bars[BAR_B_FULL + s]);
+            ptx::mbar_arrive_expect_tx(&bars[BAR_B_FULL + s], nk * B_KB_BYTES);
+            for (int k2 = 0; k2 < nk; k2++)
+              ptx::tma_load_2d(smem + L.b + s * B_STAGE_BYTES + k2 * B_KB_BYTES, &tmap_b, (2 * st + k2) * KB, n * TN,
+                               &bars[BAR_B_FULL + s]);
           }
           const int as = ac & 1;
           const uint32_t aph = (ac >> 1) & 1;
@@ -330,19 +338,31 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
         const uint32_t aph = (ac >> 1) & 1;
         TC_WAIT(BAR_ACC_EMPTY + buf, aph ^ 1, 3);
         const uint32_t d_tmem = tmem_base + TMEM_ACC0 + buf * TN;
-        for (int kb = 0; kb < nkb; kb++, pc++) {
+#pragma unroll
+        for (int st = 0; st < SPN; st++, pc++) {
           const int s = pc % B_STAGES;
           const uint32_t ph = (pc / B_STAGES) & 1;
-          if (n == 0) TC_WAIT(BAR_A_FULL + abuf * MAX_NKB + kb, a_par, 4);
+          const int nk = (2 * st + 1 < NKB) ? 2 : 1;
+          if (n == 0) {
+            TC_WAIT(BAR_A_FULL + abuf * MAX_NKB + 2 * st, a_par, 4);
+            if (nk == 2) TC_WAIT(BAR_A_FULL + abuf * MAX_NKB + 2 * st + 1, a_par, 4);
+          }
           TC_WAIT(BAR_B_FULL + s, ph, 5);
           ptx::tc_fence_after();
           if (ptx::elect_one()) {
             const uint64_t bd0 = ptx::make_smem_desc(b_base + s * B_STAGE_BYTES, 16, 1024, 2);
-            const uint32_t at = a_tmem + kb * 32;
-            ptx::umma_f16_ts(d_tmem, at, bd0, idesc, kb ? 1u : 0u);
+            const uint32_t at = a_tmem + st * 64;
+            ptx::umma_f16_ts(d_tmem, at, bd0, idesc, st ? 1u : 0u);
             ptx::umma_f16_ts(d_tmem, at + 8, bd0 + 2, idesc, 1u);     // +32 bytes along K = +2 in the address field
             ptx::umma_f16_ts(d_tmem, at + 16, bd0 + 4, idesc, 1u);
             ptx::umma_f16_ts(d_tmem, at + 24, bd0 + 6, idesc, 1u);
+            if (nk == 2) {
+              const uint64_t bd1 = bd0 + (B_KB_BYTES >> 4);
+              ptx::umma_f16_ts(d_tmem, at + 32, bd1, idesc, 1u);
+              ptx::umma_f16_ts(d_tmem, at + 40, bd1 + 2, idesc, 1u);
+              ptx::umma_f16_ts(d_tmem, at + 48, bd1 + 4, idesc, 1u);
+              ptx::umma_f16_ts(d_tmem, at + 56, bd1 + 6, idesc, 1u);
+            }
             ptx::umma_commit(&bars[BAR_B_EMPTY + s]);
           }
           __syncwarp();
@@ -800,8 +820,10 @@ cudaError_t tc_plan_create(TcPlan** out, int metric, uint32_t max_n, int D, uint
     TC_TRY(cudaEventCreate(&p->ev1[i]));
   }
   p->smem_bytes = smem_layout().total + 1024;
-  TC_TRY(cudaFuncSetAttribute(tc_assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              static_cast<int>(p->smem_bytes)));
+  TC_TRY(cudaFuncSetAttribute(tc_assign_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(p->smem_bytes)));
+  TC_TRY(cudaFuncSetAttribute(tc_assign_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(p->smem_bytes)));
+  TC_TRY(cudaFuncSetAttribute(tc_assign_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(p->smem_bytes)));
+  TC_TRY(cudaFuncSetAttribute(tc_assign_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(p->smem_bytes)));
 #undef TC_TRY
   *out = p;
   return cudaSuccess;
@@ -855,7 +877,12 @@ cudaError_t tc_assign(TcPlan* p, const float* X, const float* C, const float* cs
   const unsigned grid = min(static_cast<uint32_t>(p->num_sms), prm.ntiles);
   const int slot = static_cast<int>(p->passes % TcPlan::kEvRing);
   cudaEventRecord(p->ev0[slot], st);
-  tc_assign_kernel<<<grid, N_THREADS, p->smem_bytes, st>>>(p->tmap, tmap_x, prm);
+  switch (p->nkb) {
+    case 1: tc_assign_kernel<1><<<grid, N_THREADS, p->smem_bytes, st>>>(p->tmap, tmap_x, prm); break;
+    case 2: tc_assign_kernel<2><<<grid, N_THREADS, p->smem_bytes, st>>>(p->tmap, tmap_x, prm); break;
+    case 3: tc_assign_kernel<3><<<grid, N_THREADS, p->smem_bytes, st>>>(p->tmap, tmap_x, prm); break;
+    default: tc_assign_kernel<4><<<grid, N_THREADS, p->smem_bytes, st>>>(p->tmap, tmap_x, prm); break;
+  }
   cudaEventRecord(p->ev1[slot], st);
   p->passes++;
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
