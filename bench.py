@@ -31,6 +31,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout to the single JSON line (some hosts export NCCL_DEBUG=VERSION)
 
 METRIC = "kmeans_assign_points_per_sec"
 UNIT = "points/s"
@@ -111,6 +112,7 @@ def measured_peaks():
 def cpu_baseline(sample_points=65536):
     """the C oracle port (oracle/kmcuda_oracle.c, OpenMP) on a bounded sample of the same workload"""
     from oracle import oracle as O
+    cores = O.set_threads(os.cpu_count() or 1)   # torchrun exports OMP_NUM_THREADS=1
     rng = np.random.default_rng(777)
     X = rng.random((sample_points, D), dtype=np.float32)
     C = rng.random((K, D), dtype=np.float32)
@@ -118,16 +120,19 @@ def cpu_baseline(sample_points=65536):
     t = time.perf_counter()
     O.assign_lloyd(X, C)
     dt = time.perf_counter() - t
-    out = {"value": sample_points / dt, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+    out = {"value": sample_points / dt, "unit": UNIT, "cores": cores, "kind": "port",
            "sample": "%d points of the same %d-feature x %d-cluster workload, one pass, %.1f s" %
                      (sample_points, D, K, dt)}
     try:  # north_star's named CPU reference: sklearn KMeans labelling on the host cores
         from sklearn.cluster import KMeans
         km = KMeans(n_clusters=K, init=C, n_init=1, max_iter=1, algorithm="lloyd", tol=0).fit(X[:4096])
         km.cluster_centers_ = C.astype(km.cluster_centers_.dtype)
-        t = time.perf_counter()
-        km.predict(X)
-        dt2 = time.perf_counter() - t
+        from threadpoolctl import threadpool_limits
+        with threadpool_limits(limits=os.cpu_count()):
+            km.predict(X[:4096])
+            t = time.perf_counter()
+            km.predict(X)
+            dt2 = time.perf_counter() - t
         out["sklearn_predict"] = {"value": sample_points / dt2, "unit": UNIT, "cores": os.cpu_count(),
                                   "sample": "%d points, KMeans.predict" % sample_points}
     except Exception as e:  # pragma: no cover
@@ -305,7 +310,8 @@ def run_ours(args):
             "clocks": clocks,
         }
         line["cpu_baseline"] = cpu_baseline()
-        print(json.dumps(line))
+        sys.stdout.flush()
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -27,6 +27,21 @@
 #include <string.h>
 #include <stdio.h>
 
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* launchers such as torchrun export OMP_NUM_THREADS=1; the timing legs set the thread count explicitly */
+int ko_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+  return omp_get_max_threads();
+#else
+  (void)n;
+  return 1;
+#endif
+}
+
 #define KO_L2 0
 #define KO_COS 1
 

@@ -36,6 +36,8 @@ def lib():
     if _lib is None:
         build()
         L = ctypes.CDLL(LIB_PATH)
+        L.ko_set_threads.restype = ctypes.c_int
+        L.ko_set_threads.argtypes = [ctypes.c_int]
         L.ko_fma_rd.restype = ctypes.c_float
         L.ko_fma_rd.argtypes = [ctypes.c_float] * 3
         L.ko_fma_rd_fenv.restype = ctypes.c_float
@@ -63,6 +65,11 @@ def lib():
                              ctypes.c_uint32, _u32p, _u32p, ctypes.c_uint32, _u32p, _f64p]
         _lib = L
     return _lib
+
+
+def set_threads(n):
+    """OpenMP threads used by the oracle (returns the effective count)"""
+    return int(lib().ko_set_threads(int(n)))
 
 
 def _f(a):

@@ -99,3 +99,28 @@ def test_no_cpu_fallback_in_product_package():
             if f.endswith((".py", ".cu", ".cc", ".h", ".cuh")):
                 txt = open(os.path.join(root, f)).read()
                 assert "oracle" not in txt.replace("no oracle", ""), os.path.join(root, f)
+
+
+def test_libKMCUDA_module_imports_from_the_same_shared_object():
+    """reference src/python.cc:33-54: the .so is itself the Python module `libKMCUDA`"""
+    import importlib.util
+    import kmcuda_b200 as km
+    spec = importlib.util.spec_from_file_location("libKMCUDA", km.LIB_PATH)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert mod.supports_fp16 is True
+    arr = np.random.rand(100, 2).astype(np.float32)
+    with pytest.raises(TypeError):
+        mod.kmeans_cuda(arr, 5, metric=3)
+    with pytest.raises(ValueError):
+        mod.kmeans_cuda(arr, 1)
+    with pytest.raises(ValueError):
+        mod.kmeans_cuda(arr, 5, init="bogus")
+    with pytest.raises(ValueError):
+        mod.kmeans_cuda(arr, 5, init=np.zeros((4, 2), np.float32))
+    with pytest.raises(ValueError):
+        mod.knn_cuda(0, arr, np.zeros((5, 2), np.float32), np.zeros(100, np.uint32))
+    import torch
+    if not torch.cuda.is_available():
+        with pytest.raises(ValueError, match="No such CUDA device"):
+            mod.kmeans_cuda(arr, 5)
