@@ -36,119 +36,143 @@ cudaError_t launch_csqr(int metric, const float* C, uint32_t K, int D, float* cs
 // ------------------------------------------------------------------------------------------------
 // Exact pass over ALL K centroids.  MODE 0: Lloyd argmin (reference kmeans.cu:293-364).
 // MODE 1: Yinyang bounds refresh (reference kmeans.cu:431-485).
-// One thread per sample, 4 independent Kahan chains (4 centroids) in flight per thread.
+// A CTA owns RB sample rows (staged once in padded shared memory) and TPR threads per row; thread
+// part t of a row scans the centroid quads {t, t+TPR, ...} in ascending order with 4 independent Kahan
+// chains in flight, so a row's K*D dependent operations are spread over TPR threads and the SM holds
+// up to 32 warps.  Parts are merged towards the lowest index on equal scores == the reference's
+// ascending strict-'<' scan.  Warps are (same part, 32 consecutive rows): centroid loads are
+// warp-uniform broadcasts, sample reads are conflict-free.
 // ------------------------------------------------------------------------------------------------
 template <int METRIC, int MODE>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(1024)
 exact_pass_kernel(const float* __restrict__ X, const float* __restrict__ C,
                   const float* __restrict__ csq, uint32_t n, int D, uint32_t K,
                   const uint32_t* __restrict__ rows, const uint32_t* __restrict__ d_nrows,
-                  uint32_t* __restrict__ result, int use_smem,
+                  uint32_t* __restrict__ result, int use_smem, int RB,
                   // MODE 1 only
                   uint32_t G, const uint32_t* __restrict__ assign,
                   const uint32_t* __restrict__ groups, float* __restrict__ bounds) {
   extern __shared__ float sX[];
-  const int BS = blockDim.x;
+  const int TPR = blockDim.x / RB;
+  const int r = threadIdx.x % RB, t = threadIdx.x / RB;
+  float* s_best = sX + (use_smem ? static_cast<size_t>(RB + 1) * D : 0);   // [TPR][RB]
+  uint32_t* s_arg = reinterpret_cast<uint32_t*>(s_best + static_cast<size_t>(TPR) * RB);
   const uint32_t nrows = d_nrows ? *d_nrows : n;
   if (MODE == 0 && d_nrows && nrows <= kFewRows) return;  // exact_rows_few_kernel handles short lists
-  for (uint32_t tile0 = blockIdx.x * BS; tile0 < nrows; tile0 += gridDim.x * BS) {
-    const uint32_t slot = tile0 + threadIdx.x;
+  for (uint32_t tile0 = blockIdx.x * RB; tile0 < nrows; tile0 += gridDim.x * RB) {
+    const uint32_t slot = tile0 + r;
     const bool active = slot < nrows;
     const uint32_t row = active ? (rows ? rows[slot] : slot) : 0;
     const float* xs;
     int xstride;
+    __syncthreads();
     if (use_smem) {
-      __syncthreads();
-      const int cnt = min(static_cast<uint32_t>(BS), nrows - tile0);
-      for (int e = threadIdx.x; e < cnt * D; e += BS) {
+      const int cnt = min(static_cast<uint32_t>(RB), nrows - tile0);
+      for (int e = threadIdx.x; e < cnt * D; e += blockDim.x) {
         int s = e / D, f = e - s * D;
-        uint32_t r = rows ? rows[tile0 + s] : tile0 + s;
-        sX[f * (BS + 1) + s] = X[static_cast<size_t>(r) * D + f];
+        uint32_t rr = rows ? rows[tile0 + s] : tile0 + s;
+        sX[f * (RB + 1) + s] = X[static_cast<size_t>(rr) * D + f];
       }
-      __syncthreads();
-      xs = sX + threadIdx.x;
-      xstride = BS + 1;
+      xs = sX + r;
+      xstride = RB + 1;
     } else {
       xs = X + static_cast<size_t>(row) * D;
       xstride = 1;
     }
-    if (!active) continue;
-    if (MODE == 0) {
-      float x0 = xs[0];
-      if (x0 != x0) {  // "insane" sample: first feature NaN (kmeans.cu:312,355)
-        result[row] = K;
-        continue;
-      }
+    uint32_t mine = 0;
+    if (MODE == 1 && active) {
+      mine = assign[row];
+      if (t == 0)
+        for (uint32_t g = 0; g <= G; g++) bounds[static_cast<size_t>(n) * g + row] = FLT_MAX;
     }
+    __syncthreads();
     float best = FLT_MAX;
     uint32_t arg = UINT32_MAX;
-    uint32_t mine = 0;
-    if (MODE == 1) {
-      mine = assign[row];
-      for (uint32_t g = 0; g <= G; g++) bounds[static_cast<size_t>(n) * g + row] = FLT_MAX;
-    }
-    for (uint32_t c0 = 0; c0 < K; c0 += 4) {
-      const float* cp[4];
+    const bool insane = MODE == 0 && active && (xs[0] != xs[0]);  // first feature NaN (kmeans.cu:312,355)
+    if (active && !insane) {
+      for (uint32_t c0 = 4u * t; c0 < K; c0 += 4u * TPR) {
+        const float* cp[4];
 #pragma unroll
-      for (int j = 0; j < 4; j++) cp[j] = C + static_cast<size_t>(min(c0 + j, K - 1)) * D;
-      Kahan k[4];
-      for (int f = 0; f < D; f++) {
-        float x = xs[f * xstride];
+        for (int j = 0; j < 4; j++) cp[j] = C + static_cast<size_t>(min(c0 + j, K - 1)) * D;
+        Kahan k[4];
+        for (int f = 0; f < D; f++) {
+          float x = xs[f * xstride];
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            float cv = __ldg(cp[j] + f);
+            if (MODE == 1 && METRIC == 0) k[j].sqdiff(x, cv);
+            else k[j].mac(x, cv);
+          }
+        }
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-          float cv = __ldg(cp[j] + f);
-          if (MODE == 1 && METRIC == 0) k[j].sqdiff(x, cv);
-          else k[j].mac(x, cv);
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < 4; j++) {
-        uint32_t c = c0 + j;
-        if (c >= K) break;
-        if (MODE == 0) {
-          float score = lloyd_score<METRIC>(k[j].sum, csq[c]);
-          if (score < best) {
-            best = score;
-            arg = c;
-          }
-        } else {
-          uint32_t g = groups[c];
-          if (g >= G) continue;  // NaN centroid (kmeans.cu:464-468)
-          float dist = finalize_distance<METRIC>(k[j].sum);
-          if (c != mine) {
-            size_t gi = static_cast<size_t>(n) * (1 + g) + row;
-            if (dist < bounds[gi]) bounds[gi] = dist;
+          uint32_t c = c0 + j;
+          if (c >= K) break;
+          if (MODE == 0) {
+            float score = lloyd_score<METRIC>(k[j].sum, csq[c]);
+            if (score < best) {
+              best = score;
+              arg = c;
+            }
           } else {
-            bounds[row] = dist;
+            uint32_t g = groups[c];
+            if (g >= G) continue;  // NaN centroid (kmeans.cu:464-468)
+            float dist = finalize_distance<METRIC>(k[j].sum);
+            if (c != mine) {
+              // distances are >= +0: their bit patterns order like unsigned integers; NaN never lowers a bound
+              atomicMin(reinterpret_cast<uint32_t*>(bounds + static_cast<size_t>(n) * (1 + g) + row),
+                        __float_as_uint(dist));
+            } else {
+              bounds[row] = dist;
+            }
           }
         }
       }
     }
-    if (MODE == 0) result[row] = (arg == UINT32_MAX) ? kUntouched : arg;
+    if (MODE == 0) {
+      s_best[t * RB + r] = best;
+      s_arg[t * RB + r] = arg;
+      __syncthreads();
+      if (t == 0 && active) {
+        if (insane) {
+          result[row] = K;
+        } else {
+          for (int tt = 1; tt < TPR; tt++) {
+            float b2 = s_best[tt * RB + r];
+            uint32_t a2 = s_arg[tt * RB + r];
+            if (a2 != UINT32_MAX && (arg == UINT32_MAX || b2 < best || (b2 == best && a2 < arg))) {
+              best = b2;
+              arg = a2;
+            }
+          }
+          result[row] = (arg == UINT32_MAX) ? kUntouched : arg;
+        }
+      }
+    }
   }
 }
 
 // Row-list variant for FEW rows (the tensor-core filter's overflow list is normally a handful of rows
-// out of millions): one CTA per row, the K centroids spread over the 128 threads, so a single row does
+// out of millions): one CTA per row, the K centroids spread over the 512 threads, so a single row does
 // not serialise K*D dependent operations on one thread.  Each thread scans its centroids in ascending
 // order with strict '<'; the block reduction breaks equal scores towards the lowest index, which is
 // exactly the reference's ascending strict-'<' scan (kmeans.cu:343-346).
 
 template <int METRIC>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(512)
 exact_rows_few_kernel(const float* __restrict__ X, const float* __restrict__ C,
                       const float* __restrict__ csq, int D, uint32_t K,
                       const uint32_t* __restrict__ rows, const uint32_t* __restrict__ d_nrows,
                       uint32_t* __restrict__ result) {
   extern __shared__ float sx[];
-  __shared__ float s_best[128];
-  __shared__ uint32_t s_arg[128];
+  __shared__ float s_best[512];
+  __shared__ uint32_t s_arg[512];
   const uint32_t nrows = *d_nrows;
   if (nrows > kFewRows) return;  // the tiled kernel takes over
   for (uint32_t e = blockIdx.x; e < nrows; e += gridDim.x) {
     const uint32_t row = rows[e];
     __syncthreads();
-    for (int f = threadIdx.x; f < D; f += 128) sx[f] = X[static_cast<size_t>(row) * D + f];
+    for (int f = threadIdx.x; f < D; f += 512) sx[f] = X[static_cast<size_t>(row) * D + f];
     __syncthreads();
     if (sx[0] != sx[0]) {
       if (threadIdx.x == 0) result[row] = K;
@@ -156,7 +180,7 @@ exact_rows_few_kernel(const float* __restrict__ X, const float* __restrict__ C,
     }
     float best = FLT_MAX;
     uint32_t arg = UINT32_MAX;
-    for (uint32_t c = threadIdx.x; c < K; c += 128) {
+    for (uint32_t c = threadIdx.x; c < K; c += 512) {
       const float* cp = C + static_cast<size_t>(c) * D;
       Kahan k;
       for (int f = 0; f < D; f++) k.mac(sx[f], __ldg(cp + f));
@@ -169,7 +193,7 @@ exact_rows_few_kernel(const float* __restrict__ X, const float* __restrict__ C,
     s_best[threadIdx.x] = best;
     s_arg[threadIdx.x] = arg;
     __syncthreads();
-    for (int o = 64; o > 0; o >>= 1) {
+    for (int o = 256; o > 0; o >>= 1) {
       if (threadIdx.x < o) {
         float b2 = s_best[threadIdx.x + o];
         uint32_t a2 = s_arg[threadIdx.x + o];
@@ -186,16 +210,17 @@ exact_rows_few_kernel(const float* __restrict__ X, const float* __restrict__ C,
 }
 
 struct ExactCfg {
-  int bs, use_smem;
+  int rb, tpr, use_smem;
   size_t smem;
 };
 static ExactCfg exact_cfg(int D) {
   const size_t limit = 200 * 1024;
-  for (int bs : {128, 64, 32}) {
-    size_t need = static_cast<size_t>(bs + 1) * D * sizeof(float);
-    if (need <= limit) return {bs, 1, need};
+  for (int rb : {128, 64, 32}) {
+    int tpr = 1024 / rb > 8 ? 8 : 1024 / rb;
+    size_t need = static_cast<size_t>(rb + 1) * D * sizeof(float) + static_cast<size_t>(tpr) * rb * 8;
+    if (need <= limit) return {rb, tpr, 1, need};
   }
-  return {128, 0, 0};
+  return {128, 8, 0, static_cast<size_t>(8) * 128 * 8};
 }
 
 template <int METRIC, int MODE>
@@ -209,10 +234,10 @@ static cudaError_t launch_exact_pass(const float* X, const float* C, const float
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(cfg.smem));
   if (e != cudaSuccess) return e;
-  unsigned grid = d_nrows ? 148 * 4 : cdiv(n, cfg.bs);
+  unsigned grid = d_nrows ? 148 * 2 : cdiv(n, cfg.rb);
   if (grid == 0) return cudaSuccess;
-  kern<<<grid, cfg.bs, cfg.smem, st>>>(X, C, csq, n, D, K, rows, d_nrows, result, cfg.use_smem, G,
-                                       assign, groups, bounds);
+  kern<<<grid, cfg.rb * cfg.tpr, cfg.smem, st>>>(X, C, csq, n, D, K, rows, d_nrows, result, cfg.use_smem, cfg.rb, G,
+                                                 assign, groups, bounds);
   return cudaGetLastError();
 }
 
@@ -221,8 +246,8 @@ cudaError_t launch_assign_exact(int metric, const float* X, const float* C, cons
                                 const uint32_t* d_nrows, uint32_t* result, cudaStream_t st) {
   if (d_nrows) {  // list mode: short lists go to the one-CTA-per-row kernel (decided on the device)
     const size_t smem = sizeof(float) * D;
-    if (metric == 1) exact_rows_few_kernel<1><<<148 * 4, 128, smem, st>>>(X, C, csq, D, K, rows, d_nrows, result);
-    else exact_rows_few_kernel<0><<<148 * 4, 128, smem, st>>>(X, C, csq, D, K, rows, d_nrows, result);
+    if (metric == 1) exact_rows_few_kernel<1><<<148 * 4, 512, smem, st>>>(X, C, csq, D, K, rows, d_nrows, result);
+    else exact_rows_few_kernel<0><<<148 * 4, 512, smem, st>>>(X, C, csq, D, K, rows, d_nrows, result);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
   }
