@@ -45,7 +45,7 @@ namespace tc {
 constexpr int TM = 128;                 // samples per tile (UMMA M)
 constexpr int TN = 128;                 // centroids per n-tile (UMMA N)
 constexpr int KB = 64;                  // fp16 elements per K-block = one 128-byte swizzle row of B
-constexpr int MAX_NKB = 4;              // D <= 256 (A buffer = 32 TMEM columns per K-block)
+constexpr int MAX_NKB = 8;              // D <= 512: A needs 32 TMEM columns per K-block; double-buffered up to 4 K-blocks
 constexpr int X_STAGES = 4;             // fp32 sample stages: 32 features x 128 rows = 16 KiB
 constexpr int B_STAGES = 2;             // fp16 centroid stages: up to 2 K-blocks (128 features) x 128 rows = 32 KiB
 constexpr int X_STAGE_BYTES = TM * 128;
@@ -74,6 +74,7 @@ struct Stats {       // written by the centroid prep kernels, read by the main k
   float cmax;        // max_c ||s*c||  (finite centroids)
   float dcmax;       // max_c ||s*c - fp16(s*c)||
   uint32_t csq_max_bits;
+  uint32_t force_exact; // cosine only: a centroid with an infinite element / norm can still win -> no filtering
 };
 
 struct SmemLayout {  // byte offsets from the 1024-aligned dynamic smem base
@@ -90,7 +91,7 @@ __host__ __device__ inline SmemLayout smem_layout() {
   L.list_cm = o; o += 2 * LIST_LEN * 256 * 4;    // [tile parity][entry][epilogue thread]
   L.list_mask = o; o += 2 * LIST_LEN * 256 * 4;
   L.list_g = o; o += 2 * LIST_LEN * 256 * 2;
-  L.norms = o; o += 2 * 2 * TM * 4;   // [parity][x|d][row]
+  L.norms = o; o += 4 * 2 * TM * 4;   // [tile % 4][x|d][row]  (4 deep: the converters run up to 2 tiles ahead of the epilogue)
   L.fin = o; o += 2 * 4 * 256 * 4;    // [tile parity][M|cnt|flags|margin][epilogue thread]
   L.bars = o; o += 64 * 8;
   L.tmem_slot = o; o += 16;
@@ -132,6 +133,7 @@ struct Params {
   uint32_t* rowq;            // [3*i]: row, first pair, pair count
   uint32_t* ovf_rows;        // rows for the full exact pass
   uint32_t* counters;        // CNT_*
+  int metric;                // 0 = L2 (score x.c - ||c||^2/2), 1 = cosine (score x.c; larger dot = smaller angle)
   float* dbg_scores;         // optional [ntiles*128][nt*128] dump of the approximate scores
 };
 
@@ -149,6 +151,20 @@ __global__ void tc_prep_stats_kernel(const float* __restrict__ csq, uint32_t K, 
   if ((threadIdx.x & 31) == 0) atomicMax(&st->csq_max_bits, best);
 }
 
+// cosine: upper bound of ||c||^2 per centroid (one warp per row)
+__global__ void tc_prep_norms_kernel(const float* __restrict__ C, uint32_t K, int D, float* __restrict__ out) {
+  const uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= K) return;
+  float a = 0.f;
+  for (int f = lane; f < D; f += 32) {
+    float v = C[static_cast<size_t>(row) * D + f];
+    a = fmaf(v, v, a);
+  }
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  if (lane == 0) out[row] = a * 1.0001f;
+}
+
 __global__ void tc_prep_scale_kernel(Stats* __restrict__ st) {
   float cmax = __fsqrt_ru(__uint_as_float(st->csq_max_bits));
   float s = 1.f;
@@ -163,7 +179,7 @@ __global__ void tc_prep_scale_kernel(Stats* __restrict__ st) {
 }
 
 // one warp per centroid row (including the zero padding rows up to nt*256)
-__global__ void tc_prep_table_kernel(const float* __restrict__ C, const float* __restrict__ csq,
+__global__ void tc_prep_table_kernel(int metric, const float* __restrict__ C, const float* __restrict__ csq,
                                      uint32_t K, int D, int nkb, int nt, __half* __restrict__ table,
                                      __half* __restrict__ aug_blob, Stats* __restrict__ st) {
   const uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -181,6 +197,17 @@ __global__ void tc_prep_table_kernel(const float* __restrict__ C, const float* _
       if (!(fabsf(v) < 3.0e38f)) finite = false;
     }
     finite = __all_sync(0xffffffffu, finite);
+    if (metric == 1 && !finite) {
+      // a NaN centroid never wins (acos(NaN) fails every '<'), but one with +-Inf elements or an
+      // overflowing norm can: the filter has no bound for it, so the whole pass runs exact
+      bool has_nan = false;
+      for (int f = lane; f < D; f += 32) {
+        float v = C[static_cast<size_t>(row) * D + f];
+        has_nan |= (v != v);
+      }
+      has_nan = __any_sync(0xffffffffu, has_nan);
+      if (!has_nan && lane == 0) st->force_exact = 1u;
+    }
   }
   float d2 = 0.f;
   for (int f = lane; f < Dp; f += 32) {
@@ -196,7 +223,7 @@ __global__ void tc_prep_table_kernel(const float* __restrict__ C, const float* _
     // bias: three fp16 terms of -(s^2 ||c||^2 / 2); invalid / padded centroids get -65504
     __half b[3];
     if (finite) {
-      float h = -0.5f * s * s * csq[row];
+      float h = metric == 1 ? 0.f : -0.5f * s * s * csq[row];
       b[0] = __float2half_rn(h);
       float r1 = h - __half2float(b[0]);
       b[1] = __float2half_rn(r1);
@@ -226,6 +253,25 @@ __device__ __forceinline__ void note_timeout(uint32_t* counters, int where) {
 #define TC_WAIT(bar, parity, site) \
   do { if (!ptx::mbar_wait(&bars[bar], (parity), p.counters + CNT_ERR)) note_timeout(p.counters, site); } while (0)
 
+// in-place compaction of one epilogue thread's chunk list: entries whose chunk maximum fell below the
+// current threshold can never hold a candidate (the threshold only rises)
+__device__ __noinline__ uint32_t compact_list(float* list_cm, uint32_t* list_mask, uint16_t* list_g, int slot,
+                                              uint32_t cnt, float thr) {
+  uint32_t w = 0;
+  for (uint32_t i = 0; i < cnt; i++) {
+    const float cm = list_cm[i * 256 + slot];
+    if (cm >= thr) {
+      if (w != i) {
+        list_cm[w * 256 + slot] = cm;
+        list_mask[w * 256 + slot] = list_mask[i * 256 + slot];
+        list_g[w * 256 + slot] = list_g[i * 256 + slot];
+      }
+      w++;
+    }
+  }
+  return w;
+}
+
 template <int NKB>   // K-blocks of 64 features (compile-time: the MMA issue loop must be branch- and address-arithmetic-free)
 __global__ void __launch_bounds__(N_THREADS, 1)
 tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_x,
@@ -238,6 +284,7 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int nkb = NKB;
   constexpr int SPN = (NKB + 1) / 2;   // B stages per n-tile
+  constexpr int NBUF = NKB <= 4 ? 2 : 1;   // A operand buffers in TMEM (256 columns are available for A)
   const int nt = p.nt;
 
   if (warp == 0 && lane == 0) {
@@ -330,8 +377,8 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
     const uint32_t augb = ptx::smem_u32(smem + L.aug_b);
     uint32_t pc = 0, ac = 0, ti = 0;
     for (uint32_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ti++) {
-      const int abuf = ti & 1;
-      const uint32_t a_par = (ti >> 1) & 1;
+      const int abuf = ti % NBUF;
+      const uint32_t a_par = (ti / NBUF) & 1;
       const uint32_t a_tmem = tmem_base + TMEM_A0 + abuf * 128;
       for (int n = 0; n < nt; n++, ac++) {
         const int buf = ac & 1;
@@ -387,8 +434,8 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
     const float s = p.stats->scale;
     uint32_t xc = 0, ti = 0;
     for (uint32_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ti++) {
-      const int abuf = ti & 1;
-      TC_WAIT(BAR_A_FREE + abuf, ((ti >> 1) & 1) ^ 1, 7);   // MMAs of tile ti-2 no longer read this buffer
+      const int abuf = ti % NBUF;
+      TC_WAIT(BAR_A_FREE + abuf, ((ti / NBUF) & 1) ^ 1, 7);   // MMAs of the previous user of this buffer are done
       ptx::tc_fence_after();
       float nx = 0.f, nd = 0.f;
       for (int kb = 0; kb < nkb; kb++) {
@@ -419,7 +466,7 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
         ptx::tmem_st_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + TMEM_A0 + abuf * 128 + kb * 32, pk);
         ptx::tmem_st_wait();
         if (kb == nkb - 1) {
-          float* norms = reinterpret_cast<float*>(smem + L.norms) + (ti & 1) * 2 * TM;
+          float* norms = reinterpret_cast<float*>(smem + L.norms) + (ti & 3) * 2 * TM;
           norms[row] = nx;
           norms[TM + row] = nd;
         }
@@ -436,6 +483,9 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
     const int row = q * 32 + lane;
     const int slot = h * TM + row;             // 0..255
     const float cmax = p.stats->cmax, dcmax = p.stats->dcmax;
+    // cosine: every dot >= 1 is clamped to angle 0 by the reference, so all of them tie -> the threshold
+    // never rises above s^2 * 1 (the accumulator holds s^2 * dot)
+    const float cap = p.metric == 1 ? p.stats->scale * p.stats->scale : INFINITY;
     uint32_t ac = 0, ti = 0;
     for (uint32_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ti++) {
       const int par = ti & 1;
@@ -458,7 +508,7 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
         ptx::tmem_ld_32x32(taddr, r0);
         ptx::tmem_ld_32x32(taddr + 32, r1);
         if (n == 0) {
-          const float* norms = reinterpret_cast<const float*>(smem + L.norms) + (ti & 1) * 2 * TM;
+          const float* norms = reinterpret_cast<const float*>(smem + L.norms) + (ti & 3) * 2 * TM;
           // rigorous bound on |acc - (s^2 x.c - s^2||c||^2/2)| (see header): Cauchy-Schwarz on the
           // actual rounding residuals + accumulation + the reference's own rounding slack
           const float nx = __fsqrt_ru(norms[row]) * 1.0001f, nd = __fsqrt_ru(norms[TM + row]) * 1.0001f;
@@ -492,16 +542,34 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
         const float cm0 = fmaxf(fmaxf(fmaxf(t0[0], t0[1]), fmaxf(t0[2], t0[3])), fmaxf(fmaxf(t0[4], t0[5]), fmaxf(t0[6], t0[7])));
         const float cm1 = fmaxf(fmaxf(fmaxf(t1[0], t1[1]), fmaxf(t1[2], t1[3])), fmaxf(fmaxf(t1[4], t1[5]), fmaxf(t1[6], t1[7])));
         M = fmaxf(M, fmaxf(cm0, cm1));
-        const float thr = M - margin;
-        // candidate masks: four independent partial masks per chunk
-        uint32_t m0[4] = {0, 0, 0, 0}, m1[4] = {0, 0, 0, 0};
+        const float thr = fminf(M, cap) - margin;
+        // candidate masks on the (otherwise idle) FMA pipe instead of FSETP + LOP3 on the ALU pipe:
+        //   nc_j = sat(BIG * (thr - v_j))  is exactly 1 when v_j < thr and exactly 0 when v_j >= thr
+        //   (any representable non-zero difference times 2^100 saturates); NaN saturates to 0.
+        //   acc_k = sum_j nc_j * 2^(j mod 8) over the 8 columns of byte k -- small integers, exact in fp32.
+        // Two FFMAs per element; the byte sums are converted once per chunk.  A non-integral sum (only
+        // possible for sub-2^-100 differences) marks the row for the exact full pass.
+        const float kBig = 1.2676506e30f;  // 2^100
+        const float bt = kBig * thr;
+        float a0[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int jj = 0; jj < 32; jj++) {
-          if (__uint_as_float(r0[jj]) >= thr) m0[jj & 3] |= (1u << jj);
-          if (__uint_as_float(r1[jj]) >= thr) m1[jj & 3] |= (1u << jj);
+          const float w = static_cast<float>(1u << (jj & 7));
+          a0[jj >> 3] = fmaf(__saturatef(fmaf(__uint_as_float(r0[jj]), -kBig, bt)), w, a0[jj >> 3]);
+          a1[jj >> 3] = fmaf(__saturatef(fmaf(__uint_as_float(r1[jj]), -kBig, bt)), w, a1[jj >> 3]);
         }
-        const uint32_t mask0 = (m0[0] | m0[1]) | (m0[2] | m0[3]);
-        const uint32_t mask1 = (m1[0] | m1[1]) | (m1[2] | m1[3]);
+        uint32_t nc0 = 0, nc1 = 0, bad = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const uint32_t b0 = __float2uint_rz(a0[k]), b1 = __float2uint_rz(a1[k]);
+          bad |= (__uint2float_rn(b0) != a0[k]) | (__uint2float_rn(b1) != a1[k]);
+          nc0 |= b0 << (8 * k);
+          nc1 |= b1 << (8 * k);
+        }
+        if (bad) flags |= 4u;
+        const uint32_t mask0 = ~nc0, mask1 = ~nc1;
+        if (cnt >= LIST_LEN - 1 && (mask0 | mask1))
+          cnt = compact_list(list_cm, list_mask, list_g, slot, cnt, thr);   // rare: drop entries below the risen threshold
         if (mask0) {
           if (cnt < LIST_LEN) {
             list_cm[cnt * 256 + slot] = cm0;
@@ -534,6 +602,8 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
   } else if (warp >= FIRST_EMIT_WARP) {
     // ================================ emitters: merge column halves, write results / queues ================================
     const int row = (warp - FIRST_EMIT_WARP) * 32 + lane;
+    const float cap = p.metric == 1 ? p.stats->scale * p.stats->scale : INFINITY;
+    const uint32_t force = p.stats->force_exact ? 16u : 0u;
     uint32_t ti = 0;
     for (uint32_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ti++) {
       const int par = ti & 1;
@@ -549,8 +619,10 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
       const bool live = grow < p.n;
       if (live) {
         const float Mf = fmaxf(fin[row], fin[TM + row]);
-        const float thr = Mf - fin[768 + row];
-        fl = finu[512 + row] | finu[512 + TM + row];
+        const float thr = fminf(Mf, cap) - fin[768 + row];
+        fl = finu[512 + row] | finu[512 + TM + row] | force;
+        // cosine: if every dot may be <= -1 they all clamp to pi and the lowest index wins -> exact pass
+        if (p.metric == 1 && !(Mf >= fin[768 + row] - cap)) fl |= 8u;
         for (int hh = 0; hh < 2; hh++) {
           const int sl = hh * TM + row;
           const uint32_t c2 = finu[256 + sl];
@@ -713,6 +785,7 @@ struct TcPlan {
   __half* table = nullptr;
   __half* aug_blob = nullptr;
   tc::Stats* stats = nullptr;
+  float* cnorm2 = nullptr;         // cosine: ||c||^2 (the reference's 'csqr' is the constant 1 there)
   uint32_t *pair_row = nullptr, *pair_cand = nullptr, *rowq = nullptr, *ovf_rows = nullptr, *counters = nullptr;
   float* pair_score = nullptr;
   uint32_t* h_counters = nullptr;  // pinned
@@ -744,9 +817,8 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 bool tc_supported(int metric, uint32_t n, int D, uint32_t K) {
-  if (metric != 0) return false;                       // cosine: next round
   if (D < 4 || D % 4 != 0 || D > tc::MAX_NKB * tc::KB) return false;   // TMA row pitch must be 16-byte aligned
-  if (K < 2 || K > 65535u * 32u) return false;
+  if (K < 2 || K > 16383u * 128u) return false;        // chunk ids are 16 bit (4 per n-tile)
   if (n == 0) return false;
   return true;
 }
@@ -756,6 +828,7 @@ void tc_plan_destroy(TcPlan* p) {
   cudaFree(p->table);
   cudaFree(p->aug_blob);
   cudaFree(p->stats);
+  cudaFree(p->cnorm2);
   cudaFree(p->pair_row);
   cudaFree(p->pair_cand);
   cudaFree(p->pair_score);
@@ -791,6 +864,7 @@ cudaError_t tc_plan_create(TcPlan** out, int metric, uint32_t max_n, int D, uint
   TC_TRY(cudaMalloc(&p->table, rows_pad * p->nkb * KB * sizeof(__half)));
   TC_TRY(cudaMalloc(&p->aug_blob, static_cast<size_t>(p->nt) * AUG_B_BYTES));
   TC_TRY(cudaMalloc(&p->stats, sizeof(Stats)));
+  if (metric == 1) TC_TRY(cudaMalloc(&p->cnorm2, sizeof(float) * K));
   TC_TRY(cudaMalloc(&p->pair_row, sizeof(uint32_t) * p->max_pairs));
   TC_TRY(cudaMalloc(&p->pair_cand, sizeof(uint32_t) * p->max_pairs));
   TC_TRY(cudaMalloc(&p->pair_score, sizeof(float) * p->max_pairs));
@@ -824,6 +898,10 @@ cudaError_t tc_plan_create(TcPlan** out, int metric, uint32_t max_n, int D, uint
   TC_TRY(cudaFuncSetAttribute(tc_assign_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(p->smem_bytes)));
   TC_TRY(cudaFuncSetAttribute(tc_assign_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(p->smem_bytes)));
   TC_TRY(cudaFuncSetAttribute(tc_assign_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(p->smem_bytes)));
+  TC_TRY(cudaFuncSetAttribute(tc_assign_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(p->smem_bytes)));
+  TC_TRY(cudaFuncSetAttribute(tc_assign_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(p->smem_bytes)));
+  TC_TRY(cudaFuncSetAttribute(tc_assign_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(p->smem_bytes)));
+  TC_TRY(cudaFuncSetAttribute(tc_assign_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(p->smem_bytes)));
 #undef TC_TRY
   *out = p;
   return cudaSuccess;
@@ -852,10 +930,15 @@ cudaError_t tc_assign(TcPlan* p, const float* X, const float* C, const float* cs
   }
   if ((e = cudaMemsetAsync(p->counters, 0, sizeof(uint32_t) * CNT_N, st)) != cudaSuccess) return e;
   if ((e = cudaMemsetAsync(p->stats, 0, sizeof(Stats), st)) != cudaSuccess) return e;
-  tc_prep_stats_kernel<<<8, 256, 0, st>>>(csq, p->K, p->stats);
+  const float* nsq = csq;
+  if (p->metric == 1) {
+    tc_prep_norms_kernel<<<(p->K * 32 + 255) / 256, 256, 0, st>>>(C, p->K, p->D, p->cnorm2);
+    nsq = p->cnorm2;
+  }
+  tc_prep_stats_kernel<<<8, 256, 0, st>>>(nsq, p->K, p->stats);
   tc_prep_scale_kernel<<<1, 1, 0, st>>>(p->stats);
   const uint32_t rows_pad = static_cast<uint32_t>(p->nt) * TN;
-  tc_prep_table_kernel<<<(rows_pad * 32 + 255) / 256, 256, 0, st>>>(C, csq, p->K, p->D, p->nkb, p->nt, p->table,
+  tc_prep_table_kernel<<<(rows_pad * 32 + 255) / 256, 256, 0, st>>>(p->metric, C, nsq, p->K, p->D, p->nkb, p->nt, p->table,
                                                                     p->aug_blob, p->stats);
   Params prm;
   prm.n = n;
@@ -873,6 +956,7 @@ cudaError_t tc_assign(TcPlan* p, const float* X, const float* C, const float* cs
   prm.rowq = p->rowq;
   prm.ovf_rows = p->ovf_rows;
   prm.counters = p->counters;
+  prm.metric = p->metric;
   prm.dbg_scores = p->dbg_scores;
   const unsigned grid = min(static_cast<uint32_t>(p->num_sms), prm.ntiles);
   const int slot = static_cast<int>(p->passes % TcPlan::kEvRing);
@@ -881,15 +965,23 @@ cudaError_t tc_assign(TcPlan* p, const float* X, const float* C, const float* cs
     case 1: tc_assign_kernel<1><<<grid, N_THREADS, p->smem_bytes, st>>>(p->tmap, tmap_x, prm); break;
     case 2: tc_assign_kernel<2><<<grid, N_THREADS, p->smem_bytes, st>>>(p->tmap, tmap_x, prm); break;
     case 3: tc_assign_kernel<3><<<grid, N_THREADS, p->smem_bytes, st>>>(p->tmap, tmap_x, prm); break;
-    default: tc_assign_kernel<4><<<grid, N_THREADS, p->smem_bytes, st>>>(p->tmap, tmap_x, prm); break;
+    case 4: tc_assign_kernel<4><<<grid, N_THREADS, p->smem_bytes, st>>>(p->tmap, tmap_x, prm); break;
+    case 5: tc_assign_kernel<5><<<grid, N_THREADS, p->smem_bytes, st>>>(p->tmap, tmap_x, prm); break;
+    case 6: tc_assign_kernel<6><<<grid, N_THREADS, p->smem_bytes, st>>>(p->tmap, tmap_x, prm); break;
+    case 7: tc_assign_kernel<7><<<grid, N_THREADS, p->smem_bytes, st>>>(p->tmap, tmap_x, prm); break;
+    default: tc_assign_kernel<8><<<grid, N_THREADS, p->smem_bytes, st>>>(p->tmap, tmap_x, prm); break;
   }
   cudaEventRecord(p->ev1[slot], st);
   p->passes++;
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   // exact re-check of the multi-candidate rows, then the rows that need the full exact pass
   const unsigned rgrid = p->num_sms * 4;
-  recheck_pairs_kernel<0><<<rgrid, 128, 0, st>>>(X, C, csq, p->D, p->pair_row, p->pair_cand,
-                                                 p->counters + CNT_PAIRS, p->max_pairs, n, p->K, p->pair_score);
+  if (p->metric == 1)
+    recheck_pairs_kernel<1><<<rgrid, 128, 0, st>>>(X, C, csq, p->D, p->pair_row, p->pair_cand,
+                                                   p->counters + CNT_PAIRS, p->max_pairs, n, p->K, p->pair_score);
+  else
+    recheck_pairs_kernel<0><<<rgrid, 128, 0, st>>>(X, C, csq, p->D, p->pair_row, p->pair_cand,
+                                                   p->counters + CNT_PAIRS, p->max_pairs, n, p->K, p->pair_score);
   recheck_reduce_kernel<<<p->num_sms * 2, 256, 0, st>>>(p->rowq, p->counters + CNT_ROWQ, p->pair_cand,
                                                         p->pair_score, result);
   if ((e = launch_assign_exact(p->metric, X, C, csq, n, p->D, p->K, p->ovf_rows, p->counters + CNT_OVF, result,

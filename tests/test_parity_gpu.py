@@ -80,10 +80,11 @@ def test_assign_matches_golden(ours, name, force_exact, monkeypatch):
     assert np.array_equal(got, exp), "%s: %d mismatches" % (name, int((got != exp).sum()))
 
 
-def _shard_pass(X, C, assign=None):
+def _shard_pass(X, C, assign=None, metric="L2", force_exact=False):
     import torch
     from kmcuda_b200.shard import assign_once
-    a, prev, changed, info = assign_once(torch.from_numpy(X).cuda(), torch.from_numpy(C).cuda(),
+    os.environ["KMCUDA_B200_FORCE_EXACT"] = "1" if force_exact else "0"   # read when the shard is created
+    a, prev, changed, info = assign_once(torch.from_numpy(X).cuda(), torch.from_numpy(C).cuda(), metric=metric,
                                          assignments=None if assign is None else torch.from_numpy(
                                              assign.astype(np.int32)).cuda())
     return a.cpu().numpy().astype(np.uint32), prev.cpu().numpy().astype(np.uint32), changed, info
@@ -102,6 +103,61 @@ def test_tensor_core_path_runs_and_matches_reference_100k(ref):
     # idempotence: a second pass from the result changes nothing
     a2, prev2, changed2, _ = _shard_pass(X, C, assign=a)
     assert changed2 == 0 and np.array_equal(a2, a) and np.array_equal(prev2, a)
+
+
+def _unit(a):
+    return (a / np.linalg.norm(a, axis=1, keepdims=True)).astype(np.float32)
+
+
+@pytest.mark.parametrize("n,d,k,metric", [(20000, 256, 500, "cos"), (20000, 480, 2000, "L2"),
+                                          (20000, 480, 2000, "cos"), (30000, 64, 20000, "L2"),
+                                          (9000, 324, 700, "L2")])
+def test_tensor_core_wide_shapes_match_reference(ref, n, d, k, metric):
+    """cosine, D up to 512 (single A buffer in TMEM) and K >> 1024 (chunk-list compaction) through the
+    tcgen05 filter: bit-identical to the reference kernel"""
+    rng = np.random.default_rng(n + d + k)
+    X = rng.standard_normal((n, d)).astype(np.float32)
+    if metric == "cos":
+        X = _unit(X)
+    C = X[rng.choice(n, k, replace=False)].copy()
+    C += (rng.standard_normal(C.shape) * 0.05 * np.abs(C).mean()).astype(np.float32)
+    if metric == "cos":
+        C = _unit(C)
+    a, prev, changed, info = _shard_pass(X, C, metric=metric)
+    assert info[0], "tensor-core path not taken"
+    assert info[2] < n // 20, "too many rows fell back to the exact pass: %d" % info[2]
+    exp = one_pass(ref, X, C, metric=1 if metric == "cos" else 0)
+    assert np.array_equal(a, exp), int((a != exp).sum())
+
+
+def test_tensor_core_cosine_unnormalised_clamps():
+    """dots beyond +-1 are clamped by the reference (metric_abstraction.h:171-177): all such centroids tie
+    and the lowest index wins -- the filter must not prune them"""
+    rng = np.random.default_rng(5)
+    X = _unit(rng.standard_normal((4096, 64)))
+    C = _unit(X[rng.choice(4096, 300, replace=False)] + 0.05 * rng.standard_normal((300, 64)))
+    Xs = X.copy()
+    Xs[:1000] *= 3.0            # many dots > 1
+    Xs[1000:1500] *= 1.0001     # borderline
+    for Xc, Cc in ((Xs, C), (Xs, -np.abs(C)), (np.abs(Xs), -np.abs(C) * 4), (Xs, C * 2.5)):
+        Xc, Cc = np.ascontiguousarray(Xc, np.float32), np.ascontiguousarray(Cc, np.float32)
+        a, _, _, info = _shard_pass(Xc, Cc, metric="cos")
+        assert info[0]
+        # checker: this library's exact kernel (device acosf, as the reference; glibc's acosf in the CPU
+        # oracle rounds differently in the last ulp, so the oracle only bounds the angle here)
+        exp, _, _, info_e = _shard_pass(Xc, Cc, metric="cos", force_exact=True)
+        assert not info_e[0]
+        assert np.array_equal(a, exp), int((a != exp).sum())
+        ang = O.assign_lloyd(Xc, Cc, metric=1, with_scores=True)[3]
+        got_dot = np.clip(np.einsum("ij,ij->i", Xc.astype(np.float64), Cc[a].astype(np.float64)), -1, 1)
+        assert np.abs(np.arccos(got_dot) - ang).max() < 2e-3   # acos is ill-conditioned next to the clamp
+    Ci = C.copy()
+    Ci[7, 63] = np.inf          # an infinite LAST feature survives the Kahan loop: dot=+inf clamps to angle 0 and wins
+    Ci[9, 1] = np.nan
+    a, _, _, info = _shard_pass(Xs, Ci, metric="cos")
+    exp = _shard_pass(Xs, Ci, metric="cos", force_exact=True)[0]
+    assert np.array_equal(a, exp), int((a != exp).sum())
+    assert (a[Xs[:, 63] > 0] <= 7).all() and (a[Xs[:, 63] > 0] == 7).mean() > 0.9
 
 
 def test_edge_cases_nan_ragged_ties(ours, ref):
