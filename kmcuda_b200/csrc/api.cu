@@ -16,6 +16,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <chrono>
+#include <string>
+#include <utility>
 #include <vector>
 
 #include "kmcuda.h"
@@ -145,6 +148,40 @@ static void enable_p2p(const std::vector<int>& devs, int extra, int verbosity) {
     }
   }
 }
+
+// Optional wall-clock phase profile (KMCUDA_B200_TIMING=1): every mark() synchronises the devices and books
+// the time since the previous mark; the table goes to stderr when the call returns.  Off by default
+// (no extra synchronisation).
+struct PhaseProfile {
+  bool on = false;
+  std::vector<int> devs;
+  std::vector<std::pair<std::string, double>> acc;
+  std::chrono::steady_clock::time_point last;
+  void begin(const std::vector<int>& d) {
+    const char* e = getenv("KMCUDA_B200_TIMING");
+    on = e && e[0] == '1';
+    devs = d;
+    acc.clear();
+    last = std::chrono::steady_clock::now();
+  }
+  void mark(const char* name) {
+    if (!on) return;
+    for (int d : devs) { cudaSetDevice(d); cudaDeviceSynchronize(); }
+    auto now = std::chrono::steady_clock::now();
+    double ms = std::chrono::duration<double, std::milli>(now - last).count();
+    last = now;
+    for (auto& kv : acc) if (kv.first == name) { kv.second += ms; return; }
+    acc.emplace_back(name, ms);
+  }
+  void report(const char* what) {
+    if (!on) return;
+    double tot = 0;
+    for (auto& kv : acc) tot += kv.second;
+    fprintf(stderr, "[kmcuda_b200 timing] %s: total %.2f ms\n", what, tot);
+    for (auto& kv : acc) fprintf(stderr, "[kmcuda_b200 timing]   %-28s %10.2f ms\n", kv.first.c_str(), kv.second);
+  }
+};
+static PhaseProfile g_prof;   // the library is not re-entrant (kmcuda.h:25-26), one profile is enough
 
 class Job {
  public:
@@ -480,17 +517,20 @@ KMCUDAResult Job::lloyd(float tolerance, int* iter_out, uint32_t* changed_out) {
   for (auto& d : devs) {
     KMB_CU(cudaSetDevice(d.dev), kmcudaRuntimeError);
     KMB_CU(cudaMemsetAsync(d.ccounts.get(), 0, sizeof(uint32_t) * K, d.st), kmcudaRuntimeError);
+    KMB_RET(d.shard->reset_update_state(d.st));
     KMB_CU(cudaMemsetAsync(d.assign.get(), 0xff, sizeof(uint32_t) * d.len, d.st), kmcudaRuntimeError);
     KMB_CU(cudaMemsetAsync(d.prev.get(), 0xff, sizeof(uint32_t) * d.len, d.st), kmcudaRuntimeError);
   }
   for (int iter = 1;; iter++) {
     uint32_t changed = 0;
     KMB_RET(assign_pass(&changed));
+    g_prof.mark("assign pass");
     KMB_INFO("iteration %d: %" PRIu32 " reassignments\n", iter, changed);
     if (iter_out) *iter_out = iter;
     if (changed_out) *changed_out = changed;
     if (changed <= tolerance * N) return kmcudaSuccess;  // float compare, kmeans.cu:707
     KMB_RET(update());
+    g_prof.mark("centroid update");
   }
 }
 
@@ -529,12 +569,14 @@ KMCUDAResult Job::yinyang(float tolerance, uint32_t G) {
   if (changed <= tolerance * N) return kmcudaSuccess;
   std::vector<uint32_t> groups;
   KMB_RET(group_centroids(G, &groups));
+  g_prof.mark("yinyang: group centroids");
   for (auto& d : devs) {
     KMB_RET(d.shard->enable_yinyang(G));
     KMB_CU(cudaSetDevice(d.dev), kmcudaRuntimeError);
     KMB_CU(cudaMemcpyAsync(d.shard->groups.get(), groups.data(), sizeof(uint32_t) * K, cudaMemcpyHostToDevice, d.st),
            kmcudaMemoryCopyError);
     KMB_CU(cudaMemsetAsync(d.d_changed.get(), 0, sizeof(uint32_t), d.st), kmcudaRuntimeError);
+    KMB_RET(d.shard->yy_prepare(d.st));
   }
   KMB_RET(sync_all());
   bool refresh = true;
@@ -545,7 +587,7 @@ KMCUDAResult Job::yinyang(float tolerance, uint32_t G) {
         uint32_t c = 0, p = 0;
         KMB_CU(cudaSetDevice(d.dev), kmcudaRuntimeError);
         KMB_CU(cudaMemcpyAsync(&c, d.d_changed.get(), 4, cudaMemcpyDeviceToHost, d.st), kmcudaMemoryCopyError);
-        KMB_CU(cudaMemcpyAsync(&p, d.shard->d_npassed.get(), 4, cudaMemcpyDeviceToHost, d.st), kmcudaMemoryCopyError);
+        KMB_CU(cudaMemcpyAsync(&p, d.shard->yy_counters.get() + 1, 4, cudaMemcpyDeviceToHost, d.st), kmcudaMemoryCopyError);
         KMB_CU(cudaStreamSynchronize(d.st), kmcudaRuntimeError);
         total_changed += c;
         total_passed += p;
@@ -567,6 +609,7 @@ KMCUDAResult Job::yinyang(float tolerance, uint32_t G) {
                kmcudaRuntimeError);
       }
       refresh = false;
+      g_prof.mark("yinyang: bounds refresh");
     }
     for (auto& d : devs) {
       KMB_CU(cudaSetDevice(d.dev), kmcudaRuntimeError);
@@ -574,16 +617,20 @@ KMCUDAResult Job::yinyang(float tolerance, uint32_t G) {
                              cudaMemcpyDeviceToDevice, d.st), kmcudaMemoryCopyError);
     }
     KMB_RET(update());
+    g_prof.mark("centroid update");
     for (auto& d : devs) {
-      Shard* s = d.shard.get();
       KMB_CU(cudaSetDevice(d.dev), kmcudaRuntimeError);
-      KMB_CU(launch_yy_drifts(metric, d.C, s->oldC, K, D, G, s->groups, s->drift, s->maxdrift, d.st), kmcudaRuntimeError);
-      KMB_CU(cudaMemsetAsync(s->d_npassed.get(), 0, sizeof(uint32_t), d.st), kmcudaRuntimeError);
-      KMB_CU(launch_yy_global_filter(metric, d.X, d.C, d.len, D, G, s->drift, s->maxdrift, d.assign, d.prev,
-                                     s->bounds, s->passed, s->d_npassed, d.st), kmcudaRuntimeError);
-      KMB_CU(launch_yy_local_filter(metric, d.X, d.C, d.len, D, K, G, s->groups, s->drift, s->maxdrift,
-                                    s->passed, s->d_npassed, d.assign, s->bounds, d.d_changed, d.st),
-             kmcudaRuntimeError);
+      KMB_RET(d.shard->yy_step(d.len, d.X, d.C, d.assign, d.prev, d.d_changed, d.st));
+    }
+    g_prof.mark("yinyang: filter + local step");
+    if (g_prof.on) {   // marks synchronise, so the pinned counters of the last pass are valid
+      Shard* s0 = devs[0].shard.get();
+      uint32_t yc[4] = {0, 0, 0, 0}, rq = 0, ov = 0;
+      cudaSetDevice(devs[0].dev);
+      cudaMemcpy(yc, s0->yy_counters.get(), sizeof(yc), cudaMemcpyDeviceToHost);
+      if (s0->tc) tc_last_stats(s0->tc, &rq, &ov);
+      fprintf(stderr, "[kmcuda_b200 timing]   yy step (dev 0): tightened %u, passed %u, candidate rows %u, pairs %u, "
+              "reference-order scan rows %u\n", yc[0], yc[1], rq, s0->tc ? tc_last_pairs(s0->tc) : 0u, ov);
     }
   }
 }
@@ -655,13 +702,18 @@ KMCUDAResult kmeans_cuda(KMCUDAInitMethod init, const void* init_params, float t
   enable_p2p(dev_ids, device_ptrs, verbosity);
   const int m = metric == kmcudaDistanceMetricCosine ? 1 : 0;
   const int D = static_cast<int>(features_size) * (fp16x2 ? 2 : 1);
+  g_prof.begin(dev_ids);
   Job job(m, samples_size, D, clusters_size, verbosity);
   KMB_RET(job.setup(dev_ids, true));
+  g_prof.mark("setup (alloc, plans, nccl)");
   KMB_RET(job.ingest(samples, device_ptrs, fp16x2 != 0));
+  g_prof.mark("ingest (H2D / peer copy)");
   if (verbosity > 1) KMB_RET(print_memory_stats(dev_ids));
   KMB_RET(job.init_centroids(init, init_params, seed, device_ptrs, fp16x2 != 0, centroids));
+  g_prof.mark("init centroids");
   KMB_RET(job.yinyang(tolerance, yy_groups_size));
   if (average_distance) KMB_RET(job.average_distance(average_distance));
+  g_prof.mark("average distance");
   // copy-out: centroids from the first device (identical everywhere), assignment slices from each shard
   const size_t ccount = static_cast<size_t>(clusters_size) * D;
   {
@@ -691,6 +743,8 @@ KMCUDAResult kmeans_cuda(KMCUDAInitMethod init, const void* init_params, float t
                                  sizeof(uint32_t) * d.len, d.st), kmcudaMemoryCopyError);
   }
   KMB_RET(job.sync_all());
+  g_prof.mark("copy-out");
+  g_prof.report("kmeans_cuda");
   KMB_DEBUG("return kmcudaSuccess\n");
   return kmcudaSuccess;
 }

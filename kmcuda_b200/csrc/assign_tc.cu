@@ -62,7 +62,7 @@ constexpr int N_EPI_WARPS = 8;
 constexpr int FIRST_EMIT_WARP = FIRST_EPI_WARP + N_EPI_WARPS;  // 16: 4 emitter warps (merge + global emission)
 constexpr int N_EMIT_WARPS = 4;
 constexpr int N_THREADS = (FIRST_EMIT_WARP + N_EMIT_WARPS) * 32;  // 640
-constexpr int MAX_CAND = 16;            // candidates per row before falling back to the full exact pass
+constexpr int MAX_CAND = 32;            // candidates per row before falling back to the full exact pass (one per lane of the finishing warp)
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t TMEM_ACC0 = 0, TMEM_A0 = 256;
 
@@ -92,7 +92,7 @@ __host__ __device__ inline SmemLayout smem_layout() {
   L.list_mask = o; o += 2 * LIST_LEN * 256 * 4;
   L.list_g = o; o += 2 * LIST_LEN * 256 * 2;
   L.norms = o; o += 4 * 2 * TM * 4;   // [tile % 4][x|d][row]  (4 deep: the converters run up to 2 tiles ahead of the epilogue)
-  L.fin = o; o += 2 * 4 * 256 * 4;    // [tile parity][M|cnt|flags|margin][epilogue thread]
+  L.fin = o; o += 2 * 5 * 256 * 4;    // [tile parity][M|cnt|flags|margin|M2][epilogue thread]
   L.bars = o; o += 64 * 8;
   L.tmem_slot = o; o += 16;
   L.total = o;
@@ -134,6 +134,12 @@ struct Params {
   uint32_t* ovf_rows;        // rows for the full exact pass
   uint32_t* counters;        // CNT_*
   int metric;                // 0 = L2 (score x.c - ||c||^2/2), 1 = cosine (score x.c; larger dot = smaller angle)
+  // MODE 1 (Yinyang local step): the samples are the rows listed in rows[0 .. *d_nrows), read straight from
+  // global memory by the converter warps; every column within the margin of the row's SECOND best score is a
+  // candidate and every candidate goes to the pair queue (the caller needs exact best and second-best distances)
+  const float* X;
+  const uint32_t* rows;
+  const uint32_t* d_nrows;
   float* dbg_scores;         // optional [ntiles*128][nt*128] dump of the approximate scores
 };
 
@@ -272,7 +278,8 @@ __device__ __noinline__ uint32_t compact_list(float* list_cm, uint32_t* list_mas
   return w;
 }
 
-template <int NKB>   // K-blocks of 64 features (compile-time: the MMA issue loop must be branch- and address-arithmetic-free)
+template <int NKB, int MODE>   // NKB: K-blocks of 64 features (compile-time: the MMA issue loop must be branch- and
+                               // address-arithmetic-free); MODE 0 = Lloyd assignment, 1 = Yinyang local step (see Params)
 __global__ void __launch_bounds__(N_THREADS, 1)
 tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_x,
                  const Params p) {
@@ -286,6 +293,8 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
   constexpr int SPN = (NKB + 1) / 2;   // B stages per n-tile
   constexpr int NBUF = NKB <= 4 ? 2 : 1;   // A operand buffers in TMEM (256 columns are available for A)
   const int nt = p.nt;
+  const uint32_t n_eff = MODE == 1 ? min(*p.d_nrows, p.n) : p.n;
+  const uint32_t ntiles = MODE == 1 ? (n_eff + TM - 1) / TM : p.ntiles;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmap_b);
@@ -328,7 +337,7 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
     // ================================ TMA producer: centroid table + bias blocks ================================
     if (lane == 0) {
       uint32_t pc = 0, ac = 0;
-      for (uint32_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+      for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         for (int n = 0; n < nt; n++) {
 #pragma unroll
           for (int st = 0; st < SPN; st++, pc++) {
@@ -354,9 +363,9 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
     }
   } else if (warp == WARP_X_PRODUCER) {
     // ================================ TMA producer: fp32 sample rows ================================
-    if (lane == 0) {
+    if (MODE == 0 && lane == 0) {
       uint32_t xc = 0;
-      for (uint32_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+      for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         for (int hs = 0; hs < 2 * nkb; hs++, xc++) {
           const int s = xc % X_STAGES;
           const uint32_t ph = (xc / X_STAGES) & 1;
@@ -376,7 +385,7 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
     const uint64_t aug_ad = ptx::make_smem_desc(ptx::smem_u32(smem + L.aug_a), TM * 16, 128, 0);
     const uint32_t augb = ptx::smem_u32(smem + L.aug_b);
     uint32_t pc = 0, ac = 0, ti = 0;
-    for (uint32_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ti++) {
+    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ti++) {
       const int abuf = ti % NBUF;
       const uint32_t a_par = (ti / NBUF) & 1;
       const uint32_t a_tmem = tmem_base + TMEM_A0 + abuf * 128;
@@ -433,22 +442,35 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
     const int row = q * 32 + lane;          // this thread's sample row within the tile
     const float s = p.stats->scale;
     uint32_t xc = 0, ti = 0;
-    for (uint32_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ti++) {
+    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ti++) {
       const int abuf = ti % NBUF;
       TC_WAIT(BAR_A_FREE + abuf, ((ti / NBUF) & 1) ^ 1, 7);   // MMAs of the previous user of this buffer are done
       ptx::tc_fence_after();
       float nx = 0.f, nd = 0.f;
+      const float* xrow = nullptr;
+      if (MODE == 1) {
+        const uint32_t li = min(tile * TM + row, n_eff - 1);   // ragged tail: repeat the last listed row
+        xrow = p.X + static_cast<size_t>(p.rows[li]) * p.D;
+      }
       for (int kb = 0; kb < nkb; kb++) {
         uint32_t pk[32];
 #pragma unroll
         for (int half = 0; half < 2; half++, xc++) {
           const int st = xc % X_STAGES;
           const uint32_t ph = (xc / X_STAGES) & 1;
-          TC_WAIT(BAR_X_FULL + st, ph, 10);
+          float4 gv[8];
+          if (MODE == 0) {
+            TC_WAIT(BAR_X_FULL + st, ph, 10);
+          } else {
+            const int f0 = kb * KB + half * 32;
+#pragma unroll
+            for (int c = 0; c < 8; c++)
+              gv[c] = (f0 + c * 4 < p.D) ? ptx::ldg_nc_f4(xrow + f0 + c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
           const uint8_t* xs = smem + L.x + st * X_STAGE_BYTES + row * 128;
 #pragma unroll
           for (int c = 0; c < 8; c++) {
-            const float4 v = *reinterpret_cast<const float4*>(xs + ((c ^ (row & 7)) << 4));
+            const float4 v = MODE == 0 ? *reinterpret_cast<const float4*>(xs + ((c ^ (row & 7)) << 4)) : gv[c];
             const float a0 = v.x * s, a1 = v.y * s, a2 = v.z * s, a3 = v.w * s;
             __half2 h0 = __floats2half2_rn(a0, a1), h1 = __floats2half2_rn(a2, a3);
             const float2 b0 = __half22float2(h0), b1 = __half22float2(h1);
@@ -460,8 +482,10 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
             pk[half * 16 + c * 2] = *reinterpret_cast<uint32_t*>(&h0);
             pk[half * 16 + c * 2 + 1] = *reinterpret_cast<uint32_t*>(&h1);
           }
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(&bars[BAR_X_EMPTY + st]);
+          if (MODE == 0) {
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&bars[BAR_X_EMPTY + st]);
+          }
         }
         ptx::tmem_st_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + TMEM_A0 + abuf * 128 + kb * 32, pk);
         ptx::tmem_st_wait();
@@ -487,15 +511,15 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
     // never rises above s^2 * 1 (the accumulator holds s^2 * dot)
     const float cap = p.metric == 1 ? p.stats->scale * p.stats->scale : INFINITY;
     uint32_t ac = 0, ti = 0;
-    for (uint32_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ti++) {
+    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ti++) {
       const int par = ti & 1;
       float* list_cm = reinterpret_cast<float*>(smem + L.list_cm) + par * LIST_LEN * 256;
       uint32_t* list_mask = reinterpret_cast<uint32_t*>(smem + L.list_mask) + par * LIST_LEN * 256;
       uint16_t* list_g = reinterpret_cast<uint16_t*>(smem + L.list_g) + par * LIST_LEN * 256;
-      float* fin = reinterpret_cast<float*>(smem + L.fin) + par * 4 * 256;
+      float* fin = reinterpret_cast<float*>(smem + L.fin) + par * 5 * 256;
       // the emitter warps must have consumed this parity's lists (tile ti-2)
       TC_WAIT(BAR_EMIT_EMPTY + par, ((ti >> 1) & 1) ^ 1, 11);
-      float M = -INFINITY, margin = 0.f;
+      float M = -INFINITY, M2 = -INFINITY, margin = 0.f;   // M2: MODE 1, second largest chunk maximum
       uint32_t cnt = 0, flags = 0;
       for (int n = 0; n < nt; n++, ac++) {
         const int buf = ac & 1;
@@ -516,6 +540,7 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
           float E = nx * dcmax + nd * cmax + nd * dcmax;
           E += static_cast<float>(p.nkb * KB + 16) * 2.4e-7f * nx * cmax;   // fp32 accumulation in the tensor core
           E += 2.0e-6f * (cmax * cmax + xn * cmax);                        // reference Kahan/rd rounding, bias split
+          if (MODE == 1) E += 2.0e-6f * xn * xn;                           // true distances: rounding of sum (x-c)^2
           margin = 2.f * E * 1.001f + 1e-30f;
           if (!(margin < 1.0e30f)) flags |= 1u;                            // NaN / Inf somewhere in the row
         }
@@ -524,7 +549,7 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&bars[BAR_ACC_EMPTY + buf]);
-        if (p.dbg_scores) {
+        if (MODE == 0 && p.dbg_scores) {
           const uint64_t grow = static_cast<uint64_t>(tile) * TM + row;
           float* dst = p.dbg_scores + grow * (static_cast<uint64_t>(nt) * TN) + n * TN + h * 64;
           for (int jj = 0; jj < 32; jj++) dst[jj] = __uint_as_float(r0[jj]);
@@ -541,8 +566,18 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
         }
         const float cm0 = fmaxf(fmaxf(fmaxf(t0[0], t0[1]), fmaxf(t0[2], t0[3])), fmaxf(fmaxf(t0[4], t0[5]), fmaxf(t0[6], t0[7])));
         const float cm1 = fmaxf(fmaxf(fmaxf(t1[0], t1[1]), fmaxf(t1[2], t1[3])), fmaxf(fmaxf(t1[4], t1[5]), fmaxf(t1[6], t1[7])));
-        M = fmaxf(M, fmaxf(cm0, cm1));
-        const float thr = fminf(M, cap) - margin;
+        float thr;
+        if (MODE == 0) {
+          M = fmaxf(M, fmaxf(cm0, cm1));
+          thr = fminf(M, cap) - margin;
+        } else {
+          // two distinct columns reach min(two largest chunk maxima): a lower bound of the second best score
+          M2 = fmaxf(M2, fminf(M, cm0));
+          M = fmaxf(M, cm0);
+          M2 = fmaxf(M2, fminf(M, cm1));
+          M = fmaxf(M, cm1);
+          thr = fminf(M2, cap) - margin;
+        }
         // candidate masks on the (otherwise idle) FMA pipe instead of FSETP + LOP3 on the ALU pipe:
         //   nc_j = sat(BIG * (thr - v_j))  is exactly 1 when v_j < thr and exactly 0 when v_j >= thr
         //   (any representable non-zero difference times 2^100 saturates); NaN saturates to 0.
@@ -596,6 +631,7 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
       reinterpret_cast<uint32_t*>(fin)[256 + slot] = cnt;
       reinterpret_cast<uint32_t*>(fin)[512 + slot] = flags;
       fin[768 + slot] = margin;
+      if (MODE == 1) fin[1024 + slot] = M2;
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&bars[BAR_EMIT_FULL + par]);
     }
@@ -605,20 +641,23 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
     const float cap = p.metric == 1 ? p.stats->scale * p.stats->scale : INFINITY;
     const uint32_t force = p.stats->force_exact ? 16u : 0u;
     uint32_t ti = 0;
-    for (uint32_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ti++) {
+    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ti++) {
       const int par = ti & 1;
       const float* list_cm = reinterpret_cast<const float*>(smem + L.list_cm) + par * LIST_LEN * 256;
       const uint32_t* list_mask = reinterpret_cast<const uint32_t*>(smem + L.list_mask) + par * LIST_LEN * 256;
       const uint16_t* list_g = reinterpret_cast<const uint16_t*>(smem + L.list_g) + par * LIST_LEN * 256;
-      const float* fin = reinterpret_cast<const float*>(smem + L.fin) + par * 4 * 256;
+      const float* fin = reinterpret_cast<const float*>(smem + L.fin) + par * 5 * 256;
       const uint32_t* finu = reinterpret_cast<const uint32_t*>(fin);
       TC_WAIT(BAR_EMIT_FULL + par, (ti >> 1) & 1, 12);
-      const uint64_t grow = static_cast<uint64_t>(tile) * TM + row;
+      uint64_t grow = static_cast<uint64_t>(tile) * TM + row;
       uint32_t cand[MAX_CAND];
       uint32_t total = 0, fl = 0;
-      const bool live = grow < p.n;
+      const bool live = grow < n_eff;
+      if (MODE == 1 && live) grow = p.rows[grow];
       if (live) {
-        const float Mf = fmaxf(fin[row], fin[TM + row]);
+        float Mf = fmaxf(fin[row], fin[TM + row]);
+        if (MODE == 1)   // second largest of the two halves' (largest, second largest) pairs
+          Mf = fmaxf(fminf(fin[row], fin[TM + row]), fmaxf(fin[1024 + row], fin[1024 + TM + row]));
         const float thr = fminf(Mf, cap) - fin[768 + row];
         fl = finu[512 + row] | finu[512 + TM + row] | force;
         // cosine: if every dot may be <= -1 they all clamp to pi and the lowest index wins -> exact pass
@@ -645,8 +684,8 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
       // the lists of this parity are consumed: the epilogue may start tile ti+2
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&bars[BAR_EMIT_EMPTY + par]);
-      const bool overflow = live && (fl || total > MAX_CAND);
-      const bool multi = live && !overflow && total >= 2;
+      const bool overflow = live && (fl || total > MAX_CAND || (MODE == 1 && total == 0));
+      const bool multi = live && !overflow && total >= (MODE == 1 ? 1u : 2u);
       // warp-aggregated queue reservation: one atomic per warp for the pairs, one for the row queue
       uint32_t want = multi ? total : 0, pre = want;
 #pragma unroll
@@ -666,9 +705,9 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
       if (live) {
         if (overflow) {
           p.ovf_rows[atomicAdd(&p.counters[CNT_OVF], 1u)] = static_cast<uint32_t>(grow);
-        } else if (total == 1) {
+        } else if (MODE == 0 && total == 1) {
           p.result[grow] = cand[0];
-        } else if (total == 0) {
+        } else if (MODE == 0 && total == 0) {
           p.result[grow] = kUntouched;  // every score NaN: nothing wins (reference kmeans.cu:349-353)
         } else if (base + total <= p.max_pairs) {
           for (uint32_t i = 0; i < total; i++) {
@@ -702,7 +741,7 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
 // ---------------------------------------------------------------------------------------------------
 // exact re-check of (row, candidate) pairs + per-row reduction
 // ---------------------------------------------------------------------------------------------------
-template <int METRIC>
+template <int METRIC, int MODE>   // MODE 0: Lloyd ranking score; MODE 1: true distance (Yinyang bounds)
 __global__ void __launch_bounds__(128)
 recheck_pairs_kernel(const float* __restrict__ X, const float* __restrict__ C,
                      const float* __restrict__ csq, int D, const uint32_t* __restrict__ pair_row,
@@ -748,9 +787,14 @@ recheck_pairs_kernel(const float* __restrict__ X, const float* __restrict__ C,
       }
       __syncthreads();
       if (active)
-        for (int f = 0; f < fl; f++) k.mac(sX[f * 129 + threadIdx.x], sC[threadIdx.x * 33 + f]);
+        for (int f = 0; f < fl; f++) {
+          if (MODE == 1 && METRIC == 0) k.sqdiff(sX[f * 129 + threadIdx.x], sC[threadIdx.x * 33 + f]);
+          else k.mac(sX[f * 129 + threadIdx.x], sC[threadIdx.x * 33 + f]);
+        }
     }
-    if (active) pair_score[pidx] = lloyd_score<METRIC>(k.sum, csq[s_cand[threadIdx.x]]);
+    if (active)
+      pair_score[pidx] = MODE == 1 ? finalize_distance<METRIC>(k.sum)
+                                   : lloyd_score<METRIC>(k.sum, csq[s_cand[threadIdx.x]]);
   }
 }
 
@@ -816,6 +860,44 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+template <int MODE>
+static void tc_launch_mode(int nkb, unsigned grid, size_t smem, cudaStream_t st, const CUtensorMap& tb,
+                           const CUtensorMap& tx, const tc::Params& prm) {
+  using namespace tc;
+  switch (nkb) {
+    case 1: tc_assign_kernel<1, MODE><<<grid, N_THREADS, smem, st>>>(tb, tx, prm); break;
+    case 2: tc_assign_kernel<2, MODE><<<grid, N_THREADS, smem, st>>>(tb, tx, prm); break;
+    case 3: tc_assign_kernel<3, MODE><<<grid, N_THREADS, smem, st>>>(tb, tx, prm); break;
+    case 4: tc_assign_kernel<4, MODE><<<grid, N_THREADS, smem, st>>>(tb, tx, prm); break;
+    case 5: tc_assign_kernel<5, MODE><<<grid, N_THREADS, smem, st>>>(tb, tx, prm); break;
+    case 6: tc_assign_kernel<6, MODE><<<grid, N_THREADS, smem, st>>>(tb, tx, prm); break;
+    case 7: tc_assign_kernel<7, MODE><<<grid, N_THREADS, smem, st>>>(tb, tx, prm); break;
+    default: tc_assign_kernel<8, MODE><<<grid, N_THREADS, smem, st>>>(tb, tx, prm); break;
+  }
+}
+static void tc_launch_main(int mode, int nkb, unsigned grid, size_t smem, cudaStream_t st, const CUtensorMap& tb,
+                           const CUtensorMap& tx, const tc::Params& prm) {
+  if (mode == 1) tc_launch_mode<1>(nkb, grid, smem, st, tb, tx, prm);
+  else tc_launch_mode<0>(nkb, grid, smem, st, tb, tx, prm);
+}
+template <int NKB>
+static cudaError_t tc_set_smem_attr_one(int bytes) {
+  cudaError_t e = cudaFuncSetAttribute(tc::tc_assign_kernel<NKB, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(tc::tc_assign_kernel<NKB, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
+static cudaError_t tc_set_smem_attr(int bytes) {
+  cudaError_t e;
+  if ((e = tc_set_smem_attr_one<1>(bytes)) != cudaSuccess) return e;
+  if ((e = tc_set_smem_attr_one<2>(bytes)) != cudaSuccess) return e;
+  if ((e = tc_set_smem_attr_one<3>(bytes)) != cudaSuccess) return e;
+  if ((e = tc_set_smem_attr_one<4>(bytes)) != cudaSuccess) return e;
+  if ((e = tc_set_smem_attr_one<5>(bytes)) != cudaSuccess) return e;
+  if ((e = tc_set_smem_attr_one<6>(bytes)) != cudaSuccess) return e;
+  if ((e = tc_set_smem_attr_one<7>(bytes)) != cudaSuccess) return e;
+  return tc_set_smem_attr_one<8>(bytes);
+}
+
 bool tc_supported(int metric, uint32_t n, int D, uint32_t K) {
   if (D < 4 || D % 4 != 0 || D > tc::MAX_NKB * tc::KB) return false;   // TMA row pitch must be 16-byte aligned
   if (K < 2 || K > 16383u * 128u) return false;        // chunk ids are 16 bit (4 per n-tile)
@@ -854,7 +936,7 @@ cudaError_t tc_plan_create(TcPlan** out, int metric, uint32_t max_n, int D, uint
   p->max_n = max_n;
   p->nkb = (D + KB - 1) / KB;
   p->nt = static_cast<int>((K + TN - 1) / TN);
-  p->max_pairs = max_n < (1u << 30) ? 2 * max_n + 1024 : 0xFFFFFFF0u;
+  p->max_pairs = max_n < (1u << 28) ? 10 * max_n + 1024 : 0xFFFFFFF0u;   // Lloyd needs ~0.4 n, the Yinyang top-2 mode up to ~7 n
   cudaError_t e;
 #define TC_TRY(x) do { e = (x); if (e != cudaSuccess) { tc_plan_destroy(p); return e; } } while (0)
   cudaDeviceProp prop;
@@ -894,17 +976,52 @@ cudaError_t tc_plan_create(TcPlan** out, int metric, uint32_t max_n, int D, uint
     TC_TRY(cudaEventCreate(&p->ev1[i]));
   }
   p->smem_bytes = smem_layout().total + 1024;
-  TC_TRY(cudaFuncSetAttribute(tc_assign_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(p->smem_bytes)));
-  TC_TRY(cudaFuncSetAttribute(tc_assign_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(p->smem_bytes)));
-  TC_TRY(cudaFuncSetAttribute(tc_assign_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(p->smem_bytes)));
-  TC_TRY(cudaFuncSetAttribute(tc_assign_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(p->smem_bytes)));
-  TC_TRY(cudaFuncSetAttribute(tc_assign_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(p->smem_bytes)));
-  TC_TRY(cudaFuncSetAttribute(tc_assign_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(p->smem_bytes)));
-  TC_TRY(cudaFuncSetAttribute(tc_assign_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(p->smem_bytes)));
-  TC_TRY(cudaFuncSetAttribute(tc_assign_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(p->smem_bytes)));
+  TC_TRY(tc_set_smem_attr(static_cast<int>(p->smem_bytes)));
 #undef TC_TRY
   *out = p;
   return cudaSuccess;
+}
+
+// counters reset + centroid preparation (scale, fp16 table, bias blobs) + the parameter block shared by both modes
+static cudaError_t tc_prepare(TcPlan* p, const float* C, const float* csq, uint32_t n, tc::Params* out,
+                              cudaStream_t st) {
+  using namespace tc;
+  cudaError_t e;
+  if ((e = cudaMemsetAsync(p->counters, 0, sizeof(uint32_t) * CNT_N, st)) != cudaSuccess) return e;
+  if ((e = cudaMemsetAsync(p->stats, 0, sizeof(Stats), st)) != cudaSuccess) return e;
+  const float* nsq = csq;
+  if (p->metric == 1) {
+    tc_prep_norms_kernel<<<(p->K * 32 + 255) / 256, 256, 0, st>>>(C, p->K, p->D, p->cnorm2);
+    nsq = p->cnorm2;
+  }
+  tc_prep_stats_kernel<<<8, 256, 0, st>>>(nsq, p->K, p->stats);
+  tc_prep_scale_kernel<<<1, 1, 0, st>>>(p->stats);
+  const uint32_t rows_pad = static_cast<uint32_t>(p->nt) * TN;
+  tc_prep_table_kernel<<<(rows_pad * 32 + 255) / 256, 256, 0, st>>>(p->metric, C, nsq, p->K, p->D, p->nkb, p->nt, p->table,
+                                                                    p->aug_blob, p->stats);
+  Params prm;
+  prm.n = n;
+  prm.D = p->D;
+  prm.K = p->K;
+  prm.nkb = p->nkb;
+  prm.nt = p->nt;
+  prm.ntiles = (n + TM - 1) / TM;
+  prm.aug_blob = p->aug_blob;
+  prm.stats = p->stats;
+  prm.result = nullptr;
+  prm.pair_row = p->pair_row;
+  prm.pair_cand = p->pair_cand;
+  prm.max_pairs = p->max_pairs;
+  prm.rowq = p->rowq;
+  prm.ovf_rows = p->ovf_rows;
+  prm.counters = p->counters;
+  prm.metric = p->metric;
+  prm.X = nullptr;
+  prm.rows = nullptr;
+  prm.d_nrows = nullptr;
+  prm.dbg_scores = p->dbg_scores;
+  *out = prm;
+  return cudaGetLastError();
 }
 
 cudaError_t tc_assign(TcPlan* p, const float* X, const float* C, const float* csq, uint32_t n,
@@ -928,66 +1045,77 @@ cudaError_t tc_assign(TcPlan* p, const float* X, const float* C, const float* cs
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) return cudaErrorInvalidValue;
   }
-  if ((e = cudaMemsetAsync(p->counters, 0, sizeof(uint32_t) * CNT_N, st)) != cudaSuccess) return e;
-  if ((e = cudaMemsetAsync(p->stats, 0, sizeof(Stats), st)) != cudaSuccess) return e;
-  const float* nsq = csq;
-  if (p->metric == 1) {
-    tc_prep_norms_kernel<<<(p->K * 32 + 255) / 256, 256, 0, st>>>(C, p->K, p->D, p->cnorm2);
-    nsq = p->cnorm2;
-  }
-  tc_prep_stats_kernel<<<8, 256, 0, st>>>(nsq, p->K, p->stats);
-  tc_prep_scale_kernel<<<1, 1, 0, st>>>(p->stats);
-  const uint32_t rows_pad = static_cast<uint32_t>(p->nt) * TN;
-  tc_prep_table_kernel<<<(rows_pad * 32 + 255) / 256, 256, 0, st>>>(p->metric, C, nsq, p->K, p->D, p->nkb, p->nt, p->table,
-                                                                    p->aug_blob, p->stats);
   Params prm;
-  prm.n = n;
-  prm.D = p->D;
-  prm.K = p->K;
-  prm.nkb = p->nkb;
-  prm.nt = p->nt;
-  prm.ntiles = (n + TM - 1) / TM;
-  prm.aug_blob = p->aug_blob;
-  prm.stats = p->stats;
+  if ((e = tc_prepare(p, C, csq, n, &prm, st)) != cudaSuccess) return e;
   prm.result = result;
-  prm.pair_row = p->pair_row;
-  prm.pair_cand = p->pair_cand;
-  prm.max_pairs = p->max_pairs;
-  prm.rowq = p->rowq;
-  prm.ovf_rows = p->ovf_rows;
-  prm.counters = p->counters;
-  prm.metric = p->metric;
-  prm.dbg_scores = p->dbg_scores;
   const unsigned grid = min(static_cast<uint32_t>(p->num_sms), prm.ntiles);
   const int slot = static_cast<int>(p->passes % TcPlan::kEvRing);
   cudaEventRecord(p->ev0[slot], st);
-  switch (p->nkb) {
-    case 1: tc_assign_kernel<1><<<grid, N_THREADS, p->smem_bytes, st>>>(p->tmap, tmap_x, prm); break;
-    case 2: tc_assign_kernel<2><<<grid, N_THREADS, p->smem_bytes, st>>>(p->tmap, tmap_x, prm); break;
-    case 3: tc_assign_kernel<3><<<grid, N_THREADS, p->smem_bytes, st>>>(p->tmap, tmap_x, prm); break;
-    case 4: tc_assign_kernel<4><<<grid, N_THREADS, p->smem_bytes, st>>>(p->tmap, tmap_x, prm); break;
-    case 5: tc_assign_kernel<5><<<grid, N_THREADS, p->smem_bytes, st>>>(p->tmap, tmap_x, prm); break;
-    case 6: tc_assign_kernel<6><<<grid, N_THREADS, p->smem_bytes, st>>>(p->tmap, tmap_x, prm); break;
-    case 7: tc_assign_kernel<7><<<grid, N_THREADS, p->smem_bytes, st>>>(p->tmap, tmap_x, prm); break;
-    default: tc_assign_kernel<8><<<grid, N_THREADS, p->smem_bytes, st>>>(p->tmap, tmap_x, prm); break;
-  }
+  tc_launch_main(0, p->nkb, grid, p->smem_bytes, st, p->tmap, tmap_x, prm);
   cudaEventRecord(p->ev1[slot], st);
   p->passes++;
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   // exact re-check of the multi-candidate rows, then the rows that need the full exact pass
   const unsigned rgrid = p->num_sms * 4;
   if (p->metric == 1)
-    recheck_pairs_kernel<1><<<rgrid, 128, 0, st>>>(X, C, csq, p->D, p->pair_row, p->pair_cand,
-                                                   p->counters + CNT_PAIRS, p->max_pairs, n, p->K, p->pair_score);
+    recheck_pairs_kernel<1, 0><<<rgrid, 128, 0, st>>>(X, C, csq, p->D, p->pair_row, p->pair_cand,
+                                                      p->counters + CNT_PAIRS, p->max_pairs, n, p->K, p->pair_score);
   else
-    recheck_pairs_kernel<0><<<rgrid, 128, 0, st>>>(X, C, csq, p->D, p->pair_row, p->pair_cand,
-                                                   p->counters + CNT_PAIRS, p->max_pairs, n, p->K, p->pair_score);
+    recheck_pairs_kernel<0, 0><<<rgrid, 128, 0, st>>>(X, C, csq, p->D, p->pair_row, p->pair_cand,
+                                                      p->counters + CNT_PAIRS, p->max_pairs, n, p->K, p->pair_score);
   recheck_reduce_kernel<<<p->num_sms * 2, 256, 0, st>>>(p->rowq, p->counters + CNT_ROWQ, p->pair_cand,
                                                         p->pair_score, result);
   if ((e = launch_assign_exact(p->metric, X, C, csq, n, p->D, p->K, p->ovf_rows, p->counters + CNT_OVF, result,
                                st)) != cudaSuccess)
     return e;
   return cudaMemcpyAsync(p->h_counters, p->counters, sizeof(uint32_t) * CNT_N, cudaMemcpyDeviceToHost, st);
+}
+
+// Yinyang local step, candidate generation: for the listed rows, every centroid whose approximate score is
+// within the rigorous margin of the row's second best, with its exact TRUE distance (reference
+// METRIC::distance, metric_abstraction.h:59-101,179-222).  Results stay in the plan's queues (tc_queues()).
+// Rows the filter cannot bound (NaN/Inf, > MAX_CAND candidates, queue full) are put on the overflow list.
+cudaError_t tc_yy_candidates(TcPlan* p, const float* X, const float* C, const float* csq, uint32_t n,
+                             const uint32_t* rows, const uint32_t* d_nrows, cudaStream_t st) {
+  using namespace tc;
+  if (n > p->max_n) return cudaErrorInvalidValue;
+  if (reinterpret_cast<uintptr_t>(X) & 15) return cudaErrorMisalignedAddress;
+  cudaError_t e;
+  Params prm;
+  if ((e = tc_prepare(p, C, csq, n, &prm, st)) != cudaSuccess) return e;
+  prm.X = X;
+  prm.rows = rows;
+  prm.d_nrows = d_nrows;
+  const unsigned grid = min(static_cast<uint32_t>(p->num_sms), prm.ntiles);
+  tc_launch_main(1, p->nkb, grid, p->smem_bytes, st, p->tmap, p->tmap /* unused */, prm);
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  if ((e = tc_exact_distances(p, X, C, n, p->pair_row, p->pair_cand, p->counters + CNT_PAIRS, p->max_pairs,
+                              p->pair_score, st)) != cudaSuccess)
+    return e;
+  return cudaMemcpyAsync(p->h_counters, p->counters, sizeof(uint32_t) * CNT_N, cudaMemcpyDeviceToHost, st);
+}
+
+// exact true distances of (row, centroid) pairs: 128 pairs per CTA, coalesced staging (see recheck_pairs_kernel)
+cudaError_t tc_exact_distances(TcPlan* p, const float* X, const float* C, uint32_t n, const uint32_t* pair_row,
+                               const uint32_t* pair_cand, const uint32_t* d_npairs, uint32_t max_pairs,
+                               float* pair_score, cudaStream_t st) {
+  const unsigned rgrid = p->num_sms * 4;
+  if (p->metric == 1)
+    recheck_pairs_kernel<1, 1><<<rgrid, 128, 0, st>>>(X, C, nullptr, p->D, pair_row, pair_cand, d_npairs, max_pairs,
+                                                      n, p->K, pair_score);
+  else
+    recheck_pairs_kernel<0, 1><<<rgrid, 128, 0, st>>>(X, C, nullptr, p->D, pair_row, pair_cand, d_npairs, max_pairs,
+                                                      n, p->K, pair_score);
+  return cudaGetLastError();
+}
+
+void tc_queues(TcPlan* p, TcQueues* q) {
+  q->rowq = p->rowq;
+  q->d_nrowq = p->counters + tc::CNT_ROWQ;
+  q->pair_cand = p->pair_cand;
+  q->pair_score = p->pair_score;
+  q->ovf_rows = p->ovf_rows;
+  q->d_novf = p->counters + tc::CNT_OVF;
 }
 
 // valid after the stream has been synchronised
@@ -997,6 +1125,7 @@ void tc_last_stats(TcPlan* p, uint32_t* n_recheck, uint32_t* n_overflow) {
 }
 
 uint32_t tc_last_error(TcPlan* p) { return p->h_counters[tc::CNT_ERR]; }
+uint32_t tc_last_pairs(TcPlan* p) { return p->h_counters[tc::CNT_PAIRS]; }
 
 // device time (ms) of the main kernel in the most recent passes, oldest first; call after a sync
 int tc_kernel_times(TcPlan* p, float* ms_out, int max_out) {

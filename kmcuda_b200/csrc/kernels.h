@@ -48,25 +48,33 @@ cudaError_t launch_partial_sums(const float* X, uint32_t n, int D, uint32_t K, c
                                 UpdateWorkspace& ws, float* sums, uint32_t* counts, cudaStream_t st);
 // C = sums/count (L2, NaN for empty) or sums/||sums|| (cosine); ccounts = counts
 cudaError_t launch_normalize(int metric, const float* sums, const uint32_t* counts, uint32_t K, int D,
-                             float* C, uint32_t* ccounts, cudaStream_t st);
+                             float* C, uint32_t* ccounts, float* prev_sums, cudaStream_t st);
 
 // ---- Yinyang -------------------------------------------------------------------------------------
-// bounds layout [(G+1)][n]: row 0 = upper bound, row 1+g = lower bound of group g
+// bounds layout [n][G+1] (one contiguous record per sample): [0] = upper bound, [1+g] = lower bound of group g
 cudaError_t launch_yy_init(int metric, const float* X, const float* C, uint32_t n, int D, uint32_t K,
                            uint32_t G, const uint32_t* assign, const uint32_t* groups, float* bounds,
                            cudaStream_t st);
 cudaError_t launch_yy_drifts(int metric, const float* Cnew, const float* Cold, uint32_t K, int D,
                              uint32_t G, const uint32_t* groups, float* drift, float* maxdrift,
                              cudaStream_t st);
-cudaError_t launch_yy_global_filter(int metric, const float* X, const float* C, uint32_t n, int D,
-                                    uint32_t G, const float* drift, const float* maxdrift,
-                                    const uint32_t* assign, uint32_t* prev, float* bounds,
-                                    uint32_t* passed, uint32_t* d_npassed, cudaStream_t st);
-cudaError_t launch_yy_local_filter(int metric, const float* X, const float* C, uint32_t n, int D,
-                                   uint32_t K, uint32_t G, const uint32_t* groups, const float* drift,
-                                   const float* maxdrift, const uint32_t* passed,
-                                   const uint32_t* d_npassed, uint32_t* assign, float* bounds,
-                                   uint32_t* d_changed, cudaStream_t st);
+struct TcPlan;
+// one Yinyang iteration after the centroid update (yinyang.cu): bound decay + group filter, exact tightening of
+// the upper bound, tensor-core candidate pass over the surviving rows, bound / assignment update
+struct YyWorkspace {
+  float* minlb;            // [n]
+  uint32_t* tight_rows;    // [n]
+  uint32_t* tight_cand;    // [n]
+  float* tight_score;      // [n]
+  uint32_t* passed;        // [n]
+  uint32_t* gsize;         // [G] members per group (NaN centroids excluded)
+  uint32_t* counters;      // [4]: tight, passed, (spare)
+};
+cudaError_t launch_yy_group_sizes(const uint32_t* groups, uint32_t K, uint32_t G, uint32_t* gsize, cudaStream_t st);
+cudaError_t launch_yy_step(int metric, TcPlan* plan, const float* X, const float* C, const float* csq, uint32_t n,
+                           int D, uint32_t K, uint32_t G, const uint32_t* groups, const float* drift,
+                           const float* maxdrift, uint32_t* assign, uint32_t* prev, float* bounds,
+                           const YyWorkspace& ws, uint32_t* d_changed, bool reference_order_scan, cudaStream_t st);
 
 // ---- misc ------------------------------------------------------------------------------------------
 cudaError_t launch_average_distance(int metric, const float* X, const float* C, uint32_t n, int D,
@@ -102,8 +110,24 @@ cudaError_t tc_assign(TcPlan* plan, const float* X, const float* C, const float*
                       uint32_t* result, cudaStream_t st);
 // statistics of the last pass (for logging / bench): queue length and overflow rows
 void tc_last_stats(TcPlan* plan, uint32_t* n_recheck, uint32_t* n_overflow);
+// Yinyang local step (assign_tc.cu): candidate pairs with exact true distances for the listed rows
+struct TcQueues {
+  const uint32_t* rowq;       // [3*i]: row, first pair, pair count
+  const uint32_t* d_nrowq;
+  const uint32_t* pair_cand;
+  const float* pair_score;    // exact distance of (row, pair_cand)
+  const uint32_t* ovf_rows;   // rows the filter could not bound
+  const uint32_t* d_novf;
+};
+cudaError_t tc_yy_candidates(TcPlan* plan, const float* X, const float* C, const float* csq, uint32_t n,
+                             const uint32_t* rows, const uint32_t* d_nrows, cudaStream_t st);
+cudaError_t tc_exact_distances(TcPlan* plan, const float* X, const float* C, uint32_t n, const uint32_t* pair_row,
+                               const uint32_t* pair_cand, const uint32_t* d_npairs, uint32_t max_pairs,
+                               float* pair_score, cudaStream_t st);
+void tc_queues(TcPlan* plan, TcQueues* q);
 // 0 = clean; 0x1000+site = a pipeline wait timed out at `site` (results of that pass are invalid)
 uint32_t tc_last_error(TcPlan* plan);
+uint32_t tc_last_pairs(TcPlan* plan);
 int tc_kernel_times(TcPlan* plan, float* ms_out, int max_out);
 // diagnostics (KMCUDA_B200_DUMP_SCORES=1): approximate scores [tiles*128][nt*256], prep statistics
 const float* tc_debug_scores(TcPlan* plan, size_t* row_stride);

@@ -33,6 +33,10 @@ KMCUDAResult Shard::create(bool with_update) {
     ws.offsets = ws_offsets;
     ws.partial = ws_partial;
     ws.cub_tmp = ws_cub.get();
+    if (metric == 1) {
+      KMB_CU(prev_sums.alloc(static_cast<size_t>(K) * D), kmcudaMemoryAllocationFailure);
+      KMB_CU(cudaMemset(prev_sums.get(), 0, sizeof(float) * static_cast<size_t>(K) * D), kmcudaRuntimeError);
+    }
   }
   if (!force_exact && tc_supported(metric, max_n, D, K)) {
     cudaError_t e = tc_plan_create(&tc, metric, max_n, D, K, device);
@@ -55,7 +59,37 @@ KMCUDAResult Shard::enable_yinyang(uint32_t groups_size) {
   KMB_CU(oldC.alloc(static_cast<size_t>(K) * D), kmcudaMemoryAllocationFailure);
   KMB_CU(passed.alloc(max_n), kmcudaMemoryAllocationFailure);
   KMB_CU(groups.alloc(K), kmcudaMemoryAllocationFailure);
-  KMB_CU(d_npassed.alloc(1), kmcudaMemoryAllocationFailure);
+  KMB_CU(yy_counters.alloc(4), kmcudaMemoryAllocationFailure);
+  KMB_CU(yy_minlb.alloc(max_n), kmcudaMemoryAllocationFailure);
+  KMB_CU(yy_tight_rows.alloc(max_n), kmcudaMemoryAllocationFailure);
+  KMB_CU(yy_tight_cand.alloc(max_n), kmcudaMemoryAllocationFailure);
+  KMB_CU(yy_tight_score.alloc(max_n), kmcudaMemoryAllocationFailure);
+  KMB_CU(yy_gsize.alloc(G), kmcudaMemoryAllocationFailure);
+  return kmcudaSuccess;
+}
+
+// start of a run (the counts are reset to zero by the caller): forget the cached member sums (cosine update)
+KMCUDAResult Shard::reset_update_state(cudaStream_t st) {
+  if (prev_sums.get())
+    KMB_CU(cudaMemsetAsync(prev_sums.get(), 0, sizeof(float) * static_cast<size_t>(K) * D, st), kmcudaRuntimeError);
+  return kmcudaSuccess;
+}
+
+// after `groups` has been filled
+KMCUDAResult Shard::yy_prepare(cudaStream_t st) {
+  KMB_CU(launch_yy_group_sizes(groups, K, G, yy_gsize, st), kmcudaRuntimeError);
+  return kmcudaSuccess;
+}
+
+// one Yinyang iteration after the centroid update: reference kmeans.cu:1180-1262 (drifts, global and local filter)
+KMCUDAResult Shard::yy_step(uint32_t n, const float* X, const float* C, uint32_t* assignments, uint32_t* prev,
+                            uint32_t* d_changed, cudaStream_t st) {
+  if (n > max_n) return kmcudaInvalidArguments;
+  KMB_CU(launch_yy_drifts(metric, C, oldC, K, D, G, groups, drift, maxdrift, st), kmcudaRuntimeError);
+  if (tc) KMB_CU(launch_csqr(metric, C, K, D, csq, st), kmcudaRuntimeError);
+  YyWorkspace ws{yy_minlb, yy_tight_rows, yy_tight_cand, yy_tight_score, passed, yy_gsize, yy_counters};
+  KMB_CU(launch_yy_step(metric, tc, X, C, csq, n, D, K, G, groups, drift, maxdrift, assignments, prev, bounds, ws,
+                        d_changed, force_exact, st), kmcudaRuntimeError);
   return kmcudaSuccess;
 }
 
@@ -84,7 +118,7 @@ KMCUDAResult Shard::partial_sums(uint32_t n, const float* X, const uint32_t* ass
 
 KMCUDAResult Shard::finish_update(const float* sums, const uint32_t* counts, float* C,
                                   uint32_t* ccounts, cudaStream_t st) {
-  KMB_CU(launch_normalize(metric, sums, counts, K, D, C, ccounts, st), kmcudaRuntimeError);
+  KMB_CU(launch_normalize(metric, sums, counts, K, D, C, ccounts, prev_sums, st), kmcudaRuntimeError);
   return kmcudaSuccess;
 }
 

@@ -96,6 +96,10 @@ class Shard {
 
   KMCUDAResult create(bool with_update);
   KMCUDAResult enable_yinyang(uint32_t G);
+  KMCUDAResult reset_update_state(cudaStream_t st);
+  KMCUDAResult yy_prepare(cudaStream_t st);
+  KMCUDAResult yy_step(uint32_t n, const float* X, const float* C, uint32_t* assignments, uint32_t* prev,
+                       uint32_t* d_changed, cudaStream_t st);
 
   // hot path
   KMCUDAResult assign(uint32_t n, const float* X, const float* C, uint32_t* assignments,
@@ -121,6 +125,7 @@ class Shard {
   UpdateWorkspace ws;
   DevBuf<uint32_t> ws_keys_out, ws_vals_in, ws_vals_out, ws_offsets;
   DevBuf<float> ws_partial;
+  DevBuf<float> prev_sums;   // cosine update: member sums of the previous iteration
   DevBuf<char> ws_cub;
   TcPlan* tc = nullptr;
 
@@ -128,7 +133,9 @@ class Shard {
   uint32_t G = 0;
   DevBuf<float> bounds, drift, maxdrift, oldC;
   DevBuf<uint32_t> passed, groups;
-  DevBuf<uint32_t> d_npassed;
+  DevBuf<uint32_t> yy_counters;      // [0] rows needing the exact upper bound, [1] rows passed to the local step
+  DevBuf<float> yy_minlb, yy_tight_score;
+  DevBuf<uint32_t> yy_tight_rows, yy_tight_cand, yy_gsize;
 };
 
 }  // namespace kmb

@@ -83,7 +83,7 @@ exact_pass_kernel(const float* __restrict__ X, const float* __restrict__ C,
     if (MODE == 1 && active) {
       mine = assign[row];
       if (t == 0)
-        for (uint32_t g = 0; g <= G; g++) bounds[static_cast<size_t>(n) * g + row] = FLT_MAX;
+        for (uint32_t g = 0; g <= G; g++) bounds[static_cast<size_t>(row) * (G + 1) + g] = FLT_MAX;
     }
     __syncthreads();
     float best = FLT_MAX;
@@ -120,10 +120,10 @@ exact_pass_kernel(const float* __restrict__ X, const float* __restrict__ C,
             float dist = finalize_distance<METRIC>(k[j].sum);
             if (c != mine) {
               // distances are >= +0: their bit patterns order like unsigned integers; NaN never lowers a bound
-              atomicMin(reinterpret_cast<uint32_t*>(bounds + static_cast<size_t>(n) * (1 + g) + row),
+              atomicMin(reinterpret_cast<uint32_t*>(bounds + static_cast<size_t>(row) * (G + 1) + 1 + g),
                         __float_as_uint(dist));
             } else {
-              bounds[row] = dist;
+              bounds[static_cast<size_t>(row) * (G + 1)] = dist;
             }
           }
         }
@@ -505,32 +505,46 @@ cudaError_t launch_knn_inverse(const uint32_t* assign, uint32_t n, uint32_t K, u
   return cudaGetLastError();
 }
 
-// reference metric_abstraction.h:138-144 (L2: multiply by __frcp_rn(count)) and :255-272 (cosine)
+// reference kmeans_adjust (kmeans.cu:366-429) + METRIC::normalize (metric_abstraction.h:138-144 L2: multiply by
+// __frcp_rn(count); :255-272 cosine).  The reference updates incrementally: centroid * old count, plus the samples
+// that joined, minus the samples that left, then normalise.  For L2 that is the mean of the current members (what
+// the segmented sums give directly).  For the cosine metric the stored centroid is the UNIT vector, so
+// "centroid * old count" is not the old member sum and the recurrence is its own algorithm:
+//     raw_new = count_old * c_old + (S_cur - S_prev),   c_new = raw_new / ||raw_new||
+// with S_* the member sums of the current / previous assignment (prev_sums caches S_prev between iterations).
 template <int METRIC>
 __global__ void normalize_kernel(const float* __restrict__ sums, const uint32_t* __restrict__ counts,
                                  uint32_t K, int D, float* __restrict__ C,
-                                 uint32_t* __restrict__ ccounts) {
+                                 uint32_t* __restrict__ ccounts, float* __restrict__ prev_sums) {
   uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= K) return;
   const float* s = sums + static_cast<size_t>(c) * D;
   float* o = C + static_cast<size_t>(c) * D;
   uint32_t cnt = counts[c];
-  float scale;
   if (METRIC == 1) {
+    float* ps = prev_sums + static_cast<size_t>(c) * D;
+    const float old_cnt = static_cast<float>(ccounts[c]);
     Kahan k;
-    for (int f = 0; f < D; f++) k.mac(s[f], s[f]);
-    scale = __frcp_rn(__fsqrt_rn(k.sum));
+    for (int f = 0; f < D; f++) {
+      const float cur = s[f];
+      const float raw = o[f] * old_cnt + (cur - ps[f]);
+      ps[f] = cur;
+      o[f] = raw;
+      k.mac(raw, raw);
+    }
+    const float scale = __frcp_rn(__fsqrt_rn(k.sum));
+    for (int f = 0; f < D; f++) o[f] = o[f] * scale;
   } else {
-    scale = __frcp_rn(static_cast<float>(cnt));
+    const float scale = __frcp_rn(static_cast<float>(cnt));
+    for (int f = 0; f < D; f++) o[f] = s[f] * scale;
   }
-  for (int f = 0; f < D; f++) o[f] = s[f] * scale;
   ccounts[c] = cnt;
 }
 
 cudaError_t launch_normalize(int metric, const float* sums, const uint32_t* counts, uint32_t K, int D,
-                             float* C, uint32_t* ccounts, cudaStream_t st) {
-  if (metric == 1) normalize_kernel<1><<<cdiv(K, 64), 64, 0, st>>>(sums, counts, K, D, C, ccounts);
-  else normalize_kernel<0><<<cdiv(K, 64), 64, 0, st>>>(sums, counts, K, D, C, ccounts);
+                             float* C, uint32_t* ccounts, float* prev_sums, cudaStream_t st) {
+  if (metric == 1) normalize_kernel<1><<<cdiv(K, 64), 64, 0, st>>>(sums, counts, K, D, C, ccounts, prev_sums);
+  else normalize_kernel<0><<<cdiv(K, 64), 64, 0, st>>>(sums, counts, K, D, C, ccounts, prev_sums);
   return cudaGetLastError();
 }
 
@@ -564,130 +578,6 @@ cudaError_t launch_yy_drifts(int metric, const float* Cnew, const float* Cold, u
   if (metric == 1) yy_drifts_kernel<1><<<cdiv(K, 64), 64, 0, st>>>(Cnew, Cold, K, D, drift);
   else yy_drifts_kernel<0><<<cdiv(K, 64), 64, 0, st>>>(Cnew, Cold, K, D, drift);
   yy_group_max_kernel<<<cdiv(G, 64), 64, 0, st>>>(drift, groups, K, G, maxdrift);
-  return cudaGetLastError();
-}
-
-template <int METRIC>
-__global__ void yy_global_filter_kernel(const float* __restrict__ X, const float* __restrict__ C,
-                                        uint32_t n, int D, uint32_t G,
-                                        const float* __restrict__ drift,
-                                        const float* __restrict__ maxdrift,
-                                        const uint32_t* __restrict__ assign,
-                                        uint32_t* __restrict__ prev, float* __restrict__ bounds,
-                                        uint32_t* __restrict__ passed, uint32_t* __restrict__ d_npassed) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  bool pass = false;
-  if (i < n) {
-    uint32_t a = assign[i];
-    prev[i] = a;
-    float ub = bounds[i] + drift[a];
-    float minlb = FLT_MAX;
-    for (uint32_t g = 0; g < G; g++) {
-      size_t gi = static_cast<size_t>(n) * (1 + g) + i;
-      float lb = bounds[gi] - maxdrift[g];
-      bounds[gi] = lb;
-      if (lb < minlb) minlb = lb;
-    }
-    if (minlb >= ub) {
-      bounds[i] = ub;
-    } else {
-      ub = distance_exact<METRIC>(X + static_cast<size_t>(i) * D, C + static_cast<size_t>(a) * D, D);
-      bounds[i] = ub;
-      pass = !(minlb >= ub);
-    }
-  }
-  unsigned mask = __ballot_sync(0xffffffffu, pass);
-  if (mask) {
-    int lane = threadIdx.x & 31, leader = __ffs(mask) - 1;
-    uint32_t base = 0;
-    if (lane == leader) base = atomicAdd(d_npassed, __popc(mask));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    if (pass) passed[base + __popc(mask & ((1u << lane) - 1))] = i;
-  }
-}
-
-cudaError_t launch_yy_global_filter(int metric, const float* X, const float* C, uint32_t n, int D,
-                                    uint32_t G, const float* drift, const float* maxdrift,
-                                    const uint32_t* assign, uint32_t* prev, float* bounds,
-                                    uint32_t* passed, uint32_t* d_npassed, cudaStream_t st) {
-  if (n == 0) return cudaSuccess;
-  if (metric == 1)
-    yy_global_filter_kernel<1><<<cdiv(n, 256), 256, 0, st>>>(X, C, n, D, G, drift, maxdrift, assign, prev,
-                                                            bounds, passed, d_npassed);
-  else
-    yy_global_filter_kernel<0><<<cdiv(n, 256), 256, 0, st>>>(X, C, n, D, G, drift, maxdrift, assign, prev,
-                                                            bounds, passed, d_npassed);
-  return cudaGetLastError();
-}
-
-template <int METRIC>
-__global__ void yy_local_filter_kernel(const float* __restrict__ X, const float* __restrict__ C,
-                                       uint32_t n, int D, uint32_t K, uint32_t G,
-                                       const uint32_t* __restrict__ groups,
-                                       const float* __restrict__ drift,
-                                       const float* __restrict__ maxdrift,
-                                       const uint32_t* __restrict__ passed,
-                                       const uint32_t* __restrict__ d_npassed,
-                                       uint32_t* __restrict__ assign, float* __restrict__ bounds,
-                                       uint32_t* __restrict__ d_changed) {
-  const uint32_t np = *d_npassed;
-  int changed = 0;
-  for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < np; p += gridDim.x * blockDim.x) {
-    const uint32_t i = passed[p];
-    const float ub = bounds[i];
-    const uint32_t a = assign[i];
-    float mn = ub, sec = FLT_MAX;
-    uint32_t near = a;
-    const float* x = X + static_cast<size_t>(i) * D;
-    for (uint32_t c = 0; c < K; c++) {
-      if (c == a) continue;
-      uint32_t g = groups[c];
-      if (g >= G) continue;
-      float lb = bounds[static_cast<size_t>(n) * (1 + g) + i];
-      if (lb >= ub) {
-        if (lb < sec) sec = lb;
-        continue;
-      }
-      lb += maxdrift[g] - drift[c];
-      if (sec < lb) continue;
-      float d = distance_exact<METRIC>(x, C + static_cast<size_t>(c) * D, D);
-      if (d < mn) {
-        sec = mn;
-        mn = d;
-        near = c;
-      } else if (d < sec) {
-        sec = d;
-      }
-    }
-    uint32_t ng = groups[near], pg = groups[a];
-    bounds[static_cast<size_t>(n) * (1 + ng) + i] = sec;
-    if (ng != pg) {
-      size_t gi = static_cast<size_t>(n) * (1 + pg) + i;
-      if (bounds[gi] > ub) bounds[gi] = ub;
-    }
-    bounds[i] = mn;
-    if (near != a) {
-      assign[i] = near;
-      changed++;
-    }
-  }
-  for (int o = 16; o > 0; o >>= 1) changed += __shfl_down_sync(0xffffffffu, changed, o);
-  if ((threadIdx.x & 31) == 0 && changed) atomicAdd(d_changed, changed);
-}
-
-cudaError_t launch_yy_local_filter(int metric, const float* X, const float* C, uint32_t n, int D,
-                                   uint32_t K, uint32_t G, const uint32_t* groups, const float* drift,
-                                   const float* maxdrift, const uint32_t* passed,
-                                   const uint32_t* d_npassed, uint32_t* assign, float* bounds,
-                                   uint32_t* d_changed, cudaStream_t st) {
-  if (n == 0) return cudaSuccess;
-  unsigned grid = min(cdiv(n, 128), 148u * 16u);
-  if (metric == 1)
-    yy_local_filter_kernel<1><<<grid, 128, 0, st>>>(X, C, n, D, K, G, groups, drift, maxdrift, passed,
-                                                    d_npassed, assign, bounds, d_changed);
-  else
-    yy_local_filter_kernel<0><<<grid, 128, 0, st>>>(X, C, n, D, K, G, groups, drift, maxdrift, passed,
-                                                    d_npassed, assign, bounds, d_changed);
   return cudaGetLastError();
 }
 

@@ -83,10 +83,17 @@ def test_assign_matches_golden(ours, name, force_exact, monkeypatch):
 def _shard_pass(X, C, assign=None, metric="L2", force_exact=False):
     import torch
     from kmcuda_b200.shard import assign_once
+    old = os.environ.get("KMCUDA_B200_FORCE_EXACT")
     os.environ["KMCUDA_B200_FORCE_EXACT"] = "1" if force_exact else "0"   # read when the shard is created
-    a, prev, changed, info = assign_once(torch.from_numpy(X).cuda(), torch.from_numpy(C).cuda(), metric=metric,
-                                         assignments=None if assign is None else torch.from_numpy(
-                                             assign.astype(np.int32)).cuda())
+    try:
+        a, prev, changed, info = assign_once(torch.from_numpy(X).cuda(), torch.from_numpy(C).cuda(), metric=metric,
+                                             assignments=None if assign is None else torch.from_numpy(
+                                                 assign.astype(np.int32)).cuda())
+    finally:
+        if old is None:
+            os.environ.pop("KMCUDA_B200_FORCE_EXACT", None)
+        else:
+            os.environ["KMCUDA_B200_FORCE_EXACT"] = old
     return a.cpu().numpy().astype(np.uint32), prev.cpu().numpy().astype(np.uint32), changed, info
 
 
@@ -273,6 +280,60 @@ def test_kmeans_runs_match_reference_trajectory(ours, ref):
         np.testing.assert_allclose(C1[ok], C2[ok], rtol=0, atol=2e-2)
 
 
+def _mixture(n, d, k, seed, sigma=0.25):
+    """overlapping Gaussian blobs, initial centroids next to the true centres (no cluster runs empty: the
+    reference library aborts in its Yinyang grouping when a centroid is NaN)"""
+    rng = np.random.default_rng(seed)
+    centers = rng.random((k, d), dtype=np.float32)
+    X = centers[rng.integers(0, k, n)] + sigma * rng.standard_normal((n, d), dtype=np.float32)
+    C0 = centers + 0.1 * rng.standard_normal((k, d), dtype=np.float32)
+    return np.ascontiguousarray(X), np.ascontiguousarray(C0)
+
+
+@pytest.mark.parametrize("n,d,k,metric", [(60000, 64, 256, 0), (40000, 100, 120, 0), (30000, 32, 64, 1)])
+def test_yinyang_tensor_core_local_step_equals_reference_order_scan(ours, ref, n, d, k, metric, monkeypatch):
+    """Yinyang iterations: the tcgen05 candidate pass + exact finish (yinyang.cu) must give the same run as the
+    reference-order per-row scan (KMCUDA_B200_FORCE_EXACT=1), and both the same as the reference library"""
+    rng = np.random.default_rng(42 + d)
+    X = rng.random((n, d), dtype=np.float32) if metric == 0 else rng.standard_normal((n, d)).astype(np.float32)
+    C0 = X[rng.choice(n, k, replace=False)].copy()     # structureless data: dozens of slow Yinyang iterations
+    if metric == 1:
+        X, C0 = _unit(X), _unit(C0)
+    runs = {}
+    for fe in ("0", "1"):
+        monkeypatch.setenv("KMCUDA_B200_FORCE_EXACT", fe)
+        runs[fe] = c_kmeans(ours, X, C0, 0.0005, 0.1, metric=metric)
+    monkeypatch.setenv("KMCUDA_B200_FORCE_EXACT", "0")
+    assert np.array_equal(runs["0"][1], runs["1"][1]), int((runs["0"][1] != runs["1"][1]).sum())
+    np.testing.assert_array_equal(runs["0"][0], runs["1"][0])
+    # Trajectory-independent check of the Yinyang result: the library returns the centroids of the LAST assignment
+    # step (kmeans.cu:991-997), and a correct bound filter leaves every sample at the argmin over those centroids
+    # (README.md:74-75) -- up to fp32 near-ties between the true-distance and the Lloyd ranking formulas.
+    C_last, A_last = runs["0"]
+    assert (one_pass(ours, X, C_last, metric=metric) == A_last).mean() > 0.9995
+    # the reference library on the same input: same property, and the same run while the runs are short (over
+    # dozens of iterations on structureless data 1e-7 centroid differences flip near-tie samples and any two
+    # implementations drift apart)
+    Co, Ao = c_kmeans(ours, X, C0, 0.04, 0.1, metric=metric)
+    Cr, Ar = c_kmeans(ref, X, C0, 0.04, 0.1, metric=metric)
+    assert (one_pass(ours, X, Cr, metric=metric) == Ar).mean() > 0.9995
+    assert (Ao == Ar).mean() > 0.99, (Ao != Ar).mean()
+
+
+def test_yinyang_log_lines_match_reference(ours, ref, capfd):
+    """the per-iteration reassignment counts (stdout contract, kmeans.cu:706) of a Yinyang run"""
+    X, C0 = _mixture(50000, 16, 200, 9, sigma=0.12)
+    outs = []
+    for lib in (ours, ref):
+        capfd.readouterr()
+        c_kmeans(lib, X, C0, 0.0002, 0.1, verbosity=1)
+        out = capfd.readouterr().out
+        outs.append([ln for ln in out.splitlines() if ln.startswith("iteration") or "refreshing" in ln])
+    print(outs[0])
+    assert len(outs[0]) > 5 and any("refreshing" in ln for ln in outs[0])
+    assert outs[0][:8] == outs[1][:8]
+
+
 def test_fp16_and_average_distance(km):
     X = cases.blobs()
     c32, a32, avg = km.kmeans_cuda(X, 50, init="k-means++", device=1, seed=3, tolerance=0.01, yinyang_t=0,
@@ -295,6 +356,20 @@ def test_cosine_lloyd(km):
     assert ((X @ cent.T).argmax(1) != asg).mean() < 0.02
     with pytest.raises(ValueError):                               # un-normalised samples are rejected
         km.kmeans_cuda(X * 2, 20, metric="cos", device=1)
+
+
+def test_cosine_runs_follow_reference_update_rule(ours, ref):
+    """angular metric, whole runs: the reference's incremental update (centroid * old count + joined - left, then
+    L2-normalise, kmeans.cu:366-429) is NOT the spherical mean once the centroid has been normalised; the runs only
+    agree if that recurrence is reproduced"""
+    rng = np.random.default_rng(74)
+    X = _unit(rng.standard_normal((30000, 32)))
+    C0 = X[rng.choice(30000, 64, replace=False)].copy()
+    for tol, yy in ((0.12, 0.0), (0.04, 0.0), (0.04, 0.1)):
+        Co, Ao = c_kmeans(ours, X, C0, tol, yy, metric=1)
+        Cr, Ar = c_kmeans(ref, X, C0, tol, yy, metric=1)
+        assert (Ao == Ar).mean() > 0.999, (tol, yy, (Ao != Ar).mean())
+        assert (np.abs(Co - Cr).max(1) < 1e-4).mean() > 0.9
 
 
 def test_knn_matches_sklearn_exactly(km):
