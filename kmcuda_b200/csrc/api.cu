@@ -848,8 +848,38 @@ KMCUDAResult knn_cuda(uint16_t k, KMCUDADistanceMetric metric, uint32_t samples_
     KNN_CU(launch_knn_inverse(d.assign, N, K, d.iota, d.inv_keys, d.inv, d.off, d.counts, ws, d.st), kmcudaRuntimeError);
     KNN_CU(launch_knn_radii(m, d.X, d.C, N, D, K, d.assign, d.radii, d.st), kmcudaRuntimeError);
     KNN_CU(launch_knn_centroid_distances(m, d.C, K, D, d.cd, d.st), kmcudaRuntimeError);
-    KNN_CU(launch_knn_search(m, k, d.X, d.C, N, D, K, plan[i].first, qlen, d.assign, d.inv, d.off, d.cd,
-                             d.radii, d.heap, d.neigh, d.pairs, d.st), kmcudaRuntimeError);
+    KNN_CU(launch_knn_radii_fix(d.off, K, d.radii, d.st), kmcudaRuntimeError);
+    bool searched = false;
+    const char* fx = getenv("KMCUDA_B200_FORCE_EXACT");
+    if (dev_ids.size() == 1 && !(fx && fx[0] == '1') && tc_knn_supported(m, k, N, D, K)) {
+      // tensor-core candidate search; the rows it cannot serve go through the reference-order search below
+      uint32_t nv = 0, tc_err = 0;
+      KNN_CU(cudaMemcpyAsync(&nv, d.off.get() + K, sizeof(nv), cudaMemcpyDeviceToHost, d.st), kmcudaMemoryCopyError);
+      KNN_CU(cudaStreamSynchronize(d.st), kmcudaRuntimeError);
+      DevBuf<uint32_t> fb_rows, d_nfb;
+      KNN_CU(fb_rows.alloc(N), kmcudaMemoryAllocationFailure);
+      KNN_CU(d_nfb.alloc(1), kmcudaMemoryAllocationFailure);
+      KNN_CU(cudaMemsetAsync(d_nfb.get(), 0, sizeof(uint32_t), d.st), kmcudaRuntimeError);
+      cudaError_t te = cudaSuccess;
+      if (nv >= 4096)
+        te = tc_knn_search(k, d.X, d.C, N, D, K, d.assign, d.inv, d.off, d.cd, d.radii, nv, d.neigh, fb_rows, d_nfb,
+                           d.pairs, &tc_err, d.st);
+      if (nv >= 4096 && te == cudaSuccess && tc_err == 0) {
+        KNN_CU(launch_knn_tail_rows(d.inv, nv, N, fb_rows, d_nfb, d.st), kmcudaRuntimeError);
+        KNN_CU(launch_knn_search(m, k, d.X, d.C, N, D, K, 0, qlen, d.assign, d.inv, d.off, d.cd, d.radii, d.heap,
+                                 d.neigh, d.pairs, fb_rows, d_nfb, d.st), kmcudaRuntimeError);
+        KNN_CU(cudaStreamSynchronize(d.st), kmcudaRuntimeError);   // fb_rows goes out of scope
+        searched = true;
+      } else if (te != cudaSuccess || tc_err) {
+        KMB_INFO("tensor-core k-NN pass failed (%s, 0x%x): exact search for every query\n", cudaGetErrorString(te), tc_err);
+        if (te == cudaErrorMemoryAllocation) cudaGetLastError();
+        else if (te != cudaSuccess) { cleanup(); return kmcudaRuntimeError; }
+        KNN_CU(cudaMemsetAsync(d.pairs.get(), 0, sizeof(unsigned long long), d.st), kmcudaRuntimeError);
+      }
+    }
+    if (!searched)
+      KNN_CU(launch_knn_search(m, k, d.X, d.C, N, D, K, plan[i].first, qlen, d.assign, d.inv, d.off, d.cd,
+                               d.radii, d.heap, d.neigh, d.pairs, nullptr, nullptr, d.st), kmcudaRuntimeError);
   }
   for (size_t i = 0; i < dev_ids.size(); i++) {
     KDev& d = *kd[i];

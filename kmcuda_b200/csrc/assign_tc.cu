@@ -33,7 +33,10 @@
 #include <cuda_fp16.h>
 
 #include <cstdio>
+#include <algorithm>
 #include <cstring>
+
+#include <cub/cub.cuh>
 
 #include "exact.cuh"
 #include "kernels.h"
@@ -63,6 +66,8 @@ constexpr int FIRST_EMIT_WARP = FIRST_EPI_WARP + N_EPI_WARPS;  // 16: 4 emitter 
 constexpr int N_EMIT_WARPS = 4;
 constexpr int N_THREADS = (FIRST_EMIT_WARP + N_EMIT_WARPS) * 32;  // 640
 constexpr int MAX_CAND = 32;            // candidates per row before falling back to the full exact pass (one per lane of the finishing warp)
+constexpr int KNN_CAP = 40;             // k-NN: (chunk, mask) entries per half-row in global memory
+constexpr int KNN_MAX_KK = 16;          // k + 1 <= 16 on the tensor-core path
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t TMEM_ACC0 = 0, TMEM_A0 = 256;
 
@@ -140,6 +145,29 @@ struct Params {
   const float* X;
   const uint32_t* rows;
   const uint32_t* d_nrows;
+  // MODE 2 (k-NN candidate pass): queries AND candidates are the cluster-sorted samples.  Query tile t covers
+  // sorted positions [tile_r0[t], +tile_nrows[t]) (one cluster, <= 128 rows, gathered through rows[] = the inverse
+  // assignment order); its candidate blocks (128 sorted positions each = one n-tile of the fp16 sample table) are
+  // the ranges knn_ranges[knn_roff[t] .. +knn_rcount[t]).  Every column within the margin of the row's kk-th
+  // largest chunk maximum (kk = k + 1, self included) is recorded as (chunk maximum, mask, chunk id) in the
+  // row's global entry list; the running top-kk (4-column group) maxima persist in knn_topk between the two passes.
+  const uint32_t* d_ntiles;
+  const uint32_t* tile_r0;
+  const uint32_t* tile_nrows;
+  const uint2* knn_ranges;
+  const uint32_t* knn_roff;
+  const uint32_t* knn_rcount;
+  const uint32_t* knn_nblk;      // blocks per tile (sum over its ranges)
+  int kk;
+  int knn_first_pass;            // 1: the per-row state starts empty; the tile's ranges hold its own cluster TWICE:
+                                 //    the first sweep only builds the top-kk threshold, the second one only records
+  uint32_t knn_stride;           // = 2 * (number of sorted positions): stride of the [kk][stride] top-kk state
+  float* knn_topk;               // [kk][stride] descending chunk maxima of half-row (pos * 2 + h)
+  uint32_t* knn_cnt;             // [stride] entries used
+  uint32_t* knn_flags;           // [stride]
+  float* knn_margin;             // [stride / 2]
+  float* knn_dub;                // [stride] upper bound of the exact distance to the kk-th nearest candidate seen so far
+  uint4* knn_entries;            // [stride][KNN_CAP]: (chunk max bits, mask, chunk id, -)
   float* dbg_scores;         // optional [ntiles*128][nt*128] dump of the approximate scores
 };
 
@@ -158,17 +186,21 @@ __global__ void tc_prep_stats_kernel(const float* __restrict__ csq, uint32_t K, 
 }
 
 // cosine: upper bound of ||c||^2 per centroid (one warp per row)
-__global__ void tc_prep_norms_kernel(const float* __restrict__ C, uint32_t K, int D, float* __restrict__ out) {
+// (k-NN: the "centroids" are the samples in cluster-sorted order, row r = C[gather[r]], and the value feeds the bias
+// term, so no safety factor is applied)
+__global__ void tc_prep_norms_kernel(const float* __restrict__ C, uint32_t K, int D, float* __restrict__ out,
+                                     const uint32_t* __restrict__ gather, float factor) {
   const uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= K) return;
+  const float* src = C + static_cast<size_t>(gather ? gather[row] : row) * D;
   float a = 0.f;
   for (int f = lane; f < D; f += 32) {
-    float v = C[static_cast<size_t>(row) * D + f];
+    float v = src[f];
     a = fmaf(v, v, a);
   }
   for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-  if (lane == 0) out[row] = a * 1.0001f;
+  if (lane == 0) out[row] = a * factor;
 }
 
 __global__ void tc_prep_scale_kernel(Stats* __restrict__ st) {
@@ -187,7 +219,8 @@ __global__ void tc_prep_scale_kernel(Stats* __restrict__ st) {
 // one warp per centroid row (including the zero padding rows up to nt*256)
 __global__ void tc_prep_table_kernel(int metric, const float* __restrict__ C, const float* __restrict__ csq,
                                      uint32_t K, int D, int nkb, int nt, __half* __restrict__ table,
-                                     __half* __restrict__ aug_blob, Stats* __restrict__ st) {
+                                     __half* __restrict__ aug_blob, Stats* __restrict__ st,
+                                     const uint32_t* __restrict__ gather) {
   const uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t rows_pad = static_cast<uint32_t>(nt) * TN;
@@ -195,11 +228,12 @@ __global__ void tc_prep_table_kernel(int metric, const float* __restrict__ C, co
   const int Dp = nkb * KB;
   const float s = st->scale;
   bool finite = row < K;
+  const float* Crow = C + static_cast<size_t>((finite && gather) ? gather[row] : row) * D;
   if (finite) {
     float q = csq[row];
     finite = (q == q) && q < 3.0e38f;
     for (int f = lane; f < D; f += 32) {
-      float v = C[static_cast<size_t>(row) * D + f];
+      float v = Crow[f];
       if (!(fabsf(v) < 3.0e38f)) finite = false;
     }
     finite = __all_sync(0xffffffffu, finite);
@@ -208,7 +242,7 @@ __global__ void tc_prep_table_kernel(int metric, const float* __restrict__ C, co
       // overflowing norm can: the filter has no bound for it, so the whole pass runs exact
       bool has_nan = false;
       for (int f = lane; f < D; f += 32) {
-        float v = C[static_cast<size_t>(row) * D + f];
+        float v = Crow[f];
         has_nan |= (v != v);
       }
       has_nan = __any_sync(0xffffffffu, has_nan);
@@ -217,7 +251,7 @@ __global__ void tc_prep_table_kernel(int metric, const float* __restrict__ C, co
   }
   float d2 = 0.f;
   for (int f = lane; f < Dp; f += 32) {
-    float v = (finite && f < D) ? C[static_cast<size_t>(row) * D + f] * s : 0.f;
+    float v = (finite && f < D) ? Crow[f] * s : 0.f;
     __half h = __float2half_rn(v);
     float r = v - __half2float(h);
     d2 = fmaf(r, r, d2);
@@ -278,6 +312,67 @@ __device__ __noinline__ uint32_t compact_list(float* list_cm, uint32_t* list_mas
   return w;
 }
 
+// enumerates the n-tiles (blocks of 128 table rows) one sample tile is multiplied with
+template <int MODE>
+struct BlockIter {
+  uint32_t cur, hi, left;        // current block, end of the current range, blocks left including cur
+  const uint2* rg;
+  __device__ __forceinline__ BlockIter(const Params& p, uint32_t tile) {
+    if (MODE == 2) {
+      left = p.knn_nblk[tile];
+      rg = p.knn_ranges + p.knn_roff[tile];
+      if (left) { cur = rg->x; hi = rg->y; } else { cur = hi = 0; }
+    } else {
+      left = static_cast<uint32_t>(p.nt);
+      cur = 0;
+      hi = left - 1;
+      rg = nullptr;
+    }
+  }
+  __device__ __forceinline__ bool valid() const { return left != 0; }
+  __device__ __forceinline__ bool last() const { return left == 1; }
+  __device__ __forceinline__ void next() {
+    left--;
+    if (cur == hi && left) { rg++; cur = rg->x; hi = rg->y; } else { cur++; }
+  }
+};
+
+// k-NN epilogue helpers (rare paths, kept out of line): sorted insert into the half-row's descending top-kk column
+// in shared memory; returns the new kk-th largest value
+__device__ __noinline__ float knn_topk_insert(float* col, int kk, float v) {
+  int j = kk - 1;
+  while (j > 0 && col[(j - 1) * 256] < v) {
+    col[j * 256] = col[(j - 1) * 256];
+    j--;
+  }
+  col[j * 256] = v;
+  return col[(kk - 1) * 256];
+}
+// top kk of the union of two descending lists (the two column halves of one row hold disjoint columns)
+__device__ __noinline__ void knn_merge(const float* a, size_t astride, const float* b, size_t bstride, int kk,
+                                       float* out) {
+  int i = 0, j = 0;
+  for (int o = 0; o < kk; o++) {
+    const float av = a[i * astride], bv = b[j * bstride];
+    if (av >= bv) { out[o] = av; i++; } else { out[o] = bv; j++; }
+  }
+}
+// append to the half-row's global entry list; when full, drop the entries whose chunk maximum fell below thr
+__device__ __noinline__ uint32_t knn_append(uint4* ent, uint32_t cnt, float thr, float cm, uint32_t mask, uint32_t cid,
+                                            uint32_t* flags) {
+  if (cnt == KNN_CAP) {
+    uint32_t w = 0;
+    for (uint32_t i = 0; i < cnt; i++) {
+      const uint4 e = ent[i];
+      if (__uint_as_float(e.x) >= thr) ent[w++] = e;
+    }
+    cnt = w;
+    if (cnt == KNN_CAP) { *flags |= 2u; return cnt; }
+  }
+  ent[cnt] = make_uint4(__float_as_uint(cm), mask, cid, 0u);
+  return cnt + 1;
+}
+
 template <int NKB, int MODE>   // NKB: K-blocks of 64 features (compile-time: the MMA issue loop must be branch- and
                                // address-arithmetic-free); MODE 0 = Lloyd assignment, 1 = Yinyang local step (see Params)
 __global__ void __launch_bounds__(N_THREADS, 1)
@@ -294,7 +389,7 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
   constexpr int NBUF = NKB <= 4 ? 2 : 1;   // A operand buffers in TMEM (256 columns are available for A)
   const int nt = p.nt;
   const uint32_t n_eff = MODE == 1 ? min(*p.d_nrows, p.n) : p.n;
-  const uint32_t ntiles = MODE == 1 ? (n_eff + TM - 1) / TM : p.ntiles;
+  const uint32_t ntiles = MODE == 1 ? (n_eff + TM - 1) / TM : (MODE == 2 ? *p.d_ntiles : p.ntiles);
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmap_b);
@@ -338,7 +433,8 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
     if (lane == 0) {
       uint32_t pc = 0, ac = 0;
       for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        for (int n = 0; n < nt; n++) {
+        for (BlockIter<MODE> it(p, tile); it.valid(); it.next()) {
+          const int n = static_cast<int>(it.cur);
 #pragma unroll
           for (int st = 0; st < SPN; st++, pc++) {
             const int s = pc % B_STAGES;
@@ -385,11 +481,13 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
     const uint64_t aug_ad = ptx::make_smem_desc(ptx::smem_u32(smem + L.aug_a), TM * 16, 128, 0);
     const uint32_t augb = ptx::smem_u32(smem + L.aug_b);
     uint32_t pc = 0, ac = 0, ti = 0;
-    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ti++) {
+    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      if (MODE == 2 && p.knn_nblk[tile] == 0) continue;   // nothing to visit: every role skips the tile
       const int abuf = ti % NBUF;
       const uint32_t a_par = (ti / NBUF) & 1;
       const uint32_t a_tmem = tmem_base + TMEM_A0 + abuf * 128;
-      for (int n = 0; n < nt; n++, ac++) {
+      bool first = true;
+      for (BlockIter<MODE> it(p, tile); it.valid(); it.next(), ac++, first = false) {
         const int buf = ac & 1;
         const uint32_t aph = (ac >> 1) & 1;
         TC_WAIT(BAR_ACC_EMPTY + buf, aph ^ 1, 3);
@@ -399,7 +497,7 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
           const int s = pc % B_STAGES;
           const uint32_t ph = (pc / B_STAGES) & 1;
           const int nk = (2 * st + 1 < NKB) ? 2 : 1;
-          if (n == 0) {
+          if (first) {
             TC_WAIT(BAR_A_FULL + abuf * MAX_NKB + 2 * st, a_par, 4);
             if (nk == 2) TC_WAIT(BAR_A_FULL + abuf * MAX_NKB + 2 * st + 1, a_par, 4);
           }
@@ -431,10 +529,11 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
           ptx::umma_f16(d_tmem, aug_ad, bd, idesc, 1u);
           ptx::umma_commit(&bars[BAR_AUG_EMPTY + buf]);
           ptx::umma_commit(&bars[BAR_ACC_FULL + buf]);
-          if (n == nt - 1) ptx::umma_commit(&bars[BAR_A_FREE + abuf]);  // every MMA reading this A buffer is done
+          if (it.last()) ptx::umma_commit(&bars[BAR_A_FREE + abuf]);  // every MMA reading this A buffer is done
         }
         __syncwarp();
       }
+      ti++;
     }
   } else if (warp >= FIRST_CONV_WARP && warp < FIRST_EPI_WARP) {
     // ================================ converters: fp32 smem stage -> fp16 A operand in TMEM ================================
@@ -442,7 +541,8 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
     const int row = q * 32 + lane;          // this thread's sample row within the tile
     const float s = p.stats->scale;
     uint32_t xc = 0, ti = 0;
-    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ti++) {
+    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      if (MODE == 2 && p.knn_nblk[tile] == 0) continue;
       const int abuf = ti % NBUF;
       TC_WAIT(BAR_A_FREE + abuf, ((ti / NBUF) & 1) ^ 1, 7);   // MMAs of the previous user of this buffer are done
       ptx::tc_fence_after();
@@ -450,6 +550,10 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
       const float* xrow = nullptr;
       if (MODE == 1) {
         const uint32_t li = min(tile * TM + row, n_eff - 1);   // ragged tail: repeat the last listed row
+        xrow = p.X + static_cast<size_t>(p.rows[li]) * p.D;
+      }
+      if (MODE == 2) {   // rows past the tile's own cluster are computed but never recorded
+        const uint32_t li = min(p.tile_r0[tile] + row, p.n - 1);
         xrow = p.X + static_cast<size_t>(p.rows[li]) * p.D;
       }
       for (int kb = 0; kb < nkb; kb++) {
@@ -498,6 +602,7 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&bars[BAR_A_FULL + abuf * MAX_NKB + kb]);
       }
+      ti++;
     }
   } else if (warp >= FIRST_EPI_WARP && warp < FIRST_EMIT_WARP) {
     // ================================ epilogue ================================
@@ -511,17 +616,42 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
     // never rises above s^2 * 1 (the accumulator holds s^2 * dot)
     const float cap = p.metric == 1 ? p.stats->scale * p.stats->scale : INFINITY;
     uint32_t ac = 0, ti = 0;
-    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ti++) {
+    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      if (MODE == 2 && p.knn_nblk[tile] == 0) continue;
       const int par = ti & 1;
       float* list_cm = reinterpret_cast<float*>(smem + L.list_cm) + par * LIST_LEN * 256;
       uint32_t* list_mask = reinterpret_cast<uint32_t*>(smem + L.list_mask) + par * LIST_LEN * 256;
       uint16_t* list_g = reinterpret_cast<uint16_t*>(smem + L.list_g) + par * LIST_LEN * 256;
       float* fin = reinterpret_cast<float*>(smem + L.fin) + par * 5 * 256;
       // the emitter warps must have consumed this parity's lists (tile ti-2)
-      TC_WAIT(BAR_EMIT_EMPTY + par, ((ti >> 1) & 1) ^ 1, 11);
+      if (MODE != 2) TC_WAIT(BAR_EMIT_EMPTY + par, ((ti >> 1) & 1) ^ 1, 11);
       float M = -INFINITY, M2 = -INFINITY, margin = 0.f;   // M2: MODE 1, second largest chunk maximum
       uint32_t cnt = 0, flags = 0;
-      for (int n = 0; n < nt; n++, ac++) {
+      // MODE 2: this half-row's persistent state (global) and its top-kk column (the list_cm region is free)
+      float* topk = reinterpret_cast<float*>(smem + L.list_cm) + slot;   // [kk][256], kk <= 16 < 2 * LIST_LEN rows
+      uint32_t kslot = 0;
+      bool klive = false;
+      uint4* kent = nullptr;
+      if (MODE == 2) {
+        klive = static_cast<uint32_t>(row) < p.tile_nrows[tile];
+        kslot = (min(p.tile_r0[tile] + row, p.n - 1)) * 2u + h;
+        kent = p.knn_entries + static_cast<size_t>(kslot) * KNN_CAP;
+        if (p.knn_first_pass || !klive) {
+          for (int j = 0; j < p.kk; j++) topk[j * 256] = -INFINITY;
+        } else {
+          // second pass: both halves saved the same merged list at the end of the first pass (no insertion happens
+          // in the recording sweep); from here on each half adds its own, disjoint, columns
+          for (int j = 0; j < p.kk; j++) topk[j * 256] = p.knn_topk[static_cast<size_t>(j) * p.knn_stride + kslot];
+          cnt = p.knn_cnt[kslot];
+          flags = p.knn_flags[kslot];
+        }
+        M = topk[(p.kk - 1) * 256];                 // MODE 2: M holds the kk-th largest chunk maximum
+      }
+      bool first = true;
+      uint32_t warm = 0, bidx = 0;      // MODE 2, first pass: blocks [0, warm) = threshold sweep
+      if (MODE == 2 && p.knn_first_pass) warm = p.knn_nblk[tile] >> 1;
+      for (BlockIter<MODE> it(p, tile); it.valid(); it.next(), ac++, first = false, bidx++) {
+        const int n = static_cast<int>(it.cur);
         const int buf = ac & 1;
         const uint32_t aph = (ac >> 1) & 1;
         TC_WAIT(BAR_ACC_FULL + buf, aph, 8);
@@ -531,7 +661,7 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + TMEM_ACC0 + buf * TN + h * 64;
         ptx::tmem_ld_32x32(taddr, r0);
         ptx::tmem_ld_32x32(taddr + 32, r1);
-        if (n == 0) {
+        if (first) {
           const float* norms = reinterpret_cast<const float*>(smem + L.norms) + (ti & 3) * 2 * TM;
           // rigorous bound on |acc - (s^2 x.c - s^2||c||^2/2)| (see header): Cauchy-Schwarz on the
           // actual rounding residuals + accumulation + the reference's own rounding slack
@@ -540,7 +670,7 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
           float E = nx * dcmax + nd * cmax + nd * dcmax;
           E += static_cast<float>(p.nkb * KB + 16) * 2.4e-7f * nx * cmax;   // fp32 accumulation in the tensor core
           E += 2.0e-6f * (cmax * cmax + xn * cmax);                        // reference Kahan/rd rounding, bias split
-          if (MODE == 1) E += 2.0e-6f * xn * xn;                           // true distances: rounding of sum (x-c)^2
+          if (MODE >= 1) E += 2.0e-6f * xn * xn;                           // true distances: rounding of sum (x-c)^2
           margin = 2.f * E * 1.001f + 1e-30f;
           if (!(margin < 1.0e30f)) flags |= 1u;                            // NaN / Inf somewhere in the row
         }
@@ -570,13 +700,40 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
         if (MODE == 0) {
           M = fmaxf(M, fmaxf(cm0, cm1));
           thr = fminf(M, cap) - margin;
-        } else {
+        } else if (MODE == 1) {
           // two distinct columns reach min(two largest chunk maxima): a lower bound of the second best score
           M2 = fmaxf(M2, fminf(M, cm0));
           M = fmaxf(M, cm0);
           M2 = fmaxf(M2, fminf(M, cm1));
           M = fmaxf(M, cm1);
           thr = fminf(M2, cap) - margin;
+        } else {
+          // kk distinct columns reach the kk-th largest chunk maximum: a lower bound of the kk-th best score
+          if (p.knn_first_pass && bidx == warm) {
+            // threshold sweep done: both column halves of the row adopt the merged top-kk (the partner warp
+            // e ^ 4 sits on the same row quarter); named barrier per quarter, 64 threads
+            float mg[KNN_MAX_KK];
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+            knn_merge(topk, 256, reinterpret_cast<float*>(smem + L.list_cm) + ((1 - h) * TM + row), 256, p.kk, mg);
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+            for (int j = 0; j < p.kk; j++) topk[j * 256] = mg[j];
+            M = mg[p.kk - 1];
+          }
+          if (!p.knn_first_pass || bidx < warm) {
+            // 4-column group maxima (first level of the max tree): kk distinct columns reach the kk-th largest of
+            // them; finer than whole chunks because the nearest neighbours sit close together in the sorted order
+            if (cm0 > M) {
+#pragma unroll
+              for (int i = 0; i < 8; i++)
+                if (t0[i] > M) M = knn_topk_insert(topk, p.kk, t0[i]);
+            }
+            if (cm1 > M) {
+#pragma unroll
+              for (int i = 0; i < 8; i++)
+                if (t1[i] > M) M = knn_topk_insert(topk, p.kk, t1[i]);
+            }
+          }
+          thr = M - margin;
         }
         // candidate masks on the (otherwise idle) FMA pipe instead of FSETP + LOP3 on the ALU pipe:
         //   nc_j = sat(BIG * (thr - v_j))  is exactly 1 when v_j < thr and exactly 0 when v_j >= thr
@@ -603,6 +760,13 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
         }
         if (bad) flags |= 4u;
         const uint32_t mask0 = ~nc0, mask1 = ~nc1;
+        if (MODE == 2) {
+          if (klive && bidx >= warm) {
+            if (mask0) cnt = knn_append(kent, cnt, thr, cm0, mask0, static_cast<uint32_t>(n) * 4 + h * 2, &flags);
+            if (mask1) cnt = knn_append(kent, cnt, thr, cm1, mask1, static_cast<uint32_t>(n) * 4 + h * 2 + 1, &flags);
+          }
+          continue;
+        }
         if (cnt >= LIST_LEN - 1 && (mask0 | mask1))
           cnt = compact_list(list_cm, list_mask, list_g, slot, cnt, thr);   // rare: drop entries below the risen threshold
         if (mask0) {
@@ -626,6 +790,23 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
           }
         }
       }
+      if (MODE == 2) {
+        if (klive) {
+          for (int j = 0; j < p.kk; j++) p.knn_topk[static_cast<size_t>(j) * p.knn_stride + kslot] = topk[j * 256];
+          p.knn_cnt[kslot] = cnt;
+          p.knn_flags[kslot] = flags;
+          if (h == 0) p.knn_margin[kslot >> 1] = margin;
+          // exact distance to the kk-th nearest candidate, upper bound in the caller's units:
+          // s^2 d^2 = ||s x||^2 - 2 (s^2 x.y - s^2 ||y||^2 / 2) <= (nx + nd)^2 - 2 (M - margin)
+          const float* norms = reinterpret_cast<const float*>(smem + L.norms) + (ti & 3) * 2 * TM;
+          const float xn = (__fsqrt_ru(norms[row]) + __fsqrt_ru(norms[TM + row])) * 1.0001f;
+          const float sc = p.stats->scale;
+          const float d2 = fmaxf(0.f, xn * xn - 2.f * (M - margin));
+          p.knn_dub[kslot] = (M > -INFINITY && !flags) ? __fsqrt_ru(d2) / sc * 1.0001f : INFINITY;
+        }
+        ti++;
+        continue;
+      }
       // publish this half-row's state; the emitter warps merge the halves and write the results
       fin[slot] = M;
       reinterpret_cast<uint32_t*>(fin)[256 + slot] = cnt;
@@ -634,8 +815,9 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
       if (MODE == 1) fin[1024 + slot] = M2;
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&bars[BAR_EMIT_FULL + par]);
+      ti++;
     }
-  } else if (warp >= FIRST_EMIT_WARP) {
+  } else if (warp >= FIRST_EMIT_WARP && MODE != 2) {
     // ================================ emitters: merge column halves, write results / queues ================================
     const int row = (warp - FIRST_EMIT_WARP) * 32 + lane;
     const float cap = p.metric == 1 ? p.stats->scale * p.stats->scale : INFINITY;
@@ -877,12 +1059,15 @@ static void tc_launch_mode(int nkb, unsigned grid, size_t smem, cudaStream_t st,
 }
 static void tc_launch_main(int mode, int nkb, unsigned grid, size_t smem, cudaStream_t st, const CUtensorMap& tb,
                            const CUtensorMap& tx, const tc::Params& prm) {
-  if (mode == 1) tc_launch_mode<1>(nkb, grid, smem, st, tb, tx, prm);
+  if (mode == 2) tc_launch_mode<2>(nkb, grid, smem, st, tb, tx, prm);
+  else if (mode == 1) tc_launch_mode<1>(nkb, grid, smem, st, tb, tx, prm);
   else tc_launch_mode<0>(nkb, grid, smem, st, tb, tx, prm);
 }
 template <int NKB>
 static cudaError_t tc_set_smem_attr_one(int bytes) {
   cudaError_t e = cudaFuncSetAttribute(tc::tc_assign_kernel<NKB, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(tc::tc_assign_kernel<NKB, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   if (e != cudaSuccess) return e;
   return cudaFuncSetAttribute(tc::tc_assign_kernel<NKB, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
 }
@@ -991,14 +1176,14 @@ static cudaError_t tc_prepare(TcPlan* p, const float* C, const float* csq, uint3
   if ((e = cudaMemsetAsync(p->stats, 0, sizeof(Stats), st)) != cudaSuccess) return e;
   const float* nsq = csq;
   if (p->metric == 1) {
-    tc_prep_norms_kernel<<<(p->K * 32 + 255) / 256, 256, 0, st>>>(C, p->K, p->D, p->cnorm2);
+    tc_prep_norms_kernel<<<(p->K * 32 + 255) / 256, 256, 0, st>>>(C, p->K, p->D, p->cnorm2, nullptr, 1.0001f);
     nsq = p->cnorm2;
   }
   tc_prep_stats_kernel<<<8, 256, 0, st>>>(nsq, p->K, p->stats);
   tc_prep_scale_kernel<<<1, 1, 0, st>>>(p->stats);
   const uint32_t rows_pad = static_cast<uint32_t>(p->nt) * TN;
   tc_prep_table_kernel<<<(rows_pad * 32 + 255) / 256, 256, 0, st>>>(p->metric, C, nsq, p->K, p->D, p->nkb, p->nt, p->table,
-                                                                    p->aug_blob, p->stats);
+                                                                    p->aug_blob, p->stats, nullptr);
   Params prm;
   prm.n = n;
   prm.D = p->D;
@@ -1019,6 +1204,15 @@ static cudaError_t tc_prepare(TcPlan* p, const float* C, const float* csq, uint3
   prm.X = nullptr;
   prm.rows = nullptr;
   prm.d_nrows = nullptr;
+  prm.d_ntiles = nullptr;
+  prm.tile_r0 = prm.tile_nrows = prm.knn_roff = prm.knn_rcount = prm.knn_nblk = nullptr;
+  prm.knn_ranges = nullptr;
+  prm.kk = 0;
+  prm.knn_first_pass = 0;
+  prm.knn_stride = 0;
+  prm.knn_topk = prm.knn_margin = prm.knn_dub = nullptr;
+  prm.knn_cnt = prm.knn_flags = nullptr;
+  prm.knn_entries = nullptr;
   prm.dbg_scores = p->dbg_scores;
   *out = prm;
   return cudaGetLastError();
@@ -1151,5 +1345,425 @@ void tc_debug_stats(TcPlan* p, float* out4) {
   out4[2] = st.dcmax;
   out4[3] = __builtin_bit_cast(float, st.csq_max_bits);
 }
+
+// ===================================================================================================
+// k-NN on the tensor cores (reference knn.cu:177-347: cluster-pruned exact k nearest neighbours)
+//
+// Queries and candidates are the samples in cluster-sorted order (the inverse assignment).  Pass 1 multiplies
+// every query tile (<= 128 queries of one cluster) with the blocks covering its own cluster; that yields, per
+// query, an upper bound of the distance to its k-th neighbour.  The reference's skip test
+// `Cd[B][A] - d(q, A) - R[B] > kth` (knn.cu:218-225) is then evaluated per tile (a cluster is visited if ANY
+// query of the tile needs it) and pass 2 visits the surviving clusters' blocks.  The epilogue records every
+// column whose fp16 score is within the rigorous margin of the row's (k+1)-th best (self included); those
+// candidates get their exact distance (reference METRIC::distance) and the k smallest are written in
+// ascending order.  Any superset of the reference's visited clusters gives the same exact top-k.
+// ===================================================================================================
+namespace knn {
+
+__global__ void tile_count_kernel(const uint32_t* __restrict__ off, uint32_t K, uint32_t* __restrict__ ntile) {
+  uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < K) ntile[c] = (off[c + 1] - off[c] + tc::TM - 1) / tc::TM;
+}
+
+__global__ void tile_fill_kernel(const uint32_t* __restrict__ off, uint32_t K, const uint32_t* __restrict__ tile_off,
+                                 uint32_t* __restrict__ tile_r0, uint32_t* __restrict__ tile_nrows,
+                                 uint32_t* __restrict__ tile_cluster, uint2* __restrict__ ranges1,
+                                 uint32_t* __restrict__ roff1, uint32_t* __restrict__ rcount1,
+                                 uint32_t* __restrict__ nblk1, uint32_t* __restrict__ d_ntiles,
+                                 unsigned long long* __restrict__ d_pairs) {
+  uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= K) return;
+  const uint32_t b = off[c], e = off[c + 1], m = e - b;
+  const uint32_t t0 = tile_off[c], nt = (m + tc::TM - 1) / tc::TM;
+  for (uint32_t i = 0; i < nt; i++) {
+    const uint32_t t = t0 + i;
+    tile_r0[t] = b + i * tc::TM;
+    tile_nrows[t] = min(static_cast<uint32_t>(tc::TM), m - i * tc::TM);
+    tile_cluster[t] = c;
+    ranges1[2 * t] = ranges1[2 * t + 1] = make_uint2(b / tc::TN, (e - 1) / tc::TN);   // threshold sweep + recording sweep
+    roff1[t] = 2 * t;
+    rcount1[t] = 2;
+    nblk1[t] = 2 * ((e - 1) / tc::TN - b / tc::TN + 1);
+  }
+  if (m) atomicAdd(d_pairs, static_cast<unsigned long long>(m) * m);   // statistics: own-cluster pairs
+  if (c == K - 1) *d_ntiles = t0 + nt;
+}
+
+// exact distance of every sorted sample to its own centroid (knn.cu:199)
+template <int METRIC>
+__global__ void own_distance_kernel(const float* __restrict__ X, const float* __restrict__ C, int D,
+                                    const uint32_t* __restrict__ inv, const uint32_t* __restrict__ assign,
+                                    uint32_t nv, float* __restrict__ dA) {
+  uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pos >= nv) return;
+  const uint32_t s = inv[pos];
+  dA[pos] = distance_exact<METRIC>(X + static_cast<size_t>(s) * D, C + static_cast<size_t>(assign[s]) * D, D);
+}
+
+// one warp per tile: which clusters must be visited in pass 2, as merged ranges of 128-sample blocks
+__global__ void __launch_bounds__(256)
+range_build_kernel(const uint32_t* __restrict__ d_ntiles, const uint32_t* __restrict__ tile_r0,
+                   const uint32_t* __restrict__ tile_nrows, const uint32_t* __restrict__ tile_cluster,
+                   const uint2* __restrict__ ranges1, const uint32_t* __restrict__ off, uint32_t K,
+                   const float* __restrict__ cd, const float* __restrict__ radii, const float* __restrict__ dA,
+                   const float* __restrict__ dub, uint2* __restrict__ pool, uint32_t pool_cap,
+                   uint32_t* __restrict__ pool_used, uint32_t* __restrict__ roff2, uint32_t* __restrict__ rcount2,
+                   uint32_t* __restrict__ nblk2, uint32_t* __restrict__ d_error,
+                   unsigned long long* __restrict__ d_pairs) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t T = *d_ntiles;
+  for (uint32_t t = warp; t < T; t += nwarps) {
+    const uint32_t r0 = tile_r0[t], nr = tile_nrows[t], A = tile_cluster[t];
+    const uint2 own = ranges1[2 * t];
+    // W = max over the tile's queries of d(q, A) + (upper bound of the distance to the k-th neighbour so far)
+    float W = 0.f;
+    for (uint32_t r = lane; r < nr; r += 32) {
+      const uint32_t pos = r0 + r;
+      const float du = fminf(dub[2 * pos], dub[2 * pos + 1]);
+      const float w = dA[pos] + du;
+      W = (w > W || !(w == w)) ? (w == w ? w : INFINITY) : W;
+    }
+    for (int o = 16; o > 0; o >>= 1) W = fmaxf(W, __shfl_xor_sync(0xffffffffu, W, o));
+    W = W * 1.000002f + 1e-30f;   // the reference rounds `cd - dA - R` twice: stay on the visiting side
+    for (int pass = 0; pass < 2; pass++) {   // pass 0 counts the merged ranges, pass 1 writes them
+      uint32_t count = 0, blocks = 0, base = 0;
+      if (pass == 1) {
+        uint32_t c0 = rcount2[t];
+        if (lane == 0) base = atomicAdd(pool_used, c0);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base + c0 > pool_cap) {
+          if (lane == 0) { *d_error = 1u; rcount2[t] = 0; nblk2[t] = 0; roff2[t] = 0; }
+          break;
+        }
+        if (lane == 0) roff2[t] = base;
+      }
+      uint32_t cur_lo = 1, cur_hi = 0;   // empty
+      unsigned long long pairs = 0;
+      for (uint32_t B0 = 0; B0 < K; B0 += 32) {
+        const uint32_t B = B0 + lane;
+        bool visit = false;
+        uint32_t blo = 0, bhi = 0;
+        if (B < K && B != A) {
+          const uint32_t b = off[B], e = off[B + 1];
+          const float c = cd[static_cast<size_t>(B) * K + A];
+          if (e > b && c == c && !(c - radii[B] > W)) {
+            blo = b / tc::TN;
+            bhi = (e - 1) / tc::TN;
+            if (B < A) { if (bhi >= own.x) bhi = own.x - 1; visit = own.x > 0 && blo <= bhi && blo < own.x; }
+            else { if (blo <= own.y) blo = own.y + 1; visit = blo <= bhi; }
+            if (pass == 0 && lane < 32) pairs += static_cast<unsigned long long>(e - b) * nr;
+          }
+        }
+        unsigned m = __ballot_sync(0xffffffffu, visit);
+        while (m) {
+          const int src = __ffs(m) - 1;
+          m &= m - 1;
+          const uint32_t lo = __shfl_sync(0xffffffffu, blo, src), hi = __shfl_sync(0xffffffffu, bhi, src);
+          if (cur_lo <= cur_hi && lo <= cur_hi + 1) {
+            if (hi > cur_hi) { blocks += hi - cur_hi; cur_hi = hi; }
+          } else {
+            if (cur_lo <= cur_hi) {
+              if (pass == 1 && lane == 0) pool[base + count] = make_uint2(cur_lo, cur_hi);
+              count++;
+            }
+            cur_lo = lo;
+            cur_hi = hi;
+            blocks += hi - lo + 1;
+          }
+        }
+      }
+      if (cur_lo <= cur_hi) {
+        if (pass == 1 && lane == 0) pool[base + count] = make_uint2(cur_lo, cur_hi);
+        count++;
+      }
+      if (pass == 0) {
+        if (lane == 0) { rcount2[t] = count; nblk2[t] = blocks; }
+        for (int o = 16; o > 0; o >>= 1) pairs += __shfl_xor_sync(0xffffffffu, pairs, o);
+        if (lane == 0 && pairs) atomicAdd(d_pairs, pairs);
+        __syncwarp();
+      }
+    }
+  }
+}
+
+// one warp per sorted query: final threshold, expansion of the recorded (chunk, mask) entries into candidate pairs
+__global__ void __launch_bounds__(256)
+expand_kernel(uint32_t nv, int kk, uint32_t stride, const float* __restrict__ topk, const uint32_t* __restrict__ cnts,
+              const uint32_t* __restrict__ flags, const float* __restrict__ margin,
+              const uint4* __restrict__ entries, const uint32_t* __restrict__ inv, uint32_t max_pairs,
+              uint32_t* __restrict__ pair_row, uint32_t* __restrict__ pair_cand, uint32_t* __restrict__ rowq,
+              uint32_t* __restrict__ fb_rows, uint32_t* __restrict__ counters, uint32_t* __restrict__ dbg) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t pos = warp; pos < nv; pos += nwarps) {
+    const uint32_t s0 = 2 * pos, s1 = 2 * pos + 1;
+    const float k0 = topk[static_cast<size_t>(kk - 1) * stride + s0], k1 = topk[static_cast<size_t>(kk - 1) * stride + s1];
+    const float kth = fmaxf(k0, k1);   // each half saw kk distinct columns at or above its own value
+    const uint32_t fl = flags[s0] | flags[s1];
+    const uint32_t c0 = cnts[s0], c1 = cnts[s1];
+    bool fallback = fl != 0 || !(kth > -INFINITY);
+    if (lane == 0 && dbg) { if (fl & 1) atomicAdd(dbg + 0, 1u); if (fl & 2) atomicAdd(dbg + 1, 1u); if (fl & 4) atomicAdd(dbg + 2, 1u); if (!(kth > -INFINITY)) atomicAdd(dbg + 3, 1u); }
+    const float thr = kth - margin[pos];
+    // each lane takes entries lane, lane+32, ... of the concatenated (half 0, half 1) lists
+    uint32_t mine = 0;
+    const uint32_t total_e = c0 + c1;
+    for (uint32_t i = lane; i < total_e && !fallback; i += 32) {
+      const uint4 e = i < c0 ? entries[static_cast<size_t>(s0) * tc::KNN_CAP + i]
+                             : entries[static_cast<size_t>(s1) * tc::KNN_CAP + (i - c0)];
+      if (__uint_as_float(e.x) >= thr) {
+        uint32_t m = e.y;
+        const uint32_t p0 = (e.z >> 2) * 128u + ((e.z >> 1) & 1u) * 64u + (e.z & 1u) * 32u;
+        while (m) {
+          const uint32_t cp = p0 + __ffs(m) - 1;
+          m &= m - 1;
+          if (cp < nv && cp != pos) mine++;
+        }
+      }
+    }
+    uint32_t pre = mine;
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t v = __shfl_up_sync(0xffffffffu, pre, o);
+      if (lane >= o) pre += v;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, pre, 31);
+    if (lane == 0 && dbg && !fallback) { if (total > 64) atomicAdd(dbg + 4, 1u); if (total < static_cast<uint32_t>(kk - 1)) atomicAdd(dbg + 5, 1u); atomicAdd(dbg + 6, total); }
+    if (total > 64 || total < static_cast<uint32_t>(kk - 1)) fallback = true;
+    uint32_t base = 0;
+    if (!fallback) {
+      if (lane == 0) base = atomicAdd(&counters[tc::CNT_PAIRS], total);
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (base + total > max_pairs) fallback = true;
+    }
+    if (fallback) {
+      if (lane == 0) fb_rows[atomicAdd(&counters[tc::CNT_OVF], 1u)] = inv[pos];
+      continue;
+    }
+    const uint32_t self = inv[pos];
+    uint32_t w = base + pre - mine;
+    for (uint32_t i = lane; i < total_e; i += 32) {
+      const uint4 e = i < c0 ? entries[static_cast<size_t>(s0) * tc::KNN_CAP + i]
+                             : entries[static_cast<size_t>(s1) * tc::KNN_CAP + (i - c0)];
+      if (__uint_as_float(e.x) >= thr) {
+        uint32_t m = e.y;
+        const uint32_t p0 = (e.z >> 2) * 128u + ((e.z >> 1) & 1u) * 64u + (e.z & 1u) * 32u;
+        while (m) {
+          const uint32_t cp = p0 + __ffs(m) - 1;
+          m &= m - 1;
+          if (cp < nv && cp != pos) {
+            pair_row[w] = self;
+            pair_cand[w] = inv[cp];
+            w++;
+          }
+        }
+      }
+    }
+    if (lane == 0) {
+      const uint32_t q = atomicAdd(&counters[tc::CNT_ROWQ], 1u);
+      rowq[3 * q] = self;
+      rowq[3 * q + 1] = base;
+      rowq[3 * q + 2] = total;
+    }
+  }
+}
+
+// one warp per query: the k smallest exact distances in ascending order (knn.cu:239-242)
+__global__ void __launch_bounds__(256)
+select_kernel(int k, const uint32_t* __restrict__ rowq, const uint32_t* __restrict__ counters,
+              const uint32_t* __restrict__ pair_cand, const float* __restrict__ pair_score, uint32_t q_offset,
+              uint32_t* __restrict__ neighbors) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t nq = counters[tc::CNT_ROWQ];
+  for (uint32_t q = warp; q < nq; q += nwarps) {
+    const uint32_t row = rowq[3 * q], base = rowq[3 * q + 1], cnt = rowq[3 * q + 2];
+    float d[2];
+    uint32_t id[2];
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+      const uint32_t i = lane + 32 * j;
+      d[j] = INFINITY;
+      id[j] = UINT32_MAX;
+      if (i < cnt) {
+        const float v = pair_score[base + i];
+        if (v == v) { d[j] = v; id[j] = pair_cand[base + i]; }
+      }
+    }
+    for (int r = 0; r < k; r++) {
+      // lexicographic (distance, index) minimum over the 64 slots
+      float bd = d[0];
+      uint32_t bi = id[0];
+      if (d[1] < bd || (d[1] == bd && id[1] < bi)) { bd = d[1]; bi = id[1]; }
+      for (int o = 16; o > 0; o >>= 1) {
+        const float od = __shfl_xor_sync(0xffffffffu, bd, o);
+        const uint32_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+      }
+      if (lane == 0) neighbors[static_cast<size_t>(row - q_offset) * k + r] = bi;
+      if (id[0] == bi) { d[0] = INFINITY; id[0] = UINT32_MAX; }
+      if (id[1] == bi) { d[1] = INFINITY; id[1] = UINT32_MAX; }
+    }
+  }
+}
+
+}  // namespace knn
+
+bool tc_knn_supported(int metric, int k, uint32_t N, int D, uint32_t K) {
+  if (metric != 0) return false;                                   // angular k-NN: SIMT path
+  if (k + 1 > tc::KNN_MAX_KK) return false;
+  if (D < 4 || D % 4 != 0 || D > tc::MAX_NKB * tc::KB) return false;
+  if (N < 4096 || N > (1u << 30)) return false;                    // tiny inputs: not worth the set-up
+  if (static_cast<uint64_t>(K) * K > (1ull << 31)) return false;
+  return true;
+}
+
+#define KNN_TRY(x) do { e = (x); if (e != cudaSuccess) goto done; } while (0)
+
+// neighbors: device array [q_length][k] for the queries q_offset .. q_offset+q_length (original sample indices;
+// this build shards k-NN queries only on the SIMT path, so q_offset = 0 and q_length = N here).
+// Rows the filter cannot serve are appended to fb_rows / d_nfb for the caller's exact search.
+cudaError_t tc_knn_search(int k, const float* X, const float* C, uint32_t N, int D, uint32_t K,
+                          const uint32_t* assign, const uint32_t* inv, const uint32_t* off, const float* cd,
+                          const float* radii, uint32_t nv, uint32_t* neighbors, uint32_t* fb_rows, uint32_t* d_nfb,
+                          unsigned long long* d_pairs, uint32_t* h_error, cudaStream_t st) {
+  using namespace tc;
+  cudaError_t e = cudaSuccess;
+  *h_error = 0;
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return cudaErrorNotSupported;
+  int dev = 0, num_sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+  const int nkb = (D + KB - 1) / KB, kk = k + 1;
+  const uint32_t nblk = (nv + TN - 1) / TN, rows_pad = nblk * TN;
+  const uint32_t tmax = nv / TM + K + 1;
+  const uint32_t stride = 2 * nv;
+  const uint64_t want_pool = static_cast<uint64_t>(tmax) * (K / 2 + 2);
+  const uint32_t pool_cap = static_cast<uint32_t>(want_pool < (32u << 20) ? want_pool : (32u << 20));
+  const uint32_t max_pairs = nv < (1u << 25) ? 64u * nv : 0xFFFFFFF0u;   // hard per-row cap is 64 candidates
+  // pairs are expanded lazily: average ~20-40 per row; allocate 48 per row and fall back beyond
+  const uint32_t pair_cap = static_cast<uint32_t>(std::min<uint64_t>(48ull * nv + 1024, max_pairs));
+  __half *table = nullptr, *blobs = nullptr;
+  float *xsq = nullptr, *dA = nullptr, *topk = nullptr, *kmargin = nullptr, *dub = nullptr, *pair_score = nullptr;
+  Stats* stats = nullptr;
+  uint32_t *u32 = nullptr, *kcnt = nullptr, *kflags = nullptr, *pair_row = nullptr, *pair_cand = nullptr, *rowq = nullptr;
+  uint32_t* counters = nullptr;
+  uint2 *ranges1 = nullptr, *pool = nullptr;
+  uint4* entries = nullptr;
+  void* cub_tmp = nullptr;
+  size_t cub_bytes = 0;
+  uint32_t h_cnt[CNT_N + 2] = {0};
+  uint32_t h_dbg[8] = {0};
+  CUtensorMap tmap;
+  Params prm;
+  unsigned grid = static_cast<unsigned>(num_sms);
+  const size_t smem_bytes = smem_layout().total + 1024;
+  // per-tile u32 arrays: ntile[K], tile_off[K+1], r0, nrows, cluster, roff1, rcount1, nblk1, roff2, rcount2, nblk2
+  uint32_t *ntile, *tile_off, *t_r0, *t_nrows, *t_cluster, *roff1, *rcount1, *nblk1, *roff2, *rcount2, *nblk2, *d_ntiles,
+      *pool_used, *d_err;
+  {
+    const size_t words = static_cast<size_t>(K) + (K + 1) + 9ull * tmax + 16;
+    KNN_TRY(cudaMalloc(&u32, words * sizeof(uint32_t)));
+    KNN_TRY(cudaMemsetAsync(u32, 0, words * sizeof(uint32_t), st));
+    uint32_t* q = u32;
+    ntile = q; q += K;
+    tile_off = q; q += K + 1;
+    t_r0 = q; q += tmax; t_nrows = q; q += tmax; t_cluster = q; q += tmax;
+    roff1 = q; q += tmax; rcount1 = q; q += tmax; nblk1 = q; q += tmax;
+    roff2 = q; q += tmax; rcount2 = q; q += tmax; nblk2 = q; q += tmax;
+    d_ntiles = q++; pool_used = q++; d_err = q++;   // pool_used + 2 .. + 9: debug counters of expand_kernel
+  }
+  KNN_TRY(cudaMalloc(&table, static_cast<size_t>(rows_pad) * nkb * KB * sizeof(__half)));
+  KNN_TRY(cudaMalloc(&blobs, static_cast<size_t>(nblk) * AUG_B_BYTES));
+  KNN_TRY(cudaMalloc(&xsq, sizeof(float) * rows_pad));
+  KNN_TRY(cudaMalloc(&stats, sizeof(Stats)));
+  KNN_TRY(cudaMalloc(&dA, sizeof(float) * nv));
+  KNN_TRY(cudaMalloc(&topk, sizeof(float) * static_cast<size_t>(kk) * stride));
+  KNN_TRY(cudaMalloc(&kmargin, sizeof(float) * nv));
+  KNN_TRY(cudaMalloc(&dub, sizeof(float) * stride));
+  KNN_TRY(cudaMalloc(&kcnt, sizeof(uint32_t) * stride));
+  KNN_TRY(cudaMalloc(&kflags, sizeof(uint32_t) * stride));
+  KNN_TRY(cudaMalloc(&entries, sizeof(uint4) * static_cast<size_t>(stride) * KNN_CAP));
+  KNN_TRY(cudaMalloc(&ranges1, sizeof(uint2) * 2ull * tmax));
+  KNN_TRY(cudaMalloc(&pool, sizeof(uint2) * pool_cap));
+  KNN_TRY(cudaMalloc(&pair_row, sizeof(uint32_t) * pair_cap));
+  KNN_TRY(cudaMalloc(&pair_cand, sizeof(uint32_t) * pair_cap));
+  KNN_TRY(cudaMalloc(&pair_score, sizeof(float) * pair_cap));
+  KNN_TRY(cudaMalloc(&rowq, sizeof(uint32_t) * 3ull * nv));
+  KNN_TRY(cudaMalloc(&counters, sizeof(uint32_t) * CNT_N));
+  KNN_TRY(cudaMemsetAsync(counters, 0, sizeof(uint32_t) * CNT_N, st));
+  KNN_TRY(cudaMemsetAsync(stats, 0, sizeof(Stats), st));
+  KNN_TRY(cudaMemsetAsync(kcnt, 0, sizeof(uint32_t) * stride, st));
+  KNN_TRY(cudaMemsetAsync(kflags, 0, sizeof(uint32_t) * stride, st));
+  KNN_TRY(tc_set_smem_attr(static_cast<int>(smem_bytes)));
+  // fp16 table of the cluster-sorted samples + bias blobs + statistics
+  tc_prep_norms_kernel<<<(nv * 32 + 255) / 256, 256, 0, st>>>(X, nv, D, xsq, inv, 1.0f);
+  tc_prep_stats_kernel<<<8, 256, 0, st>>>(xsq, nv, stats);
+  tc_prep_scale_kernel<<<1, 1, 0, st>>>(stats);
+  tc_prep_table_kernel<<<(rows_pad * 32 + 255) / 256, 256, 0, st>>>(0, X, xsq, nv, D, nkb, static_cast<int>(nblk), table,
+                                                                    blobs, stats, inv);
+  KNN_TRY(cudaGetLastError());
+  {
+    cuuint64_t gdim[2] = {static_cast<cuuint64_t>(nkb * KB), static_cast<cuuint64_t>(rows_pad)};
+    cuuint64_t gstride[1] = {static_cast<cuuint64_t>(nkb * KB) * sizeof(__half)};
+    cuuint32_t box[2] = {KB, TN};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, table, gdim, gstride, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) { e = cudaErrorInvalidValue; goto done; }
+  }
+  // tiles (<= 128 queries of one cluster each) and their own-cluster block ranges
+  knn::tile_count_kernel<<<(K + 255) / 256, 256, 0, st>>>(off, K, ntile);
+  KNN_TRY(cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, ntile, tile_off, static_cast<int>(K), st));
+  KNN_TRY(cudaMalloc(&cub_tmp, cub_bytes ? cub_bytes : 16));
+  KNN_TRY(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, ntile, tile_off, static_cast<int>(K), st));
+  knn::tile_fill_kernel<<<(K + 255) / 256, 256, 0, st>>>(off, K, tile_off, t_r0, t_nrows, t_cluster, ranges1, roff1,
+                                                         rcount1, nblk1, d_ntiles, d_pairs);
+  knn::own_distance_kernel<0><<<(nv + 127) / 128, 128, 0, st>>>(X, C, D, inv, assign, nv, dA);
+  KNN_TRY(cudaGetLastError());
+  prm.n = nv; prm.D = D; prm.K = nv; prm.nkb = nkb; prm.nt = static_cast<int>(nblk); prm.ntiles = 0;
+  prm.aug_blob = blobs; prm.stats = stats; prm.result = nullptr; prm.pair_row = nullptr; prm.pair_cand = nullptr;
+  prm.max_pairs = 0; prm.rowq = nullptr; prm.ovf_rows = nullptr; prm.counters = counters; prm.metric = 0;
+  prm.X = X; prm.rows = inv; prm.d_nrows = nullptr; prm.d_ntiles = d_ntiles; prm.tile_r0 = t_r0;
+  prm.tile_nrows = t_nrows; prm.knn_ranges = ranges1; prm.knn_roff = roff1; prm.knn_rcount = rcount1;
+  prm.knn_nblk = nblk1; prm.kk = kk; prm.knn_first_pass = 1; prm.knn_stride = stride; prm.knn_topk = topk;
+  prm.knn_cnt = kcnt; prm.knn_flags = kflags; prm.knn_margin = kmargin; prm.knn_dub = dub; prm.knn_entries = entries;
+  prm.dbg_scores = nullptr;
+  tc_launch_main(2, nkb, grid, smem_bytes, st, tmap, tmap, prm);
+  KNN_TRY(cudaGetLastError());
+  knn::range_build_kernel<<<num_sms * 4, 256, 0, st>>>(d_ntiles, t_r0, t_nrows, t_cluster, ranges1, off, K, cd, radii, dA,
+                                                       dub, pool, pool_cap, pool_used, roff2, rcount2, nblk2, d_err,
+                                                       d_pairs);
+  KNN_TRY(cudaGetLastError());
+  prm.knn_ranges = pool; prm.knn_roff = roff2; prm.knn_rcount = rcount2; prm.knn_nblk = nblk2; prm.knn_first_pass = 0;
+  tc_launch_main(2, nkb, grid, smem_bytes, st, tmap, tmap, prm);
+  KNN_TRY(cudaGetLastError());
+  knn::expand_kernel<<<num_sms * 8, 256, 0, st>>>(nv, kk, stride, topk, kcnt, kflags, kmargin, entries, inv, pair_cap,
+                                                  pair_row, pair_cand, rowq, fb_rows, counters, pool_used + 2);
+  KNN_TRY(cudaGetLastError());
+  recheck_pairs_kernel<0, 1><<<num_sms * 4, 128, 0, st>>>(X, X, nullptr, D, pair_row, pair_cand, counters + CNT_PAIRS,
+                                                          pair_cap, N, N, pair_score);
+  knn::select_kernel<<<num_sms * 8, 256, 0, st>>>(k, rowq, counters, pair_cand, pair_score, 0u, neighbors);
+  KNN_TRY(cudaGetLastError());
+  KNN_TRY(cudaMemcpyAsync(h_cnt, counters, sizeof(uint32_t) * CNT_N, cudaMemcpyDeviceToHost, st));
+  KNN_TRY(cudaMemcpyAsync(h_cnt + CNT_N, d_err, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  KNN_TRY(cudaMemcpyAsync(d_nfb, counters + CNT_OVF, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+  KNN_TRY(cudaMemcpyAsync(h_dbg, pool_used + 2, sizeof(h_dbg), cudaMemcpyDeviceToHost, st));
+  KNN_TRY(cudaStreamSynchronize(st));
+  *h_error = h_cnt[CNT_ERR] | (h_cnt[CNT_N] ? 0x80000000u : 0u);
+  if (getenv("KMCUDA_B200_TIMING"))
+    fprintf(stderr, "[kmcuda_b200 timing]   knn tensor-core path: %u rows, %u candidate pairs, %u rows to the exact search, "
+            "error word 0x%x; fallback reasons: nan/inf %u, list full %u, tiny diff %u, no threshold %u, >64 cand %u, "
+            "<k cand %u; candidates seen %u\n", h_cnt[CNT_ROWQ], h_cnt[CNT_PAIRS], h_cnt[CNT_OVF], *h_error, h_dbg[0],
+            h_dbg[1], h_dbg[2], h_dbg[3], h_dbg[4], h_dbg[5], h_dbg[6]);
+done:
+  cudaFree(u32); cudaFree(table); cudaFree(blobs); cudaFree(xsq); cudaFree(stats); cudaFree(dA); cudaFree(topk);
+  cudaFree(kmargin); cudaFree(dub); cudaFree(kcnt); cudaFree(kflags); cudaFree(entries); cudaFree(ranges1);
+  cudaFree(pool); cudaFree(pair_row); cudaFree(pair_cand); cudaFree(pair_score); cudaFree(rowq); cudaFree(counters);
+  cudaFree(cub_tmp);
+  return e;
+}
+#undef KNN_TRY
 
 }  // namespace kmb

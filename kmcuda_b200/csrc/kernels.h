@@ -98,7 +98,11 @@ cudaError_t launch_knn_search(int metric, int k, const float* X, const float* C,
                               uint32_t K, uint32_t q_offset, uint32_t q_length, const uint32_t* assign,
                               const uint32_t* inv, const uint32_t* inv_off, const float* cd,
                               const float* radii, float* heap_scratch, uint32_t* neighbors,
-                              unsigned long long* d_pairs, cudaStream_t st);
+                              unsigned long long* d_pairs, const uint32_t* rows, const uint32_t* d_nrows,
+                              cudaStream_t st);
+cudaError_t launch_knn_radii_fix(const uint32_t* inv_off, uint32_t K, float* radii, cudaStream_t st);
+cudaError_t launch_knn_tail_rows(const uint32_t* inv, uint32_t nv, uint32_t n, uint32_t* rows, uint32_t* d_nrows,
+                                 cudaStream_t st);
 
 // ---- tensor-core filter (assign_tc.cu) -----------------------------------------------------------
 struct TcPlan;  // opaque; owns the fp16 centroid table, tensor maps, queues
@@ -125,6 +129,12 @@ cudaError_t tc_exact_distances(TcPlan* plan, const float* X, const float* C, uin
                                const uint32_t* pair_cand, const uint32_t* d_npairs, uint32_t max_pairs,
                                float* pair_score, cudaStream_t st);
 void tc_queues(TcPlan* plan, TcQueues* q);
+// k-NN candidate search on the tensor cores (assign_tc.cu); see the comment there
+bool tc_knn_supported(int metric, int k, uint32_t N, int D, uint32_t K);
+cudaError_t tc_knn_search(int k, const float* X, const float* C, uint32_t N, int D, uint32_t K,
+                          const uint32_t* assign, const uint32_t* inv, const uint32_t* off, const float* cd,
+                          const float* radii, uint32_t nv, uint32_t* neighbors, uint32_t* fb_rows, uint32_t* d_nfb,
+                          unsigned long long* d_pairs, uint32_t* h_error, cudaStream_t st);
 // 0 = clean; 0x1000+site = a pipeline wait timed out at `site` (results of that pass are invalid)
 uint32_t tc_last_error(TcPlan* plan);
 uint32_t tc_last_pairs(TcPlan* plan);

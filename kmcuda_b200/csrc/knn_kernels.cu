@@ -114,10 +114,13 @@ knn_search_kernel(int k, const float* __restrict__ X, const float* __restrict__ 
                   const uint32_t* __restrict__ inv, const uint32_t* __restrict__ inv_off,
                   const float* __restrict__ cd, const float* __restrict__ radii,
                   float* __restrict__ heap_scratch, uint32_t* __restrict__ neighbors,
-                  unsigned long long* __restrict__ d_pairs) {
-  uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= q_length) return;
-  const uint32_t s = q_offset + q;
+                  unsigned long long* __restrict__ d_pairs,
+                  // list mode (rows != nullptr): the queries are rows[0 .. *d_nrows), heap column = list slot
+                  const uint32_t* __restrict__ rows, const uint32_t* __restrict__ d_nrows) {
+  const uint32_t count = rows ? min(*d_nrows, q_length) : q_length;
+  for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < count; q += gridDim.x * blockDim.x) {
+  const uint32_t s = rows ? rows[q] : q_offset + q;
+  const uint32_t oq = s - q_offset;          // output row
   const float* xs = X + static_cast<size_t>(s) * D;
   const size_t stride = q_length;
   float* hp = heap_scratch + q;
@@ -160,27 +163,46 @@ knn_search_kernel(int k, const float* __restrict__ X, const float* __restrict__ 
     }
   }
   for (int i = k - 1; i >= 0; i--) {
-    neighbors[static_cast<size_t>(q) * k + i] = __float_as_uint(hp[stride]);
+    neighbors[static_cast<size_t>(oq) * k + i] = __float_as_uint(hp[stride]);
     heap_push(k, -1.f, UINT32_MAX, hp, stride);
   }
   atomicAdd(d_pairs, pairs);
+  }
 }
 
 cudaError_t launch_knn_search(int metric, int k, const float* X, const float* C, uint32_t N, int D,
                               uint32_t K, uint32_t q_offset, uint32_t q_length, const uint32_t* assign,
                               const uint32_t* inv, const uint32_t* inv_off, const float* cd,
                               const float* radii, float* heap_scratch, uint32_t* neighbors,
-                              unsigned long long* d_pairs, cudaStream_t st) {
+                              unsigned long long* d_pairs, const uint32_t* rows, const uint32_t* d_nrows,
+                              cudaStream_t st) {
   if (q_length == 0) return cudaSuccess;
-  knn_radii_fix_kernel<<<cdivk(K, 128), 128, 0, st>>>(inv_off, K, const_cast<float*>(radii));
+  const unsigned grid = rows ? 148u * 8u : cdivk(q_length, 128);
   if (metric == 1)
-    knn_search_kernel<1><<<cdivk(q_length, 128), 128, 0, st>>>(k, X, C, N, D, K, q_offset, q_length, assign,
-                                                              inv, inv_off, cd, radii, heap_scratch,
-                                                              neighbors, d_pairs);
+    knn_search_kernel<1><<<grid, 128, 0, st>>>(k, X, C, N, D, K, q_offset, q_length, assign, inv, inv_off, cd, radii,
+                                               heap_scratch, neighbors, d_pairs, rows, d_nrows);
   else
-    knn_search_kernel<0><<<cdivk(q_length, 128), 128, 0, st>>>(k, X, C, N, D, K, q_offset, q_length, assign,
-                                                              inv, inv_off, cd, radii, heap_scratch,
-                                                              neighbors, d_pairs);
+    knn_search_kernel<0><<<grid, 128, 0, st>>>(k, X, C, N, D, K, q_offset, q_length, assign, inv, inv_off, cd, radii,
+                                               heap_scratch, neighbors, d_pairs, rows, d_nrows);
+  return cudaGetLastError();
+}
+
+// empty clusters have no radius (NaN, knn.cu:56); run once after launch_knn_radii + the inverse assignment
+cudaError_t launch_knn_radii_fix(const uint32_t* inv_off, uint32_t K, float* radii, cudaStream_t st) {
+  knn_radii_fix_kernel<<<cdivk(K, 128), 128, 0, st>>>(inv_off, K, radii);
+  return cudaGetLastError();
+}
+
+// rows of the sorted order past `nv` (samples whose assignment is not a valid cluster) join the exact-search list
+__global__ void knn_tail_rows_kernel(const uint32_t* __restrict__ inv, uint32_t nv, uint32_t n,
+                                     uint32_t* __restrict__ rows, uint32_t* __restrict__ d_nrows) {
+  uint32_t i = nv + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) rows[atomicAdd(d_nrows, 1u)] = inv[i];
+}
+cudaError_t launch_knn_tail_rows(const uint32_t* inv, uint32_t nv, uint32_t n, uint32_t* rows, uint32_t* d_nrows,
+                                 cudaStream_t st) {
+  if (nv >= n) return cudaSuccess;
+  knn_tail_rows_kernel<<<cdivk(n - nv, 256), 256, 0, st>>>(inv, nv, n, rows, d_nrows);
   return cudaGetLastError();
 }
 

@@ -405,6 +405,51 @@ def test_knn_matches_reference(ours, ref):
     assert (outs[0] != outs[1]).mean() < 1e-4
 
 
+def _knn(lib, k, X, C, A, metric=0):
+    out = np.zeros((len(X), k), np.uint32)
+    rc = lib.knn_cuda(k, metric, X.shape[0], X.shape[1], C.shape[0], 1, -1, 0, 0, X.ctypes.data, C.ctypes.data,
+                      A.ctypes.data, out.ctypes.data)
+    assert rc == 0, rc
+    return out
+
+
+@pytest.mark.parametrize("kind,n,d,kc,k", [("uniform", 30000, 48, 200, 10), ("mixture", 60000, 64, 300, 10),
+                                           ("mixture", 50000, 256, 100, 3), ("uniform", 20000, 100, 50, 15)])
+def test_knn_tensor_core_path_matches_reference(ours, ref, capfd, monkeypatch, kind, n, d, kc, k):
+    """knn_cuda through the tcgen05 candidate pass (cluster-sorted tiles, two passes, exact re-check + selection):
+    same neighbours as the reference library, and as a float64 brute force on a sample of the queries"""
+    rng = np.random.default_rng(n + d)
+    if kind == "uniform":
+        X = rng.random((n, d), dtype=np.float32)
+        C0 = X[rng.choice(n, kc, replace=False)].copy()
+    else:
+        X, C0 = _mixture(n, d, kc, 5, sigma=0.15)
+    C, A = c_kmeans(ours, X, C0, 0.05, 0.0)
+    monkeypatch.setenv("KMCUDA_B200_TIMING", "1")
+    capfd.readouterr()
+    got = _knn(ours, k, X, C, A)
+    err = capfd.readouterr().err
+    monkeypatch.delenv("KMCUDA_B200_TIMING")
+    line = [ln for ln in err.splitlines() if "knn tensor-core path" in ln]
+    assert line, "tensor-core k-NN path not taken: " + err[-300:]
+    served = int(line[0].split("path:")[1].split("rows")[0])
+    assert served > 0.98 * n, line[0]
+    exp = _knn(ref, k, X, C, A)
+    assert (got != exp).mean() < 1e-4, (got != exp).mean()
+    # independent check: float64 brute force for 300 queries (ties at the k-th place aside)
+    qs = rng.choice(n, 300, replace=False)
+    Xd = X.astype(np.float64)
+    bad = 0
+    for q in qs:
+        dist = ((Xd - Xd[q]) ** 2).sum(1)
+        dist[q] = np.inf
+        order = np.argsort(dist, kind="stable")[:k + 1]
+        if abs(dist[order[k]] - dist[order[k - 1]]) < 1e-9 * max(1.0, dist[order[k]]):
+            continue
+        bad += set(got[q].tolist()) != set(order[:k].tolist())
+    assert bad == 0, bad
+
+
 def test_device_pointer_api(km):
     """reference src/test.py:348-372: raw device pointers in, raw device pointers out; samples untouched"""
     import torch
