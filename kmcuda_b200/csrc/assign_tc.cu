@@ -80,6 +80,7 @@ struct Stats {       // written by the centroid prep kernels, read by the main k
   float dcmax;       // max_c ||s*c - fp16(s*c)||
   uint32_t csq_max_bits;
   uint32_t force_exact; // cosine only: a centroid with an infinite element / norm can still win -> no filtering
+  float yabs;           // k-NN: max over samples of s * (|y| + |c(y)|): bounds the rounding of the centring y - c
 };
 
 struct SmemLayout {  // byte offsets from the 1024-aligned dynamic smem base
@@ -96,7 +97,7 @@ __host__ __device__ inline SmemLayout smem_layout() {
   L.list_cm = o; o += 2 * LIST_LEN * 256 * 4;    // [tile parity][entry][epilogue thread]
   L.list_mask = o; o += 2 * LIST_LEN * 256 * 4;
   L.list_g = o; o += 2 * LIST_LEN * 256 * 2;
-  L.norms = o; o += 4 * 2 * TM * 4;   // [tile % 4][x|d][row]  (4 deep: the converters run up to 2 tiles ahead of the epilogue)
+  L.norms = o; o += 4 * 4 * TM * 4;   // [tile % 4][x|d][row]  x~^2 | residual^2 | (k-NN) exact s^2|x-c|^2 | (k-NN) s^2(|x|+|c|)^2; 4 deep: the converters run up to 2 segments ahead
   L.fin = o; o += 2 * 5 * 256 * 4;    // [tile parity][M|cnt|flags|margin|M2][epilogue thread]
   L.bars = o; o += 64 * 8;
   L.tmem_slot = o; o += 16;
@@ -145,29 +146,32 @@ struct Params {
   const float* X;
   const uint32_t* rows;
   const uint32_t* d_nrows;
-  // MODE 2 (k-NN candidate pass): queries AND candidates are the cluster-sorted samples.  Query tile t covers
-  // sorted positions [tile_r0[t], +tile_nrows[t]) (one cluster, <= 128 rows, gathered through rows[] = the inverse
-  // assignment order); its candidate blocks (128 sorted positions each = one n-tile of the fp16 sample table) are
-  // the ranges knn_ranges[knn_roff[t] .. +knn_rcount[t]).  Every column within the margin of the row's kk-th
-  // largest chunk maximum (kk = k + 1, self included) is recorded as (chunk maximum, mask, chunk id) in the
-  // row's global entry list; the running top-kk (4-column group) maxima persist in knn_topk between the two passes.
+  // MODE 2 (k-NN candidate pass): queries AND candidates are the samples in the cluster-aligned table order: cluster
+  // c owns the blocks [blk_first[c], blk_first[c+1]) of 128 table rows (zero-padded), rows[] maps a table row to the
+  // original sample (UINT32_MAX = padding), so query tile t IS block t.  A tile is multiplied with a list of
+  // SEGMENTS knn_ranges[knn_roff[t] .. +knn_rcount[t]): each segment is the block range of ONE candidate cluster B,
+  // and for it the queries are re-converted relative to B's centroid -- both operands are then small vectors
+  // (x - c_B, y - c_B), which is what gives the fp16 product enough resolution inside tight clusters.  The per-row
+  // constant s^2 |x - c_B|^2 / 2 is folded into the threshold, so everything the epilogue keeps (top-kk list, entry
+  // maxima) lives in the translation-invariant score g = -s^2 d^2 / 2.  Every column within the margin of the row's
+  // kk-th largest 4-column-group maximum (kk = k + 1, self included) is recorded as (max, mask, chunk id, margin).
   const uint32_t* d_ntiles;
-  const uint32_t* tile_r0;
   const uint32_t* tile_nrows;
+  const uint32_t* blk_cluster;
+  const float* C;                // centroids [K][D] (fp32)
   const uint2* knn_ranges;
   const uint32_t* knn_roff;
   const uint32_t* knn_rcount;
-  const uint32_t* knn_nblk;      // blocks per tile (sum over its ranges)
+  const uint32_t* knn_nblk;      // blocks per tile (sum over its segments)
   int kk;
-  int knn_first_pass;            // 1: the per-row state starts empty; the tile's ranges hold its own cluster TWICE:
+  int knn_first_pass;            // 1: the per-row state starts empty; the tile has TWO segments, both its own cluster:
                                  //    the first sweep only builds the top-kk threshold, the second one only records
-  uint32_t knn_stride;           // = 2 * (number of sorted positions): stride of the [kk][stride] top-kk state
-  float* knn_topk;               // [kk][stride] descending chunk maxima of half-row (pos * 2 + h)
+  uint32_t knn_stride;           // = 2 * (table rows): stride of the [kk][stride] top-kk state
+  float* knn_topk;               // [kk][stride] descending group maxima (g-space) of half-row (table row * 2 + h)
   uint32_t* knn_cnt;             // [stride] entries used
   uint32_t* knn_flags;           // [stride]
-  float* knn_margin;             // [stride / 2]
   float* knn_dub;                // [stride] upper bound of the exact distance to the kk-th nearest candidate seen so far
-  uint4* knn_entries;            // [stride][KNN_CAP]: (chunk max bits, mask, chunk id, -)
+  uint4* knn_entries;            // [stride][KNN_CAP]: (group max bits (g-space), mask, chunk id, margin bits)
   float* dbg_scores;         // optional [ntiles*128][nt*128] dump of the approximate scores
 };
 
@@ -312,28 +316,30 @@ __device__ __noinline__ uint32_t compact_list(float* list_cm, uint32_t* list_mas
   return w;
 }
 
-// enumerates the n-tiles (blocks of 128 table rows) one sample tile is multiplied with
+// enumerates the n-tiles (blocks of 128 table rows) one sample tile is multiplied with, segment by segment
+// (MODE 0 / 1: one segment = the whole table; MODE 2: one segment per candidate cluster)
 template <int MODE>
 struct BlockIter {
-  uint32_t cur, hi, left;        // current block, end of the current range, blocks left including cur
+  uint32_t cur, lo, hi, left;    // current block, bounds of the current segment, blocks left including cur
   const uint2* rg;
   __device__ __forceinline__ BlockIter(const Params& p, uint32_t tile) {
     if (MODE == 2) {
       left = p.knn_nblk[tile];
       rg = p.knn_ranges + p.knn_roff[tile];
-      if (left) { cur = rg->x; hi = rg->y; } else { cur = hi = 0; }
+      if (left) { lo = cur = rg->x; hi = rg->y; } else { lo = cur = hi = 0; }
     } else {
       left = static_cast<uint32_t>(p.nt);
-      cur = 0;
+      lo = cur = 0;
       hi = left - 1;
       rg = nullptr;
     }
   }
   __device__ __forceinline__ bool valid() const { return left != 0; }
-  __device__ __forceinline__ bool last() const { return left == 1; }
+  __device__ __forceinline__ bool seg_first() const { return cur == lo; }
+  __device__ __forceinline__ bool seg_last() const { return cur == hi; }
   __device__ __forceinline__ void next() {
     left--;
-    if (cur == hi && left) { rg++; cur = rg->x; hi = rg->y; } else { cur++; }
+    if (cur == hi && left) { rg++; lo = cur = rg->x; hi = rg->y; } else { cur++; }
   }
 };
 
@@ -357,19 +363,20 @@ __device__ __noinline__ void knn_merge(const float* a, size_t astride, const flo
     if (av >= bv) { out[o] = av; i++; } else { out[o] = bv; j++; }
   }
 }
-// append to the half-row's global entry list; when full, drop the entries whose chunk maximum fell below thr
-__device__ __noinline__ uint32_t knn_append(uint4* ent, uint32_t cnt, float thr, float cm, uint32_t mask, uint32_t cid,
-                                            uint32_t* flags) {
+// append to the half-row's global entry list; when full, drop the entries that fell below the current kk-th
+// best minus their own margin (g-space)
+__device__ __noinline__ uint32_t knn_append(uint4* ent, uint32_t cnt, float kth, float cm, uint32_t mask, uint32_t cid,
+                                            float margin, uint32_t* flags) {
   if (cnt == KNN_CAP) {
     uint32_t w = 0;
     for (uint32_t i = 0; i < cnt; i++) {
       const uint4 e = ent[i];
-      if (__uint_as_float(e.x) >= thr) ent[w++] = e;
+      if (__uint_as_float(e.x) >= kth - __uint_as_float(e.w)) ent[w++] = e;
     }
     cnt = w;
     if (cnt == KNN_CAP) { *flags |= 2u; return cnt; }
   }
-  ent[cnt] = make_uint4(__float_as_uint(cm), mask, cid, 0u);
+  ent[cnt] = make_uint4(__float_as_uint(cm), mask, cid, __float_as_uint(margin));
   return cnt + 1;
 }
 
@@ -480,14 +487,14 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
     const uint32_t b_base = ptx::smem_u32(smem + L.b);
     const uint64_t aug_ad = ptx::make_smem_desc(ptx::smem_u32(smem + L.aug_a), TM * 16, 128, 0);
     const uint32_t augb = ptx::smem_u32(smem + L.aug_b);
-    uint32_t pc = 0, ac = 0, ti = 0;
+    uint32_t pc = 0, ac = 0, si = 0;                      // si: segments (= A operand conversions) so far
     for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       if (MODE == 2 && p.knn_nblk[tile] == 0) continue;   // nothing to visit: every role skips the tile
-      const int abuf = ti % NBUF;
-      const uint32_t a_par = (ti / NBUF) & 1;
-      const uint32_t a_tmem = tmem_base + TMEM_A0 + abuf * 128;
-      bool first = true;
-      for (BlockIter<MODE> it(p, tile); it.valid(); it.next(), ac++, first = false) {
+      for (BlockIter<MODE> it(p, tile); it.valid(); it.next(), ac++) {
+        const bool first = it.seg_first();
+        const int abuf = si % NBUF;
+        const uint32_t a_par = (si / NBUF) & 1;
+        const uint32_t a_tmem = tmem_base + TMEM_A0 + abuf * 128;
         const int buf = ac & 1;
         const uint32_t aph = (ac >> 1) & 1;
         TC_WAIT(BAR_ACC_EMPTY + buf, aph ^ 1, 3);
@@ -529,80 +536,100 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
           ptx::umma_f16(d_tmem, aug_ad, bd, idesc, 1u);
           ptx::umma_commit(&bars[BAR_AUG_EMPTY + buf]);
           ptx::umma_commit(&bars[BAR_ACC_FULL + buf]);
-          if (it.last()) ptx::umma_commit(&bars[BAR_A_FREE + abuf]);  // every MMA reading this A buffer is done
+          if (it.seg_last()) ptx::umma_commit(&bars[BAR_A_FREE + abuf]);  // every MMA reading this A buffer is done
         }
         __syncwarp();
+        if (it.seg_last()) si++;
       }
-      ti++;
     }
   } else if (warp >= FIRST_CONV_WARP && warp < FIRST_EPI_WARP) {
     // ================================ converters: fp32 smem stage -> fp16 A operand in TMEM ================================
     const int q = warp & 3;                 // TMEM lane quarter
     const int row = q * 32 + lane;          // this thread's sample row within the tile
     const float s = p.stats->scale;
-    uint32_t xc = 0, ti = 0;
+    uint32_t xc = 0, si = 0;
     for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       if (MODE == 2 && p.knn_nblk[tile] == 0) continue;
-      const int abuf = ti % NBUF;
-      TC_WAIT(BAR_A_FREE + abuf, ((ti / NBUF) & 1) ^ 1, 7);   // MMAs of the previous user of this buffer are done
-      ptx::tc_fence_after();
-      float nx = 0.f, nd = 0.f;
       const float* xrow = nullptr;
       if (MODE == 1) {
         const uint32_t li = min(tile * TM + row, n_eff - 1);   // ragged tail: repeat the last listed row
         xrow = p.X + static_cast<size_t>(p.rows[li]) * p.D;
       }
-      if (MODE == 2) {   // rows past the tile's own cluster are computed but never recorded
-        const uint32_t li = min(p.tile_r0[tile] + row, p.n - 1);
-        xrow = p.X + static_cast<size_t>(p.rows[li]) * p.D;
-      }
-      for (int kb = 0; kb < nkb; kb++) {
-        uint32_t pk[32];
+      if (MODE == 2)   // padding rows of the table repeat sample 0; they are never recorded
+        xrow = p.X + static_cast<size_t>(min(p.rows[tile * TM + row], p.n - 1)) * p.D;
+      const uint32_t nseg = MODE == 2 ? p.knn_rcount[tile] : 1u;
+      for (uint32_t seg = 0; seg < nseg; seg++, si++) {
+        const int abuf = si % NBUF;
+        TC_WAIT(BAR_A_FREE + abuf, ((si / NBUF) & 1) ^ 1, 7);   // MMAs of the previous user of this buffer are done
+        ptx::tc_fence_after();
+        float nx = 0.f, nd = 0.f;
+        float a2 = 0.f, a2c = 0.f, nraw = 0.f;     // MODE 2: Kahan sum of the exact (x-c)^2 s^2, and s^2 (|x|+|c|)^2
+        const float* crow = nullptr;
+        if (MODE == 2) crow = p.C + static_cast<size_t>(p.blk_cluster[p.knn_ranges[p.knn_roff[tile] + seg].x]) * p.D;
+        for (int kb = 0; kb < nkb; kb++) {
+          uint32_t pk[32];
 #pragma unroll
-        for (int half = 0; half < 2; half++, xc++) {
-          const int st = xc % X_STAGES;
-          const uint32_t ph = (xc / X_STAGES) & 1;
-          float4 gv[8];
-          if (MODE == 0) {
-            TC_WAIT(BAR_X_FULL + st, ph, 10);
-          } else {
+          for (int half = 0; half < 2; half++, xc++) {
+            const int st = xc % X_STAGES;
+            const uint32_t ph = (xc / X_STAGES) & 1;
+            float4 gv[8];
             const int f0 = kb * KB + half * 32;
+            if (MODE == 0) {
+              TC_WAIT(BAR_X_FULL + st, ph, 10);
+            } else {
 #pragma unroll
-            for (int c = 0; c < 8; c++)
-              gv[c] = (f0 + c * 4 < p.D) ? ptx::ldg_nc_f4(xrow + f0 + c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-          const uint8_t* xs = smem + L.x + st * X_STAGE_BYTES + row * 128;
+              for (int c = 0; c < 8; c++)
+                gv[c] = (f0 + c * 4 < p.D) ? ptx::ldg_nc_f4(xrow + f0 + c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            const uint8_t* xs = smem + L.x + st * X_STAGE_BYTES + row * 128;
 #pragma unroll
-          for (int c = 0; c < 8; c++) {
-            const float4 v = MODE == 0 ? *reinterpret_cast<const float4*>(xs + ((c ^ (row & 7)) << 4)) : gv[c];
-            const float a0 = v.x * s, a1 = v.y * s, a2 = v.z * s, a3 = v.w * s;
-            __half2 h0 = __floats2half2_rn(a0, a1), h1 = __floats2half2_rn(a2, a3);
-            const float2 b0 = __half22float2(h0), b1 = __half22float2(h1);
-            nx = fmaf(b0.x, b0.x, nx); nx = fmaf(b0.y, b0.y, nx);
-            nx = fmaf(b1.x, b1.x, nx); nx = fmaf(b1.y, b1.y, nx);
-            const float d0 = a0 - b0.x, d1 = a1 - b0.y, d2 = a2 - b1.x, d3 = a3 - b1.y;
-            nd = fmaf(d0, d0, nd); nd = fmaf(d1, d1, nd);
-            nd = fmaf(d2, d2, nd); nd = fmaf(d3, d3, nd);
-            pk[half * 16 + c * 2] = *reinterpret_cast<uint32_t*>(&h0);
-            pk[half * 16 + c * 2 + 1] = *reinterpret_cast<uint32_t*>(&h1);
+            for (int c = 0; c < 8; c++) {
+              float4 v = MODE == 0 ? *reinterpret_cast<const float4*>(xs + ((c ^ (row & 7)) << 4)) : gv[c];
+              if (MODE == 2) {
+                const float4 cv = (f0 + c * 4 < p.D) ? ptx::ldg_nc_f4(crow + f0 + c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float r0 = fabsf(v.x) + fabsf(cv.x), r1 = fabsf(v.y) + fabsf(cv.y);
+                const float r2 = fabsf(v.z) + fabsf(cv.z), r3 = fabsf(v.w) + fabsf(cv.w);
+                nraw = fmaf(r0, r0, nraw); nraw = fmaf(r1, r1, nraw); nraw = fmaf(r2, r2, nraw); nraw = fmaf(r3, r3, nraw);
+                v.x -= cv.x; v.y -= cv.y; v.z -= cv.z; v.w -= cv.w;
+              }
+              const float a0 = v.x * s, a1 = v.y * s, a2_ = v.z * s, a3 = v.w * s;
+              __half2 h0 = __floats2half2_rn(a0, a1), h1 = __floats2half2_rn(a2_, a3);
+              const float2 b0 = __half22float2(h0), b1 = __half22float2(h1);
+              nx = fmaf(b0.x, b0.x, nx); nx = fmaf(b0.y, b0.y, nx);
+              nx = fmaf(b1.x, b1.x, nx); nx = fmaf(b1.y, b1.y, nx);
+              const float d0 = a0 - b0.x, d1 = a1 - b0.y, d2 = a2_ - b1.x, d3 = a3 - b1.y;
+              nd = fmaf(d0, d0, nd); nd = fmaf(d1, d1, nd);
+              nd = fmaf(d2, d2, nd); nd = fmaf(d3, d3, nd);
+              if (MODE == 2) {   // compensated: this sum is subtracted from scores of the same magnitude
+                const float q4 = fmaf(a0, a0, fmaf(a1, a1, fmaf(a2_, a2_, a3 * a3)));
+                const float y = q4 - a2c, t = a2 + y;
+                a2c = (t - a2) - y;
+                a2 = t;
+              }
+              pk[half * 16 + c * 2] = *reinterpret_cast<uint32_t*>(&h0);
+              pk[half * 16 + c * 2 + 1] = *reinterpret_cast<uint32_t*>(&h1);
+            }
+            if (MODE == 0) {
+              __syncwarp();
+              if (lane == 0) ptx::mbar_arrive(&bars[BAR_X_EMPTY + st]);
+            }
           }
-          if (MODE == 0) {
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&bars[BAR_X_EMPTY + st]);
+          ptx::tmem_st_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + TMEM_A0 + abuf * 128 + kb * 32, pk);
+          ptx::tmem_st_wait();
+          if (kb == nkb - 1) {
+            float* norms = reinterpret_cast<float*>(smem + L.norms) + (si & 3) * 4 * TM;
+            norms[row] = nx;
+            norms[TM + row] = nd;
+            if (MODE == 2) {
+              norms[2 * TM + row] = a2;
+              norms[3 * TM + row] = nraw * s * s;
+            }
           }
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&bars[BAR_A_FULL + abuf * MAX_NKB + kb]);
         }
-        ptx::tmem_st_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + TMEM_A0 + abuf * 128 + kb * 32, pk);
-        ptx::tmem_st_wait();
-        if (kb == nkb - 1) {
-          float* norms = reinterpret_cast<float*>(smem + L.norms) + (ti & 3) * 2 * TM;
-          norms[row] = nx;
-          norms[TM + row] = nd;
-        }
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&bars[BAR_A_FULL + abuf * MAX_NKB + kb]);
       }
-      ti++;
     }
   } else if (warp >= FIRST_EPI_WARP && warp < FIRST_EMIT_WARP) {
     // ================================ epilogue ================================
@@ -615,7 +642,7 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
     // cosine: every dot >= 1 is clamped to angle 0 by the reference, so all of them tie -> the threshold
     // never rises above s^2 * 1 (the accumulator holds s^2 * dot)
     const float cap = p.metric == 1 ? p.stats->scale * p.stats->scale : INFINITY;
-    uint32_t ac = 0, ti = 0;
+    uint32_t ac = 0, ti = 0, si = 0;
     for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       if (MODE == 2 && p.knn_nblk[tile] == 0) continue;
       const int par = ti & 1;
@@ -632,9 +659,11 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
       uint32_t kslot = 0;
       bool klive = false;
       uint4* kent = nullptr;
+      float goff = 0.f, mmax = 0.f;     // MODE 2: s^2 |x - c_B|^2 / 2 of the current segment; largest margin so far
+      uint32_t seg = 0;
       if (MODE == 2) {
         klive = static_cast<uint32_t>(row) < p.tile_nrows[tile];
-        kslot = (min(p.tile_r0[tile] + row, p.n - 1)) * 2u + h;
+        kslot = (tile * TM + row) * 2u + h;
         kent = p.knn_entries + static_cast<size_t>(kslot) * KNN_CAP;
         if (p.knn_first_pass || !klive) {
           for (int j = 0; j < p.kk; j++) topk[j * 256] = -INFINITY;
@@ -645,12 +674,9 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
           cnt = p.knn_cnt[kslot];
           flags = p.knn_flags[kslot];
         }
-        M = topk[(p.kk - 1) * 256];                 // MODE 2: M holds the kk-th largest chunk maximum
+        M = topk[(p.kk - 1) * 256];                 // MODE 2: M holds the kk-th largest group maximum (g-space)
       }
-      bool first = true;
-      uint32_t warm = 0, bidx = 0;      // MODE 2, first pass: blocks [0, warm) = threshold sweep
-      if (MODE == 2 && p.knn_first_pass) warm = p.knn_nblk[tile] >> 1;
-      for (BlockIter<MODE> it(p, tile); it.valid(); it.next(), ac++, first = false, bidx++) {
+      for (BlockIter<MODE> it(p, tile); it.valid(); it.next(), ac++) {
         const int n = static_cast<int>(it.cur);
         const int buf = ac & 1;
         const uint32_t aph = (ac >> 1) & 1;
@@ -661,8 +687,8 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + TMEM_ACC0 + buf * TN + h * 64;
         ptx::tmem_ld_32x32(taddr, r0);
         ptx::tmem_ld_32x32(taddr + 32, r1);
-        if (first) {
-          const float* norms = reinterpret_cast<const float*>(smem + L.norms) + (ti & 3) * 2 * TM;
+        if (it.seg_first()) {
+          const float* norms = reinterpret_cast<const float*>(smem + L.norms) + (si & 3) * 4 * TM;
           // rigorous bound on |acc - (s^2 x.c - s^2||c||^2/2)| (see header): Cauchy-Schwarz on the
           // actual rounding residuals + accumulation + the reference's own rounding slack
           const float nx = __fsqrt_ru(norms[row]) * 1.0001f, nd = __fsqrt_ru(norms[TM + row]) * 1.0001f;
@@ -671,8 +697,27 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
           E += static_cast<float>(p.nkb * KB + 16) * 2.4e-7f * nx * cmax;   // fp32 accumulation in the tensor core
           E += 2.0e-6f * (cmax * cmax + xn * cmax);                        // reference Kahan/rd rounding, bias split
           if (MODE >= 1) E += 2.0e-6f * xn * xn;                           // true distances: rounding of sum (x-c)^2
+          if (MODE == 2) {
+            goff = 0.5f * norms[2 * TM + row];
+            // centring x - c_B and y - c_B rounds in fp32 (relative to |x|+|c|), and the row constant is subtracted
+            // from scores of its own magnitude
+            E += 1.2e-7f * (__fsqrt_ru(norms[3 * TM + row]) * cmax + p.stats->yabs * xn) + 4.8e-7f * (goff + xn * cmax);
+          }
           margin = 2.f * E * 1.001f + 1e-30f;
           if (!(margin < 1.0e30f)) flags |= 1u;                            // NaN / Inf somewhere in the row
+          if (MODE == 2) {
+            mmax = fmaxf(mmax, margin);
+            if (p.knn_first_pass && seg == 1) {
+              // threshold sweep done: both column halves of the row adopt the merged top-kk (the partner warp
+              // e ^ 4 sits on the same row quarter); named barrier per quarter, 64 threads
+              float mg[KNN_MAX_KK];
+              asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+              knn_merge(topk, 256, reinterpret_cast<float*>(smem + L.list_cm) + ((1 - h) * TM + row), 256, p.kk, mg);
+              asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+              for (int j = 0; j < p.kk; j++) topk[j * 256] = mg[j];
+              M = mg[p.kk - 1];
+            }
+          }
         }
         ptx::tmem_ld_wait();
         // the accumulator values are in registers: hand the TMEM buffer back to the MMA warp right away
@@ -708,32 +753,23 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
           M = fmaxf(M, cm1);
           thr = fminf(M2, cap) - margin;
         } else {
-          // kk distinct columns reach the kk-th largest chunk maximum: a lower bound of the kk-th best score
-          if (p.knn_first_pass && bidx == warm) {
-            // threshold sweep done: both column halves of the row adopt the merged top-kk (the partner warp
-            // e ^ 4 sits on the same row quarter); named barrier per quarter, 64 threads
-            float mg[KNN_MAX_KK];
-            asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
-            knn_merge(topk, 256, reinterpret_cast<float*>(smem + L.list_cm) + ((1 - h) * TM + row), 256, p.kk, mg);
-            asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
-            for (int j = 0; j < p.kk; j++) topk[j * 256] = mg[j];
-            M = mg[p.kk - 1];
-          }
-          if (!p.knn_first_pass || bidx < warm) {
-            // 4-column group maxima (first level of the max tree): kk distinct columns reach the kk-th largest of
-            // them; finer than whole chunks because the nearest neighbours sit close together in the sorted order
-            if (cm0 > M) {
+          // kk distinct columns reach the kk-th largest 4-column-group maximum (first level of the max tree): a
+          // lower bound of the kk-th best score; finer than whole chunks because near neighbours sit close together
+          // in the table.  M and the list live in g-space (score - goff).
+          if (!p.knn_first_pass || seg == 0) {
+            const float lim = M + goff;
+            if (cm0 > lim) {
 #pragma unroll
               for (int i = 0; i < 8; i++)
-                if (t0[i] > M) M = knn_topk_insert(topk, p.kk, t0[i]);
+                if (t0[i] - goff > M) M = knn_topk_insert(topk, p.kk, t0[i] - goff);
             }
-            if (cm1 > M) {
+            if (cm1 > lim) {
 #pragma unroll
               for (int i = 0; i < 8; i++)
-                if (t1[i] > M) M = knn_topk_insert(topk, p.kk, t1[i]);
+                if (t1[i] - goff > M) M = knn_topk_insert(topk, p.kk, t1[i] - goff);
             }
           }
-          thr = M - margin;
+          thr = (M - margin) + goff;
         }
         // candidate masks on the (otherwise idle) FMA pipe instead of FSETP + LOP3 on the ALU pipe:
         //   nc_j = sat(BIG * (thr - v_j))  is exactly 1 when v_j < thr and exactly 0 when v_j >= thr
@@ -761,12 +797,16 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
         if (bad) flags |= 4u;
         const uint32_t mask0 = ~nc0, mask1 = ~nc1;
         if (MODE == 2) {
-          if (klive && bidx >= warm) {
-            if (mask0) cnt = knn_append(kent, cnt, thr, cm0, mask0, static_cast<uint32_t>(n) * 4 + h * 2, &flags);
-            if (mask1) cnt = knn_append(kent, cnt, thr, cm1, mask1, static_cast<uint32_t>(n) * 4 + h * 2 + 1, &flags);
+          if (klive && !(p.knn_first_pass && seg == 0)) {
+            if (mask0)
+              cnt = knn_append(kent, cnt, M, cm0 - goff, mask0, static_cast<uint32_t>(n) * 4 + h * 2, margin, &flags);
+            if (mask1)
+              cnt = knn_append(kent, cnt, M, cm1 - goff, mask1, static_cast<uint32_t>(n) * 4 + h * 2 + 1, margin, &flags);
           }
+          if (it.seg_last()) { si++; seg++; }
           continue;
         }
+        if (it.seg_last()) si++;
         if (cnt >= LIST_LEN - 1 && (mask0 | mask1))
           cnt = compact_list(list_cm, list_mask, list_g, slot, cnt, thr);   // rare: drop entries below the risen threshold
         if (mask0) {
@@ -795,13 +835,10 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
           for (int j = 0; j < p.kk; j++) p.knn_topk[static_cast<size_t>(j) * p.knn_stride + kslot] = topk[j * 256];
           p.knn_cnt[kslot] = cnt;
           p.knn_flags[kslot] = flags;
-          if (h == 0) p.knn_margin[kslot >> 1] = margin;
-          // exact distance to the kk-th nearest candidate, upper bound in the caller's units:
-          // s^2 d^2 = ||s x||^2 - 2 (s^2 x.y - s^2 ||y||^2 / 2) <= (nx + nd)^2 - 2 (M - margin)
-          const float* norms = reinterpret_cast<const float*>(smem + L.norms) + (ti & 3) * 2 * TM;
-          const float xn = (__fsqrt_ru(norms[row]) + __fsqrt_ru(norms[TM + row])) * 1.0001f;
+          // exact distance to the kk-th nearest candidate seen so far, upper bound in the caller's units:
+          // every recorded score is within its margin of g = -s^2 d^2 / 2
           const float sc = p.stats->scale;
-          const float d2 = fmaxf(0.f, xn * xn - 2.f * (M - margin));
+          const float d2 = fmaxf(0.f, -2.f * (M - mmax));
           p.knn_dub[kslot] = (M > -INFINITY && !flags) ? __fsqrt_ru(d2) / sc * 1.0001f : INFINITY;
         }
         ti++;
@@ -1205,12 +1242,13 @@ static cudaError_t tc_prepare(TcPlan* p, const float* C, const float* csq, uint3
   prm.rows = nullptr;
   prm.d_nrows = nullptr;
   prm.d_ntiles = nullptr;
-  prm.tile_r0 = prm.tile_nrows = prm.knn_roff = prm.knn_rcount = prm.knn_nblk = nullptr;
+  prm.tile_nrows = prm.blk_cluster = prm.knn_roff = prm.knn_rcount = prm.knn_nblk = nullptr;
+  prm.C = nullptr;
   prm.knn_ranges = nullptr;
   prm.kk = 0;
   prm.knn_first_pass = 0;
   prm.knn_stride = 0;
-  prm.knn_topk = prm.knn_margin = prm.knn_dub = nullptr;
+  prm.knn_topk = prm.knn_dub = nullptr;
   prm.knn_cnt = prm.knn_flags = nullptr;
   prm.knn_entries = nullptr;
   prm.dbg_scores = p->dbg_scores;
@@ -1365,71 +1403,153 @@ __global__ void tile_count_kernel(const uint32_t* __restrict__ off, uint32_t K, 
   if (c < K) ntile[c] = (off[c + 1] - off[c] + tc::TM - 1) / tc::TM;
 }
 
-__global__ void tile_fill_kernel(const uint32_t* __restrict__ off, uint32_t K, const uint32_t* __restrict__ tile_off,
-                                 uint32_t* __restrict__ tile_r0, uint32_t* __restrict__ tile_nrows,
-                                 uint32_t* __restrict__ tile_cluster, uint2* __restrict__ ranges1,
-                                 uint32_t* __restrict__ roff1, uint32_t* __restrict__ rcount1,
-                                 uint32_t* __restrict__ nblk1, uint32_t* __restrict__ d_ntiles,
-                                 unsigned long long* __restrict__ d_pairs) {
+// per cluster: its blocks (= query tiles), the two own-cluster segments of pass 1
+__global__ void tile_fill_kernel(const uint32_t* __restrict__ off, uint32_t K, const uint32_t* __restrict__ blk_first,
+                                 uint32_t* __restrict__ tile_nrows, uint32_t* __restrict__ blk_cluster,
+                                 uint2* __restrict__ ranges1, uint32_t* __restrict__ roff1,
+                                 uint32_t* __restrict__ rcount1, uint32_t* __restrict__ nblk1,
+                                 uint32_t* __restrict__ d_ntiles, unsigned long long* __restrict__ d_pairs) {
   uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= K) return;
-  const uint32_t b = off[c], e = off[c + 1], m = e - b;
-  const uint32_t t0 = tile_off[c], nt = (m + tc::TM - 1) / tc::TM;
+  const uint32_t m = off[c + 1] - off[c];
+  const uint32_t t0 = blk_first[c], nt = (m + tc::TM - 1) / tc::TM;
   for (uint32_t i = 0; i < nt; i++) {
     const uint32_t t = t0 + i;
-    tile_r0[t] = b + i * tc::TM;
     tile_nrows[t] = min(static_cast<uint32_t>(tc::TM), m - i * tc::TM);
-    tile_cluster[t] = c;
-    ranges1[2 * t] = ranges1[2 * t + 1] = make_uint2(b / tc::TN, (e - 1) / tc::TN);   // threshold sweep + recording sweep
+    blk_cluster[t] = c;
+    ranges1[2 * t] = ranges1[2 * t + 1] = make_uint2(t0, t0 + nt - 1);   // threshold sweep + recording sweep
     roff1[t] = 2 * t;
     rcount1[t] = 2;
-    nblk1[t] = 2 * ((e - 1) / tc::TN - b / tc::TN + 1);
+    nblk1[t] = 2 * nt;
   }
   if (m) atomicAdd(d_pairs, static_cast<unsigned long long>(m) * m);   // statistics: own-cluster pairs
   if (c == K - 1) *d_ntiles = t0 + nt;
 }
 
-// exact distance of every sorted sample to its own centroid (knn.cu:199)
-template <int METRIC>
-__global__ void own_distance_kernel(const float* __restrict__ X, const float* __restrict__ C, int D,
-                                    const uint32_t* __restrict__ inv, const uint32_t* __restrict__ assign,
-                                    uint32_t nv, float* __restrict__ dA) {
+// table row of every valid sorted position (cluster-aligned, zero padded): tab2orig[row] = original sample index
+__global__ void layout_kernel(const uint32_t* __restrict__ inv, const uint32_t* __restrict__ assign,
+                              const uint32_t* __restrict__ off, const uint32_t* __restrict__ blk_first, uint32_t nv,
+                              uint32_t* __restrict__ tab2orig) {
   uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x;
   if (pos >= nv) return;
-  const uint32_t s = inv[pos];
-  dA[pos] = distance_exact<METRIC>(X + static_cast<size_t>(s) * D, C + static_cast<size_t>(assign[s]) * D, D);
+  const uint32_t s = inv[pos], c = assign[s];
+  tab2orig[blk_first[c] * tc::TM + (pos - off[c])] = s;
 }
 
-// one warp per tile: which clusters must be visited in pass 2, as merged ranges of 128-sample blocks
+// one warp per table row: ||y - c||^2 (fp32) and the largest s-free magnitude |y| + |c| (for the centring error)
+__global__ void prep_norms_kernel(const float* __restrict__ X, const float* __restrict__ C, int D,
+                                  const uint32_t* __restrict__ tab2orig, const uint32_t* __restrict__ blk_cluster,
+                                  const uint32_t* __restrict__ d_ntiles, float* __restrict__ ysq,
+                                  float* __restrict__ yabs_max) {
+  const uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= *d_ntiles * tc::TM) return;
+  const uint32_t sidx = tab2orig[row];
+  if (sidx == UINT32_MAX) {
+    if (lane == 0) ysq[row] = 0.f;
+    return;
+  }
+  const float* x = X + static_cast<size_t>(sidx) * D;
+  const float* c = C + static_cast<size_t>(blk_cluster[row / tc::TM]) * D;
+  float a = 0.f, r = 0.f;
+  for (int f = lane; f < D; f += 32) {
+    const float xv = x[f], cv = c[f], d = xv - cv, m = fabsf(xv) + fabsf(cv);
+    a = fmaf(d, d, a);
+    r = fmaf(m, m, r);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    r += __shfl_xor_sync(0xffffffffu, r, o);
+  }
+  if (lane == 0) {
+    ysq[row] = a;
+    if (r == r && r < 3.0e38f) atomicMax(reinterpret_cast<uint32_t*>(yabs_max), __float_as_uint(__fsqrt_ru(r)));
+  }
+}
+
+// one warp per table row: fp16(s (y - c)), rounding residual, bias -(s^2 |y - c|^2 / 2) in three fp16 terms;
+// padding and non-finite rows: zero vector, bias -65504
+__global__ void prep_table_kernel(const float* __restrict__ X, const float* __restrict__ C, int D, int nkb,
+                                  const uint32_t* __restrict__ tab2orig, const uint32_t* __restrict__ blk_cluster,
+                                  const uint32_t* __restrict__ d_ntiles, const float* __restrict__ ysq,
+                                  __half* __restrict__ table, __half* __restrict__ aug_blob,
+                                  tc::Stats* __restrict__ st, const float* __restrict__ yabs_max) {
+  using namespace tc;
+  const uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= *d_ntiles * TM) return;
+  const int Dp = nkb * KB;
+  const float s = st->scale;
+  if (row == 0 && lane == 0) st->yabs = *yabs_max * s * 1.0001f;
+  const uint32_t sidx = tab2orig[row];
+  bool finite = sidx != UINT32_MAX;
+  const float* x = X + static_cast<size_t>(finite ? sidx : 0) * D;
+  const float* c = C + static_cast<size_t>(blk_cluster[row / TM]) * D;
+  if (finite) {
+    const float q = ysq[row];
+    finite = (q == q) && q < 3.0e38f;
+    finite = __all_sync(0xffffffffu, finite);
+  }
+  float d2 = 0.f;
+  for (int f = lane; f < Dp; f += 32) {
+    const float v = (finite && f < D) ? (x[f] - c[f]) * s : 0.f;
+    const __half h = __float2half_rn(v);
+    const float r = v - __half2float(h);
+    d2 = fmaf(r, r, d2);
+    table[static_cast<size_t>(row) * Dp + f] = h;
+  }
+  for (int o = 16; o > 0; o >>= 1) d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+  if (lane == 0) {
+    if (finite) atomicMax(reinterpret_cast<uint32_t*>(&st->dcmax), __float_as_uint(__fsqrt_ru(d2) * 1.0001f));
+    __half b[3];
+    if (finite) {
+      const float hh = -0.5f * s * s * ysq[row];
+      b[0] = __float2half_rn(hh);
+      const float r1 = hh - __half2float(b[0]);
+      b[1] = __float2half_rn(r1);
+      b[2] = __float2half_rn(r1 - __half2float(b[1]));
+    } else {
+      b[0] = __float2half_rn(-65504.f);
+      b[1] = b[2] = __float2half_rn(0.f);
+    }
+    const uint32_t t = row / TN, r = row % TN;
+    __half* blob = aug_blob + static_cast<size_t>(t) * (AUG_B_BYTES / 2);
+    for (int k = 0; k < 16; k++) {
+      const int j = k >> 3, e = k & 7;
+      blob[(j * (TN * 16) + (r >> 3) * 128 + (r & 7) * 16) / 2 + e] = k < 3 ? b[k] : __float2half_rn(0.f);
+    }
+  }
+}
+
+// one warp per tile: the clusters pass 2 must visit, one segment (block range) per cluster
 __global__ void __launch_bounds__(256)
-range_build_kernel(const uint32_t* __restrict__ d_ntiles, const uint32_t* __restrict__ tile_r0,
-                   const uint32_t* __restrict__ tile_nrows, const uint32_t* __restrict__ tile_cluster,
-                   const uint2* __restrict__ ranges1, const uint32_t* __restrict__ off, uint32_t K,
-                   const float* __restrict__ cd, const float* __restrict__ radii, const float* __restrict__ dA,
-                   const float* __restrict__ dub, uint2* __restrict__ pool, uint32_t pool_cap,
-                   uint32_t* __restrict__ pool_used, uint32_t* __restrict__ roff2, uint32_t* __restrict__ rcount2,
-                   uint32_t* __restrict__ nblk2, uint32_t* __restrict__ d_error,
-                   unsigned long long* __restrict__ d_pairs) {
+range_build_kernel(const uint32_t* __restrict__ d_ntiles, const uint32_t* __restrict__ tile_nrows,
+                   const uint32_t* __restrict__ blk_cluster, const uint32_t* __restrict__ blk_first,
+                   const uint32_t* __restrict__ off, uint32_t K, const float* __restrict__ cd,
+                   const float* __restrict__ radii, const float* __restrict__ ysq, const float* __restrict__ dub,
+                   uint2* __restrict__ pool, uint32_t pool_cap, uint32_t* __restrict__ pool_used,
+                   uint32_t* __restrict__ roff2, uint32_t* __restrict__ rcount2, uint32_t* __restrict__ nblk2,
+                   uint32_t* __restrict__ d_error, unsigned long long* __restrict__ d_pairs) {
   const int lane = threadIdx.x & 31;
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
   const uint32_t T = *d_ntiles;
   for (uint32_t t = warp; t < T; t += nwarps) {
-    const uint32_t r0 = tile_r0[t], nr = tile_nrows[t], A = tile_cluster[t];
-    const uint2 own = ranges1[2 * t];
-    // W = max over the tile's queries of d(q, A) + (upper bound of the distance to the k-th neighbour so far)
+    const uint32_t nr = tile_nrows[t], A = blk_cluster[t];
+    // W = max over the tile's queries of d(q, A) + (upper bound of the distance to the k-th neighbour so far);
+    // d(q, A) is bounded by the fp32 centred norm (the reference's Kahan value differs by rounding only)
     float W = 0.f;
     for (uint32_t r = lane; r < nr; r += 32) {
-      const uint32_t pos = r0 + r;
-      const float du = fminf(dub[2 * pos], dub[2 * pos + 1]);
-      const float w = dA[pos] + du;
-      W = (w > W || !(w == w)) ? (w == w ? w : INFINITY) : W;
+      const uint32_t row = t * tc::TM + r;
+      const float w = __fsqrt_ru(ysq[row]) * 1.00001f + fminf(dub[2 * row], dub[2 * row + 1]);
+      W = (w == w) ? fmaxf(W, w) : INFINITY;
     }
     for (int o = 16; o > 0; o >>= 1) W = fmaxf(W, __shfl_xor_sync(0xffffffffu, W, o));
     W = W * 1.000002f + 1e-30f;   // the reference rounds `cd - dA - R` twice: stay on the visiting side
-    for (int pass = 0; pass < 2; pass++) {   // pass 0 counts the merged ranges, pass 1 writes them
+    for (int pass = 0; pass < 2; pass++) {   // pass 0 counts, pass 1 writes
       uint32_t count = 0, blocks = 0, base = 0;
+      unsigned long long pairs = 0;
       if (pass == 1) {
-        uint32_t c0 = rcount2[t];
+        const uint32_t c0 = rcount2[t];
         if (lane == 0) base = atomicAdd(pool_used, c0);
         base = __shfl_sync(0xffffffffu, base, 0);
         if (base + c0 > pool_cap) {
@@ -1438,44 +1558,28 @@ range_build_kernel(const uint32_t* __restrict__ d_ntiles, const uint32_t* __rest
         }
         if (lane == 0) roff2[t] = base;
       }
-      uint32_t cur_lo = 1, cur_hi = 0;   // empty
-      unsigned long long pairs = 0;
       for (uint32_t B0 = 0; B0 < K; B0 += 32) {
         const uint32_t B = B0 + lane;
         bool visit = false;
-        uint32_t blo = 0, bhi = 0;
+        uint32_t lo = 0, hi = 0;
         if (B < K && B != A) {
-          const uint32_t b = off[B], e = off[B + 1];
+          const uint32_t m = off[B + 1] - off[B];
           const float c = cd[static_cast<size_t>(B) * K + A];
-          if (e > b && c == c && !(c - radii[B] > W)) {
-            blo = b / tc::TN;
-            bhi = (e - 1) / tc::TN;
-            if (B < A) { if (bhi >= own.x) bhi = own.x - 1; visit = own.x > 0 && blo <= bhi && blo < own.x; }
-            else { if (blo <= own.y) blo = own.y + 1; visit = blo <= bhi; }
-            if (pass == 0 && lane < 32) pairs += static_cast<unsigned long long>(e - b) * nr;
+          if (m && c == c && !(c - radii[B] > W)) {
+            visit = true;
+            lo = blk_first[B];
+            hi = blk_first[B + 1] - 1;
+            pairs += static_cast<unsigned long long>(m) * nr;
           }
         }
-        unsigned m = __ballot_sync(0xffffffffu, visit);
-        while (m) {
-          const int src = __ffs(m) - 1;
-          m &= m - 1;
-          const uint32_t lo = __shfl_sync(0xffffffffu, blo, src), hi = __shfl_sync(0xffffffffu, bhi, src);
-          if (cur_lo <= cur_hi && lo <= cur_hi + 1) {
-            if (hi > cur_hi) { blocks += hi - cur_hi; cur_hi = hi; }
-          } else {
-            if (cur_lo <= cur_hi) {
-              if (pass == 1 && lane == 0) pool[base + count] = make_uint2(cur_lo, cur_hi);
-              count++;
-            }
-            cur_lo = lo;
-            cur_hi = hi;
-            blocks += hi - lo + 1;
-          }
+        const unsigned mk = __ballot_sync(0xffffffffu, visit);
+        if (visit) {
+          if (pass == 1) pool[base + count + __popc(mk & ((1u << lane) - 1))] = make_uint2(lo, hi);
         }
-      }
-      if (cur_lo <= cur_hi) {
-        if (pass == 1 && lane == 0) pool[base + count] = make_uint2(cur_lo, cur_hi);
-        count++;
+        uint32_t nb = visit ? hi - lo + 1 : 0;
+        for (int o = 16; o > 0; o >>= 1) nb += __shfl_xor_sync(0xffffffffu, nb, o);
+        blocks += nb;
+        count += __popc(mk);
       }
       if (pass == 0) {
         if (lane == 0) { rcount2[t] = count; nblk2[t] = blocks; }
@@ -1487,37 +1591,45 @@ range_build_kernel(const uint32_t* __restrict__ d_ntiles, const uint32_t* __rest
   }
 }
 
-// one warp per sorted query: final threshold, expansion of the recorded (chunk, mask) entries into candidate pairs
+// one warp per query (table row): final threshold, expansion of the recorded entries into candidate pairs
 __global__ void __launch_bounds__(256)
-expand_kernel(uint32_t nv, int kk, uint32_t stride, const float* __restrict__ topk, const uint32_t* __restrict__ cnts,
-              const uint32_t* __restrict__ flags, const float* __restrict__ margin,
-              const uint4* __restrict__ entries, const uint32_t* __restrict__ inv, uint32_t max_pairs,
+expand_kernel(const uint32_t* __restrict__ d_ntiles, int kk, uint32_t stride, const float* __restrict__ topk,
+              const uint32_t* __restrict__ cnts, const uint32_t* __restrict__ flags,
+              const uint4* __restrict__ entries, const uint32_t* __restrict__ tab2orig, uint32_t max_pairs,
               uint32_t* __restrict__ pair_row, uint32_t* __restrict__ pair_cand, uint32_t* __restrict__ rowq,
               uint32_t* __restrict__ fb_rows, uint32_t* __restrict__ counters, uint32_t* __restrict__ dbg) {
   const int lane = threadIdx.x & 31;
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-  for (uint32_t pos = warp; pos < nv; pos += nwarps) {
-    const uint32_t s0 = 2 * pos, s1 = 2 * pos + 1;
+  const uint32_t nrows = *d_ntiles * tc::TM;
+  for (uint32_t row = warp; row < nrows; row += nwarps) {
+    const uint32_t self = tab2orig[row];
+    if (self == UINT32_MAX) continue;   // padding
+    const uint32_t s0 = 2 * row, s1 = 2 * row + 1;
     const float k0 = topk[static_cast<size_t>(kk - 1) * stride + s0], k1 = topk[static_cast<size_t>(kk - 1) * stride + s1];
     const float kth = fmaxf(k0, k1);   // each half saw kk distinct columns at or above its own value
     const uint32_t fl = flags[s0] | flags[s1];
     const uint32_t c0 = cnts[s0], c1 = cnts[s1];
     bool fallback = fl != 0 || !(kth > -INFINITY);
-    if (lane == 0 && dbg) { if (fl & 1) atomicAdd(dbg + 0, 1u); if (fl & 2) atomicAdd(dbg + 1, 1u); if (fl & 4) atomicAdd(dbg + 2, 1u); if (!(kth > -INFINITY)) atomicAdd(dbg + 3, 1u); }
-    const float thr = kth - margin[pos];
-    // each lane takes entries lane, lane+32, ... of the concatenated (half 0, half 1) lists
+    if (lane == 0 && dbg) {
+      if (fl & 1) atomicAdd(dbg + 0, 1u);
+      if (fl & 2) atomicAdd(dbg + 1, 1u);
+      if (fl & 4) atomicAdd(dbg + 2, 1u);
+      if (!(kth > -INFINITY)) atomicAdd(dbg + 3, 1u);
+    }
+    // each lane takes entries lane, lane+32, ... of the concatenated (half 0, half 1) lists; an entry survives if
+    // its group maximum is within ITS margin of the final kk-th best
     uint32_t mine = 0;
     const uint32_t total_e = c0 + c1;
     for (uint32_t i = lane; i < total_e && !fallback; i += 32) {
       const uint4 e = i < c0 ? entries[static_cast<size_t>(s0) * tc::KNN_CAP + i]
                              : entries[static_cast<size_t>(s1) * tc::KNN_CAP + (i - c0)];
-      if (__uint_as_float(e.x) >= thr) {
+      if (__uint_as_float(e.x) >= kth - __uint_as_float(e.w)) {
         uint32_t m = e.y;
         const uint32_t p0 = (e.z >> 2) * 128u + ((e.z >> 1) & 1u) * 64u + (e.z & 1u) * 32u;
         while (m) {
           const uint32_t cp = p0 + __ffs(m) - 1;
           m &= m - 1;
-          if (cp < nv && cp != pos) mine++;
+          if (cp != row && tab2orig[cp] != UINT32_MAX) mine++;
         }
       }
     }
@@ -1527,7 +1639,11 @@ expand_kernel(uint32_t nv, int kk, uint32_t stride, const float* __restrict__ to
       if (lane >= o) pre += v;
     }
     const uint32_t total = __shfl_sync(0xffffffffu, pre, 31);
-    if (lane == 0 && dbg && !fallback) { if (total > 64) atomicAdd(dbg + 4, 1u); if (total < static_cast<uint32_t>(kk - 1)) atomicAdd(dbg + 5, 1u); atomicAdd(dbg + 6, total); }
+    if (lane == 0 && dbg && !fallback) {
+      if (total > 64) atomicAdd(dbg + 4, 1u);
+      if (total < static_cast<uint32_t>(kk - 1)) atomicAdd(dbg + 5, 1u);
+      atomicAdd(dbg + 6, total);
+    }
     if (total > 64 || total < static_cast<uint32_t>(kk - 1)) fallback = true;
     uint32_t base = 0;
     if (!fallback) {
@@ -1536,23 +1652,23 @@ expand_kernel(uint32_t nv, int kk, uint32_t stride, const float* __restrict__ to
       if (base + total > max_pairs) fallback = true;
     }
     if (fallback) {
-      if (lane == 0) fb_rows[atomicAdd(&counters[tc::CNT_OVF], 1u)] = inv[pos];
+      if (lane == 0) fb_rows[atomicAdd(&counters[tc::CNT_OVF], 1u)] = self;
       continue;
     }
-    const uint32_t self = inv[pos];
     uint32_t w = base + pre - mine;
     for (uint32_t i = lane; i < total_e; i += 32) {
       const uint4 e = i < c0 ? entries[static_cast<size_t>(s0) * tc::KNN_CAP + i]
                              : entries[static_cast<size_t>(s1) * tc::KNN_CAP + (i - c0)];
-      if (__uint_as_float(e.x) >= thr) {
+      if (__uint_as_float(e.x) >= kth - __uint_as_float(e.w)) {
         uint32_t m = e.y;
         const uint32_t p0 = (e.z >> 2) * 128u + ((e.z >> 1) & 1u) * 64u + (e.z & 1u) * 32u;
         while (m) {
           const uint32_t cp = p0 + __ffs(m) - 1;
           m &= m - 1;
-          if (cp < nv && cp != pos) {
+          const uint32_t o = tab2orig[cp];
+          if (cp != row && o != UINT32_MAX) {
             pair_row[w] = self;
-            pair_cand[w] = inv[cp];
+            pair_cand[w] = o;
             w++;
           }
         }
@@ -1619,9 +1735,8 @@ bool tc_knn_supported(int metric, int k, uint32_t N, int D, uint32_t K) {
 
 #define KNN_TRY(x) do { e = (x); if (e != cudaSuccess) goto done; } while (0)
 
-// neighbors: device array [q_length][k] for the queries q_offset .. q_offset+q_length (original sample indices;
-// this build shards k-NN queries only on the SIMT path, so q_offset = 0 and q_length = N here).
-// Rows the filter cannot serve are appended to fb_rows / d_nfb for the caller's exact search.
+// neighbors: device array [N][k] indexed by the original sample index (this build shards k-NN queries only on the
+// SIMT path).  Rows the filter cannot serve are appended to fb_rows / d_nfb for the caller's exact search.
 cudaError_t tc_knn_search(int k, const float* X, const float* C, uint32_t N, int D, uint32_t K,
                           const uint32_t* assign, const uint32_t* inv, const uint32_t* off, const float* cd,
                           const float* radii, uint32_t nv, uint32_t* neighbors, uint32_t* fb_rows, uint32_t* d_nfb,
@@ -1635,19 +1750,17 @@ cudaError_t tc_knn_search(int k, const float* X, const float* C, uint32_t N, int
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
   const int nkb = (D + KB - 1) / KB, kk = k + 1;
-  const uint32_t nblk = (nv + TN - 1) / TN, rows_pad = nblk * TN;
-  const uint32_t tmax = nv / TM + K + 1;
-  const uint32_t stride = 2 * nv;
-  const uint64_t want_pool = static_cast<uint64_t>(tmax) * (K / 2 + 2);
-  const uint32_t pool_cap = static_cast<uint32_t>(want_pool < (32u << 20) ? want_pool : (32u << 20));
-  const uint32_t max_pairs = nv < (1u << 25) ? 64u * nv : 0xFFFFFFF0u;   // hard per-row cap is 64 candidates
-  // pairs are expanded lazily: average ~20-40 per row; allocate 48 per row and fall back beyond
-  const uint32_t pair_cap = static_cast<uint32_t>(std::min<uint64_t>(48ull * nv + 1024, max_pairs));
+  const uint32_t tmax = nv / TM + K + 1;                 // upper bound of the number of cluster-aligned blocks
+  const uint32_t rows_max = tmax * TM;
+  const uint32_t stride = 2 * rows_max;
+  const uint64_t want_pool = static_cast<uint64_t>(tmax) * K;
+  const uint32_t pool_cap = static_cast<uint32_t>(want_pool < (48u << 20) ? want_pool : (48u << 20));
+  const uint32_t pair_cap = static_cast<uint32_t>(std::min<uint64_t>(40ull * nv + 4096, 0xFFFFFFF0ull));
   __half *table = nullptr, *blobs = nullptr;
-  float *xsq = nullptr, *dA = nullptr, *topk = nullptr, *kmargin = nullptr, *dub = nullptr, *pair_score = nullptr;
+  float *ysq = nullptr, *topk = nullptr, *dub = nullptr, *pair_score = nullptr, *yabs = nullptr;
   Stats* stats = nullptr;
   uint32_t *u32 = nullptr, *kcnt = nullptr, *kflags = nullptr, *pair_row = nullptr, *pair_cand = nullptr, *rowq = nullptr;
-  uint32_t* counters = nullptr;
+  uint32_t *counters = nullptr, *tab2orig = nullptr;
   uint2 *ranges1 = nullptr, *pool = nullptr;
   uint4* entries = nullptr;
   void* cub_tmp = nullptr;
@@ -1656,30 +1769,29 @@ cudaError_t tc_knn_search(int k, const float* X, const float* C, uint32_t N, int
   uint32_t h_dbg[8] = {0};
   CUtensorMap tmap;
   Params prm;
-  unsigned grid = static_cast<unsigned>(num_sms);
+  const unsigned grid = static_cast<unsigned>(num_sms);
   const size_t smem_bytes = smem_layout().total + 1024;
-  // per-tile u32 arrays: ntile[K], tile_off[K+1], r0, nrows, cluster, roff1, rcount1, nblk1, roff2, rcount2, nblk2
-  uint32_t *ntile, *tile_off, *t_r0, *t_nrows, *t_cluster, *roff1, *rcount1, *nblk1, *roff2, *rcount2, *nblk2, *d_ntiles,
+  uint32_t *ntile, *blk_first, *t_nrows, *blk_cluster, *roff1, *rcount1, *nblk1, *roff2, *rcount2, *nblk2, *d_ntiles,
       *pool_used, *d_err;
   {
-    const size_t words = static_cast<size_t>(K) + (K + 1) + 9ull * tmax + 16;
+    const size_t words = static_cast<size_t>(K) + (K + 1) + 8ull * tmax + 16;
     KNN_TRY(cudaMalloc(&u32, words * sizeof(uint32_t)));
     KNN_TRY(cudaMemsetAsync(u32, 0, words * sizeof(uint32_t), st));
     uint32_t* q = u32;
     ntile = q; q += K;
-    tile_off = q; q += K + 1;
-    t_r0 = q; q += tmax; t_nrows = q; q += tmax; t_cluster = q; q += tmax;
+    blk_first = q; q += K + 1;
+    t_nrows = q; q += tmax; blk_cluster = q; q += tmax;
     roff1 = q; q += tmax; rcount1 = q; q += tmax; nblk1 = q; q += tmax;
     roff2 = q; q += tmax; rcount2 = q; q += tmax; nblk2 = q; q += tmax;
     d_ntiles = q++; pool_used = q++; d_err = q++;   // pool_used + 2 .. + 9: debug counters of expand_kernel
   }
-  KNN_TRY(cudaMalloc(&table, static_cast<size_t>(rows_pad) * nkb * KB * sizeof(__half)));
-  KNN_TRY(cudaMalloc(&blobs, static_cast<size_t>(nblk) * AUG_B_BYTES));
-  KNN_TRY(cudaMalloc(&xsq, sizeof(float) * rows_pad));
+  KNN_TRY(cudaMalloc(&table, static_cast<size_t>(rows_max) * nkb * KB * sizeof(__half)));
+  KNN_TRY(cudaMalloc(&blobs, static_cast<size_t>(tmax) * AUG_B_BYTES));
+  KNN_TRY(cudaMalloc(&ysq, sizeof(float) * rows_max));
+  KNN_TRY(cudaMalloc(&yabs, sizeof(float)));
   KNN_TRY(cudaMalloc(&stats, sizeof(Stats)));
-  KNN_TRY(cudaMalloc(&dA, sizeof(float) * nv));
+  KNN_TRY(cudaMalloc(&tab2orig, sizeof(uint32_t) * rows_max));
   KNN_TRY(cudaMalloc(&topk, sizeof(float) * static_cast<size_t>(kk) * stride));
-  KNN_TRY(cudaMalloc(&kmargin, sizeof(float) * nv));
   KNN_TRY(cudaMalloc(&dub, sizeof(float) * stride));
   KNN_TRY(cudaMalloc(&kcnt, sizeof(uint32_t) * stride));
   KNN_TRY(cudaMalloc(&kflags, sizeof(uint32_t) * stride));
@@ -1693,18 +1805,30 @@ cudaError_t tc_knn_search(int k, const float* X, const float* C, uint32_t N, int
   KNN_TRY(cudaMalloc(&counters, sizeof(uint32_t) * CNT_N));
   KNN_TRY(cudaMemsetAsync(counters, 0, sizeof(uint32_t) * CNT_N, st));
   KNN_TRY(cudaMemsetAsync(stats, 0, sizeof(Stats), st));
+  KNN_TRY(cudaMemsetAsync(yabs, 0, sizeof(float), st));
+  KNN_TRY(cudaMemsetAsync(ysq, 0, sizeof(float) * rows_max, st));   // rows past the last block stay 0 for the max
   KNN_TRY(cudaMemsetAsync(kcnt, 0, sizeof(uint32_t) * stride, st));
   KNN_TRY(cudaMemsetAsync(kflags, 0, sizeof(uint32_t) * stride, st));
+  KNN_TRY(cudaMemsetAsync(tab2orig, 0xff, sizeof(uint32_t) * rows_max, st));
   KNN_TRY(tc_set_smem_attr(static_cast<int>(smem_bytes)));
-  // fp16 table of the cluster-sorted samples + bias blobs + statistics
-  tc_prep_norms_kernel<<<(nv * 32 + 255) / 256, 256, 0, st>>>(X, nv, D, xsq, inv, 1.0f);
-  tc_prep_stats_kernel<<<8, 256, 0, st>>>(xsq, nv, stats);
+  // cluster-aligned table layout: blocks per cluster, first block of every cluster, table row -> sample
+  knn::tile_count_kernel<<<(K + 255) / 256, 256, 0, st>>>(off, K, ntile);
+  KNN_TRY(cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, ntile, blk_first, static_cast<int>(K), st));
+  KNN_TRY(cudaMalloc(&cub_tmp, cub_bytes ? cub_bytes : 16));
+  KNN_TRY(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, ntile, blk_first, static_cast<int>(K), st));
+  knn::tile_fill_kernel<<<(K + 255) / 256, 256, 0, st>>>(off, K, blk_first, t_nrows, blk_cluster, ranges1, roff1, rcount1,
+                                                         nblk1, d_ntiles, d_pairs);
+  KNN_TRY(cudaMemcpyAsync(blk_first + K, d_ntiles, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+  knn::layout_kernel<<<(nv + 255) / 256, 256, 0, st>>>(inv, assign, off, blk_first, nv, tab2orig);
+  // fp16 table of the centred samples + bias blobs + statistics
+  knn::prep_norms_kernel<<<(rows_max / 8) + 1, 256, 0, st>>>(X, C, D, tab2orig, blk_cluster, d_ntiles, ysq, yabs);
+  tc_prep_stats_kernel<<<8, 256, 0, st>>>(ysq, rows_max, stats);
   tc_prep_scale_kernel<<<1, 1, 0, st>>>(stats);
-  tc_prep_table_kernel<<<(rows_pad * 32 + 255) / 256, 256, 0, st>>>(0, X, xsq, nv, D, nkb, static_cast<int>(nblk), table,
-                                                                    blobs, stats, inv);
+  knn::prep_table_kernel<<<(rows_max / 8) + 1, 256, 0, st>>>(X, C, D, nkb, tab2orig, blk_cluster, d_ntiles, ysq, table,
+                                                             blobs, stats, yabs);
   KNN_TRY(cudaGetLastError());
   {
-    cuuint64_t gdim[2] = {static_cast<cuuint64_t>(nkb * KB), static_cast<cuuint64_t>(rows_pad)};
+    cuuint64_t gdim[2] = {static_cast<cuuint64_t>(nkb * KB), static_cast<cuuint64_t>(rows_max)};
     cuuint64_t gstride[1] = {static_cast<cuuint64_t>(nkb * KB) * sizeof(__half)};
     cuuint32_t box[2] = {KB, TN};
     cuuint32_t estr[2] = {1, 1};
@@ -1713,33 +1837,25 @@ cudaError_t tc_knn_search(int k, const float* X, const float* C, uint32_t N, int
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) { e = cudaErrorInvalidValue; goto done; }
   }
-  // tiles (<= 128 queries of one cluster each) and their own-cluster block ranges
-  knn::tile_count_kernel<<<(K + 255) / 256, 256, 0, st>>>(off, K, ntile);
-  KNN_TRY(cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, ntile, tile_off, static_cast<int>(K), st));
-  KNN_TRY(cudaMalloc(&cub_tmp, cub_bytes ? cub_bytes : 16));
-  KNN_TRY(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, ntile, tile_off, static_cast<int>(K), st));
-  knn::tile_fill_kernel<<<(K + 255) / 256, 256, 0, st>>>(off, K, tile_off, t_r0, t_nrows, t_cluster, ranges1, roff1,
-                                                         rcount1, nblk1, d_ntiles, d_pairs);
-  knn::own_distance_kernel<0><<<(nv + 127) / 128, 128, 0, st>>>(X, C, D, inv, assign, nv, dA);
-  KNN_TRY(cudaGetLastError());
-  prm.n = nv; prm.D = D; prm.K = nv; prm.nkb = nkb; prm.nt = static_cast<int>(nblk); prm.ntiles = 0;
+  prm.n = N; prm.D = D; prm.K = K; prm.nkb = nkb; prm.nt = 0; prm.ntiles = 0;
   prm.aug_blob = blobs; prm.stats = stats; prm.result = nullptr; prm.pair_row = nullptr; prm.pair_cand = nullptr;
   prm.max_pairs = 0; prm.rowq = nullptr; prm.ovf_rows = nullptr; prm.counters = counters; prm.metric = 0;
-  prm.X = X; prm.rows = inv; prm.d_nrows = nullptr; prm.d_ntiles = d_ntiles; prm.tile_r0 = t_r0;
-  prm.tile_nrows = t_nrows; prm.knn_ranges = ranges1; prm.knn_roff = roff1; prm.knn_rcount = rcount1;
-  prm.knn_nblk = nblk1; prm.kk = kk; prm.knn_first_pass = 1; prm.knn_stride = stride; prm.knn_topk = topk;
-  prm.knn_cnt = kcnt; prm.knn_flags = kflags; prm.knn_margin = kmargin; prm.knn_dub = dub; prm.knn_entries = entries;
+  prm.X = X; prm.rows = tab2orig; prm.d_nrows = nullptr; prm.d_ntiles = d_ntiles; prm.tile_nrows = t_nrows;
+  prm.blk_cluster = blk_cluster; prm.C = C;
+  prm.knn_ranges = ranges1; prm.knn_roff = roff1; prm.knn_rcount = rcount1; prm.knn_nblk = nblk1;
+  prm.kk = kk; prm.knn_first_pass = 1; prm.knn_stride = stride; prm.knn_topk = topk;
+  prm.knn_cnt = kcnt; prm.knn_flags = kflags; prm.knn_dub = dub; prm.knn_entries = entries;
   prm.dbg_scores = nullptr;
   tc_launch_main(2, nkb, grid, smem_bytes, st, tmap, tmap, prm);
   KNN_TRY(cudaGetLastError());
-  knn::range_build_kernel<<<num_sms * 4, 256, 0, st>>>(d_ntiles, t_r0, t_nrows, t_cluster, ranges1, off, K, cd, radii, dA,
+  knn::range_build_kernel<<<num_sms * 4, 256, 0, st>>>(d_ntiles, t_nrows, blk_cluster, blk_first, off, K, cd, radii, ysq,
                                                        dub, pool, pool_cap, pool_used, roff2, rcount2, nblk2, d_err,
                                                        d_pairs);
   KNN_TRY(cudaGetLastError());
   prm.knn_ranges = pool; prm.knn_roff = roff2; prm.knn_rcount = rcount2; prm.knn_nblk = nblk2; prm.knn_first_pass = 0;
   tc_launch_main(2, nkb, grid, smem_bytes, st, tmap, tmap, prm);
   KNN_TRY(cudaGetLastError());
-  knn::expand_kernel<<<num_sms * 8, 256, 0, st>>>(nv, kk, stride, topk, kcnt, kflags, kmargin, entries, inv, pair_cap,
+  knn::expand_kernel<<<num_sms * 8, 256, 0, st>>>(d_ntiles, kk, stride, topk, kcnt, kflags, entries, tab2orig, pair_cap,
                                                   pair_row, pair_cand, rowq, fb_rows, counters, pool_used + 2);
   KNN_TRY(cudaGetLastError());
   recheck_pairs_kernel<0, 1><<<num_sms * 4, 128, 0, st>>>(X, X, nullptr, D, pair_row, pair_cand, counters + CNT_PAIRS,
@@ -1758,8 +1874,8 @@ cudaError_t tc_knn_search(int k, const float* X, const float* C, uint32_t N, int
             "<k cand %u; candidates seen %u\n", h_cnt[CNT_ROWQ], h_cnt[CNT_PAIRS], h_cnt[CNT_OVF], *h_error, h_dbg[0],
             h_dbg[1], h_dbg[2], h_dbg[3], h_dbg[4], h_dbg[5], h_dbg[6]);
 done:
-  cudaFree(u32); cudaFree(table); cudaFree(blobs); cudaFree(xsq); cudaFree(stats); cudaFree(dA); cudaFree(topk);
-  cudaFree(kmargin); cudaFree(dub); cudaFree(kcnt); cudaFree(kflags); cudaFree(entries); cudaFree(ranges1);
+  cudaFree(u32); cudaFree(table); cudaFree(blobs); cudaFree(ysq); cudaFree(yabs); cudaFree(stats); cudaFree(tab2orig);
+  cudaFree(topk); cudaFree(dub); cudaFree(kcnt); cudaFree(kflags); cudaFree(entries); cudaFree(ranges1);
   cudaFree(pool); cudaFree(pair_row); cudaFree(pair_cand); cudaFree(pair_score); cudaFree(rowq); cudaFree(counters);
   cudaFree(cub_tmp);
   return e;
