@@ -773,6 +773,7 @@ KMCUDAResult knn_cuda(uint16_t k, KMCUDADistanceMetric metric, uint32_t samples_
   const uint32_t N = samples_size, K = clusters_size;
   auto plan = split_rows(N, static_cast<uint32_t>(D) * sizeof(float), dev_ids.size());
   unsigned long long total_pairs = 0;
+  g_prof.begin(dev_ids);
   struct KDev {
     DevBuf<float> X, C, cd, radii, heap;
     DevBuf<uint32_t> assign, inv_keys, iota, inv, off, counts, neigh;
@@ -845,10 +846,12 @@ KMCUDAResult knn_cuda(uint16_t k, KMCUDADistanceMetric metric, uint32_t samples_
     ws.cub_tmp_bytes = update_cub_bytes(N);
     KNN_CU(d.cub.alloc(ws.cub_tmp_bytes), kmcudaMemoryAllocationFailure);
     ws.cub_tmp = d.cub.get();
+    g_prof.mark("knn: alloc + ingest");
     KNN_CU(launch_knn_inverse(d.assign, N, K, d.iota, d.inv_keys, d.inv, d.off, d.counts, ws, d.st), kmcudaRuntimeError);
     KNN_CU(launch_knn_radii(m, d.X, d.C, N, D, K, d.assign, d.radii, d.st), kmcudaRuntimeError);
     KNN_CU(launch_knn_centroid_distances(m, d.C, K, D, d.cd, d.st), kmcudaRuntimeError);
     KNN_CU(launch_knn_radii_fix(d.off, K, d.radii, d.st), kmcudaRuntimeError);
+    g_prof.mark("knn: inverse, radii, centroid distances");
     bool searched = false;
     const char* fx = getenv("KMCUDA_B200_FORCE_EXACT");
     if (dev_ids.size() == 1 && !(fx && fx[0] == '1') && tc_knn_supported(m, k, N, D, K)) {
@@ -864,6 +867,7 @@ KMCUDAResult knn_cuda(uint16_t k, KMCUDADistanceMetric metric, uint32_t samples_
       if (nv >= 4096)
         te = tc_knn_search(k, d.X, d.C, N, D, K, d.assign, d.inv, d.off, d.cd, d.radii, nv, d.neigh, fb_rows, d_nfb,
                            d.pairs, &tc_err, d.st);
+      g_prof.mark("knn: tensor-core candidate search");
       if (nv >= 4096 && te == cudaSuccess && tc_err == 0) {
         KNN_CU(launch_knn_tail_rows(d.inv, nv, N, fb_rows, d_nfb, d.st), kmcudaRuntimeError);
         KNN_CU(launch_knn_search(m, k, d.X, d.C, N, D, K, 0, qlen, d.assign, d.inv, d.off, d.cd, d.radii, d.heap,
@@ -899,6 +903,8 @@ KMCUDAResult knn_cuda(uint16_t k, KMCUDADistanceMetric metric, uint32_t samples_
     total_pairs += p;
   }
 #undef KNN_CU
+  g_prof.mark("knn: exact search of the remainder + copy-out");
+  g_prof.report("knn_cuda");
   cleanup();
   KMB_INFO("calculated %f of all the distances\n",
            static_cast<double>(total_pairs) / (static_cast<double>(N) * N));  // reference knn.cu:530

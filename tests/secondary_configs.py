@@ -145,7 +145,18 @@ def c5(ours, ref, res, n_full=3000000, n_ref=200000):
             r[name + "_queries_per_s"] = n / dt
             r[name + "_nb"] = nb
         if "reference_nb" in r:
-            r["rows_equal_frac"] = float((r["ours_nb"] == r["reference_nb"]).all(1).mean())
+            same = (r["ours_nb"] == r["reference_nb"]).all(1)
+            r["rows_equal_frac"] = float(same.mean())
+            # rows that differ: are the two answers the same multiset of exact (reference-arithmetic) distances?
+            L = O.lib()
+            fp = ctypes.POINTER(ctypes.c_float)
+            ties = 0
+            for q in np.nonzero(~same)[0][:200]:
+                d = [sorted(L.ko_distance(0, Xs[q].ctypes.data_as(fp), Xs[int(j)].ctypes.data_as(fp), Xs.shape[1])
+                            for j in r[name + "_nb"][q]) for name in ("ours", "reference")]
+                ties += d[0] == d[1]
+            r["differing_rows"] = int((~same).sum())
+            r["differing_rows_checked_equal_distance_multisets"] = int(ties)
         for kk in [kk for kk in r if kk.endswith("_nb")]:
             del r[kk]
         out["n%d" % n] = r
