@@ -20,7 +20,7 @@ import time
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libKMCUDA.so")
+LIB_PATH = os.environ.get("KMCUDA_B200_LIB") or os.path.join(_HERE, "libKMCUDA.so")   # override: A/B timing of builds
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(

@@ -299,7 +299,7 @@ __device__ __forceinline__ void note_timeout(uint32_t* counters, int where) {
 
 // in-place compaction of one epilogue thread's chunk list: entries whose chunk maximum fell below the
 // current threshold can never hold a candidate (the threshold only rises)
-__device__ __noinline__ uint32_t compact_list(float* list_cm, uint32_t* list_mask, uint16_t* list_g, int slot,
+__device__ __forceinline__ uint32_t compact_list(float* list_cm, uint32_t* list_mask, uint16_t* list_g, int slot,
                                               uint32_t cnt, float thr) {
   uint32_t w = 0;
   for (uint32_t i = 0; i < cnt; i++) {
@@ -339,6 +339,7 @@ struct BlockIter {
   __device__ __forceinline__ bool seg_last() const { return cur == hi; }
   __device__ __forceinline__ void next() {
     left--;
+    if (MODE != 2) { cur++; return; }   // (keeps the range-list load out of the Lloyd / Yinyang loops: measured 0.65 ms per pass)
     if (cur == hi && left) { rg++; lo = cur = rg->x; hi = rg->y; } else { cur++; }
   }
 };
