@@ -17,6 +17,7 @@
 #include <cstring>
 #include <memory>
 #include <chrono>
+#include <map>
 #include <string>
 #include <utility>
 #include <vector>
@@ -190,7 +191,7 @@ class Job {
   ~Job() {
     for (auto& d : devs) {
       cudaSetDevice(d.dev);
-      if (d.comm) nccl_api().CommDestroy(d.comm);
+      d.comm = nullptr;   // owned by the per-process cache (Job::setup)
       d.shard.reset();
       if (d.st) cudaStreamDestroy(d.st);
     }
@@ -247,13 +248,21 @@ KMCUDAResult Job::setup(const std::vector<int>& dev_ids, bool alloc_samples) {
       KMB_INFO("multi-GPU jobs need NCCL (libnccl.so.2), which could not be loaded\n");
       return kmcudaRuntimeError;
     }
-    std::vector<ncclComm_t> comms(devs.size());
-    ncclResult_t r = nccl_api().CommInitAll(comms.data(), static_cast<int>(devs.size()), dev_ids.data());
-    if (r != ncclSuccess) {
-      KMB_INFO("ncclCommInitAll failed: %s\n", nccl_api().GetErrorString(r));
-      return kmcudaRuntimeError;
+    // Communicators are cached per device list for the life of the process: ncclCommInitAll costs seconds to
+    // minutes (measured ~100 s on the 2-GPU test box, all inside NCCL's bootstrap) and the library is not
+    // re-entrant anyway (kmcuda.h:25-26).
+    static std::map<std::vector<int>, std::vector<ncclComm_t>> comm_cache;
+    auto it = comm_cache.find(dev_ids);
+    if (it == comm_cache.end()) {
+      std::vector<ncclComm_t> comms(devs.size());
+      ncclResult_t r = nccl_api().CommInitAll(comms.data(), static_cast<int>(devs.size()), dev_ids.data());
+      if (r != ncclSuccess) {
+        KMB_INFO("ncclCommInitAll failed: %s\n", nccl_api().GetErrorString(r));
+        return kmcudaRuntimeError;
+      }
+      it = comm_cache.emplace(dev_ids, comms).first;
     }
-    for (size_t i = 0; i < devs.size(); i++) devs[i].comm = comms[i];
+    for (size_t i = 0; i < devs.size(); i++) devs[i].comm = it->second[i];
   }
   if (verbosity > 1) {
     printf("plans: [");

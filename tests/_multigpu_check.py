@@ -22,3 +22,7 @@ print("clustered: 1 vs 2 gpus equal %.6f; all-gpu yinyang vs 1-gpu lloyd %.6f; c
 nb1 = km.knn_cuda(5, X[:20000], c1, a1[:20000], device=1)
 nb2 = km.knn_cuda(5, X[:20000], c1, a1[:20000], device=3)
 print("knn 1 vs 2 gpus equal:", np.array_equal(nb1, nb2), flush=True)
+# Yinyang iterations on two shards (bounds, tensor-core local step and NCCL update per shard)
+y1, b1 = km.kmeans_cuda(X, 100, init=C0, device=1, tolerance=0.03, yinyang_t=0.1)
+y2, b2 = km.kmeans_cuda(X, 100, init=C0, device=3, tolerance=0.03, yinyang_t=0.1)
+print("yinyang 1 vs 2 gpus: assignments equal %.6f, centroid max rel diff %.3g" % ((b1 == b2).mean(), np.abs(y1 - y2).max() / np.abs(y1).max()), flush=True)
