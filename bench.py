@@ -31,7 +31,17 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout to the single JSON line (some hosts export NCCL_DEBUG=VERSION)
+os.environ.pop("NCCL_DEBUG", None)   # some hosts export NCCL_DEBUG=VERSION; NCCL prints its banner on stdout
+# stdout carries exactly ONE JSON line: everything else that writes to fd 1 (NCCL banners, C-library progress
+# messages) is sent to stderr, the JSON line goes to the saved descriptor
+_JSON_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(obj):
+    _JSON_OUT.write(json.dumps(obj) + "\n")
+    _JSON_OUT.flush()
+
 
 METRIC = "kmeans_assign_points_per_sec"
 UNIT = "points/s"
@@ -48,15 +58,20 @@ def _rank_info():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)"""
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe).
+
+    nvidia-smi needs a few hundred ms to start, longer than the default timed region, so it is started early
+    (`start`, then `wait_ready`), the caller brackets the timed region with `mark()` and only the samples whose
+    timestamps fall inside the marks are used."""
 
     def __init__(self, index):
         self.path = tempfile.mktemp(prefix="clocks_", suffix=".csv")
         self.proc = None
         self.index = index
+        self.marks = []
 
     def start(self):
-        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+        q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
@@ -66,26 +81,52 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def wait_ready(self, timeout=5.0):
+        t = time.time()
+        while self.proc and time.time() - t < timeout:
+            try:
+                if os.path.getsize(self.path) > 0:
+                    return True
+            except OSError:
+                pass
+            time.sleep(0.02)
+        return False
+
+    def mark(self):
+        self.marks.append(time.time())
+
     def stop(self):
+        import datetime
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         if not self.proc:
             return out
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons, all_sm = [], [], [], set(), []
+        lo, hi = (self.marks[0] - 0.02, self.marks[1] + 0.02) if len(self.marks) >= 2 else (0.0, 1e18)
         try:
             for line in open(self.path):
                 f = [x.strip() for x in line.split(",")]
                 if len(f) < 9:
                     continue
                 try:
-                    sm.append(float(f[1]))
-                    mx.append(float(f[2]))
+                    ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                    clk, cmax = float(f[1]), float(f[2])
                 except ValueError:
                     continue
+                all_sm.append(clk)
+                if not (lo <= ts <= hi):
+                    continue
+                sm.append(clk)
+                mx.append(cmax)
+                try:
+                    pw.append(float(f[3]))
+                except ValueError:
+                    pass
                 for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"],
                                    f[5:9]):
                     if v.lower().startswith("active"):
@@ -94,11 +135,14 @@ class ClockSampler:
         except Exception:
             pass
         if sm:
-            busy = [x for x in sm if x > min(sm)] or sm
-            out["sm_mhz"] = statistics.median(busy)
+            out["sm_mhz"] = statistics.median(sm)
             out["sm_max_mhz"] = max(mx)
             out["reasons"] = sorted(reasons)
             out["samples"] = len(sm)
+            if pw:
+                out["power_w_max"] = max(pw)
+        elif all_sm:
+            out["note"] = "no sample fell inside the timed region (%d outside it)" % len(all_sm)
         return out
 
 
@@ -204,7 +248,7 @@ def run_reference(args):
     line.update({"value": v, "ms_per_step": dt * 1e3,
                  "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": note},
                  "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
-    print(json.dumps(line))
+    emit(line)
 
 
 def run_ours(args):
@@ -232,21 +276,24 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(args.warmup):
         a.fill_(-1)
         sh.assign(X, C, a, prev, changed)
     barrier()
     if sh.last_error():
         raise RuntimeError("tensor-core pipeline error 0x%x" % sh.last_error())
-    sampler = ClockSampler(local)
-    sampler.start()
+    sampler.wait_ready()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.mark()
     e0.record()
     for _ in range(args.steps):
         sh.assign(X, C, a, prev, changed)
     e1.record()
     barrier()
+    sampler.mark()
     clocks = sampler.stop()
     ms = e0.elapsed_time(e1)
     tms = torch.tensor([ms], device="cuda", dtype=torch.float64)
@@ -261,8 +308,8 @@ def run_ours(args):
 
     if args.skip_extras:
         if rank == 0:
-            print(json.dumps({"metric": METRIC, "value": world * n / (ms_per_step * 1e-3), "unit": UNIT,
-                              "ms_per_step": ms_per_step, "kernel_ms": kernel_ms, "note": "profiling run, extras skipped"}))
+            emit({"metric": METRIC, "value": world * n / (ms_per_step * 1e-3), "unit": UNIT,
+                  "ms_per_step": ms_per_step, "kernel_ms": kernel_ms, "note": "profiling run, extras skipped"})
         return
     # ---- end to end through the reference-facing C ABI with host buffers (pinned), rank-local shard
     e2e_steps = max(1, min(args.steps, 3))
@@ -310,8 +357,7 @@ def run_ours(args):
             "clocks": clocks,
         }
         line["cpu_baseline"] = cpu_baseline()
-        sys.stdout.flush()
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
