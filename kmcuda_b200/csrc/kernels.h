@@ -12,7 +12,6 @@
 namespace kmb {
 
 constexpr uint32_t kUntouched = 0xFFFFFFFEu;  // "no centroid won": leave the assignment alone
-constexpr int kMaxCand = 4;                   // candidates carried per re-check queue entry
 
 // ---- exact Lloyd assignment (all K centroids), optional row list -------------------------------
 // result[i] = argmin (strict <, ascending index), K for "insane" rows, kUntouched if nothing wins.
@@ -21,12 +20,6 @@ cudaError_t launch_csqr(int metric, const float* C, uint32_t K, int D, float* cs
 cudaError_t launch_assign_exact(int metric, const float* X, const float* C, const float* csq,
                                 uint32_t n, int D, uint32_t K, const uint32_t* rows,
                                 const uint32_t* d_nrows, uint32_t* result, cudaStream_t st);
-
-// ---- exact re-check of short candidate lists produced by the tensor-core filter ----------------
-// queue entry q: row = qrow[q], candidates qcand[q*kMaxCand .. +kMaxCand) (ascending, UINT32_MAX pad)
-cudaError_t launch_recheck(int metric, const float* X, const float* C, const float* csq, int D,
-                           const uint32_t* qrow, const uint32_t* qcand, const uint32_t* d_nq,
-                           uint32_t max_q, uint32_t* result, cudaStream_t st);
 
 // prev[i]=assign[i]; assign[i]=result[i] unless kUntouched; *changed += #(assign changed)
 cudaError_t launch_finalize_assign(uint32_t n, const uint32_t* result, uint32_t* assign,

@@ -268,93 +268,6 @@ cudaError_t launch_yy_init(int metric, const float* X, const float* C, uint32_t 
                                  bounds, st);
 }
 
-// ------------------------------------------------------------------------------------------------
-// Exact re-check of the short candidate lists emitted by the tensor-core filter.
-// 128 queue entries per CTA, features streamed through shared memory 32 at a time (coalesced
-// 128-byte row segments), Kahan state of the <=4 candidate chains lives in registers.
-// ------------------------------------------------------------------------------------------------
-template <int METRIC>
-__global__ void __launch_bounds__(128)
-recheck_kernel(const float* __restrict__ X, const float* __restrict__ C,
-               const float* __restrict__ csq, int D, const uint32_t* __restrict__ qrow,
-               const uint32_t* __restrict__ qcand, const uint32_t* __restrict__ d_nq, uint32_t max_q,
-               uint32_t* __restrict__ result) {
-  __shared__ float sXc[32 * 129];
-  extern __shared__ float sCc[];  // [kMaxCand*128][33]
-  const uint32_t nq = min(*d_nq, max_q);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (uint32_t tile0 = blockIdx.x * 128; tile0 < nq; tile0 += gridDim.x * 128) {
-    const uint32_t e = tile0 + threadIdx.x;
-    const bool active = e < nq;
-    uint32_t cand[kMaxCand];
-#pragma unroll
-    for (int j = 0; j < kMaxCand; j++) cand[j] = active ? qcand[static_cast<size_t>(e) * kMaxCand + j] : UINT32_MAX;
-    Kahan k[kMaxCand];
-    for (int f0 = 0; f0 < D; f0 += 32) {
-      const int fl = min(32, D - f0);
-      __syncthreads();
-      for (int i = 0; i < 32; i++) {  // sample chunk: warp w stages entries 32w..32w+31
-        uint32_t ent = tile0 + warp * 32 + i;
-        if (ent < nq && lane < fl) {
-          uint32_t r = qrow[ent];
-          sXc[lane * 129 + warp * 32 + i] = X[static_cast<size_t>(r) * D + f0 + lane];
-        }
-      }
-      for (int i = 0; i < kMaxCand * 32; i++) {  // candidate centroid chunks
-        int rowid = warp * (kMaxCand * 32) + i;   // = j*128 + entry
-        int j = rowid >> 7, ent_l = rowid & 127;
-        uint32_t ent = tile0 + ent_l;
-        if (ent < nq && lane < fl) {
-          uint32_t c = qcand[static_cast<size_t>(ent) * kMaxCand + j];
-          if (c != UINT32_MAX) sCc[rowid * 33 + lane] = C[static_cast<size_t>(c) * D + f0 + lane];
-        }
-      }
-      __syncthreads();
-      if (active) {
-        for (int f = 0; f < fl; f++) {
-          float x = sXc[f * 129 + threadIdx.x];
-#pragma unroll
-          for (int j = 0; j < kMaxCand; j++)
-            if (cand[j] != UINT32_MAX) k[j].mac(x, sCc[(j * 128 + threadIdx.x) * 33 + f]);
-        }
-      }
-    }
-    if (active) {
-      float best = FLT_MAX;
-      uint32_t arg = UINT32_MAX;
-#pragma unroll
-      for (int j = 0; j < kMaxCand; j++) {
-        if (cand[j] == UINT32_MAX) continue;
-        float score = lloyd_score<METRIC>(k[j].sum, csq[cand[j]]);
-        if (score < best) {
-          best = score;
-          arg = cand[j];
-        }
-      }
-      result[qrow[e]] = (arg == UINT32_MAX) ? kUntouched : arg;
-    }
-  }
-}
-
-cudaError_t launch_recheck(int metric, const float* X, const float* C, const float* csq, int D,
-                           const uint32_t* qrow, const uint32_t* qcand, const uint32_t* d_nq,
-                           uint32_t max_q, uint32_t* result, cudaStream_t st) {
-  size_t smem = static_cast<size_t>(kMaxCand) * 128 * 33 * sizeof(float);
-  unsigned grid = 148 * 2;
-  if (max_q == 0) return cudaSuccess;
-  grid = min(grid, cdiv(max_q, 128));
-  cudaError_t e;
-  if (metric == 1) {
-    e = cudaFuncSetAttribute(recheck_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    recheck_kernel<1><<<grid, 128, smem, st>>>(X, C, csq, D, qrow, qcand, d_nq, max_q, result);
-  } else {
-    e = cudaFuncSetAttribute(recheck_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    recheck_kernel<0><<<grid, 128, smem, st>>>(X, C, csq, D, qrow, qcand, d_nq, max_q, result);
-  }
-  return cudaGetLastError();
-}
 
 // ------------------------------------------------------------------------------------------------
 // prev/assign bookkeeping + reassignment counter (reference kmeans.cu:358-363)

@@ -124,3 +124,21 @@ def test_libKMCUDA_module_imports_from_the_same_shared_object():
     if not torch.cuda.is_available():
         with pytest.raises(ValueError, match="No such CUDA device"):
             mod.kmeans_cuda(arr, 5)
+
+
+def test_bench_reference_arm_prints_exactly_one_json_line():
+    """bench.py contract: stdout carries ONE JSON line (library chatter and NCCL banners go to stderr).  Without a
+    GPU the reference arm times the CPU oracle port on a bounded sample."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
+                        "--warmup", "1"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-500:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, r.stdout[:500]
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "kmeans_assign_points_per_sec" and d["unit"] == "points/s"
+    assert d["higher_is_better"] is True and d["value"] > 0
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["cpu_baseline"]["kind"] in ("reference", "port")
