@@ -28,7 +28,17 @@
 //   bit-identical to the reference kernel's, ties included.
 //
 // TMEM map (512 columns): [0,128) accumulator 0, [128,256) accumulator 1, [256,384) A buffer 0,
-// [384,512) A buffer 1 (128 rows x 256 fp16 = 128 lanes x 128 32-bit columns).
+// [384,512) A buffer 1 (128 rows x 256 fp16 = 128 lanes x 128 32-bit columns); for D > 256 one A buffer of up to
+// 256 columns.
+//
+// The same kernel template serves two more callers (MODE template parameter, see tc::Params):
+//   MODE 1  Yinyang local step (reference kmeans.cu:584-672): the samples are a compacted row list read straight
+//           from global memory by the converter warps; candidates = every centroid within the margin of the
+//           row's SECOND best; all of them get their exact true distance (yinyang.cu finishes the step).
+//   MODE 2  k-NN (reference knn.cu:177-347): queries and candidates are the samples in a cluster-aligned table;
+//           a tile is multiplied with one segment per candidate cluster, both operands centred on that
+//           cluster's centroid; the epilogue keeps the k+1 largest 4-column-group maxima per half-row as its
+//           threshold and records candidate masks in global lists (namespace knn below has the passes around it).
 #include <cuda.h>
 #include <cuda_fp16.h>
 
