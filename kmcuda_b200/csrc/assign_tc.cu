@@ -365,13 +365,20 @@ __device__ __noinline__ float knn_topk_insert(float* col, int kk, float v) {
   col[j * 256] = v;
   return col[(kk - 1) * 256];
 }
-// top kk of the union of two descending lists (the two column halves of one row hold disjoint columns)
-__device__ __noinline__ void knn_merge(const float* a, size_t astride, const float* b, size_t bstride, int kk,
-                                       float* out) {
-  int i = 0, j = 0;
+// threshold sweep of the k-NN pass: every half-row keeps 32 running maxima over disjoint column buckets (branch
+// free); afterwards the kk largest of the row's 64 buckets (both halves) become the descending top-kk list
+__device__ __noinline__ void knn_select_buckets(const float* mine, const float* partner, int kk, float goff,
+                                                float* out) {
+  unsigned long long taken = 0ull;
   for (int o = 0; o < kk; o++) {
-    const float av = a[i * astride], bv = b[j * bstride];
-    if (av >= bv) { out[o] = av; i++; } else { out[o] = bv; j++; }
+    float best = -INFINITY;
+    int bi = -1;
+    for (int j = 0; j < 64; j++) {
+      const float v = j < 32 ? mine[j * 256] : partner[(j - 32) * 256];
+      if (!((taken >> j) & 1ull) && v > best) { best = v; bi = j; }
+    }
+    if (bi >= 0) taken |= 1ull << bi;
+    out[o] = best - goff;
   }
 }
 // append to the half-row's global entry list; when full, drop the entries that fell below the current kk-th
@@ -678,6 +685,8 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
         kent = p.knn_entries + static_cast<size_t>(kslot) * KNN_CAP;
         if (p.knn_first_pass || !klive) {
           for (int j = 0; j < p.kk; j++) topk[j * 256] = -INFINITY;
+          if (p.knn_first_pass)
+            for (int j = 0; j < 32; j++) topk[(16 + j) * 256] = -INFINITY;   // bucket maxima: rows 16..47 of the region
         } else {
           // second pass: both halves saved the same merged list at the end of the first pass (no insertion happens
           // in the recording sweep); from here on each half adds its own, disjoint, columns
@@ -723,7 +732,8 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
               // e ^ 4 sits on the same row quarter); named barrier per quarter, 64 threads
               float mg[KNN_MAX_KK];
               asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
-              knn_merge(topk, 256, reinterpret_cast<float*>(smem + L.list_cm) + ((1 - h) * TM + row), 256, p.kk, mg);
+              knn_select_buckets(topk + 16 * 256, reinterpret_cast<float*>(smem + L.list_cm) + ((1 - h) * TM + row) + 16 * 256,
+                                 p.kk, goff, mg);
               asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
               for (int j = 0; j < p.kk; j++) topk[j * 256] = mg[j];
               M = mg[p.kk - 1];
@@ -767,7 +777,16 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
           // kk distinct columns reach the kk-th largest 4-column-group maximum (first level of the max tree): a
           // lower bound of the kk-th best score; finer than whole chunks because near neighbours sit close together
           // in the table.  M and the list live in g-space (score - goff).
-          if (!p.knn_first_pass || seg == 0) {
+          if (p.knn_first_pass && seg == 0) {
+            // threshold sweep: bucket (block parity, 4-column group) <- max; raw scores, the row constant is
+            // subtracted once at the end of the sweep
+            float* bk = topk + (16 + 16 * (n & 1)) * 256;
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+              bk[i * 256] = fmaxf(bk[i * 256], t0[i]);
+              bk[(8 + i) * 256] = fmaxf(bk[(8 + i) * 256], t1[i]);
+            }
+          } else if (!p.knn_first_pass) {
             const float lim = M + goff;
             if (cm0 > lim) {
 #pragma unroll
