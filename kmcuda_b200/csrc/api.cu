@@ -18,6 +18,7 @@
 #include <memory>
 #include <chrono>
 #include <map>
+#include <random>
 #include <string>
 #include <utility>
 #include <vector>
@@ -213,6 +214,7 @@ class Job {
                               int device_ptrs, bool fp16x2, const float* user_centroids);
   KMCUDAResult init_random();
   KMCUDAResult init_plusplus();
+  KMCUDAResult init_afkmc2(uint32_t m, uint32_t seed);
   KMCUDAResult assign_pass(uint32_t* changed);
   KMCUDAResult update();
   KMCUDAResult lloyd(float tolerance, int* iter_out, uint32_t* changed_out);
@@ -418,6 +420,126 @@ KMCUDAResult Job::init_plusplus() {
   return set_centroids_from_host(hostC.data());
 }
 
+// AFK-MC2 (Bachem et al. 2016; reference kmcuda.cc:337-396, kernels kmeans.cu:69-212): proposal distribution
+// q = 1/(2N) + d(x, c0)^2 / (2 sum d^2), then for every further centroid a Markov chain of length m over
+// candidates drawn from q, accepting with probability min(1, (p'/q')/(p/q)) where p = squared distance to the
+// nearest chosen centroid.  The reference draws candidates and acceptance thresholds with cuRAND on the device;
+// here the chain is driven by a host generator seeded with `seed` (deterministic per seed; the reference's own q
+// depends on float atomics, so its runs are only statistically reproducible as well).  The distance work (q and
+// the candidates' nearest-centroid distances) runs on the shards that own the samples.
+KMCUDAResult Job::init_afkmc2(uint32_t m, uint32_t seed) {
+  std::vector<float> hostC(static_cast<size_t>(K) * D);
+  std::vector<float> host_dists(N);
+  uint32_t first_index;
+  float smoke = NAN;
+  do {   // kmcuda.cc:346-353
+    first_index = rand() % N;
+    std::vector<float> row(D);
+    KMB_RET(fetch_row(first_index, row.data()));
+    smoke = row[0];
+    if (smoke == smoke) memcpy(hostC.data(), row.data(), sizeof(float) * D);
+  } while (smoke != smoke);
+  KMB_INFO("afkmc2: calculating q (c0 = %" PRIu32 ")... ", first_index);
+  for (auto& d : devs) {
+    KMB_CU(cudaSetDevice(d.dev), kmcudaRuntimeError);
+    KMB_CU(d.dists.alloc(std::max<size_t>(d.len, 2 * static_cast<size_t>(m))), kmcudaMemoryAllocationFailure);
+    KMB_CU(cudaMemcpyAsync(d.C.get(), hostC.data(), sizeof(float) * D, cudaMemcpyHostToDevice, d.st), kmcudaMemoryCopyError);
+    KMB_CU(cudaMemsetAsync(d.d_dsum.get(), 0, sizeof(double), d.st), kmcudaRuntimeError);
+    KMB_CU(launch_plusplus_step(metric, d.X, d.len, D, d.C.get(), 1, d.dists, d.d_dsum, d.st), kmcudaRuntimeError);
+    KMB_CU(cudaMemcpyAsync(host_dists.data() + d.off, d.dists.get(), sizeof(float) * d.len, cudaMemcpyDeviceToHost, d.st),
+           kmcudaMemoryCopyError);
+  }
+  KMB_RET(sync_all());
+  std::vector<float> q(N);
+  std::vector<double> cdf(N);
+  {
+    double dsum = 0;
+    for (uint32_t i = 0; i < N; i++) {
+      const double d2 = static_cast<double>(host_dists[i]) * host_dists[i];
+      if (d2 == d2) dsum += d2;
+    }
+    double acc = 0;
+    for (uint32_t i = 0; i < N; i++) {
+      double d2 = static_cast<double>(host_dists[i]) * host_dists[i];
+      if (!(d2 == d2)) d2 = 0;
+      const double qi = 1.0 / (2.0 * N) + (dsum > 0 ? d2 / (2.0 * dsum) : 1.0 / (2.0 * N));
+      q[i] = static_cast<float>(qi);
+      acc += qi;
+      cdf[i] = acc;
+    }
+  }
+  KMB_INFO("done\n");
+  std::mt19937_64 gen(seed);
+  auto uniform = [&gen]() { return (static_cast<double>(gen() >> 11) + 0.5) * (1.0 / 9007199254740992.0); };
+  std::vector<uint32_t> cand(m), local(m);
+  std::vector<float> p_cand(m), rand_a(m);
+  struct Scratch { DevBuf<uint32_t> rows; DevBuf<float> mind; std::vector<uint32_t> slots; std::vector<float> host; };
+  std::vector<Scratch> sc(devs.size());
+  for (size_t i = 0; i < devs.size(); i++) {
+    KMB_CU(cudaSetDevice(devs[i].dev), kmcudaRuntimeError);
+    KMB_CU(sc[i].rows.alloc(m), kmcudaMemoryAllocationFailure);
+    KMB_CU(sc[i].mind.alloc(m), kmcudaMemoryAllocationFailure);
+    sc[i].host.resize(m);
+  }
+  for (uint32_t k = 1; k < K; k++) {
+    if (verbosity > 1 || (verbosity > 0 && (K < 100 || k % (K / 100) == 0))) {
+      printf("\rstep %d", k);
+      fflush(stdout);
+    }
+    for (uint32_t j = 0; j < m; j++) {   // kmeans_afkmc2_random_step: first index whose cumulative q reaches the draw
+      const double part = uniform() * cdf[N - 1];
+      cand[j] = static_cast<uint32_t>(std::min<size_t>(std::lower_bound(cdf.begin(), cdf.end(), part) - cdf.begin(), N - 1));
+      rand_a[j] = static_cast<float>(uniform());
+    }
+    for (size_t i = 0; i < devs.size(); i++) {
+      Dev& d = devs[i];
+      sc[i].slots.clear();
+      uint32_t cnt = 0;
+      for (uint32_t j = 0; j < m; j++)
+        if (cand[j] >= d.off && cand[j] < d.off + d.len) {
+          local[cnt++] = cand[j] - d.off;
+          sc[i].slots.push_back(j);
+        }
+      if (cnt == 0) continue;
+      KMB_CU(cudaSetDevice(d.dev), kmcudaRuntimeError);
+      KMB_CU(cudaMemcpyAsync(sc[i].rows.get(), local.data(), sizeof(uint32_t) * cnt, cudaMemcpyHostToDevice, d.st),
+             kmcudaMemoryCopyError);
+      KMB_CU(cudaStreamSynchronize(d.st), kmcudaRuntimeError);   // `local` is reused for the next shard
+      KMB_CU(launch_afkmc2_min_dist(metric, d.X, d.C, D, k, sc[i].rows, cnt, sc[i].mind, d.st), kmcudaRuntimeError);
+      KMB_CU(cudaMemcpyAsync(sc[i].host.data(), sc[i].mind.get(), sizeof(float) * cnt, cudaMemcpyDeviceToHost, d.st),
+             kmcudaMemoryCopyError);
+    }
+    for (size_t i = 0; i < devs.size(); i++) {
+      if (sc[i].slots.empty()) continue;
+      KMB_CU(cudaSetDevice(devs[i].dev), kmcudaRuntimeError);
+      KMB_CU(cudaStreamSynchronize(devs[i].st), kmcudaRuntimeError);
+      for (size_t t = 0; t < sc[i].slots.size(); t++) {
+        const float dmin = sc[i].host[t];
+        p_cand[sc[i].slots[t]] = dmin * dmin;
+      }
+    }
+    float curr_prob = 0;
+    uint32_t curr_ind = 0;
+    for (uint32_t j = 0; j < m; j++) {   // kmcuda.cc:382-389
+      const float cand_prob = p_cand[j] / q[cand[j]];
+      if (curr_prob == 0 || cand_prob / curr_prob > rand_a[j]) {
+        curr_ind = j;
+        curr_prob = cand_prob;
+      }
+    }
+    float* dst = hostC.data() + static_cast<size_t>(k) * D;
+    KMB_RET(fetch_row(cand[curr_ind], dst));
+    for (auto& d : devs) {
+      KMB_CU(cudaSetDevice(d.dev), kmcudaRuntimeError);
+      KMB_CU(cudaMemcpyAsync(d.C.get() + static_cast<size_t>(k) * D, dst, sizeof(float) * D, cudaMemcpyHostToDevice, d.st),
+             kmcudaMemoryCopyError);
+    }
+  }
+  KMB_RET(sync_all());
+  for (auto& d : devs) d.dists.release();
+  return set_centroids_from_host(hostC.data());
+}
+
 KMCUDAResult Job::init_centroids(KMCUDAInitMethod method, const void* init_params, uint32_t seed,
                                  int device_ptrs, bool fp16x2, const float* user_centroids) {
   if (metric == 1 && !fp16x2) {  // three probe samples must be unit length (kmcuda.cc:195-219)
@@ -465,10 +587,17 @@ KMCUDAResult Job::init_centroids(KMCUDAInitMethod method, const void* init_param
     case kmcudaInitMethodPlusPlus:
       KMB_RET(init_plusplus());
       break;
-    case kmcudaInitMethodAFKMC2:
-      (void)init_params;
-      KMB_INFO("afkmc2 initialisation is not built into this library yet (use k-means++ / random / import)\n");
-      return kmcudaInvalidArguments;
+    case kmcudaInitMethodAFKMC2: {
+      uint32_t m = init_params ? *reinterpret_cast<const uint32_t*>(init_params) : 0;
+      if (m == 0) {
+        m = 200;
+      } else if (m > N / 2) {
+        KMB_INFO("afkmc2: m > %" PRIu32 " is not supported (got %" PRIu32 ")\n", N / 2, m);
+        return kmcudaInvalidArguments;
+      }
+      KMB_RET(init_afkmc2(m, seed));
+      break;
+    }
     default:
       return kmcudaInvalidArguments;
   }

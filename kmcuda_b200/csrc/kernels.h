@@ -72,6 +72,8 @@ cudaError_t launch_yy_step(int metric, TcPlan* plan, const float* X, const float
 // ---- misc ------------------------------------------------------------------------------------------
 cudaError_t launch_average_distance(int metric, const float* X, const float* C, uint32_t n, int D,
                                     const uint32_t* assign, double* d_sum, cudaStream_t st);
+cudaError_t launch_afkmc2_min_dist(int metric, const float* X, const float* C, int D, uint32_t k,
+                                   const uint32_t* rows, uint32_t m, float* min_dists, cudaStream_t st);
 cudaError_t launch_plusplus_step(int metric, const float* X, uint32_t n, int D, const float* centroid,
                                  int first, float* dists, double* d_sum, cudaStream_t st);
 cudaError_t launch_half_to_float(const void* src, float* dst, size_t n, cudaStream_t st);

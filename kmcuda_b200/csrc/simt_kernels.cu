@@ -542,6 +542,35 @@ cudaError_t launch_plusplus_step(int metric, const float* X, uint32_t n, int D, 
   return cudaGetLastError();
 }
 
+// AFK-MC2 (reference kmeans_afkmc2_min_dist, kmeans.cu:159-176): for every candidate sample the distance to the
+// nearest of the first k centroids.  One thread per (candidate, centroid) pair (the reference walks the k
+// centroids serially per candidate); the minimum is taken on the float bit patterns (distances are >= 0, NaN
+// never lowers it).  rows[] are shard-local sample indices.
+template <int METRIC>
+__global__ void afkmc2_min_dist_kernel(const float* __restrict__ X, const float* __restrict__ C, int D, uint32_t k,
+                                       const uint32_t* __restrict__ rows, uint32_t m,
+                                       uint32_t* __restrict__ min_bits) {
+  const uint64_t p = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (p >= static_cast<uint64_t>(m) * k) return;
+  const uint32_t cand = static_cast<uint32_t>(p / k), c = static_cast<uint32_t>(p % k);
+  const float d = distance_exact<METRIC>(X + static_cast<size_t>(rows[cand]) * D, C + static_cast<size_t>(c) * D, D);
+  if (d == d) atomicMin(min_bits + cand, __float_as_uint(fmaxf(d, 0.f)));
+}
+
+cudaError_t launch_afkmc2_min_dist(int metric, const float* X, const float* C, int D, uint32_t k,
+                                   const uint32_t* rows, uint32_t m, float* min_dists, cudaStream_t st) {
+  if (m == 0 || k == 0) return cudaSuccess;
+  cudaError_t e = cudaMemsetAsync(min_dists, 0x7f, sizeof(float) * m, st);   // 0x7f7f7f7f = 3.39e38: "no centroid yet"
+  if (e != cudaSuccess) return e;
+  const uint64_t pairs = static_cast<uint64_t>(m) * k;
+  const unsigned grid = static_cast<unsigned>((pairs + 127) / 128);
+  if (metric == 1)
+    afkmc2_min_dist_kernel<1><<<grid, 128, 0, st>>>(X, C, D, k, rows, m, reinterpret_cast<uint32_t*>(min_dists));
+  else
+    afkmc2_min_dist_kernel<0><<<grid, 128, 0, st>>>(X, C, D, k, rows, m, reinterpret_cast<uint32_t*>(min_dists));
+  return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------------
 // fp16x2 ingest / egress (exact widening; centroids narrowed round-to-nearest on the way out)
 // ------------------------------------------------------------------------------------------------

@@ -254,9 +254,10 @@ def _validate(X, centroids, assignments, tolerance):
     assert (d.argmin(1) != assignments).mean() < tolerance
 
 
-@pytest.mark.parametrize("init,yy", [("random", 0.0), ("k-means++", 0.0), ("k-means++", 0.1)])
+@pytest.mark.parametrize("init,yy", [("random", 0.0), ("k-means++", 0.0), ("k-means++", 0.1), ("afkmc2", 0.0),
+                                     (("afkmc2", 100), 0.1)])
 def test_kmeans_python_surface_validates(km, init, yy, capfd):
-    """reference src/test.py:207-233 (random Lloyd / kmeans++ Lloyd / kmeans++ Yinyang)"""
+    """reference src/test.py:207-233,248-281 (random Lloyd / kmeans++ Lloyd / kmeans++ Yinyang / AFK-MC2)"""
     X = cases.blobs()
     cent, asg = km.kmeans_cuda(X, 50, init=init, device=1, verbosity=2, seed=3, tolerance=0.01, yinyang_t=yy)
     out = capfd.readouterr().out
@@ -265,6 +266,10 @@ def test_kmeans_python_surface_validates(km, init, yy, capfd):
     assert cent.shape == (50, 2) and asg.shape == (13000,) and asg.dtype == np.uint32
     assert not np.isnan(cent).any()
     _validate(X, cent, asg, 0.01)
+    if "afkmc2" in str(init):   # the seeding must spread over the six blobs, like k-means++ does
+        assert "afkmc2: calculating q" in out
+        quadrant = (np.sign(np.round(cent[:, 0] / 2)) * 3 + np.sign(np.round(cent[:, 1] / 2))).astype(int)
+        assert len(set(quadrant.tolist())) >= 5
 
 
 def test_kmeans_runs_match_reference_trajectory(ours, ref):
