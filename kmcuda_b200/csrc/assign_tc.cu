@@ -277,7 +277,7 @@ __global__ void tc_prep_table_kernel(int metric, const float* __restrict__ C, co
     // bias: three fp16 terms of -(s^2 ||c||^2 / 2); invalid / padded centroids get -65504
     __half b[3];
     if (finite) {
-      float h = metric == 1 ? 0.f : -0.5f * s * s * csq[row];
+      float h = metric == 1 ? 0.f : -0.5f * ((s * csq[row]) * s);   // s = 2^k: exact; this order cannot overflow for tiny data
       b[0] = __float2half_rn(h);
       float r1 = h - __half2float(b[0]);
       b[1] = __float2half_rn(r1);
@@ -1533,7 +1533,7 @@ __global__ void prep_table_kernel(const float* __restrict__ X, const float* __re
     if (finite) atomicMax(reinterpret_cast<uint32_t*>(&st->dcmax), __float_as_uint(__fsqrt_ru(d2) * 1.0001f));
     __half b[3];
     if (finite) {
-      const float hh = -0.5f * s * s * ysq[row];
+      const float hh = -0.5f * ((s * ysq[row]) * s);
       b[0] = __float2half_rn(hh);
       const float r1 = hh - __half2float(b[0]);
       b[1] = __float2half_rn(r1);

@@ -1,0 +1,118 @@
+"""CPU model of the tensor-core filter's error bound (kmcuda_b200/csrc/assign_tc.cu).
+
+The CUDA kernel only FILTERS with fp16 operands; it is correct iff the margin it derives per row really bounds
+|approximate score - exact score|, so that the reference's fp32 winner is always among the candidates.  This test
+re-derives the same quantities in numpy (fp16 rounding = round-to-nearest-even as `__float2half_rn`, products
+accumulated in fp32) on adversarially scaled random data and checks the two properties the design rests on:
+
+  1. |acc - s^2 (x.c - |c|^2 / 2)| <= E for every (row, centroid), with E exactly as the epilogue computes it;
+  2. the float64 arg-min centroid of every row lies within `margin = 2 E (1.001)` of the row's best score.
+
+It needs no GPU: it validates the arithmetic argument, not the kernel's plumbing (the GPU parity tests do that).
+"""
+import numpy as np
+import pytest
+
+KB = 64
+
+
+def _scale_for(cmax):
+    """tc_prep_scale_kernel: s = 2^k with s * cmax in [32, 64)"""
+    if not (cmax > 0):
+        return 1.0
+    _, e = np.frexp(np.float32(cmax))
+    return float(np.ldexp(1.0, 6 - int(e)))
+
+
+def _filter_model(X, C):
+    """returns (acc [n][K] fp32, E [n], s) following the kernel's prep + converter + MMA + bias step"""
+    X = X.astype(np.float32)
+    C = C.astype(np.float32)
+    n, D = X.shape
+    nkb = (D + KB - 1) // KB
+    csq = (C.astype(np.float64) ** 2).sum(1).astype(np.float32)           # the reference's ||c||^2 (exact to ~1 ulp)
+    cmax_raw = np.sqrt(csq.max())
+    s = np.float32(_scale_for(cmax_raw))
+    cmax = np.float32(cmax_raw * s * 1.001)
+    cs = (C * s).astype(np.float32)
+    ch = cs.astype(np.float16)                                            # fp16 centroid table
+    dcmax = np.float32(np.sqrt(((cs - ch.astype(np.float32)).astype(np.float64) ** 2).sum(1)).max() * 1.0001)
+    # bias: -(s^2 ||c||^2 / 2) as three fp16 terms
+    h = (np.float32(-0.5) * ((s * csq).astype(np.float32) * s)).astype(np.float32)   # same order as the prep kernel
+    b0 = h.astype(np.float16)
+    r1 = (h - b0.astype(np.float32)).astype(np.float32)
+    b1 = r1.astype(np.float16)
+    b2 = (r1 - b1.astype(np.float32)).astype(np.float32).astype(np.float16)
+    # converter: a = x * s (fp32), fp16 RN, norms of the rounded vector and of the residual
+    a = (X * s).astype(np.float32)
+    ah = a.astype(np.float16)
+    nx = np.sqrt((ah.astype(np.float64) ** 2).sum(1)) * 1.0001
+    nd = np.sqrt(((a - ah.astype(np.float32)).astype(np.float64) ** 2).sum(1)) * 1.0001
+    # MMA: fp16 x fp16 products are exact in fp32; accumulation order inside the tensor core is unspecified ->
+    # model it with fp32 accumulation (np.matmul on float32 inputs), the bound has an explicit term for it
+    acc = ah.astype(np.float32) @ ch.astype(np.float32).T
+    acc = (acc + b0.astype(np.float32)[None] + b1.astype(np.float32)[None] + b2.astype(np.float32)[None]).astype(np.float32)
+    xn = nx + nd
+    E = nx * dcmax + nd * cmax + nd * dcmax
+    E = E + (nkb * KB + 16) * 2.4e-7 * nx * cmax
+    E = E + 2.0e-6 * (cmax * cmax + xn * cmax)
+    return acc, E.astype(np.float64), float(s)
+
+
+def _cases():
+    rng = np.random.default_rng(12345)
+    out = []
+    for (n, d, k, kind) in [(300, 256, 64, "uniform"), (200, 100, 33, "normal"), (200, 480, 50, "offset"),
+                            (300, 32, 16, "wide"), (100, 8, 5, "tiny"), (200, 64, 40, "huge"), (150, 256, 30, "blobs")]:
+        if kind == "uniform":
+            X = rng.random((n, d))
+        elif kind == "normal":
+            X = rng.standard_normal((n, d))
+        elif kind == "offset":            # far from the origin relative to the spread: the hard case for the filter
+            X = 50.0 + rng.standard_normal((n, d))
+        elif kind == "wide":
+            X = rng.standard_normal((n, d)) * (10.0 ** rng.integers(-6, 6, size=d))
+        elif kind == "tiny":
+            X = rng.standard_normal((n, d)) * 1e-20
+        elif kind == "huge":
+            X = rng.standard_normal((n, d)) * 1e15
+        else:
+            centers = rng.random((k, d))
+            X = centers[rng.integers(0, k, n)] + 0.01 * rng.standard_normal((n, d))
+        X = X.astype(np.float32)
+        C = X[rng.choice(n, k, replace=False)] + (0.01 * np.abs(X).mean() * rng.standard_normal((k, d))).astype(np.float32)
+        out.append(pytest.param(X, C.astype(np.float32), id="%s_%dx%d_k%d" % (kind, n, d, k)))
+    return out
+
+
+@pytest.mark.parametrize("X,C", _cases())
+def test_margin_bounds_the_fp16_filter_error(X, C):
+    acc, E, s = _filter_model(X, C)
+    Xd, Cd = X.astype(np.float64), C.astype(np.float64)
+    exact = (s * s) * (Xd @ Cd.T - 0.5 * (Cd ** 2).sum(1)[None])
+    err = np.abs(acc.astype(np.float64) - exact)
+    assert np.isfinite(acc).all()
+    worst = (err / E[:, None]).max()
+    assert worst <= 1.0, "error exceeds the bound: %.3f x E" % worst
+    # the bound is meant to be tight enough to be useful, not just safe (except when every operand rounds exactly)
+    assert worst > 1e-4 or err.max() == 0
+    # containment: the true nearest centroid is within the margin of the row's best approximate score
+    margin = 2.0 * E * 1.001 + 1e-30
+    best_true = exact.argmax(1)
+    rows = np.arange(len(X))
+    assert (acc[rows, best_true] >= acc.max(1) - margin).all()
+
+
+def test_candidate_counts_are_small_on_the_benchmark_distribution():
+    """U[0,1)^256 @ 1024 (the reference's benchmark data): most rows have ONE candidate, the rest a handful --
+    what makes the exact re-check cheap (18 % of rows, 2.3 candidates each)"""
+    rng = np.random.default_rng(777)
+    X = rng.random((2000, 256), dtype=np.float32)
+    C = X[rng.choice(2000, 1024, replace=False)].copy()
+    C += (0.01 * rng.standard_normal(C.shape)).astype(np.float32)
+    acc, E, _ = _filter_model(X, C)
+    margin = 2.0 * E * 1.001
+    cand = (acc >= (acc.max(1) - margin)[:, None]).sum(1)
+    assert (cand >= 1).all()
+    assert 0.05 < (cand > 1).mean() < 0.35
+    assert cand.max() <= 16
