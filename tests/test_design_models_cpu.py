@@ -1,0 +1,107 @@
+"""CPU models of two algorithmic claims the CUDA code relies on (no GPU needed).
+
+1. Yinyang local step (kmcuda_b200/csrc/yinyang.cu): the reference scans the centroids in
+   index order with a running (min, second) pair and a per-centroid skip test (kmeans.cu:620-668).  The library
+   instead takes the two smallest elements of the multiset {ub} U {distances of all unpruned centroids} U {bounds
+   of the pruned groups}.  With valid bounds both give the same (nearest, ub', bound of the nearest's group) --
+   including ties.  Checked here on random instances built from consistent geometry (distances that moved by at
+   most the drift), with integer distances to provoke ties.
+
+2. k-NN threshold (assign_tc.cu MODE 2): the kk-th largest of per-bucket maxima over
+   DISJOINT column buckets is a lower bound of the kk-th largest value, and it is reasonably tight when there are
+   many more buckets than kk.
+"""
+import numpy as np
+import pytest
+
+FLT_MAX = np.float32(3.4028235e38)
+
+
+def reference_scan(ub, a, lb, groups, drift, maxdrift, dist):
+    """kmeans.cu:620-668 restated (also yinyang.cu::yy_local_scan_kernel)"""
+    mn, sec, near = ub, FLT_MAX, a
+    for c in range(len(groups)):
+        if c == a:
+            continue
+        g = groups[c]
+        b = lb[g]
+        if b >= ub:
+            if b < sec:
+                sec = b
+            continue
+        b = b + maxdrift[g] - drift[c]
+        if sec < b:
+            continue
+        d = dist[c]
+        if d < mn:
+            sec, mn, near = mn, d, c
+        elif d < sec:
+            sec = d
+    return near, mn, sec
+
+
+def two_smallest(ub, a, lb, groups, drift, maxdrift, dist):
+    """yinyang.cu::yy_finish_kernel / yy_rows_cta_kernel: order independent"""
+    G = len(lb)
+    gsize = np.bincount(groups, minlength=G)
+    p1 = FLT_MAX
+    for g in range(G):
+        if lb[g] >= ub and gsize[g] - (1 if g == groups[a] else 0) > 0:
+            p1 = min(p1, lb[g])
+    cand = [(dist[c], c) for c in range(len(groups)) if c != a and not (lb[groups[c]] >= ub)]
+    if cand:
+        dmin, cbest = min(cand)
+    else:
+        dmin, cbest = FLT_MAX, None
+    moved = cbest is not None and dmin < ub
+    near = cbest if moved else a
+    mn = dmin if moved else ub
+    rest = min([d for (d, c) in cand if not (moved and c == cbest)] + [p1])
+    sec = min(ub, rest) if moved else rest
+    return near, mn, sec
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_two_smallest_equals_reference_order_scan(seed):
+    rng = np.random.default_rng(seed)
+    K = int(rng.integers(3, 40))
+    G = int(rng.integers(1, max(2, K // 3)))
+    groups = rng.integers(0, G, K)
+    levels = int(rng.integers(3, 30))                      # few distinct values -> many exact ties
+    d_prev = rng.integers(1, levels + 1, K).astype(np.float32)
+    drift = rng.integers(0, 3, K).astype(np.float32)
+    move = np.array([rng.integers(-int(t), int(t) + 1) for t in drift], dtype=np.float32)
+    dist = np.maximum(d_prev + move, 0).astype(np.float32)  # |dist - d_prev| <= drift
+    a = int(rng.integers(0, K))
+    ub = dist[a]                                            # tightened upper bound = exact distance to the own centroid
+    maxdrift = np.array([drift[groups == g].max() if (groups == g).any() else 0 for g in range(G)], dtype=np.float32)
+    lb = np.empty(G, np.float32)
+    for g in range(G):
+        members = [c for c in range(K) if groups[c] == g and c != a]
+        true_min_prev = min([d_prev[c] for c in members]) if members else FLT_MAX
+        slack = np.float32(rng.integers(0, 3))              # bounds are valid, not necessarily tight
+        lb_old = np.float32(max(true_min_prev - slack, 0)) if members else np.float32(rng.integers(0, levels))
+        lb[g] = lb_old - maxdrift[g]                        # the decayed bound the local step sees
+    exp = reference_scan(ub, a, lb, groups, drift, maxdrift, dist)
+    got = two_smallest(ub, a, lb, groups, drift, maxdrift, dist)
+    assert got == exp, (got, exp)
+
+
+@pytest.mark.parametrize("kk", [2, 4, 11, 16])
+def test_bucket_maxima_give_a_valid_and_tight_knn_threshold(kk):
+    rng = np.random.default_rng(kk)
+    ranks = []
+    for _ in range(200):
+        ncols = int(rng.integers(3 * 128, 40 * 128))
+        v = rng.standard_normal(ncols).astype(np.float32)
+        # 64 disjoint buckets per row: (column half, block parity, 4-column group within the 64-column half)
+        col = np.arange(ncols)
+        blk, within = col // 128, col % 128
+        bucket = (within // 64) * 32 + (blk % 2) * 16 + (within % 64) // 4
+        bmax = np.full(64, -np.inf, np.float32)
+        np.maximum.at(bmax, bucket, v)
+        thr = np.sort(bmax)[::-1][kk - 1]
+        kth = np.sort(v)[::-1][kk - 1]
+        assert thr <= kth                                   # valid: kk distinct columns reach thr
+        ranks.append(int((v >= thr).sum()))                 # how many columns the threshold lets through
+    assert np.median(ranks) <= 2 * kk + 2                   # tight: about kk..2kk candidates before the margin
