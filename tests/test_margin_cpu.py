@@ -116,3 +116,75 @@ def test_candidate_counts_are_small_on_the_benchmark_distribution():
     assert (cand >= 1).all()
     assert 0.05 < (cand > 1).mean() < 0.35
     assert cand.max() <= 16
+
+
+def _knn_model(X, C, assign):
+    """MODE 2: for every query x and candidate y (cluster B = assign[y]) the epilogue's translation-invariant score
+    g = (x - c_B)~ . (y - c_B)~ + bias(y) - s^2 |x - c_B|^2 / 2  and the margin E of the segment (x, B)"""
+    X = X.astype(np.float32)
+    C = C.astype(np.float32)
+    n, D = X.shape
+    nkb = (D + KB - 1) // KB
+    Yc = (X - C[assign]).astype(np.float32)                                  # table rows, centred on their own cluster
+    ysq = (Yc.astype(np.float64) ** 2).sum(1).astype(np.float32)
+    yabs_raw = np.sqrt(((np.abs(X) + np.abs(C[assign])).astype(np.float64) ** 2).sum(1)).max()
+    cmax_raw = np.sqrt(ysq.max())
+    s = np.float32(_scale_for(cmax_raw))
+    cmax = np.float32(cmax_raw * s * 1.001)
+    ys = (Yc * s).astype(np.float32)
+    yh = ys.astype(np.float16)
+    dcmax = np.float32(np.sqrt(((ys - yh.astype(np.float32)).astype(np.float64) ** 2).sum(1)).max() * 1.0001)
+    yabs = np.float32(yabs_raw * s * 1.0001)
+    h = (np.float32(-0.5) * ((s * ysq).astype(np.float32) * s)).astype(np.float32)
+    b0 = h.astype(np.float16)
+    r1 = (h - b0.astype(np.float32)).astype(np.float32)
+    b1 = r1.astype(np.float16)
+    b2 = (r1 - b1.astype(np.float32)).astype(np.float32).astype(np.float16)
+    bias = b0.astype(np.float32) + b1.astype(np.float32) + b2.astype(np.float32)
+    g = np.empty((n, n), np.float32)
+    E = np.empty((n, n), np.float64)
+    for B in np.unique(assign):
+        cols = np.nonzero(assign == B)[0]
+        a = ((X - C[B]).astype(np.float32) * s).astype(np.float32)          # the converter's re-centred query
+        ah = a.astype(np.float16)
+        nx = np.sqrt((ah.astype(np.float64) ** 2).sum(1)) * 1.0001
+        nd = np.sqrt(((a - ah.astype(np.float32)).astype(np.float64) ** 2).sum(1)) * 1.0001
+        a2 = (a.astype(np.float64) ** 2).sum(1).astype(np.float32)          # Kahan sum in the kernel
+        nraw = np.sqrt(((np.abs(X) + np.abs(C[B])).astype(np.float64) ** 2).sum(1)) * s
+        goff = (np.float32(0.5) * a2).astype(np.float32)
+        acc = (ah.astype(np.float32) @ yh[cols].astype(np.float32).T + bias[cols][None]).astype(np.float32)
+        g[:, cols] = (acc - goff[:, None]).astype(np.float32)
+        xn = nx + nd
+        e = nx * dcmax + nd * cmax + nd * dcmax + (nkb * KB + 16) * 2.4e-7 * nx * cmax
+        e = e + 2.0e-6 * (cmax * cmax + xn * cmax) + 2.0e-6 * xn * xn
+        e = e + 1.2e-7 * (nraw * cmax + yabs * xn) + 4.8e-7 * (goff + xn * cmax)
+        E[:, cols] = e[:, None]
+    return g, E, float(s)
+
+
+@pytest.mark.parametrize("kind", ["blobs_far_from_origin", "uniform", "offset_uniform"])
+def test_knn_centred_score_error_is_bounded_and_resolves_tight_clusters(kind):
+    rng = np.random.default_rng(len(kind))
+    n, d, k = 600, 128, 12
+    if kind == "blobs_far_from_origin":       # the case that defeats uncentred fp16 operands
+        centers = 20.0 + rng.random((k, d))
+        assign = rng.integers(0, k, n)
+        X = (centers[assign] + 0.05 * rng.standard_normal((n, d))).astype(np.float32)
+    else:
+        X = rng.random((n, d)).astype(np.float32) + (100.0 if kind == "offset_uniform" else 0.0)
+        X = X.astype(np.float32)
+        centers = X[rng.choice(n, k, replace=False)]
+        assign = ((X[:, None, :] - centers[None]) ** 2).sum(-1).argmin(1)
+    C = np.stack([X[assign == c].mean(0) if (assign == c).any() else centers[c] for c in range(k)]).astype(np.float32)
+    g, E, s = _knn_model(X, C, assign)
+    Xd = X.astype(np.float64)
+    d2 = ((Xd[:, None, :] - Xd[None]) ** 2).sum(-1)
+    g_true = -0.5 * s * s * d2
+    err = np.abs(g.astype(np.float64) - g_true)
+    assert (err <= E).all(), (err / E).max()
+    # usefulness: with margin 2E the 11 nearest (self included) pull in only a few extra candidates per query
+    kk = 11
+    order = np.sort(g, axis=1)[:, ::-1]
+    thr = order[:, kk - 1] - 2.0 * 1.001 * E.max(1)
+    extra = (g >= thr[:, None]).sum(1) - kk
+    assert np.median(extra) <= 6, np.median(extra)
