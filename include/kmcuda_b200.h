@@ -57,10 +57,23 @@ KMCUDAResult kmcuda_b200_partial_sums(kmcuda_b200_shard *shard, uint32_t samples
                                       const float *samples, const uint32_t *assignments, float *sums,
                                       uint32_t *counts, void *stream);
 
-/* centroids [K][D] = normalised sums; ccounts [K] = counts. */
+/* centroids [K][D] = normalised sums; ccounts [K] = counts.
+ * STATEFUL for the angular metric: the reference's incremental update (src/kmeans.cu:366-429) is reproduced as
+ * centroid * old count + (member sums now - member sums of the previous call), so the handle remembers the
+ * previous member sums.  Call kmcuda_b200_shard_reset() before the first update of every new run (with ccounts
+ * zeroed), otherwise the first update of the second run subtracts the last sums of the first. */
 KMCUDAResult kmcuda_b200_finish_update(kmcuda_b200_shard *shard, const float *sums,
                                        const uint32_t *counts, float *centroids, uint32_t *ccounts,
                                        void *stream);
+
+/* Start of a new clustering run on a reused handle: forgets the cached member sums (see above). */
+KMCUDAResult kmcuda_b200_shard_reset(kmcuda_b200_shard *shard, void *stream);
+
+/* Pipeline status of the most recent tensor-core pass, valid after `stream` has been synchronised:
+ * 0 = clean; non-zero = a barrier wait inside the kernel timed out (preemption, debugger, a pipeline bug) and
+ * the results of that pass must not be used.  kmeans_cuda() / knn_cuda() check this themselves and return
+ * kmcudaRuntimeError. */
+uint32_t kmcuda_b200_last_error(kmcuda_b200_shard *shard);
 
 /* Device-memory helpers for language bindings that hand out raw device pointers (the reference's
  * Python binding calls cudaMalloc / cudaMemcpy directly, src/python.cc:298-313,343-352; a ctypes

@@ -67,14 +67,31 @@ static const NcclApi& nccl_api() {
   return api;
 }
 
+// NCCL communicators (fallback exchange, see Job::update) are cached per device list for the life of the process:
+// ncclCommInitAll costs seconds to minutes and the library is not re-entrant anyway (kmcuda.h:25-26)
+static std::map<std::vector<int>, std::vector<ncclComm_t>>& comm_cache() {
+  static std::map<std::vector<int>, std::vector<ncclComm_t>> cache;
+  return cache;
+}
+static void drop_cached_comms() {
+  for (auto& kv : comm_cache())
+    for (ncclComm_t c : kv.second)
+      if (c) nccl_api().CommDestroy(c);
+  comm_cache().clear();
+}
+
 struct Dev {
   int dev = 0;
   cudaStream_t st = nullptr;
   uint32_t off = 0, len = 0;
   std::unique_ptr<Shard> shard;
   DevBuf<float> X, C, sums, dists;
+  DevBuf<float> rsums;           // multi-GPU: the shard sums reduced over all devices (peer loads, fixed order)
+  DevBuf<uint32_t> rcounts;
   DevBuf<uint32_t> assign, prev, ccounts, counts, d_changed;
   DevBuf<double> d_dsum;
+  cudaEvent_t ev_partial = nullptr;   // this device's partial sums are complete
+  cudaEvent_t ev_reduced = nullptr;   // this device has finished reading every peer's partial sums
   ncclComm_t comm = nullptr;
 };
 
@@ -194,6 +211,8 @@ class Job {
       cudaSetDevice(d.dev);
       d.comm = nullptr;   // owned by the per-process cache (Job::setup)
       d.shard.reset();
+      if (d.ev_partial) cudaEventDestroy(d.ev_partial);
+      if (d.ev_reduced) cudaEventDestroy(d.ev_reduced);
       if (d.st) cudaStreamDestroy(d.st);
     }
   }
@@ -204,6 +223,7 @@ class Job {
   const uint32_t K;
   const int verbosity;
   std::vector<Dev> devs;
+  bool peer_exchange = false;   // multi-GPU update through peer memory (NVLink / NVSwitch) instead of NCCL
 
   KMCUDAResult setup(const std::vector<int>& dev_ids, bool alloc_samples);
   KMCUDAResult ingest(const float* samples, int device_ptrs, bool fp16x2);
@@ -246,25 +266,46 @@ KMCUDAResult Job::setup(const std::vector<int>& dev_ids, bool alloc_samples) {
     KMB_RET(d.shard->create(true));
   }
   if (devs.size() > 1) {
-    if (!nccl_api().ok) {
-      KMB_INFO("multi-GPU jobs need NCCL (libnccl.so.2), which could not be loaded\n");
-      return kmcudaRuntimeError;
-    }
-    // Communicators are cached per device list for the life of the process: ncclCommInitAll costs seconds to
-    // minutes (measured ~100 s on the 2-GPU test box, all inside NCCL's bootstrap) and the library is not
-    // re-entrant anyway (kmcuda.h:25-26).
-    static std::map<std::vector<int>, std::vector<ncclComm_t>> comm_cache;
-    auto it = comm_cache.find(dev_ids);
-    if (it == comm_cache.end()) {
-      std::vector<ncclComm_t> comms(devs.size());
-      ncclResult_t r = nccl_api().CommInitAll(comms.data(), static_cast<int>(devs.size()), dev_ids.data());
-      if (r != ncclSuccess) {
-        KMB_INFO("ncclCommInitAll failed: %s\n", nccl_api().GetErrorString(r));
+    // Exchange step of the centroid update.  Preferred: every GPU reads its peers' partial sums straight from
+    // peer memory (NVLink 5 / NVSwitch: K*D*4 bytes per peer, 1 MB at 1024 x 256) and adds them in device order,
+    // so all GPUs hold bit-identical centroids and no communicator has to be bootstrapped (ncclCommInitAll took
+    // ~100 s on the first multi-GPU call in round 1).  Fallback when some pair has no peer access, or
+    // KMCUDA_B200_EXCHANGE=nccl: one grouped ncclAllReduce of sums + counts per iteration.
+    const char* ex = getenv("KMCUDA_B200_EXCHANGE");
+    peer_exchange = !(ex && strcmp(ex, "nccl") == 0);
+    for (size_t i = 0; i < devs.size() && peer_exchange; i++)
+      for (size_t j = 0; j < devs.size() && peer_exchange; j++) {
+        if (i == j) continue;
+        int access = 0;
+        if (cudaDeviceCanAccessPeer(&access, devs[i].dev, devs[j].dev) != cudaSuccess || !access) peer_exchange = false;
+      }
+    if (peer_exchange) {
+      for (auto& d : devs) {
+        KMB_CU(cudaSetDevice(d.dev), kmcudaNoSuchDevice);
+        KMB_CU(d.rsums.alloc(static_cast<size_t>(K) * D), kmcudaMemoryAllocationFailure);
+        KMB_CU(d.rcounts.alloc(K), kmcudaMemoryAllocationFailure);
+        KMB_CU(cudaEventCreateWithFlags(&d.ev_partial, cudaEventDisableTiming), kmcudaRuntimeError);
+        KMB_CU(cudaEventCreateWithFlags(&d.ev_reduced, cudaEventDisableTiming), kmcudaRuntimeError);
+      }
+      KMB_DEBUG("centroid update exchange: peer memory, %zu devices\n", devs.size());
+    } else {
+      if (!nccl_api().ok) {
+        KMB_INFO("multi-GPU jobs without full peer access need NCCL (libnccl.so.2), which could not be loaded\n");
         return kmcudaRuntimeError;
       }
-      it = comm_cache.emplace(dev_ids, comms).first;
+      auto it = comm_cache().find(dev_ids);
+      if (it == comm_cache().end()) {
+        std::vector<ncclComm_t> comms(devs.size());
+        ncclResult_t r = nccl_api().CommInitAll(comms.data(), static_cast<int>(devs.size()), dev_ids.data());
+        if (r != ncclSuccess) {
+          KMB_INFO("ncclCommInitAll failed: %s\n", nccl_api().GetErrorString(r));
+          return kmcudaRuntimeError;
+        }
+        it = comm_cache().emplace(dev_ids, comms).first;
+      }
+      for (size_t i = 0; i < devs.size(); i++) devs[i].comm = it->second[i];
+      KMB_DEBUG("centroid update exchange: NCCL all-reduce, %zu ranks\n", devs.size());
     }
-    for (size_t i = 0; i < devs.size(); i++) devs[i].comm = it->second[i];
   }
   if (verbosity > 1) {
     printf("plans: [");
@@ -619,27 +660,58 @@ KMCUDAResult Job::assign_pass(uint32_t* changed) {
     KMB_CU(cudaMemcpyAsync(&mine, d.d_changed.get(), sizeof(mine), cudaMemcpyDeviceToHost, d.st), kmcudaMemoryCopyError);
     KMB_CU(cudaStreamSynchronize(d.st), kmcudaRuntimeError);
     total += mine;
+    KMB_RET(d.shard->check_pipeline());
   }
   *changed = total;
   return kmcudaSuccess;
 }
 
-// centroid update: shard partial sums -> NCCL all-reduce (sum) -> normalise on every GPU
+// centroid update: shard partial sums -> exchange (peer-memory reduce, or NCCL all-reduce) -> normalise on every GPU
 KMCUDAResult Job::update() {
+  if (devs.size() > 1 && peer_exchange) {
+    // nobody may overwrite its partial sums while a peer of the previous iteration is still reading them
+    for (auto& d : devs) {
+      KMB_CU(cudaSetDevice(d.dev), kmcudaRuntimeError);
+      for (auto& e : devs)
+        if (&e != &d) KMB_CU(cudaStreamWaitEvent(d.st, e.ev_reduced, 0), kmcudaRuntimeError);
+    }
+  }
   for (auto& d : devs) {
     KMB_CU(cudaSetDevice(d.dev), kmcudaRuntimeError);
     KMB_RET(d.shard->partial_sums(d.len, d.X, d.assign, d.sums, d.counts, d.st));
+    if (devs.size() > 1 && peer_exchange) KMB_CU(cudaEventRecord(d.ev_partial, d.st), kmcudaRuntimeError);
+  }
+  if (devs.size() > 1 && peer_exchange) {
+    PeerBuffers pb;
+    pb.n = static_cast<int>(devs.size());
+    for (size_t i = 0; i < devs.size(); i++) {
+      pb.sums[i] = devs[i].sums.get();
+      pb.counts[i] = devs[i].counts.get();
+    }
+    for (auto& d : devs) {
+      KMB_CU(cudaSetDevice(d.dev), kmcudaRuntimeError);
+      for (auto& e : devs)
+        if (&e != &d) KMB_CU(cudaStreamWaitEvent(d.st, e.ev_partial, 0), kmcudaRuntimeError);
+      KMB_CU(launch_peer_reduce(pb, K, D, d.rsums, d.rcounts, d.st), kmcudaRuntimeError);
+      KMB_CU(cudaEventRecord(d.ev_reduced, d.st), kmcudaRuntimeError);
+      KMB_RET(d.shard->finish_update(d.rsums, d.rcounts, d.C, d.ccounts, d.st));
+    }
+    return kmcudaSuccess;
   }
   if (devs.size() > 1) {
     const NcclApi& nc = nccl_api();
-    nc.GroupStart();
+    ncclResult_t r = nc.GroupStart();
     for (auto& d : devs) {
-      nc.AllReduce(d.sums.get(), d.sums.get(), static_cast<size_t>(K) * D, ncclFloat32, ncclSum, d.comm, d.st);
-      nc.AllReduce(d.counts.get(), d.counts.get(), K, ncclUint32, ncclSum, d.comm, d.st);
+      if (r != ncclSuccess) break;
+      r = nc.AllReduce(d.sums.get(), d.sums.get(), static_cast<size_t>(K) * D, ncclFloat32, ncclSum, d.comm, d.st);
+      if (r == ncclSuccess)
+        r = nc.AllReduce(d.counts.get(), d.counts.get(), K, ncclUint32, ncclSum, d.comm, d.st);
     }
-    ncclResult_t r = nc.GroupEnd();
+    ncclResult_t rend = nc.GroupEnd();
+    if (r == ncclSuccess) r = rend;
     if (r != ncclSuccess) {
       KMB_INFO("ncclAllReduce failed: %s\n", nc.GetErrorString(r));
+      drop_cached_comms();   // a communicator that reported an error is not reused by later calls
       return kmcudaRuntimeError;
     }
   }
@@ -727,6 +799,7 @@ KMCUDAResult Job::yinyang(float tolerance, uint32_t G) {
         KMB_CU(cudaMemcpyAsync(&c, d.d_changed.get(), 4, cudaMemcpyDeviceToHost, d.st), kmcudaMemoryCopyError);
         KMB_CU(cudaMemcpyAsync(&p, d.shard->yy_counters.get() + 1, 4, cudaMemcpyDeviceToHost, d.st), kmcudaMemoryCopyError);
         KMB_CU(cudaStreamSynchronize(d.st), kmcudaRuntimeError);
+        KMB_RET(d.shard->check_pipeline());
         total_changed += c;
         total_passed += p;
       }

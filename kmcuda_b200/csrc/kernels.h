@@ -39,6 +39,16 @@ size_t update_cub_bytes(uint32_t n);
 // sums[K][D] (fp32) and counts[K] (uint32) of this shard's samples
 cudaError_t launch_partial_sums(const float* X, uint32_t n, int D, uint32_t K, const uint32_t* assign,
                                 UpdateWorkspace& ws, float* sums, uint32_t* counts, cudaStream_t st);
+// multi-GPU exchange through peer memory: out_sums = sums[0] + sums[1] + ... (device order, so every GPU computes
+// the same bits), out_counts likewise; the pointers may live on other GPUs (peer access enabled by the caller)
+constexpr int kMaxPeers = 32;
+struct PeerBuffers {
+  int n;
+  const float* sums[kMaxPeers];
+  const uint32_t* counts[kMaxPeers];
+};
+cudaError_t launch_peer_reduce(const PeerBuffers& pb, uint32_t K, int D, float* out_sums, uint32_t* out_counts,
+                               cudaStream_t st);
 // C = sums/count (L2, NaN for empty) or sums/||sums|| (cosine); ccounts = counts
 cudaError_t launch_normalize(int metric, const float* sums, const uint32_t* counts, uint32_t K, int D,
                              float* C, uint32_t* ccounts, float* prev_sums, cudaStream_t st);
@@ -104,9 +114,11 @@ struct TcPlan;  // opaque; owns the fp16 centroid table, tensor maps, queues
 bool tc_supported(int metric, uint32_t n, int D, uint32_t K);
 cudaError_t tc_plan_create(TcPlan** plan, int metric, uint32_t max_n, int D, uint32_t K, int device);
 void tc_plan_destroy(TcPlan* plan);
-// one full assignment pass: result[i] as launch_assign_exact would produce it
+// one full assignment pass.  assign == nullptr: result[i] as launch_assign_exact would produce it.  Otherwise the
+// pass's bookkeeping (launch_finalize_assign) is fused: prev[i] = assign[i], assign[i] = winner, *d_changed +=
+// changes; result[] is then scratch for the few rows that take the exact full pass.
 cudaError_t tc_assign(TcPlan* plan, const float* X, const float* C, const float* csq, uint32_t n,
-                      uint32_t* result, cudaStream_t st);
+                      uint32_t* result, uint32_t* assign, uint32_t* prev, uint32_t* d_changed, cudaStream_t st);
 // statistics of the last pass (for logging / bench): queue length and overflow rows
 void tc_last_stats(TcPlan* plan, uint32_t* n_recheck, uint32_t* n_overflow);
 // Yinyang local step (assign_tc.cu): candidate pairs with exact true distances for the listed rows

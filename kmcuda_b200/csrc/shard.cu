@@ -99,14 +99,23 @@ KMCUDAResult Shard::assign(uint32_t n, const float* X, const float* C, uint32_t*
   KMB_CU(launch_csqr(metric, C, K, D, csq, st), kmcudaRuntimeError);
   last_tc = false;
   if (tc && n > 0) {
-    KMB_CU(tc_assign(tc, X, C, csq, n, result, st), kmcudaRuntimeError);
+    KMB_CU(tc_assign(tc, X, C, csq, n, result, assignments, prev, d_changed, st), kmcudaRuntimeError);
     last_tc = true;
   } else {
     KMB_CU(launch_assign_exact(metric, X, C, csq, n, D, K, nullptr, nullptr, result, st),
            kmcudaRuntimeError);
+    KMB_CU(launch_finalize_assign(n, result, assignments, prev, d_changed, st), kmcudaRuntimeError);
   }
-  KMB_CU(launch_finalize_assign(n, result, assignments, prev, d_changed, st), kmcudaRuntimeError);
   return kmcudaSuccess;
+}
+
+KMCUDAResult Shard::check_pipeline() {
+  if (!tc) return kmcudaSuccess;
+  const uint32_t err = tc_last_error(tc);
+  if (err == 0) return kmcudaSuccess;
+  // never a silent success on garbage: the caller gets an error code (reference convention: RuntimeError)
+  KMB_INFO("tensor-core pipeline error 0x%x on device %d: a barrier wait timed out, the pass is invalid\n", err, device);
+  return kmcudaRuntimeError;
 }
 
 KMCUDAResult Shard::partial_sums(uint32_t n, const float* X, const uint32_t* assignments, float* sums,
@@ -190,6 +199,16 @@ KMCUDAResult kmcuda_b200_finish_update(kmcuda_b200_shard* shard, const float* su
                                        void* stream) {
   if (!shard || !sums || !counts || !centroids || !ccounts) return kmcudaInvalidArguments;
   return shard->impl->finish_update(sums, counts, centroids, ccounts, static_cast<cudaStream_t>(stream));
+}
+
+KMCUDAResult kmcuda_b200_shard_reset(kmcuda_b200_shard* shard, void* stream) {
+  if (!shard) return kmcudaInvalidArguments;
+  return shard->impl->reset_update_state(static_cast<cudaStream_t>(stream));
+}
+
+uint32_t kmcuda_b200_last_error(kmcuda_b200_shard* shard) {
+  if (!shard || !shard->impl->tc) return 0;
+  return kmb::tc_last_error(shard->impl->tc);
 }
 
 // ---- diagnostics (used by tests; not part of the drop-in surface) ----

@@ -108,6 +108,9 @@ class Shard {
                             uint32_t* counts, cudaStream_t st);
   KMCUDAResult finish_update(const float* sums, const uint32_t* counts, float* C, uint32_t* ccounts,
                              cudaStream_t st);
+  // after the stream has been synchronised: kmcudaRuntimeError if the tensor-core pipeline of the last pass
+  // reported a timed-out barrier (its results are not valid), kmcudaSuccess otherwise
+  KMCUDAResult check_pipeline();
 
   const int metric, device;
   const uint32_t max_n;

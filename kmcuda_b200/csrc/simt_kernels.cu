@@ -7,6 +7,8 @@
 // broadcast loads.
 #include <cub/device/device_radix_sort.cuh>
 
+#include <algorithm>
+
 #include "exact.cuh"
 #include "kernels.h"
 
@@ -452,6 +454,41 @@ __global__ void normalize_kernel(const float* __restrict__ sums, const uint32_t*
     for (int f = 0; f < D; f++) o[f] = s[f] * scale;
   }
   ccounts[c] = cnt;
+}
+
+// all-reduce of the update's partial sums over peer memory: every GPU gathers and adds all shards' sums itself (K*D*4
+// bytes per peer over NVLink; 16-byte loads, each peer's buffer read exactly once, coalesced)
+__global__ void __launch_bounds__(256)
+peer_reduce_kernel(const PeerBuffers pb, size_t nvec4, size_t nsums, uint32_t K, float* __restrict__ out_sums,
+                   uint32_t* __restrict__ out_counts) {
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec4; i += stride) {
+    float4 acc = reinterpret_cast<const float4*>(pb.sums[0])[i];
+    for (int d = 1; d < pb.n; d++) {
+      const float4 v = reinterpret_cast<const float4*>(pb.sums[d])[i];
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    reinterpret_cast<float4*>(out_sums)[i] = acc;
+  }
+  for (size_t i = nvec4 * 4 + static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nsums; i += stride) {
+    float acc = pb.sums[0][i];
+    for (int d = 1; d < pb.n; d++) acc += pb.sums[d][i];
+    out_sums[i] = acc;
+  }
+  for (size_t c = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; c < K; c += stride) {
+    uint32_t acc = 0;
+    for (int d = 0; d < pb.n; d++) acc += pb.counts[d][c];   // exact integer sum (counts never go through fp32)
+    out_counts[c] = acc;
+  }
+}
+
+cudaError_t launch_peer_reduce(const PeerBuffers& pb, uint32_t K, int D, float* out_sums, uint32_t* out_counts,
+                               cudaStream_t st) {
+  const size_t nsums = static_cast<size_t>(K) * D;
+  const size_t nvec4 = nsums / 4;
+  const unsigned grid = static_cast<unsigned>(std::min<size_t>(148 * 4, (nvec4 + 255) / 256 + 1));
+  peer_reduce_kernel<<<grid, 256, 0, st>>>(pb, nvec4, nsums, K, out_sums, out_counts);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_normalize(int metric, const float* sums, const uint32_t* counts, uint32_t K, int D,

@@ -38,28 +38,102 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                : "memory");
 }
-// Bounded wait: a stuck pipeline must not hang the GPU box.  Returns false after ~1 s of SM clocks
+// Bounded wait: a stuck pipeline must not hang the GPU box.  Returns false after ~2 s of SM clocks
 // or as soon as another thread has published an error in *err (global memory).
-__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, volatile uint32_t* err) {
-  const uint32_t addr = smem_u32(bar);
-  long long t0 = 0;
-  for (uint32_t spin = 0;; spin++) {
-    uint32_t done;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(addr), "r"(parity)
-        : "memory");
-    if (done) return true;
-    if ((spin & 63) == 63) {
+// The try_wait carries a suspend-time hint, which ptxas turns into TRYWAIT + NANOSLEEP.SYNCS: a waiting warp
+// sleeps until the barrier's phase flips (or the hint expires) instead of competing for issue slots.  Round 1
+// spun without a hint: 14 SASS instructions per probe and ~40 % of all issued instructions of the kernel were
+// such probes (profiles/r01_tc_assign_v4: 150 M SYNCS + 350 M BRA), stolen from the converter / epilogue warps
+// of the same scheduler.
+__device__ __forceinline__ bool mbar_try_wait(uint32_t addr, uint32_t parity, uint32_t hint_ns) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(addr), "r"(parity), "r"(hint_ns)
+      : "memory");
+  return done != 0;
+}
+#ifndef KMB_WAIT_HINT_NS
+#define KMB_WAIT_HINT_NS 2000   // 0 = A/B build: plain polling without a suspend hint
+#endif
+__device__ __forceinline__ bool mbar_try_wait_nohint(uint32_t addr, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(addr), "r"(parity)
+      : "memory");
+  return done != 0;
+}
+__device__ __noinline__ bool mbar_wait_slow(uint32_t addr, uint32_t parity, volatile uint32_t* err) {
+  long long t0 = clock64();
+  for (uint32_t spin = 1;; spin++) {
+#if KMB_WAIT_HINT_NS > 0
+    if (mbar_try_wait(addr, parity, 20000u)) return true;
+    if ((spin & 15) == 0) {
+#else
+    if (mbar_try_wait_nohint(addr, parity)) return true;
+    if ((spin & 1023) == 0) {
+#endif
       if (*err) return false;
-      long long now = clock64();
-      if (t0 == 0) t0 = now;
-      else if (now - t0 > 2000000000ll) return false;
+      if (clock64() - t0 > 4000000000ll) return false;
     }
   }
+}
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, volatile uint32_t* err) {
+  const uint32_t addr = smem_u32(bar);
+#if KMB_WAIT_HINT_NS > 0
+  if (mbar_try_wait(addr, parity, KMB_WAIT_HINT_NS)) return true;    // common case: one probe (it may sleep up to the hint)
+  if (mbar_try_wait(addr, parity, 20000u)) return true;
+#else
+#pragma unroll 1
+  for (int i = 0; i < 64; i++)
+    if (mbar_try_wait_nohint(addr, parity)) return true;
+#endif
+  return mbar_wait_slow(addr, parity, err);
+}
+
+// ---------------------------------------------------------------------------- packed fp32 pairs (sm_100: FADD2 / FMUL2 / FFMA2)
+// One instruction, two IEEE fp32 operations (same rounding as the scalar forms).  Used where every lane walks a
+// whole row: halves the issue slots of the converter and of the epilogue's threshold compare.
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t fsub2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t fmul2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+// three-input maximum (FMNMX3); NaN operands are ignored like fmaxf
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
 }
 
 // generic-proxy writes to shared memory -> visible to the async proxy (UMMA / TMA reads)

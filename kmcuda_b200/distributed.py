@@ -43,12 +43,16 @@ def sharded_lloyd(backend, X, C, total_samples, tolerance=0.01, max_iter=0, log=
     sums = torch.zeros((K, X.shape[1]), dtype=torch.float32, device=dev)
     counts = torch.zeros(K, dtype=torch.int32, device=dev)
     ccounts = torch.zeros(K, dtype=torch.int32, device=dev)
+    if hasattr(backend, "reset"):
+        backend.reset()          # a reused shard must not carry the previous run's member sums (angular update)
     it = 0
     while True:
         it += 1
         changed.zero_()
         backend.assign(X, C, assign, prev, changed)
-        total_changed = allreduce_scalar(changed.item(), dev)
+        total_changed = allreduce_scalar(changed.item(), dev)     # .item() synchronises the stream
+        if hasattr(backend, "last_error") and backend.last_error():
+            raise RuntimeError("tensor-core pipeline error 0x%x: the assignment pass is invalid" % backend.last_error())
         if log:
             log("iteration %d: %d reassignments" % (it, total_changed))
         if float(total_changed) <= float(tolerance) * float(total_samples):

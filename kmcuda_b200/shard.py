@@ -24,6 +24,10 @@ _lib.kmcuda_b200_partial_sums.restype = ctypes.c_int
 _lib.kmcuda_b200_partial_sums.argtypes = [ctypes.c_void_p, ctypes.c_uint32] + [ctypes.c_void_p] * 5
 _lib.kmcuda_b200_finish_update.restype = ctypes.c_int
 _lib.kmcuda_b200_finish_update.argtypes = [ctypes.c_void_p] + [ctypes.c_void_p] * 5
+_lib.kmcuda_b200_shard_reset.restype = ctypes.c_int
+_lib.kmcuda_b200_shard_reset.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+_lib.kmcuda_b200_last_error.restype = ctypes.c_uint32
+_lib.kmcuda_b200_last_error.argtypes = [ctypes.c_void_p]
 _lib.kmcuda_b200_kernel_times.restype = ctypes.c_int32
 _lib.kmcuda_b200_kernel_times.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32]
 _lib.kmcuda_b200_debug_last_error.restype = ctypes.c_uint32
@@ -85,7 +89,12 @@ class Shard:
         return buf[:n].tolist()
 
     def last_error(self):
-        return int(_lib.kmcuda_b200_debug_last_error(self._h))
+        """pipeline status of the last tensor-core pass (0 = clean); sync first"""
+        return int(_lib.kmcuda_b200_last_error(self._h))
+
+    def reset(self):
+        """start of a new run on this handle (angular metric: forget the cached member sums)"""
+        _raise_for(_lib.kmcuda_b200_shard_reset(self._h, _stream_ptr()), "kmcuda_b200_shard_reset")
 
     def partial_sums(self, X, assignments, sums, counts):
         _raise_for(_lib.kmcuda_b200_partial_sums(self._h, X.shape[0], _ptr(X, torch.float32),
