@@ -3,19 +3,25 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--points P]
 
-A "step" is ONE assignment pass of the hot path (the reference's kmeans_assign_lloyd, src/kmeans.cu:
-293-364; here: tcgen05 distance filter + exact fp32 re-check + bookkeeping) over the rank's shard of
-synthetic samples that are already resident in HBM.  One process per GPU (torchrun for N > 1), shards
-are independent (no data-path collective in the assignment step) -> "scaling": "weak".
+Workload (BASELINE.json configs[1] / configs[3]): P = 8 000 000 samples IN TOTAL (U[0,1), the reference's own
+benchmark distribution), 256 features, 1024 centroids = rows of the samples.  With N GPUs (one process per GPU
+under torchrun) the samples are range-partitioned, P/N rows per rank -> "scaling": "strong".
 
-Keys beyond the base contract: `e2e` (same metric through the reference-facing C ABI kmeans_cuda() with
-HOST buffers: H2D of the samples and D2H of the assignments inside the timed region), `roofline` (the
-tcgen05 kernel against the measured bf16 tensor peak of MEASURED_PEAKS.json), `cpu_baseline` (the C
-oracle port on the host cores, bounded sample), `clocks`.
+A "step" is ONE assignment pass of the hot path (the reference's kmeans_assign_lloyd, src/kmeans.cu:293-364;
+here: tcgen05 distance filter + exact fp32 re-check + fused bookkeeping) over the rank's shard, resident in HBM:
+`value` = P / max-over-ranks(device time per step) (the metric is the assignment step).  The same
+run also times the FULL Lloyd iteration -- assign + per-cluster partial sums + NCCL all-reduce of the K*D fp32
+sums and K integer counts + normalise (BASELINE configs[3]) -- and reports it per phase under `iteration`.
 
-`--impl reference` times the UNMODIFIED reference (oracle/_ref/libKMCUDA.so, src-d/kmcuda rebuilt for
-sm_100 -- the reference has no CPU implementation, it is a CUDA library) through the same C ABI call on
-a bounded sample of the same workload; if that library cannot be loaded it times the CPU oracle port.
+Other keys: `e2e` (the same pass through the reference-facing C ABI kmeans_cuda() with pinned HOST buffers: H2D
+of the samples and D2H of the assignments inside the timed region), `roofline` (the tcgen05 kernel, CUDA events
+around its launches, against the measured bf16 tensor peak of MEASURED_PEAKS.json), `cpu_baseline` (scikit-learn
+KMeans labelling on all host cores, the CPU reference north_star names; the C oracle port is nested), `clocks`.
+
+`--impl reference` times the UNMODIFIED reference (oracle/_ref/libKMCUDA.so, src-d/kmcuda rebuilt for sm_100 --
+the reference has no CPU implementation, it is a CUDA library) through the same C ABI on the same P points with
+device mask (1 << N) - 1: `value` with device-resident inputs (device_ptrs = 0), `e2e` with pinned host buffers.
+If that library cannot be loaded the CPU oracle port is timed instead.
 """
 import argparse
 import ctypes
@@ -31,9 +37,8 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-os.environ.pop("NCCL_DEBUG", None)   # some hosts export NCCL_DEBUG=VERSION; NCCL prints its banner on stdout
-# stdout carries exactly ONE JSON line: everything else that writes to fd 1 (NCCL banners, C-library progress
-# messages) is sent to stderr, the JSON line goes to the saved descriptor
+# stdout carries exactly ONE JSON line: everything else that writes to fd 1 (NCCL_DEBUG output, C-library progress
+# messages) goes to stderr, the JSON line goes to the saved descriptor.  NCCL_DEBUG is left as the caller set it.
 _JSON_OUT = os.fdopen(os.dup(1), "w")
 os.dup2(2, 1)
 
@@ -46,8 +51,12 @@ def emit(obj):
 METRIC = "kmeans_assign_points_per_sec"
 UNIT = "points/s"
 N_POINTS, D, K = 8000000, 256, 1024
-WORKLOAD = "k-means assignment step, %dx%d fp32 samples (U[0,1)) @ %d clusters per GPU (BASELINE configs[1] shape)"
+WORKLOAD = ("k-means assignment step, %d x %d fp32 samples in total (U[0,1)) @ %d clusters (rows of the samples), "
+            "range-partitioned over the GPUs (BASELINE configs[1] at 1 GPU, configs[3] at 2/4/8)")
 IMPORT = 3
+# kernels of this library per assignment pass (L2, tensor-core path): csqr, mean, mu, centred norms, stats, scale,
+# table, tc_assign_kernel, recheck_pairs, recheck_reduce, exact_rows_few, finalize_rows
+LAUNCHES_PER_ASSIGN = 12
 
 
 def _rank_info():
@@ -55,6 +64,10 @@ def _rank_info():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     return rank, local, world
+
+
+def shard_range(total, rank, world):
+    return total * rank // world, total * (rank + 1) // world
 
 
 class ClockSampler:
@@ -153,52 +166,59 @@ def measured_peaks():
         return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
 
 
-def cpu_baseline(sample_points=65536):
-    """the C oracle port (oracle/kmcuda_oracle.c, OpenMP) on a bounded sample of the same workload"""
-    from oracle import oracle as O
-    cores = O.set_threads(os.cpu_count() or 1)   # torchrun exports OMP_NUM_THREADS=1
+def cpu_baseline():
+    """north_star's named CPU baseline: scikit-learn KMeans labelling (Lloyd assignment) on all host cores, bounded
+    sample of the same workload; nested: the single-source C oracle port (exact reference arithmetic, OpenMP)."""
+    cores = os.cpu_count() or 1
     rng = np.random.default_rng(777)
-    X = rng.random((sample_points, D), dtype=np.float32)
-    C = rng.random((K, D), dtype=np.float32)
-    O.assign_lloyd(X[:1024], C)  # warm the library / OpenMP pool
-    t = time.perf_counter()
-    O.assign_lloyd(X, C)
-    dt = time.perf_counter() - t
-    out = {"value": sample_points / dt, "unit": UNIT, "cores": cores, "kind": "port",
-           "sample": "%d points of the same %d-feature x %d-cluster workload, one pass, %.1f s" %
-                     (sample_points, D, K, dt)}
-    try:  # north_star's named CPU reference: sklearn KMeans labelling on the host cores
+    sample = 1000000
+    X = rng.random((sample, D), dtype=np.float32)
+    C = X[rng.choice(sample, K, replace=False)].copy()
+    out = {"unit": UNIT, "cores": cores, "kind": "port"}
+    try:
         from sklearn.cluster import KMeans
-        km = KMeans(n_clusters=K, init=C, n_init=1, max_iter=1, algorithm="lloyd", tol=0).fit(X[:4096])
-        km.cluster_centers_ = C.astype(km.cluster_centers_.dtype)
         from threadpoolctl import threadpool_limits
-        with threadpool_limits(limits=os.cpu_count()):
-            km.predict(X[:4096])
-            t = time.perf_counter()
-            km.predict(X)
-            dt2 = time.perf_counter() - t
-        out["sklearn_predict"] = {"value": sample_points / dt2, "unit": UNIT, "cores": os.cpu_count(),
-                                  "sample": "%d points, KMeans.predict" % sample_points}
+        km = KMeans(n_clusters=K, init=C, n_init=1, max_iter=1, algorithm="lloyd", tol=0).fit(X[:8192])
+        km.cluster_centers_ = C.astype(km.cluster_centers_.dtype)
+        with threadpool_limits(limits=cores):
+            km.predict(X[:65536])
+            best, spent, reps = 1e30, 0.0, 0
+            while spent < 10.0 and reps < 8:
+                t = time.perf_counter()
+                km.predict(X)
+                dt = time.perf_counter() - t
+                best, spent, reps = min(best, dt), spent + dt, reps + 1
+        out.update({"value": sample / best, "implementation": "sklearn.cluster.KMeans.predict (Lloyd labelling)",
+                    "sample": "%d points of the same %d-feature x %d-cluster workload, best of %d passes, %.1f s of CPU "
+                              "work on %d threads" % (sample, D, K, reps, spent, cores)})
     except Exception as e:  # pragma: no cover
-        out["sklearn_predict"] = {"unavailable": repr(e)[:100]}
+        out["sklearn_unavailable"] = repr(e)[:120]
+    try:
+        from oracle import oracle as O
+        ocores = O.set_threads(cores)   # torchrun exports OMP_NUM_THREADS=1
+        small = 16384
+        O.assign_lloyd(X[:1024], C)
+        t = time.perf_counter()
+        O.assign_lloyd(X[:small], C)
+        dt = time.perf_counter() - t
+        out["oracle_port"] = {"value": small / dt, "unit": UNIT, "cores": ocores,
+                              "sample": "%d points, C restatement of the reference arithmetic (TwoSum round-down FMA), "
+                                        "%.1f s" % (small, dt)}
+        if "value" not in out:
+            out.update({"value": small / dt, "cores": ocores, "sample": out["oracle_port"]["sample"]})
+    except Exception as e:  # pragma: no cover
+        out["oracle_unavailable"] = repr(e)[:120]
     return out
 
 
-def c_api(path):
-    from oracle import oracle as O
-    return O.load_c_api(path)
-
-
-def time_c_abi_host(lib, X_host, C_host, device_mask, steps, warmup):
-    """kmeans_cuda(init=import, tolerance=1.0, yinyang_t=0): exactly one assignment pass, host buffers"""
-    n = X_host.shape[0]
-    A = np.empty(n, np.uint32)
-    Cw = np.array(C_host, copy=True)
+def time_c_abi(lib, n, x_ptr, c_ptr, a_ptr, device_mask, device_ptrs, steps, warmup):
+    """kmeans_cuda(init=import, tolerance=1.0, yinyang_t=0): exactly one assignment pass (reference src/test.py:
+    512-519); wall clock per call"""
     m = ctypes.c_uint32(0)
 
     def call():
-        rc = lib.kmeans_cuda(IMPORT, ctypes.byref(m), 1.0, 0.0, 0, n, D, K, 0, device_mask, -1, 0, 0,
-                             X_host.ctypes.data, Cw.ctypes.data, A.ctypes.data, None)
+        rc = lib.kmeans_cuda(IMPORT, ctypes.byref(m), 1.0, 0.0, 0, n, D, K, 0, device_mask, device_ptrs, 0, 0,
+                             x_ptr, c_ptr, a_ptr, None)
         if rc != 0:
             raise RuntimeError("kmeans_cuda returned %d" % rc)
 
@@ -207,7 +227,7 @@ def time_c_abi_host(lib, X_host, C_host, device_mask, steps, warmup):
     t = time.perf_counter()
     for _ in range(steps):
         call()
-    return (time.perf_counter() - t) / steps, A
+    return (time.perf_counter() - t) / steps
 
 
 def run_reference(args):
@@ -215,39 +235,65 @@ def run_reference(args):
     if rank != 0:
         return
     from oracle import oracle as O
-    sample = min(args.points, 2000000)
-    rng = np.random.default_rng(777)
-    X = rng.random((sample, D), dtype=np.float32)
-    C = X[rng.choice(sample, K, replace=False)].copy()
+    import torch
+    n = args.points
+    mask = (1 << args.gpus) - 1
     line = {"impl": "reference", "metric": METRIC, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "warmup": args.warmup, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD % (args.points, D, K), "l2": "inputs larger than L2"}}
-    kind, note = "reference", ""
+            "config": {"workload": WORKLOAD % (n, D, K), "l2": "inputs larger than L2",
+                       "parallelism": "single process, device mask 0x%x (the reference replicates the samples on "
+                                      "every GPU and splits the kernel ranges)" % mask}}
     try:
-        import torch
         if not (O.reference_available() and torch.cuda.is_available()):
             raise RuntimeError("oracle/_ref/libKMCUDA.so or GPU missing")
         ref = O.reference_lib()
-        dt, _ = time_c_abi_host(ref, X, C, 1 << local, args.steps, args.warmup)
-        note = ("unmodified src-d/kmcuda rebuilt for sm_100 (oracle/_ref), one GPU, kmeans_cuda(import, tolerance=1, "
-                "yinyang_t=0) with host buffers = H2D + transpose + one assign pass + D2H; bounded sample of %d points"
-                % sample)
-        cores = 0
+        torch.cuda.set_device(0)
+        g = torch.Generator(device="cuda").manual_seed(777)
+        X = torch.rand((n, D), generator=g, device="cuda", dtype=torch.float32)
+        C = X[torch.randperm(n, generator=g, device="cuda")[:K]].contiguous()
+        A = torch.zeros(n, dtype=torch.int32, device="cuda")
+        torch.cuda.synchronize()
+        # resident: device pointers on GPU 0 (the reference still allocates, copies and transposes internally: its
+        # public API has no finer-grained entry point)
+        t0 = time.perf_counter()
+        time_c_abi(ref, n, X.data_ptr(), C.data_ptr(), A.data_ptr(), mask, 0, 1, 0)
+        first = time.perf_counter() - t0
+        steps = args.steps if first * (args.steps + args.warmup) < 150 else max(3, int(150 / first) - args.warmup)
+        dt = time_c_abi(ref, n, X.data_ptr(), C.data_ptr(), A.data_ptr(), mask, 0, steps, max(0, args.warmup - 1))
+        # end to end: pinned host buffers, H2D + D2H inside the call
+        Xh = torch.empty((n, D), dtype=torch.float32, pin_memory=True)
+        Xh.copy_(X)
+        Ch = C.cpu().numpy().copy()
+        Ah = torch.empty(n, dtype=torch.int32, pin_memory=True)
+        del X, A
+        torch.cuda.empty_cache()
+        e2e_steps = max(1, min(steps, 3))
+        dte = time_c_abi(ref, n, Xh.data_ptr(), Ch.ctypes.data, Ah.data_ptr(), mask, -1, e2e_steps, 1)
+        note = ("unmodified src-d/kmcuda rebuilt for sm_100 (oracle/_ref), device mask 0x%x, kmeans_cuda(import, "
+                "tolerance=1, yinyang_t=0) = one assign pass on all %d points; `value`: device-resident inputs "
+                "(device_ptrs=0), %d timed calls; `e2e`: pinned host buffers, %d calls" % (mask, n, steps, e2e_steps))
+        v = n / dt
+        line.update({"value": v, "ms_per_step": dt * 1e3, "steps_timed": steps,
+                     "cpu_baseline": {"value": v, "unit": UNIT, "cores": 0, "kind": "reference", "sample": note},
+                     "e2e": {"value": n / dte, "unit": UNIT, "h2d_bytes_per_step": n * D * 4 + K * D * 4,
+                             "d2h_bytes_per_step": n * 4 + K * D * 4, "steps": e2e_steps}})
     except Exception as e:
-        kind = "port"
-        sample = 65536
-        X = X[:sample]
+        sample = 16384
+        rng = np.random.default_rng(777)
+        X = rng.random((sample, D), dtype=np.float32)
+        C = X[rng.choice(sample, K, replace=False)].copy()
+        cores = O.set_threads(os.cpu_count() or 1)
+        reps = max(1, min(args.steps, 3))
         t = time.perf_counter()
-        for _ in range(max(1, min(args.steps, 3))):
+        for _ in range(reps):
             O.assign_lloyd(X, C)
-        dt = (time.perf_counter() - t) / max(1, min(args.steps, 3))
+        dt = (time.perf_counter() - t) / reps
+        v = sample / dt
         note = "CPU oracle port (reference library unavailable: %s); %d points" % (repr(e)[:80], sample)
-        cores = os.cpu_count()
-    v = sample / dt
-    line.update({"value": v, "ms_per_step": dt * 1e3,
-                 "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": note},
-                 "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+        line.update({"value": v, "ms_per_step": dt * 1e3,
+                     "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": note},
+                     "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
     emit(line)
 
 
@@ -261,11 +307,16 @@ def run_ours(args):
     import kmcuda_b200
     from kmcuda_b200.shard import Shard
 
-    n = args.points
+    total = args.points
+    lo, hi = shard_range(total, rank, world)
+    n = hi - lo
     g = torch.Generator(device="cuda").manual_seed(777 + rank)
     X = torch.rand((n, D), generator=g, device="cuda", dtype=torch.float32)
-    gc = torch.Generator(device="cuda").manual_seed(777)
-    C = torch.rand((K, D), generator=gc, device="cuda", dtype=torch.float32)  # same centroids on every rank
+    # centroids = K rows of the samples (BASELINE configs[1]); rank 0 draws them from its shard for everybody
+    C = X[torch.randperm(n, generator=g, device="cuda")[:K]].contiguous()
+    if world > 1:
+        dist.broadcast(C, src=0)
+    C0 = C.clone()
     sh = Shard(n, D, K)
     a = torch.full((n,), -1, dtype=torch.int32, device="cuda")
     prev = torch.full((n,), -1, dtype=torch.int32, device="cuda")
@@ -275,6 +326,12 @@ def run_ours(args):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     sampler = ClockSampler(local)
     sampler.start()
@@ -295,36 +352,69 @@ def run_ours(args):
     barrier()
     sampler.mark()
     clocks = sampler.stop()
-    ms = e0.elapsed_time(e1)
-    tms = torch.tensor([ms], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-    ms_per_step = float(tms.item()) / args.steps
+    ms_per_step = max_over_ranks(e0.elapsed_time(e1)) / args.steps
     tc_used, rechecked, overflowed = sh.last_pass_info()
     if not tc_used or sh.last_error():
         raise RuntimeError("the tensor-core path did not run cleanly (tc=%s err=0x%x)" % (tc_used, sh.last_error()))
     kt = sh.kernel_times(min(args.steps, 64))
-    kernel_ms = sum(kt) / len(kt)
+    kernel_ms = max_over_ranks(sum(kt) / len(kt))
+    a_ref = a.clone()
 
     if args.skip_extras:
         if rank == 0:
-            emit({"metric": METRIC, "value": world * n / (ms_per_step * 1e-3), "unit": UNIT,
+            emit({"metric": METRIC, "value": total / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world,
                   "ms_per_step": ms_per_step, "kernel_ms": kernel_ms, "note": "profiling run, extras skipped"})
+        if world > 1:
+            dist.destroy_process_group()
         return
+
+    # ---- the full Lloyd iteration (BASELINE configs[3]): assign + partial sums + NCCL all-reduce + normalise
+    sums = torch.zeros((K, D), dtype=torch.float32, device="cuda")
+    counts = torch.zeros(K, dtype=torch.int32, device="cuda")
+    ccounts = torch.zeros(K, dtype=torch.int32, device="cuda")
+    iters = max(3, min(args.steps, 10))
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(iters)]
+
+    def iteration(evs=None):
+        if evs: evs[0].record()
+        sh.assign(X, C, a, prev, changed)
+        if evs: evs[1].record()
+        sh.partial_sums(X, a, sums, counts)
+        if evs: evs[2].record()
+        if world > 1:
+            dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+            dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+        if evs: evs[3].record()
+        sh.finish_update(sums, counts, C, ccounts)
+        if evs: evs[4].record()
+
+    C.copy_(C0)
+    sh.reset()
+    for _ in range(2):
+        iteration()
+    barrier()
+    for i in range(iters):
+        iteration(ev[i])
+    barrier()
+    phase_names = ["assign", "partial_sums", "allreduce", "normalise"]
+    phases = {}
+    for j, name in enumerate(phase_names):
+        phases[name] = max_over_ranks(sum(ev[i][j].elapsed_time(ev[i][j + 1]) for i in range(iters)) / iters)
+    it_ms = max_over_ranks(ev[0][0].elapsed_time(ev[iters - 1][4]) / iters)
+    C.copy_(C0)
+
     # ---- end to end through the reference-facing C ABI with host buffers (pinned), rank-local shard
     e2e_steps = max(1, min(args.steps, 3))
     Xh = torch.empty((n, D), dtype=torch.float32, pin_memory=True)
     Xh.copy_(X)
-    Ch = C.cpu().numpy()
+    Ch = C0.cpu().numpy().copy()
+    Ah = torch.empty(n, dtype=torch.int32, pin_memory=True)
     del X
     torch.cuda.empty_cache()
     barrier()
-    dt, A = time_c_abi_host(kmcuda_b200._lib, Xh.numpy(), Ch, 1 << local, e2e_steps, 1)
-    te = torch.tensor([dt], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_dt = float(te.item())
-    same = bool((torch.from_numpy(A.astype(np.int32)).cuda() == a).all().item())
+    dt = time_c_abi(kmcuda_b200._lib, n, Xh.data_ptr(), Ch.ctypes.data, Ah.data_ptr(), 1 << local, -1, e2e_steps, 1)
+    e2e_dt = max_over_ranks(dt)
+    same = bool((Ah.cuda() == a_ref).all().item())
 
     if rank == 0:
         peaks, peak_kind = measured_peaks()
@@ -333,27 +423,37 @@ def run_ours(args):
         achieved = flops / (kernel_ms * 1e-3) / 1e12
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get("dram_bytes_per_launch")
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json"))).get("dram_bytes_per_launch")
         except Exception:
             pass
         line = {
-            "metric": METRIC, "value": world * n / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world,
+            "metric": METRIC, "value": total / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f16 tensor-core filter (f32 accumulate) + f32 exact re-check",
-            "data": "synthetic",
-            "config": {"workload": WORKLOAD % (n, D, K), "parallelism": "sample-sharded x%d, no collective in the step" % world,
-                       "l2": "inputs (%.1f GB per GPU) larger than L2, no flush needed" % (n * D * 4 / 1e9),
+            "scaling": "strong", "vs_baseline": None,
+            "dtype": "f16 tensor-core filter (f32 accumulate) + f32 exact re-check", "data": "synthetic",
+            "config": {"workload": WORKLOAD % (total, D, K),
+                       "parallelism": "%d rows per GPU x %d GPUs (one process per GPU); the assignment step needs no "
+                                      "collective, the centroid update one NCCL all-reduce (see `iteration`)" % (n, world),
+                       "l2": "inputs (%.2f GB per GPU) larger than L2, no flush needed" % (n * D * 4 / 1e9),
                        "rows_rechecked_exactly": rechecked, "rows_full_exact_fallback": overflowed},
-            "e2e": {"value": world * n / e2e_dt, "unit": UNIT, "h2d_bytes_per_step": n * D * 4 + K * D * 4,
+            "step_tflops": 2.0 * total * K * D / (ms_per_step * 1e-3) / 1e12 / world,
+            "iteration": {"what": "full Lloyd iteration: assign + partial sums + all-reduce(K*D f32 + K i32) + normalise",
+                          "value": total / (it_ms * 1e-3), "unit": UNIT, "ms": it_ms, "iterations": iters,
+                          "phase_ms": phases, "allreduce_bytes": K * D * 4 + K * 4,
+                          "collective": "torch.distributed NCCL all_reduce x2" if world > 1 else "none (1 GPU)"},
+            "e2e": {"value": total / e2e_dt, "unit": UNIT, "h2d_bytes_per_step": n * D * 4 + K * D * 4,
                     "d2h_bytes_per_step": n * 4 + K * D * 4, "steps": e2e_steps,
-                    "call": "kmeans_cuda(init=import, tolerance=1.0, yinyang_t=0) with pinned host buffers",
+                    "call": "kmeans_cuda(init=import, tolerance=1.0, yinyang_t=0) with pinned host buffers, one call "
+                            "per rank on its shard",
                     "equal_to_resident_result": same},
-            "gpu_launches": args.steps * 9,
+            "gpu_launches": args.steps * LAUNCHES_PER_ASSIGN,
             "roofline": {"bound": "tensor", "kernel": "tc_assign_kernel", "achieved": achieved, "peak": peak_tf,
                          "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": traffic,
-                         "peak_source": "%s bf16_tflops (burst) of MEASURED_PEAKS.json; fp16 and bf16 share the tcgen05 rate" % peak_kind,
+                         "peak_source": "%s bf16_tflops (burst) of MEASURED_PEAKS.json; fp16 and bf16 share the "
+                                        "tcgen05 rate" % peak_kind,
                          "kernel_ms": kernel_ms, "algorithmic_flops_per_launch": flops,
-                         "algorithmic_hbm_bytes_per_launch": n * (D * 4 + 4)},
+                         "algorithmic_hbm_bytes_per_launch": n * (D * 4 + 4),
+                         "whole_step_frac": 2.0 * n * K * D / (ms_per_step * 1e-3) / 1e12 / peak_tf},
             "clocks": clocks,
         }
         line["cpu_baseline"] = cpu_baseline()
@@ -369,8 +469,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--points", type=int, default=N_POINTS, help="samples per GPU (default: the headline 8M)")
-    ap.add_argument("--skip-extras", action="store_true", help="profiling runs: no e2e / cpu_baseline legs")
+    ap.add_argument("--points", type=int, default=N_POINTS, help="samples IN TOTAL (default: the headline 8M)")
+    ap.add_argument("--skip-extras", action="store_true", help="profiling runs: no iteration / e2e / cpu_baseline legs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
     if args.impl == "reference":

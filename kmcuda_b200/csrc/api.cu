@@ -786,7 +786,7 @@ KMCUDAResult Job::yinyang(float tolerance, uint32_t G) {
     KMB_CU(cudaMemcpyAsync(d.shard->groups.get(), groups.data(), sizeof(uint32_t) * K, cudaMemcpyHostToDevice, d.st),
            kmcudaMemoryCopyError);
     KMB_CU(cudaMemsetAsync(d.d_changed.get(), 0, sizeof(uint32_t), d.st), kmcudaRuntimeError);
-    KMB_RET(d.shard->yy_prepare(d.st));
+    KMB_RET(d.shard->yy_prepare(groups.data(), d.st));
   }
   KMB_RET(sync_all());
   bool refresh = true;
@@ -816,8 +816,7 @@ KMCUDAResult Job::yinyang(float tolerance, uint32_t G) {
       KMB_INFO("refreshing Yinyang bounds...\n");
       for (auto& d : devs) {
         KMB_CU(cudaSetDevice(d.dev), kmcudaRuntimeError);
-        KMB_CU(launch_yy_init(metric, d.X, d.C, d.len, D, K, G, d.assign, d.shard->groups, d.shard->bounds, d.st),
-               kmcudaRuntimeError);
+        KMB_RET(d.shard->yy_refresh(d.len, d.X, d.C, d.assign, d.st));
       }
       refresh = false;
       g_prof.mark("yinyang: bounds refresh");

@@ -45,6 +45,7 @@
 #include <cstdio>
 #include <algorithm>
 #include <cstring>
+#include <vector>
 
 #include <cub/cub.cuh>
 
@@ -182,6 +183,17 @@ struct Params {
   uint32_t* assign;
   uint32_t* prev;
   uint32_t* d_changed;
+  // MODE 3 (Yinyang bounds refresh, reference kmeans_yy_init kmeans.cu:431-485): the table is the GROUP-SORTED
+  // centroid list, every group padded to whole 4-column quads (yy_qgroup[(n-tile * 2 + half) * 16 + quad] = group of
+  // that quad, UINT32_MAX past the end).  The epilogue folds the quad maxima into per-group maxima and turns each
+  // into a LOWER bound of the distance to the nearest centroid of that group, d >= sqrt(|x^|^2 - 2 (max + E)) / s,
+  // merged into bounds[row][1 + g] with an atomic minimum; the sample's own group and its upper bound are exact
+  // (yy_own_group_kernel).  Valid bounds are all Yinyang needs: the assignments stay those of Lloyd's algorithm.
+  const uint32_t* yy_qgroup;
+  const uint32_t* yy_groups;     // [K] centroid -> group
+  const uint32_t* yy_assign;     // [n]
+  float* yy_bounds;              // [n][G + 1]
+  uint32_t G;
   // MODE 1 (Yinyang local step): the samples are the rows listed in rows[0 .. *d_nrows), read straight from
   // global memory by the converter warps; every column within the margin of the row's SECOND best score is a
   // candidate and every candidate goes to the pair queue (the caller needs exact best and second-best distances)
@@ -319,17 +331,29 @@ __global__ void tc_prep_scale_kernel(Stats* __restrict__ st, const float* __rest
 __global__ void tc_prep_table_kernel(int metric, const float* __restrict__ C, const float* __restrict__ csq,
                                      uint32_t K, int D, int nkb, int nt, __half* __restrict__ table,
                                      __half* __restrict__ aug_blob, Stats* __restrict__ st,
-                                     const uint32_t* __restrict__ gather, const float* __restrict__ mu) {
+                                     const uint32_t* __restrict__ gather, const float* __restrict__ mu,
+                                     int by_source) {
+  // by_source (Yinyang refresh layout): table row r holds centroid gather[r] (UINT32_MAX = padding) and csq[] is
+  // indexed by the centroid; otherwise csq[] is indexed by the table row and rows >= K are padding
   const uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t rows_pad = static_cast<uint32_t>(nt) * TN;
   if (row >= rows_pad) return;
   const int Dp = nkb * KB;
   const float s = st->scale;
+  uint32_t src = row;
   bool finite = row < K;
-  const float* Crow = C + static_cast<size_t>((finite && gather) ? gather[row] : row) * D;
+  if (by_source) {
+    src = gather[row];
+    finite = src != UINT32_MAX;
+    if (!finite) src = 0;
+  } else if (finite && gather) {
+    src = gather[row];
+  }
+  const uint32_t qrow = by_source ? src : row;
+  const float* Crow = C + static_cast<size_t>(src) * D;
   if (finite) {
-    float q = csq[row];
+    float q = csq[qrow];
     finite = (q == q) && q < 3.0e38f;
     for (int f = lane; f < D; f += 32) {
       float v = Crow[f];
@@ -362,7 +386,7 @@ __global__ void tc_prep_table_kernel(int metric, const float* __restrict__ C, co
     // bias: three fp16 terms of -(s^2 ||c - mu||^2 / 2); invalid / padded centroids get -65504
     __half b[3];
     if (finite) {
-      float h = metric == 1 ? 0.f : -0.5f * ((s * csq[row]) * s);   // s = 2^k: exact; this order cannot overflow for tiny data
+      float h = metric == 1 ? 0.f : -0.5f * ((s * csq[qrow]) * s);   // s = 2^k: exact; this order cannot overflow for tiny data
       b[0] = __float2half_rn(h);
       float r1 = h - __half2float(b[0]);
       b[1] = __float2half_rn(r1);
@@ -583,7 +607,7 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
     }
   } else if (warp == WARP_X_PRODUCER) {
     // ================================ TMA producer: fp32 sample rows ================================
-    if (MODE == 0 && lane == 0) {
+    if ((MODE == 0 || MODE == 3) && lane == 0) {
       uint32_t xc = 0;
       for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         for (int hs = 0; hs < 2 * nkb; hs++, xc++) {
@@ -668,7 +692,7 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
         TC_WAIT(BAR_A_FREE + abuf, ((si / NBUF) & 1) ^ 1, 7);   // MMAs of the previous user of this buffer are done
         ptx::tc_fence_after();
         // ||x~||^2 and ||s(x - mu) - x~||^2 as packed even/odd partial sums (FFMA2: two fp32 FMAs per issue slot)
-        uint64_t nx2 = 0ull, nd2 = 0ull;
+        uint64_t nx2 = 0ull, nd2 = 0ull, xa22 = 0ull;   // xa22 (MODE 3): |s (x - mu)|^2 before the fp16 rounding
         const uint64_t s2 = ptx::pack2(s, s);
         const float* mu = reinterpret_cast<const float*>(smem + L.mu);
         float a2 = 0.f, a2c = 0.f, nraw = 0.f;     // MODE 2: Kahan sum of the exact (x-c)^2 s^2, and s^2 (|x|+|c|)^2
@@ -682,7 +706,7 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
             const uint32_t ph = (xc / X_STAGES) & 1;
             float4 gv[8];
             const int f0 = kb * KB + half * 32;
-            if (MODE == 0) {
+            if (MODE == 0 || MODE == 3) {
               TC_WAIT(BAR_X_FULL + st, ph, 10);
             } else {
 #pragma unroll
@@ -692,7 +716,7 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
             const uint8_t* xs = smem + L.x + st * X_STAGE_BYTES + row * 128;
 #pragma unroll
             for (int c = 0; c < 8; c++) {
-              float4 v = MODE == 0 ? *reinterpret_cast<const float4*>(xs + ((c ^ (row & 7)) << 4)) : gv[c];
+              float4 v = (MODE == 0 || MODE == 3) ? *reinterpret_cast<const float4*>(xs + ((c ^ (row & 7)) << 4)) : gv[c];
               float4 m4 = make_float4(0.f, 0.f, 0.f, 0.f);
               if (MODE == 2) {
                 const float4 cv = (f0 + c * 4 < p.D) ? ptx::ldg_nc_f4(crow + f0 + c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -717,6 +741,10 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
               const uint64_t d01 = ptx::fsub2(a01, b01), d23 = ptx::fsub2(a23, b23);
               nd2 = ptx::ffma2(d01, d01, nd2);
               nd2 = ptx::ffma2(d23, d23, nd2);
+              if (MODE == 3) {
+                xa22 = ptx::ffma2(a01, a01, xa22);
+                xa22 = ptx::ffma2(a23, a23, xa22);
+              }
               if (MODE == 2) {   // compensated: this sum is subtracted from scores of the same magnitude
                 const float q4 = fmaf(a0, a0, fmaf(a1, a1, fmaf(a2_, a2_, a3 * a3)));
                 const float y = q4 - a2c, t = a2 + y;
@@ -726,7 +754,7 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
               pk[half * 16 + c * 2] = *reinterpret_cast<uint32_t*>(&h0);
               pk[half * 16 + c * 2 + 1] = *reinterpret_cast<uint32_t*>(&h1);
             }
-            if (MODE == 0) {
+            if (MODE == 0 || MODE == 3) {
               __syncwarp();
               if (lane == 0) ptx::mbar_arrive(&bars[BAR_X_EMPTY + st]);
             }
@@ -743,6 +771,11 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
             if (MODE == 2) {
               norms[2 * TM + row] = a2;
               norms[3 * TM + row] = nraw * s * s;
+            }
+            if (MODE == 3) {
+              float xl, xh;
+              ptx::unpack2(xa22, xl, xh);
+              norms[2 * TM + row] = xl + xh;
             }
           }
           ptx::tc_fence_before();
@@ -772,7 +805,7 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
       uint16_t* list_g = reinterpret_cast<uint16_t*>(smem + L.list_g) + par * LIST_LEN * 256;
       float* fin = reinterpret_cast<float*>(smem + L.fin) + par * 5 * 256;
       // the emitter warps must have consumed this parity's lists (tile ti-2)
-      if (MODE != 2) TC_WAIT(BAR_EMIT_EMPTY + par, ((ti >> 1) & 1) ^ 1, 11);
+      if (MODE < 2) TC_WAIT(BAR_EMIT_EMPTY + par, ((ti >> 1) & 1) ^ 1, 11);
       float M = -INFINITY, M2 = -INFINITY, margin = 0.f;   // M2: MODE 1, second largest chunk maximum
       uint32_t cnt = 0, flags = 0;
       // MODE 2: this half-row's persistent state (global) and its top-kk column (the list_cm region is free)
@@ -781,6 +814,20 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
       bool klive = false;
       uint4* kent = nullptr;
       float goff = 0.f, mmax = 0.f;     // MODE 2: s^2 |x - c_B|^2 / 2 of the current segment; largest margin so far
+      // MODE 3: this row's record, own group (handled exactly elsewhere), lower bound of |s (x - mu)|^2
+      float xa2lo = 0.f;
+      uint32_t gown = UINT32_MAX;
+      uint32_t* yb = nullptr;
+      bool ylive = false;
+      if (MODE == 3) {
+        const uint64_t grow = static_cast<uint64_t>(tile) * TM + row;
+        ylive = grow < p.n;
+        if (ylive) {
+          const uint32_t a = p.yy_assign[grow];
+          if (a < p.K) gown = p.yy_groups[a];
+          yb = reinterpret_cast<uint32_t*>(p.yy_bounds + grow * (p.G + 1) + 1);
+        }
+      }
       uint32_t seg = 0;
       if (MODE == 2) {
         klive = static_cast<uint32_t>(row) < p.tile_nrows[tile];
@@ -823,6 +870,11 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
           const float xu = xn + mun, cu = cmax + mun;
           E += 2.0e-6f * (cu * cu + xu * cu);
           if (MODE >= 1) E += 2.0e-6f * xu * xu;                           // true distances: rounding of sum (x-c)^2
+          if (MODE == 3) {
+            xa2lo = norms[2 * TM + row] * (1.f - 1.0e-4f);                 // lower bound of |s (x - mu)|^2 (fp32 summation error)
+            // scores this low are not separable from the padding sentinel (-65504): such rows take the exact pass
+            if (!(nx * cmax < 6.0e4f)) flags |= 1u;
+          }
           if (MODE == 2) {
             goff = 0.5f * norms[2 * TM + row];
             // centring x - c_B and y - c_B rounds in fp32 (relative to |x|+|c|), and the row constant is subtracted
@@ -859,6 +911,56 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
           for (int jj = 0; jj < 32; jj++) dst[32 + jj] = __uint_as_float(r1[jj]);
         }
 #endif
+        if (MODE == 3) {
+          // quad maxima (2 instructions per 4 columns), folded into per-group maxima along the (warp-uniform) group ids
+          // of this 64-column half; every finished group turns into a lower bound of the distance
+          float qm[16];
+#pragma unroll
+          for (int i = 0; i < 8; i++) {
+            qm[i] = fmaxf(ptx::fmax3(__uint_as_float(r0[4 * i]), __uint_as_float(r0[4 * i + 1]), __uint_as_float(r0[4 * i + 2])),
+                          __uint_as_float(r0[4 * i + 3]));
+            qm[8 + i] = fmaxf(ptx::fmax3(__uint_as_float(r1[4 * i]), __uint_as_float(r1[4 * i + 1]), __uint_as_float(r1[4 * i + 2])),
+                              __uint_as_float(r1[4 * i + 3]));
+          }
+          uint32_t gq[16];
+          {
+            const uint4* src = reinterpret_cast<const uint4*>(p.yy_qgroup) + (static_cast<size_t>(n) * 2 + h) * 4;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+              const uint4 v = __ldg(src + i);
+              gq[4 * i] = v.x; gq[4 * i + 1] = v.y; gq[4 * i + 2] = v.z; gq[4 * i + 3] = v.w;
+            }
+          }
+          const float Eb = 0.5f * margin;                       // >= E
+          const float sc = p.stats->scale;
+          const float inv_s = 1.f / sc, inv_s2 = inv_s * inv_s;   // s is a power of two: exact
+          const bool emit_ok = ylive && !(flags & 1u);
+          float run = qm[0];
+#pragma unroll
+          for (int i = 1; i <= 16; i++) {
+            if (i == 16 || gq[i] != gq[i - 1]) {                // warp-uniform: the table layout is the same for every row
+              const uint32_t g = gq[i - 1];
+              if (emit_ok && g < p.G && g != gown) {
+                float v;
+                if (p.metric == 1) {
+                  // angular: every dot of the group <= (run + E) / s^2; acos is decreasing; libdevice acosf is good to 2 ulp
+                  const float dot = fminf(1.f, fmaxf(-1.f, (run + Eb) * inv_s2));
+                  v = fmaxf(0.f, acosf(dot) - 4.0e-6f);
+                } else {
+                  // L2: s^2 d^2 = |x^|^2 - 2 score  >=  |x^|^2 - 2 (run + E)
+                  const float t = xa2lo - 2.f * (run + Eb);
+                  v = t > 0.f ? __fsqrt_rd(t) * inv_s * (1.f - 4.0e-6f) : 0.f;
+                }
+                atomicMin(yb + g, __float_as_uint(v));        // bounds are >= +0: ordered like unsigned integers
+              }
+              if (i < 16) run = qm[i];
+            } else {
+              run = fmaxf(run, qm[i]);
+            }
+          }
+          if (it.seg_last()) si++;
+          continue;
+        }
         // chunk maxima with three-input maxima (FMNMX3): 16 instructions per 32 columns
         float t0[8], t1[8];      // MODE 2 only: maxima of the 4-column groups
         float cm0, cm1;
@@ -1002,6 +1104,13 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
         ti++;
         continue;
       }
+      if (MODE == 3) {
+        // rows the filter cannot bound (non-finite data, scores beyond the sentinel range): exact refresh of the row
+        if (ylive && (flags & 1u) && h == 0)
+          p.ovf_rows[atomicAdd(&p.counters[CNT_OVF], 1u)] = static_cast<uint32_t>(tile * TM + row);
+        ti++;
+        continue;
+      }
       // publish this half-row's state; the emitter warps merge the halves and write the results
       fin[slot] = M;
       reinterpret_cast<uint32_t*>(fin)[256 + slot] = cnt;
@@ -1012,7 +1121,7 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
       if (lane == 0) ptx::mbar_arrive(&bars[BAR_EMIT_FULL + par]);
       ti++;
     }
-  } else if (warp >= FIRST_EMIT_WARP && warp < FIRST_EMIT_WARP + N_EMIT_WARPS && MODE != 2) {
+  } else if (warp >= FIRST_EMIT_WARP && warp < FIRST_EMIT_WARP + N_EMIT_WARPS && MODE < 2) {
     // ================================ emitters: merge column halves, write results / queues ================================
     const int row = (warp - FIRST_EMIT_WARP) * 32 + lane;
     const float cap = p.metric == 1 ? p.stats->scale * p.stats->scale : INFINITY;
@@ -1243,6 +1352,16 @@ struct TcPlan {
   float* neg_mu_s = nullptr;       // [nkb*64]
   bool centred = false;
   bool inject_error = false;       // test hook (KMCUDA_B200_INJECT_PIPELINE_ERROR=1): report a timed-out barrier
+  // Yinyang bounds refresh (MODE 3): group-sorted table layout, built once per run by tc_yy_layout()
+  int nt3 = 0;
+  uint32_t G3 = 0;
+  __half* table3 = nullptr;
+  __half* aug_blob3 = nullptr;
+  uint32_t* yy_perm = nullptr;     // [nt3*128] table row -> centroid (UINT32_MAX = padding)
+  uint32_t* yy_qgroup = nullptr;   // [nt3*32] group of every 4-column quad
+  uint32_t* yy_goff = nullptr;     // [G+1] CSR of the group members
+  uint32_t* yy_gmem = nullptr;     // [K]
+  CUtensorMap tmap3;
   uint32_t *pair_row = nullptr, *pair_cand = nullptr, *rowq = nullptr, *ovf_rows = nullptr, *counters = nullptr;
   float* pair_score = nullptr;
   uint32_t* h_counters = nullptr;  // pinned
@@ -1290,7 +1409,8 @@ static void tc_launch_mode(int nkb, unsigned grid, size_t smem, cudaStream_t st,
 }
 static void tc_launch_main(int mode, int nkb, unsigned grid, size_t smem, cudaStream_t st, const CUtensorMap& tb,
                            const CUtensorMap& tx, const tc::Params& prm) {
-  if (mode == 2) tc_launch_mode<2>(nkb, grid, smem, st, tb, tx, prm);
+  if (mode == 3) tc_launch_mode<3>(nkb, grid, smem, st, tb, tx, prm);
+  else if (mode == 2) tc_launch_mode<2>(nkb, grid, smem, st, tb, tx, prm);
   else if (mode == 1) tc_launch_mode<1>(nkb, grid, smem, st, tb, tx, prm);
   else tc_launch_mode<0>(nkb, grid, smem, st, tb, tx, prm);
 }
@@ -1299,6 +1419,8 @@ static cudaError_t tc_set_smem_attr_one(int bytes) {
   cudaError_t e = cudaFuncSetAttribute(tc::tc_assign_kernel<NKB, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(tc::tc_assign_kernel<NKB, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(tc::tc_assign_kernel<NKB, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   if (e != cudaSuccess) return e;
   return cudaFuncSetAttribute(tc::tc_assign_kernel<NKB, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
 }
@@ -1330,6 +1452,12 @@ void tc_plan_destroy(TcPlan* p) {
   cudaFree(p->musum);
   cudaFree(p->mu);
   cudaFree(p->neg_mu_s);
+  cudaFree(p->table3);
+  cudaFree(p->aug_blob3);
+  cudaFree(p->yy_perm);
+  cudaFree(p->yy_qgroup);
+  cudaFree(p->yy_goff);
+  cudaFree(p->yy_gmem);
   cudaFree(p->pair_row);
   cudaFree(p->pair_cand);
   cudaFree(p->pair_score);
@@ -1412,7 +1540,7 @@ cudaError_t tc_plan_create(TcPlan** out, int metric, uint32_t max_n, int D, uint
 
 // counters reset + centroid preparation (scale, fp16 table, bias blobs) + the parameter block shared by both modes
 static cudaError_t tc_prepare(TcPlan* p, const float* C, const float* csq, uint32_t n, tc::Params* out,
-                              cudaStream_t st) {
+                              cudaStream_t st, bool yy_layout = false) {
   using namespace tc;
   cudaError_t e;
   if ((e = cudaMemsetAsync(p->counters, 0, sizeof(uint32_t) * CNT_N, st)) != cudaSuccess) return e;
@@ -1435,8 +1563,12 @@ static cudaError_t tc_prepare(TcPlan* p, const float* C, const float* csq, uint3
   tc_prep_stats_kernel<<<8, 256, 0, st>>>(nsq, p->K, p->stats);
   tc_prep_scale_kernel<<<1, 1, 0, st>>>(p->stats, mu, p->D, p->nkb * KB, p->neg_mu_s);
   const uint32_t rows_pad = static_cast<uint32_t>(p->nt) * TN;
-  tc_prep_table_kernel<<<(rows_pad * 32 + 255) / 256, 256, 0, st>>>(p->metric, C, nsq, p->K, p->D, p->nkb, p->nt, p->table,
-                                                                    p->aug_blob, p->stats, nullptr, mu);
+  if (!yy_layout)
+    tc_prep_table_kernel<<<(rows_pad * 32 + 255) / 256, 256, 0, st>>>(p->metric, C, nsq, p->K, p->D, p->nkb, p->nt, p->table,
+                                                                      p->aug_blob, p->stats, nullptr, mu, 0);
+  else
+    tc_prep_table_kernel<<<(static_cast<uint32_t>(p->nt3) * TN * 32 + 255) / 256, 256, 0, st>>>(
+        p->metric, C, nsq, p->K, p->D, p->nkb, p->nt3, p->table3, p->aug_blob3, p->stats, p->yy_perm, mu, 1);
   Params prm;
   prm.n = n;
   prm.D = p->D;
@@ -1456,6 +1588,13 @@ static cudaError_t tc_prepare(TcPlan* p, const float* C, const float* csq, uint3
   prm.metric = p->metric;
   prm.neg_mu_s = p->neg_mu_s;
   prm.assign = prm.prev = prm.d_changed = nullptr;
+  prm.yy_qgroup = prm.yy_groups = prm.yy_assign = nullptr;
+  prm.yy_bounds = nullptr;
+  prm.G = 0;
+  if (yy_layout) {
+    prm.nt = p->nt3;
+    prm.aug_blob = p->aug_blob3;
+  }
   prm.X = nullptr;
   prm.rows = nullptr;
   prm.d_nrows = nullptr;
@@ -1565,6 +1704,147 @@ cudaError_t tc_exact_distances(TcPlan* p, const float* X, const float* C, uint32
     recheck_pairs_kernel<0, 1><<<rgrid, 128, 0, st>>>(X, C, nullptr, p->D, pair_row, pair_cand, d_npairs, max_pairs,
                                                       n, p->K, pair_score);
   return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Yinyang bounds refresh on the tensor cores (reference kmeans_yy_init, kmeans.cu:431-485)
+// ---------------------------------------------------------------------------------------------------
+// exact part of the refresh: upper bound = distance to the own centroid, lower bound of the OWN group = nearest other
+// member (both as the reference computes them); one warp per sample, one lane per group member
+template <int METRIC>
+__global__ void __launch_bounds__(256)
+yy_own_group_kernel(const float* __restrict__ X, const float* __restrict__ C, uint32_t n, int D, uint32_t K, uint32_t G,
+                    const uint32_t* __restrict__ assign, const uint32_t* __restrict__ groups,
+                    const uint32_t* __restrict__ goff, const uint32_t* __restrict__ gmem, float* __restrict__ bounds) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t row = warp; row < n; row += nwarps) {
+    const uint32_t a = assign[row];
+    if (a >= K) continue;                       // "insane" sample: its bounds stay FLT_MAX (reference: c != nearest for all c)
+    const uint32_t g = groups[a];
+    if (g >= G) continue;
+    const float* x = X + static_cast<size_t>(row) * D;
+    const uint32_t beg = goff[g], end = goff[g + 1];
+    float lb = FLT_MAX, ub = FLT_MAX;
+    for (uint32_t j = beg + lane; j < end; j += 32) {
+      const uint32_t c = gmem[j];
+      const float d = distance_exact<METRIC>(x, C + static_cast<size_t>(c) * D, D);
+      if (c == a) ub = d;
+      else if (d < lb) lb = d;                   // NaN never lowers a bound (as the reference's `dist < bound`)
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      lb = fminf(lb, __shfl_xor_sync(0xffffffffu, lb, o));
+      ub = fminf(ub, __shfl_xor_sync(0xffffffffu, ub, o));
+    }
+    if (lane == 0) {
+      float* b = bounds + static_cast<size_t>(row) * (G + 1);
+      b[0] = ub;
+      b[1 + g] = lb;
+    }
+  }
+}
+
+// Builds the group-sorted table layout from the centroid -> group map of this run (host vector, G groups; ids >= G
+// mark dead centroids, which get no table row).  Call again whenever the grouping changes.
+cudaError_t tc_yy_layout(TcPlan* p, const uint32_t* host_groups, uint32_t G) {
+  using namespace tc;
+  const uint32_t K = p->K;
+  std::vector<uint32_t> gsz(G, 0);
+  for (uint32_t c = 0; c < K; c++)
+    if (host_groups[c] < G) gsz[host_groups[c]]++;
+  std::vector<uint32_t> goff(G + 1, 0), gfill(G, 0), gmem(K ? K : 1, 0);
+  for (uint32_t g = 0; g < G; g++) goff[g + 1] = goff[g] + gsz[g];
+  for (uint32_t c = 0; c < K; c++)
+    if (host_groups[c] < G) gmem[goff[host_groups[c]] + gfill[host_groups[c]]++] = c;
+  size_t rows = 0;
+  for (uint32_t g = 0; g < G; g++) rows += (gsz[g] + 3) / 4 * 4;
+  const int nt3 = static_cast<int>(std::max<size_t>(1, (rows + TN - 1) / TN));
+  const size_t rows_pad = static_cast<size_t>(nt3) * TN;
+  std::vector<uint32_t> perm(rows_pad, UINT32_MAX), qgroup(rows_pad / 4, UINT32_MAX);
+  size_t r = 0;
+  for (uint32_t g = 0; g < G; g++) {
+    if (gsz[g] == 0) continue;
+    for (uint32_t j = 0; j < gsz[g]; j++) perm[r + j] = gmem[goff[g] + j];
+    const size_t padded = (gsz[g] + 3) / 4 * 4;
+    for (size_t qd = r / 4; qd < (r + padded) / 4; qd++) qgroup[qd] = g;
+    r += padded;
+  }
+  cudaError_t e;
+  if (nt3 != p->nt3 || !p->table3) {
+    cudaFree(p->table3); cudaFree(p->aug_blob3); cudaFree(p->yy_perm); cudaFree(p->yy_qgroup);
+    p->table3 = nullptr; p->aug_blob3 = nullptr; p->yy_perm = nullptr; p->yy_qgroup = nullptr;
+    if ((e = cudaMalloc(&p->table3, rows_pad * p->nkb * KB * sizeof(__half))) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&p->aug_blob3, static_cast<size_t>(nt3) * AUG_B_BYTES)) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&p->yy_perm, rows_pad * sizeof(uint32_t))) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&p->yy_qgroup, rows_pad / 4 * sizeof(uint32_t))) != cudaSuccess) return e;
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) return cudaErrorNotSupported;
+    cuuint64_t gdim[2] = {static_cast<cuuint64_t>(p->nkb * KB), static_cast<cuuint64_t>(rows_pad)};
+    cuuint64_t gstride[1] = {static_cast<cuuint64_t>(p->nkb * KB) * sizeof(__half)};
+    cuuint32_t box[2] = {KB, TN};
+    cuuint32_t estr[2] = {1, 1};
+    if (enc(&p->tmap3, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, p->table3, gdim, gstride, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return cudaErrorInvalidValue;
+    p->nt3 = nt3;
+  }
+  if (G != p->G3 || !p->yy_goff) {
+    cudaFree(p->yy_goff); cudaFree(p->yy_gmem);
+    p->yy_goff = nullptr; p->yy_gmem = nullptr;
+    if ((e = cudaMalloc(&p->yy_goff, (static_cast<size_t>(G) + 1) * sizeof(uint32_t))) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&p->yy_gmem, gmem.size() * sizeof(uint32_t))) != cudaSuccess) return e;
+    p->G3 = G;
+  }
+  if ((e = cudaMemcpy(p->yy_perm, perm.data(), perm.size() * 4, cudaMemcpyHostToDevice)) != cudaSuccess) return e;
+  if ((e = cudaMemcpy(p->yy_qgroup, qgroup.data(), qgroup.size() * 4, cudaMemcpyHostToDevice)) != cudaSuccess) return e;
+  if ((e = cudaMemcpy(p->yy_goff, goff.data(), goff.size() * 4, cudaMemcpyHostToDevice)) != cudaSuccess) return e;
+  return cudaMemcpy(p->yy_gmem, gmem.data(), gmem.size() * 4, cudaMemcpyHostToDevice);
+}
+
+bool tc_yy_layout_ready(TcPlan* p, uint32_t G) { return p && p->table3 && p->G3 == G; }
+
+// One bounds refresh: bounds[row] = {ub exact, lb[g] valid lower bounds} (see Params, MODE 3).  Rows the filter
+// cannot bound are left on the overflow list (tc_queues) for the caller's exact row refresh.
+cudaError_t tc_yy_refresh(TcPlan* p, const float* X, const float* C, const float* csq, uint32_t n,
+                          const uint32_t* assign, const uint32_t* groups, uint32_t G, float* bounds, cudaStream_t st) {
+  using namespace tc;
+  if (n > p->max_n || !tc_yy_layout_ready(p, G)) return cudaErrorInvalidValue;
+  if ((reinterpret_cast<uintptr_t>(X) & 15) || (reinterpret_cast<uintptr_t>(C) & 15)) return cudaErrorMisalignedAddress;
+  cudaError_t e;
+  CUtensorMap tmap_x;
+  {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) return cudaErrorNotSupported;
+    cuuint64_t gdim[2] = {static_cast<cuuint64_t>(p->D), static_cast<cuuint64_t>(n)};
+    cuuint64_t gstride[1] = {static_cast<cuuint64_t>(p->D) * sizeof(float)};
+    cuuint32_t box[2] = {32, TM};
+    cuuint32_t estr[2] = {1, 1};
+    if (enc(&tmap_x, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(X), gdim, gstride, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return cudaErrorInvalidValue;
+  }
+  if ((e = launch_fill_u32(reinterpret_cast<uint32_t*>(bounds), 0x7f7fffffu /* FLT_MAX */,
+                           static_cast<size_t>(n) * (G + 1), st)) != cudaSuccess)
+    return e;
+  Params prm;
+  if ((e = tc_prepare(p, C, csq, n, &prm, st, true)) != cudaSuccess) return e;
+  prm.yy_qgroup = p->yy_qgroup;
+  prm.yy_groups = groups;
+  prm.yy_assign = assign;
+  prm.yy_bounds = bounds;
+  prm.G = G;
+  const unsigned grid = min(static_cast<uint32_t>(p->num_sms), prm.ntiles);
+  tc_launch_main(3, p->nkb, grid, p->smem_bytes, st, p->tmap3, tmap_x, prm);
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  const unsigned ogrid = p->num_sms * 16;
+  if (p->metric == 1)
+    yy_own_group_kernel<1><<<ogrid, 256, 0, st>>>(X, C, n, p->D, p->K, G, assign, groups, p->yy_goff, p->yy_gmem, bounds);
+  else
+    yy_own_group_kernel<0><<<ogrid, 256, 0, st>>>(X, C, n, p->D, p->K, G, assign, groups, p->yy_goff, p->yy_gmem, bounds);
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  return cudaMemcpyAsync(p->h_counters, p->counters, sizeof(uint32_t) * CNT_N, cudaMemcpyDeviceToHost, st);
 }
 
 void tc_queues(TcPlan* p, TcQueues* q) {
@@ -2073,6 +2353,7 @@ cudaError_t tc_knn_search(int k, const float* X, const float* C, uint32_t N, int
   prm.knn_cnt = kcnt; prm.knn_flags = kflags; prm.knn_dub = dub; prm.knn_entries = entries;
   prm.dbg_scores = nullptr;
   prm.neg_mu_s = nullptr; prm.assign = prm.prev = prm.d_changed = nullptr;
+  prm.yy_qgroup = prm.yy_groups = prm.yy_assign = nullptr; prm.yy_bounds = nullptr; prm.G = 0;
   tc_launch_main(2, nkb, grid, smem_bytes, st, tmap, tmap, prm);
   KNN_TRY(cudaGetLastError());
   knn::range_build_kernel<<<num_sms * 4, 256, 0, st>>>(d_ntiles, t_nrows, blk_cluster, blk_first, off, K, cd, radii, ysq,

@@ -58,6 +58,10 @@ cudaError_t launch_normalize(int metric, const float* sums, const uint32_t* coun
 cudaError_t launch_yy_init(int metric, const float* X, const float* C, uint32_t n, int D, uint32_t K,
                            uint32_t G, const uint32_t* assign, const uint32_t* groups, float* bounds,
                            cudaStream_t st);
+// exact refresh of the listed rows only (rows[0 .. *d_nrows))
+cudaError_t launch_yy_init_rows(int metric, const float* X, const float* C, uint32_t n, int D, uint32_t K,
+                                uint32_t G, const uint32_t* assign, const uint32_t* groups, float* bounds,
+                                const uint32_t* rows, const uint32_t* d_nrows, cudaStream_t st);
 cudaError_t launch_yy_drifts(int metric, const float* Cnew, const float* Cold, uint32_t K, int D,
                              uint32_t G, const uint32_t* groups, float* drift, float* maxdrift,
                              cudaStream_t st);
@@ -136,6 +140,12 @@ cudaError_t tc_exact_distances(TcPlan* plan, const float* X, const float* C, uin
                                const uint32_t* pair_cand, const uint32_t* d_npairs, uint32_t max_pairs,
                                float* pair_score, cudaStream_t st);
 void tc_queues(TcPlan* plan, TcQueues* q);
+// Yinyang bounds refresh on the tensor cores (assign_tc.cu, MODE 3): tc_yy_layout once per grouping (host map
+// centroid -> group), then tc_yy_refresh per refresh; rows left on the overflow list need launch_yy_init_rows
+cudaError_t tc_yy_layout(TcPlan* plan, const uint32_t* host_groups, uint32_t G);
+bool tc_yy_layout_ready(TcPlan* plan, uint32_t G);
+cudaError_t tc_yy_refresh(TcPlan* plan, const float* X, const float* C, const float* csq, uint32_t n,
+                          const uint32_t* assign, const uint32_t* groups, uint32_t G, float* bounds, cudaStream_t st);
 // k-NN candidate search on the tensor cores (assign_tc.cu); see the comment there
 bool tc_knn_supported(int metric, int k, uint32_t N, int D, uint32_t K);
 cudaError_t tc_knn_search(int k, const float* X, const float* C, uint32_t N, int D, uint32_t K,

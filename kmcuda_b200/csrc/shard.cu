@@ -75,9 +75,32 @@ KMCUDAResult Shard::reset_update_state(cudaStream_t st) {
   return kmcudaSuccess;
 }
 
-// after `groups` has been filled
-KMCUDAResult Shard::yy_prepare(cudaStream_t st) {
+// after `groups` (device) has been filled; host_groups is the same map on the host
+KMCUDAResult Shard::yy_prepare(const uint32_t* host_groups, cudaStream_t st) {
   KMB_CU(launch_yy_group_sizes(groups, K, G, yy_gsize, st), kmcudaRuntimeError);
+  const char* er = getenv("KMCUDA_B200_YY_EXACT_REFRESH");   // A/B and parity tests: exact SIMT refresh
+  if (tc && !force_exact && !(er && er[0] == '1'))
+    KMB_CU(tc_yy_layout(tc, host_groups, G), kmcudaMemoryAllocationFailure);
+  return kmcudaSuccess;
+}
+
+// Bounds refresh.  Tensor-core route (assign_tc.cu MODE 3): one distance GEMM against the group-sorted table gives
+// valid lower bounds for every other group, the own centroid / own group are exact, rows the filter cannot bound
+// are refreshed exactly.  Exact route: the reference's full pass (N * K exact distances).
+KMCUDAResult Shard::yy_refresh(uint32_t n, const float* X, const float* C, const uint32_t* assignments,
+                               cudaStream_t st) {
+  if (n > max_n) return kmcudaInvalidArguments;
+  if (n == 0) return kmcudaSuccess;
+  if (tc && tc_yy_layout_ready(tc, G)) {
+    KMB_CU(launch_csqr(metric, C, K, D, csq, st), kmcudaRuntimeError);
+    KMB_CU(tc_yy_refresh(tc, X, C, csq, n, assignments, groups, G, bounds, st), kmcudaRuntimeError);
+    TcQueues q;
+    tc_queues(tc, &q);
+    KMB_CU(launch_yy_init_rows(metric, X, C, n, D, K, G, assignments, groups, bounds, q.ovf_rows, q.d_novf, st),
+           kmcudaRuntimeError);
+    return kmcudaSuccess;
+  }
+  KMB_CU(launch_yy_init(metric, X, C, n, D, K, G, assignments, groups, bounds, st), kmcudaRuntimeError);
   return kmcudaSuccess;
 }
 
@@ -231,6 +254,32 @@ int32_t kmcuda_b200_debug_scores(kmcuda_b200_shard* shard, float* host_out, uint
 int32_t kmcuda_b200_kernel_times(kmcuda_b200_shard* shard, float* ms_out, int32_t max_out) {
   if (!shard || !shard->impl->tc || !ms_out) return 0;
   return kmb::tc_kernel_times(shard->impl->tc, ms_out, max_out);
+}
+// Yinyang bounds of one refresh (reference kmeans_yy_init) for the given assignments / grouping: use_tc = 1 takes the
+// tensor-core route (valid lower bounds), 0 the exact pass.  bounds_out: device [n][G + 1].  Synchronous.
+int32_t kmcuda_b200_debug_yy_bounds(kmcuda_b200_shard* shard, uint32_t n, const float* samples, const float* centroids,
+                                    const uint32_t* assignments, const uint32_t* host_groups, uint32_t G,
+                                    int32_t use_tc, float* bounds_out) {
+  if (!shard || !samples || !centroids || !assignments || !host_groups || !bounds_out || G == 0) return -1;
+  kmb::Shard* s = shard->impl;
+  if (n > s->max_n) return -2;
+  if (s->enable_yinyang(G) != kmcudaSuccess) return -3;
+  if (cudaMemcpy(s->groups.get(), host_groups, sizeof(uint32_t) * s->K, cudaMemcpyHostToDevice) != cudaSuccess) return -4;
+  cudaStream_t st = nullptr;
+  if (use_tc) {
+    if (!s->tc) return -5;
+    if (kmb::tc_yy_layout(s->tc, host_groups, G) != cudaSuccess) return -6;
+    if (s->yy_refresh(n, samples, centroids, assignments, st) != kmcudaSuccess) return -7;
+  } else {
+    if (kmb::launch_yy_init(s->metric, samples, centroids, n, s->D, s->K, G, assignments, s->groups, s->bounds, st) !=
+        cudaSuccess)
+      return -8;
+  }
+  if (cudaMemcpyAsync(bounds_out, s->bounds.get(), sizeof(float) * static_cast<size_t>(n) * (G + 1),
+                      cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+    return -9;
+  if (cudaStreamSynchronize(st) != cudaSuccess) return -10;
+  return (use_tc && kmb::tc_last_error(s->tc)) ? -11 : 0;
 }
 int32_t kmcuda_b200_debug_stats(kmcuda_b200_shard* shard, float* out4) {
   if (!shard || !shard->impl->tc) return -1;

@@ -97,7 +97,9 @@ class Shard {
   KMCUDAResult create(bool with_update);
   KMCUDAResult enable_yinyang(uint32_t G);
   KMCUDAResult reset_update_state(cudaStream_t st);
-  KMCUDAResult yy_prepare(cudaStream_t st);
+  KMCUDAResult yy_prepare(const uint32_t* host_groups, cudaStream_t st);
+  // (re)builds the bounds of every sample of the shard: reference kmeans_yy_init, kmeans.cu:431-485
+  KMCUDAResult yy_refresh(uint32_t n, const float* X, const float* C, const uint32_t* assignments, cudaStream_t st);
   KMCUDAResult yy_step(uint32_t n, const float* X, const float* C, uint32_t* assignments, uint32_t* prev,
                        uint32_t* d_changed, cudaStream_t st);
 

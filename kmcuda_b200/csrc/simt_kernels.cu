@@ -270,6 +270,13 @@ cudaError_t launch_yy_init(int metric, const float* X, const float* C, uint32_t 
                                  bounds, st);
 }
 
+cudaError_t launch_yy_init_rows(int metric, const float* X, const float* C, uint32_t n, int D, uint32_t K,
+                                uint32_t G, const uint32_t* assign, const uint32_t* groups, float* bounds,
+                                const uint32_t* rows, const uint32_t* d_nrows, cudaStream_t st) {
+  if (metric == 1)
+    return launch_exact_pass<1, 1>(X, C, nullptr, n, D, K, rows, d_nrows, nullptr, G, assign, groups, bounds, st);
+  return launch_exact_pass<0, 1>(X, C, nullptr, n, D, K, rows, d_nrows, nullptr, G, assign, groups, bounds, st);
+}
 
 // ------------------------------------------------------------------------------------------------
 // prev/assign bookkeeping + reassignment counter (reference kmeans.cu:358-363)

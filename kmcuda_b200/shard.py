@@ -34,6 +34,10 @@ _lib.kmcuda_b200_debug_last_error.restype = ctypes.c_uint32
 _lib.kmcuda_b200_debug_last_error.argtypes = [ctypes.c_void_p]
 _lib.kmcuda_b200_debug_scores.restype = ctypes.c_int32
 _lib.kmcuda_b200_debug_scores.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32]
+_lib.kmcuda_b200_debug_yy_bounds.restype = ctypes.c_int32
+_lib.kmcuda_b200_debug_yy_bounds.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p,
+                                             ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_int32,
+                                             ctypes.c_void_p]
 _lib.kmcuda_b200_debug_stats.restype = ctypes.c_int32
 _lib.kmcuda_b200_debug_stats.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
 
@@ -113,6 +117,17 @@ class Shard:
         rc = _lib.kmcuda_b200_debug_scores(self._h, out.ctypes.data, rows, cols)
         if rc != 0:
             raise RuntimeError("debug scores unavailable (%d); set KMCUDA_B200_DUMP_SCORES=1" % rc)
+        return out
+
+    def debug_yy_bounds(self, X, C, assignments, groups, G, use_tc):
+        """Yinyang bounds [n][G + 1] of one refresh (diagnostics / parity tests); groups: host uint32 [K]"""
+        groups = np.ascontiguousarray(groups, dtype=np.uint32)
+        out = torch.empty((X.shape[0], G + 1), dtype=torch.float32, device=X.device)
+        rc = _lib.kmcuda_b200_debug_yy_bounds(self._h, X.shape[0], _ptr(X, torch.float32), _ptr(C, torch.float32),
+                                              _ptr(assignments, torch.int32), groups.ctypes.data, int(G),
+                                              1 if use_tc else 0, _ptr(out, torch.float32))
+        if rc != 0:
+            raise RuntimeError("kmcuda_b200_debug_yy_bounds failed (%d)" % rc)
         return out
 
     def debug_stats(self):

@@ -24,27 +24,35 @@ def _scale_for(cmax):
     return float(np.ldexp(1.0, 6 - int(e)))
 
 
-def _filter_model(X, C):
-    """returns (acc [n][K] fp32, E [n], s) following the kernel's prep + converter + MMA + bias step"""
+def _filter_model(X, C, centred=False):
+    """returns (acc [n][K] fp32, E [n], s, mu) following the kernel's prep + converter + MMA + bias step.
+    centred: both operands relative to mu = mean of the centroids (round 2, L2 metric): the table holds
+    fp16(s fl32(c - mu)), the converter produces fl32(s x - s mu) in one rounding, the bias is ||fl32(c - mu)||^2."""
     X = X.astype(np.float32)
     C = C.astype(np.float32)
     n, D = X.shape
     nkb = (D + KB - 1) // KB
-    csq = (C.astype(np.float64) ** 2).sum(1).astype(np.float32)           # the reference's ||c||^2 (exact to ~1 ulp)
+    mu = C.astype(np.float64).mean(0).astype(np.float32) if centred else np.zeros(D, np.float32)
+    if not np.isfinite(mu).all():
+        mu = np.zeros(D, np.float32)
+    Cc = (C - mu[None]).astype(np.float32)                                # fl32(c - mu): the table operand before scaling
+    csq = (Cc.astype(np.float64) ** 2).sum(1).astype(np.float32)          # ||c - mu||^2 (double accumulation -> fp32)
     cmax_raw = np.sqrt(csq.max())
     s = np.float32(_scale_for(cmax_raw))
     cmax = np.float32(cmax_raw * s * 1.001)
-    cs = (C * s).astype(np.float32)
+    mun = np.float32(np.sqrt(((mu.astype(np.float64) * float(s)) ** 2).sum()) * 1.001)
+    cs = (Cc * s).astype(np.float32)
     ch = cs.astype(np.float16)                                            # fp16 centroid table
     dcmax = np.float32(np.sqrt(((cs - ch.astype(np.float32)).astype(np.float64) ** 2).sum(1)).max() * 1.0001)
-    # bias: -(s^2 ||c||^2 / 2) as three fp16 terms
+    # bias: -(s^2 ||c - mu||^2 / 2) as three fp16 terms
     h = (np.float32(-0.5) * ((s * csq).astype(np.float32) * s)).astype(np.float32)   # same order as the prep kernel
     b0 = h.astype(np.float16)
     r1 = (h - b0.astype(np.float32)).astype(np.float32)
     b1 = r1.astype(np.float16)
     b2 = (r1 - b1.astype(np.float32)).astype(np.float32).astype(np.float16)
-    # converter: a = x * s (fp32), fp16 RN, norms of the rounded vector and of the residual
-    a = (X * s).astype(np.float32)
+    # converter: a = fma(x, s, -mu s) (one rounding; s = 2^k, so = s * fl32(x - mu)), fp16 RN, norms of the rounded
+    # vector and of the residual
+    a = ((X - mu[None]).astype(np.float32) * s).astype(np.float32)
     ah = a.astype(np.float16)
     nx = np.sqrt((ah.astype(np.float64) ** 2).sum(1)) * 1.0001
     nd = np.sqrt(((a - ah.astype(np.float32)).astype(np.float64) ** 2).sum(1)) * 1.0001
@@ -55,8 +63,9 @@ def _filter_model(X, C):
     xn = nx + nd
     E = nx * dcmax + nd * cmax + nd * dcmax
     E = E + (nkb * KB + 16) * 2.4e-7 * nx * cmax
-    E = E + 2.0e-6 * (cmax * cmax + xn * cmax)
-    return acc, E.astype(np.float64), float(s)
+    xu, cu = xn + mun, cmax + mun                                         # norms of the uncentred vectors (upper bounds)
+    E = E + 2.0e-6 * (cu * cu + xu * cu)
+    return acc, E.astype(np.float64), float(s), mu
 
 
 def _cases():
@@ -85,11 +94,17 @@ def _cases():
     return out
 
 
+@pytest.mark.parametrize("centred", [False, True])
 @pytest.mark.parametrize("X,C", _cases())
-def test_margin_bounds_the_fp16_filter_error(X, C):
-    acc, E, s = _filter_model(X, C)
-    Xd, Cd = X.astype(np.float64), C.astype(np.float64)
+def test_margin_bounds_the_fp16_filter_error(X, C, centred):
+    acc, E, s, mu = _filter_model(X, C, centred)
+    # exact score of the (centred) operands in real arithmetic; it differs from the uncentred score by a per-row
+    # constant only, so its arg-max is the true nearest centroid
+    Xd, Cd = X.astype(np.float64) - mu.astype(np.float64), C.astype(np.float64) - mu.astype(np.float64)
     exact = (s * s) * (Xd @ Cd.T - 0.5 * (Cd ** 2).sum(1)[None])
+    true_best = (((X.astype(np.float64)[:, None, :] - C.astype(np.float64)[None]) ** 2).sum(-1)).argmin(1)
+    gap_ok = exact[np.arange(len(X)), true_best] >= exact.max(1) - 1e-9 * np.abs(exact).max()
+    assert gap_ok.all()                      # centring is a per-row shift: same winner
     err = np.abs(acc.astype(np.float64) - exact)
     assert np.isfinite(acc).all()
     worst = (err / E[:, None]).max()
@@ -110,12 +125,17 @@ def test_candidate_counts_are_small_on_the_benchmark_distribution():
     X = rng.random((2000, 256), dtype=np.float32)
     C = X[rng.choice(2000, 1024, replace=False)].copy()
     C += (0.01 * rng.standard_normal(C.shape)).astype(np.float32)
-    acc, E, _ = _filter_model(X, C)
+    acc, E, _, _ = _filter_model(X, C)
     margin = 2.0 * E * 1.001
     cand = (acc >= (acc.max(1) - margin)[:, None]).sum(1)
     assert (cand >= 1).all()
     assert 0.05 < (cand > 1).mean() < 0.35
     assert cand.max() <= 16
+    # round 2: centred operands (|x - mu| |c - mu| is 4x smaller than |x| |c| on this data) -> 4x narrower margin
+    acc_c, E_c, _, _ = _filter_model(X, C, centred=True)
+    cand_c = (acc_c >= (acc_c.max(1) - 2.0 * E_c * 1.001)[:, None]).sum(1)
+    assert (cand_c >= 1).all()
+    assert (cand_c > 1).mean() < 0.5 * (cand > 1).mean()
 
 
 def _knn_model(X, C, assign):

@@ -365,3 +365,59 @@ except AssertionError:
     r = subprocess.run([sys.executable, "-c", code], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
                        timeout=300)
     assert "RC 4" in r.stdout and "ASSERTION" in r.stdout, r.stdout[-800:]
+
+
+# ------------------------------------------------------------------------------------------- Yinyang bounds refresh
+@pytest.mark.parametrize("metric", ["L2", "cos"])
+def test_yinyang_refresh_bounds_are_valid_and_tight(km, metric):
+    """the tensor-core bounds refresh (assign_tc.cu MODE 3) against the exact pass (reference kmeans_yy_init,
+    src/kmeans.cu:431-485): identical upper bound and own-group bound, every other lower bound valid (never above
+    the exact value) and tight (within 1e-3 of it)"""
+    import torch
+    from kmcuda_b200.shard import Shard, assign_once
+    rng = np.random.default_rng(17)
+    n, d, k, G = 40000, 96, 300, 30
+    centers = rng.random((k, d), dtype=np.float32)
+    X = (centers[rng.integers(0, k, n)] + 0.1 * rng.standard_normal((n, d), dtype=np.float32)).astype(np.float32)
+    C = (centers + 0.02 * rng.standard_normal((k, d), dtype=np.float32)).astype(np.float32)
+    if metric == "cos":
+        X, C = _unit(X - 0.5), _unit(C - 0.5)
+    groups = (rng.permutation(k) % G).astype(np.uint32)      # uneven, non-contiguous groups
+    groups[rng.choice(k, 9, replace=False)] = 7              # one larger group
+    C[5] = np.nan
+    groups[5] = G                                            # dead centroid: no group (kmeans.cu:464-468)
+    X[11, 3] = np.nan                                        # a row the filter cannot bound -> exact row refresh
+    Xt, Ct = torch.from_numpy(X).cuda(), torch.from_numpy(C).cuda()
+    a, _, _, _ = assign_once(Xt, Ct, metric=metric)
+    sh = Shard(n, d, k, metric)
+    bt = sh.debug_yy_bounds(Xt, Ct, a, groups, G, True).cpu().numpy()
+    be = sh.debug_yy_bounds(Xt, Ct, a, groups, G, False).cpu().numpy()
+    an = a.cpu().numpy()
+    ok = an < k
+    np.testing.assert_array_equal(bt[ok, 0], be[ok, 0])                       # upper bound: exact
+    own = groups[np.minimum(an, k - 1)]
+    rows = np.flatnonzero(ok)
+    np.testing.assert_array_equal(bt[rows, 1 + own[rows]], be[rows, 1 + own[rows]])   # own group: exact
+    np.testing.assert_array_equal(bt[11], be[11])                             # exact row refresh
+    lt, le = bt[:, 1:], be[:, 1:]
+    finite = np.isfinite(le) & (le < 1e30)
+    assert (lt[finite] <= le[finite]).all(), float((lt[finite] - le[finite]).max())
+    assert (lt[finite] >= le[finite] - 1e-3 * np.maximum(1.0, le[finite])).all(), float((le[finite] - lt[finite]).max())
+    assert np.array_equal(lt[~finite], le[~finite])                           # empty groups stay FLT_MAX
+
+
+def test_yinyang_run_same_with_tensor_core_and_exact_refresh(ours, monkeypatch):
+    """whole Yinyang runs with the tensor-core refresh and with the exact refresh give the same clustering: valid
+    bounds do not change what Lloyd's algorithm computes"""
+    rng = np.random.default_rng(23)
+    n, d, k = 60000, 64, 200
+    centers = rng.random((k, d), dtype=np.float32)
+    X = (centers[rng.integers(0, k, n)] + 0.15 * rng.standard_normal((n, d), dtype=np.float32)).astype(np.float32)
+    C0 = (centers + 0.1 * rng.standard_normal((k, d), dtype=np.float32)).astype(np.float32)
+    runs = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("KMCUDA_B200_YY_EXACT_REFRESH", mode)
+        runs[mode] = c_kmeans(ours, X, C0, 0.0005, 0.1)
+    monkeypatch.delenv("KMCUDA_B200_YY_EXACT_REFRESH")
+    assert (runs["0"][1] == runs["1"][1]).mean() > 0.9999
+    np.testing.assert_allclose(runs["0"][0], runs["1"][0], rtol=1e-4, atol=1e-5)
