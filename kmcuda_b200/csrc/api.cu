@@ -97,8 +97,7 @@ struct Dev {
 
 // equal split of `amount` rows over the devices, chunk starts aligned to 512 bytes without
 // breaking rows (same rule as the reference's distribute(), private.h:240-273)
-static std::vector<std::pair<uint32_t, uint32_t>> split_rows(uint32_t amount, uint32_t row_bytes,
-                                                             size_t ndev) {
+std::vector<std::pair<uint32_t, uint32_t>> split_rows(uint32_t amount, uint32_t row_bytes, size_t ndev) {
   std::vector<std::pair<uint32_t, uint32_t>> res;
   if (ndev == 0) return res;
   if (ndev == 1) {

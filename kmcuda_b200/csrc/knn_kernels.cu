@@ -1,9 +1,10 @@
-// knn_kernels.cu -- cluster-pruned exact k-NN (reference knn.cu:19-347), row-major samples.
-//
-// The search keeps the reference's decision arithmetic: true distances by Kahan-compensated
-// round-down FMA sums (exact.cuh), cluster skip test `Cd[B][A] - d(q,A) - R[B] > kth`
-// (knn.cu:218-225), insertion on `dist <= kth` into a binary max-heap (knn.cu:133-175), output in
-// ascending distance order by popping (knn.cu:239-242).
+// knn_kernels.cu -- exact parts of the cluster-pruned k-NN (reference knn.cu:19-347), row-major samples: cluster radii,
+// centroid distance matrix, and the warp-per-query exact search that serves whatever the tensor-core candidate pass
+// (assign_tc.cu MODE 2) does not.  Decision arithmetic = the reference's: true distances by Kahan-compensated
+// round-down FMA sums (exact.cuh), cluster skip test `Cd[B][A] - d(q,A) - R[B] > kth` (knn.cu:218-225), candidates
+// enter on `dist <= kth`, neighbours come out in ascending distance order.
+#include <algorithm>
+
 #include "exact.cuh"
 #include "kernels.h"
 
@@ -75,98 +76,122 @@ cudaError_t launch_knn_centroid_distances(int metric, const float* C, uint32_t K
   return cudaGetLastError();
 }
 
-// binary max-heap in a strided scratch column: element s of query q lives at hp[(2s)*stride],
-// its index at hp[(2s+1)*stride]  (reference push_sample, knn.cu:133-175)
-__device__ __forceinline__ void heap_push(int k, float dist, uint32_t index, float* hp, size_t stride) {
+// ------------------------------------------------------------------------------------------------
+// Exact cluster-pruned search for the queries the tensor-core pass does not serve (angular metric, k > 15,
+// D % 4 != 0 or D > 512, tiny inputs, rows with non-finite data).  One WARP per query:
+//   * the query row sits in shared memory, the 32 lanes evaluate 32 candidates of a cluster at a time (every lane
+//     streams its own candidate row; the exact distance is the reference's Kahan / round-down-FMA sequence of
+//     exact.cuh, so the decisions are the reference's);
+//   * the k best so far are a SORTED list (distance ascending) in the query's scratch slice, maintained by the whole
+//     warp: position by ballot + popcount, shift by one, insert -- no per-thread heap, and the output is the list
+//     itself;
+//   * clusters are visited and skipped by the reference's rule `Cd[B][A] - d(q, A) - R[B] > kth` (knn.cu:218-225),
+//     candidates enter on `dist <= kth` (knn.cu:204,234); a candidate equal to the current k-th distance displaces
+//     it, as a heap replacement does.
+// ------------------------------------------------------------------------------------------------
+constexpr int kKnnWarps = 8;           // queries per CTA
+constexpr int kKnnMaxSmemD = 2048;     // features of the query row kept in shared memory (else read through L1)
+
+// insert (d, o) into the ascending list ld[0..k) / li[0..k) of this warp's query; returns the new k-th distance
+__device__ __forceinline__ float knn_list_insert(int k, int lane, float d, uint32_t o, float* ld, uint32_t* li) {
+  // position = number of entries strictly smaller than d (the new element goes in front of its equals)
   int pos = 0;
-  for (;;) {
-    float left = 0.f, right = 0.f;
-    bool left_le, right_le;
-    if (2 * pos + 1 < k) {
-      left = hp[(2 * (2 * pos + 1)) * stride];
-      left_le = dist >= left;
-    } else {
-      left_le = true;
-    }
-    if (2 * pos + 2 < k) {
-      right = hp[(2 * (2 * pos + 2)) * stride];
-      right_le = dist >= right;
-    } else {
-      right_le = true;
-    }
-    if (left_le && right_le) {
-      hp[(2 * pos) * stride] = dist;
-      hp[(2 * pos + 1) * stride] = __uint_as_float(index);
-      return;
-    }
-    bool go_right = (!left_le && !right_le) ? (left <= right) : left_le;
-    int child = go_right ? 2 * pos + 2 : 2 * pos + 1;
-    hp[(2 * pos) * stride] = hp[(2 * child) * stride];
-    hp[(2 * pos + 1) * stride] = hp[(2 * child + 1) * stride];
-    pos = child;
+  for (int j0 = 0; j0 < k; j0 += 32) {
+    const int j = j0 + lane;
+    const bool less = j < k && ld[j] < d;
+    pos += __popc(__ballot_sync(0xffffffffu, less));
   }
+  // shift [pos, k-2] one place up, highest chunk first so that no entry is overwritten before it is read
+  for (int j0 = ((k - 1) / 32) * 32; j0 >= 0; j0 -= 32) {
+    const int j = j0 + lane;
+    float vd = 0.f;
+    uint32_t vi = 0;
+    const bool mv = j >= pos && j < k - 1;
+    if (mv) { vd = ld[j]; vi = li[j]; }
+    __syncwarp();
+    if (mv) { ld[j + 1] = vd; li[j + 1] = vi; }
+    __syncwarp();
+  }
+  if (lane == 0) { ld[pos] = d; li[pos] = o; }
+  __syncwarp();
+  return ld[k - 1];
 }
 
 template <int METRIC>
-__global__ void __launch_bounds__(128)
-knn_search_kernel(int k, const float* __restrict__ X, const float* __restrict__ C, uint32_t N, int D,
-                  uint32_t K, uint32_t q_offset, uint32_t q_length, const uint32_t* __restrict__ assign,
-                  const uint32_t* __restrict__ inv, const uint32_t* __restrict__ inv_off,
-                  const float* __restrict__ cd, const float* __restrict__ radii,
-                  float* __restrict__ heap_scratch, uint32_t* __restrict__ neighbors,
-                  unsigned long long* __restrict__ d_pairs,
-                  // list mode (rows != nullptr): the queries are rows[0 .. *d_nrows), heap column = list slot
-                  const uint32_t* __restrict__ rows, const uint32_t* __restrict__ d_nrows) {
+__global__ void __launch_bounds__(kKnnWarps * 32)
+knn_warp_search_kernel(int k, const float* __restrict__ X, const float* __restrict__ C, uint32_t N, int D,
+                       uint32_t K, uint32_t q_offset, uint32_t q_length, const uint32_t* __restrict__ assign,
+                       const uint32_t* __restrict__ inv, const uint32_t* __restrict__ inv_off,
+                       const float* __restrict__ cd, const float* __restrict__ radii,
+                       float* __restrict__ scratch, uint32_t* __restrict__ neighbors,
+                       unsigned long long* __restrict__ d_pairs,
+                       // list mode (rows != nullptr): the queries are rows[0 .. *d_nrows), scratch slice = list slot
+                       const uint32_t* __restrict__ rows, const uint32_t* __restrict__ d_nrows, int smem_d) {
+  extern __shared__ float s_query[];   // [kKnnWarps][smem_d]
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const uint32_t count = rows ? min(*d_nrows, q_length) : q_length;
-  for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < count; q += gridDim.x * blockDim.x) {
-  const uint32_t s = rows ? rows[q] : q_offset + q;
-  const uint32_t oq = s - q_offset;          // output row
-  const float* xs = X + static_cast<size_t>(s) * D;
-  const size_t stride = q_length;
-  float* hp = heap_scratch + q;
-  for (int i = 0; i < k; i++) {
-    hp[(2 * i) * stride] = FLT_MAX;
-    hp[(2 * i + 1) * stride] = __uint_as_float(UINT32_MAX);
-  }
-  const uint32_t A = assign[s];
-  unsigned long long pairs = 0;
-  float kth = FLT_MAX;
-  float dA = 0.f;
-  if (A < K) {
-    dA = distance_exact<METRIC>(xs, C + static_cast<size_t>(A) * D, D);
-    uint32_t b = inv_off[A], e = inv_off[A + 1];
-    pairs += e - b;
-    for (uint32_t p = b; p < e; p++) {
-      uint32_t o = inv[p];
-      if (o == s) continue;
-      float d = distance_exact<METRIC>(xs, X + static_cast<size_t>(o) * D, D);
-      if (d <= kth) {
-        heap_push(k, d, o, hp, stride);
-        kth = hp[0];
+  const uint32_t nwarps = gridDim.x * kKnnWarps;
+  for (uint32_t q = blockIdx.x * kKnnWarps + wib; q < count; q += nwarps) {
+    const uint32_t s = rows ? rows[q] : q_offset + q;
+    const uint32_t oq = s - q_offset;          // output row
+    const float* xg = X + static_cast<size_t>(s) * D;
+    const float* xs = xg;
+    if (smem_d) {
+      float* mine = s_query + static_cast<size_t>(wib) * smem_d;
+      __syncwarp();
+      for (int f = lane; f < D; f += 32) mine[f] = xg[f];
+      __syncwarp();
+      xs = mine;
+    }
+    float* ld = scratch + static_cast<size_t>(q) * 2 * k;
+    uint32_t* li = reinterpret_cast<uint32_t*>(ld + k);
+    for (int j = lane; j < k; j += 32) { ld[j] = FLT_MAX; li[j] = UINT32_MAX; }
+    __syncwarp();
+    const uint32_t A = assign[s];
+    unsigned long long pairs = 0;
+    float kth = FLT_MAX;
+    float dA = 0.f;
+    if (A < K) dA = distance_exact<METRIC>(xs, C + static_cast<size_t>(A) * D, D);   // every lane: same value
+    // own cluster first, then the others in ascending order; B == K + 1 ends the walk
+    for (uint32_t step = 0; step <= K; step++) {
+      uint32_t B;
+      if (step == 0) {
+        if (A >= K) continue;
+        B = A;
+      } else {
+        B = step - 1;
+        if (B == A) continue;
+        const float cdist = A < K ? cd[static_cast<size_t>(B) * K + A] : 0.f;
+        if (cdist != cdist) continue;
+        if (A < K && cdist - dA - radii[B] > kth) continue;
+      }
+      const uint32_t b = inv_off[B], e = inv_off[B + 1];
+      pairs += e - b;
+      for (uint32_t p0 = b; p0 < e; p0 += 32) {
+        const uint32_t pp = p0 + lane;
+        uint32_t o = UINT32_MAX;
+        float d = FLT_MAX;
+        bool want = false;
+        if (pp < e) {
+          o = inv[pp];
+          if (o != s) {
+            d = distance_exact<METRIC>(xs, X + static_cast<size_t>(o) * D, D);
+            want = d <= kth;
+          }
+        }
+        unsigned m = __ballot_sync(0xffffffffu, want);
+        while (m) {                          // arrival order = position order, as in the reference's sequential scan
+          const int src = __ffs(m) - 1;
+          m &= m - 1;
+          const float dd = __shfl_sync(0xffffffffu, d, src);
+          const uint32_t oo = __shfl_sync(0xffffffffu, o, src);
+          if (dd <= kth) kth = knn_list_insert(k, lane, dd, oo, ld, li);
+        }
       }
     }
-  }
-  for (uint32_t B = 0; B < K; B++) {
-    if (B == A) continue;
-    float cdist = A < K ? cd[static_cast<size_t>(B) * K + A] : 0.f;
-    if (cdist != cdist) continue;
-    if (A < K && cdist - dA - radii[B] > kth) continue;
-    uint32_t b = inv_off[B], e = inv_off[B + 1];
-    pairs += e - b;
-    for (uint32_t p = b; p < e; p++) {
-      uint32_t o = inv[p];
-      float d = distance_exact<METRIC>(xs, X + static_cast<size_t>(o) * D, D);
-      if (d <= kth) {
-        heap_push(k, d, o, hp, stride);
-        kth = hp[0];
-      }
-    }
-  }
-  for (int i = k - 1; i >= 0; i--) {
-    neighbors[static_cast<size_t>(oq) * k + i] = __float_as_uint(hp[stride]);
-    heap_push(k, -1.f, UINT32_MAX, hp, stride);
-  }
-  atomicAdd(d_pairs, pairs);
+    __syncwarp();
+    for (int j = lane; j < k; j += 32) neighbors[static_cast<size_t>(oq) * k + j] = li[j];
+    if (lane == 0) atomicAdd(d_pairs, pairs);
   }
 }
 
@@ -177,13 +202,23 @@ cudaError_t launch_knn_search(int metric, int k, const float* X, const float* C,
                               unsigned long long* d_pairs, const uint32_t* rows, const uint32_t* d_nrows,
                               cudaStream_t st) {
   if (q_length == 0) return cudaSuccess;
-  const unsigned grid = rows ? 148u * 8u : cdivk(q_length, 128);
-  if (metric == 1)
-    knn_search_kernel<1><<<grid, 128, 0, st>>>(k, X, C, N, D, K, q_offset, q_length, assign, inv, inv_off, cd, radii,
-                                               heap_scratch, neighbors, d_pairs, rows, d_nrows);
-  else
-    knn_search_kernel<0><<<grid, 128, 0, st>>>(k, X, C, N, D, K, q_offset, q_length, assign, inv, inv_off, cd, radii,
-                                               heap_scratch, neighbors, d_pairs, rows, d_nrows);
+  const int smem_d = D <= kKnnMaxSmemD ? D : 0;
+  const size_t smem = static_cast<size_t>(kKnnWarps) * smem_d * sizeof(float);
+  const unsigned grid = rows ? 148u * 8u : static_cast<unsigned>(std::min<size_t>(cdivk(q_length, kKnnWarps), 148u * 64u));
+  cudaError_t e;
+  if (metric == 1) {
+    if ((e = cudaFuncSetAttribute(knn_warp_search_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(smem))) != cudaSuccess) return e;
+    knn_warp_search_kernel<1><<<grid, kKnnWarps * 32, smem, st>>>(k, X, C, N, D, K, q_offset, q_length, assign, inv, inv_off,
+                                                                  cd, radii, heap_scratch, neighbors, d_pairs, rows, d_nrows,
+                                                                  smem_d);
+  } else {
+    if ((e = cudaFuncSetAttribute(knn_warp_search_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(smem))) != cudaSuccess) return e;
+    knn_warp_search_kernel<0><<<grid, kKnnWarps * 32, smem, st>>>(k, X, C, N, D, K, q_offset, q_length, assign, inv, inv_off,
+                                                                  cd, radii, heap_scratch, neighbors, d_pairs, rows, d_nrows,
+                                                                  smem_d);
+  }
   return cudaGetLastError();
 }
 

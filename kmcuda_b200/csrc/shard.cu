@@ -287,6 +287,18 @@ int32_t kmcuda_b200_debug_stats(kmcuda_b200_shard* shard, float* out4) {
   return 0;
 }
 
+// the static (offset, length) split of `amount` rows over `ndev` devices that kmeans_cuda / knn_cuda use
+// (api.cu::split_rows = the rule of the reference's distribute(), private.h:240-273); out: 2 * ndev values
+int32_t kmcuda_b200_debug_split_rows(uint32_t amount, uint32_t row_bytes, uint32_t ndev, uint32_t* out) {
+  if (!out || ndev == 0) return -1;
+  auto plan = kmb::split_rows(amount, row_bytes, ndev);
+  for (uint32_t i = 0; i < ndev; i++) {
+    out[2 * i] = plan[i].first;
+    out[2 * i + 1] = plan[i].second;
+  }
+  return 0;
+}
+
 KMCUDAResult kmcuda_b200_device_malloc(int32_t device, uint64_t bytes, void** ptr) {
   if (!ptr) return kmcudaInvalidArguments;
   if (cudaSetDevice(device) != cudaSuccess) return kmcudaNoSuchDevice;

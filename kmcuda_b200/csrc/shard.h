@@ -10,6 +10,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <utility>
 #include <vector>
 
 #include "kernels.h"
@@ -86,6 +87,9 @@ class DevBuf {
   T* p_ = nullptr;
   bool owned_ = false;
 };
+
+// equal split of `amount` rows over the devices, chunk starts aligned to 512 bytes (api.cu)
+std::vector<std::pair<uint32_t, uint32_t>> split_rows(uint32_t amount, uint32_t row_bytes, size_t ndev);
 
 class Shard {
  public:
