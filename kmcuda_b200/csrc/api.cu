@@ -667,6 +667,12 @@ KMCUDAResult Job::assign_pass(uint32_t* changed) {
 
 // centroid update: shard partial sums -> exchange (peer-memory reduce, or NCCL all-reduce) -> normalise on every GPU
 KMCUDAResult Job::update() {
+  if (devs.size() == 1 && devs[0].shard->strict_update) {
+    // strict parity mode: the reference's running sums in sample order (bit-identical centroids, one GPU)
+    Dev& d = devs[0];
+    KMB_CU(cudaSetDevice(d.dev), kmcudaRuntimeError);
+    return d.shard->update_reference_order(d.len, d.X, d.assign, d.prev, d.C, d.ccounts, d.st);
+  }
   if (devs.size() > 1 && peer_exchange) {
     // nobody may overwrite its partial sums while a peer of the previous iteration is still reading them
     for (auto& d : devs) {

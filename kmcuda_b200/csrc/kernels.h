@@ -39,6 +39,12 @@ size_t update_cub_bytes(uint32_t n);
 // sums[K][D] (fp32) and counts[K] (uint32) of this shard's samples
 cudaError_t launch_partial_sums(const float* X, uint32_t n, int D, uint32_t K, const uint32_t* assign,
                                 UpdateWorkspace& ws, float* sums, uint32_t* counts, cudaStream_t st);
+// strict parity mode: the reference's running-sum update replayed in sample order (simt_kernels.cu)
+size_t strict_update_cub_bytes(uint32_t n);
+cudaError_t launch_strict_update(int metric, const float* X, uint32_t n, int D, uint32_t K, const uint32_t* prev,
+                                 const uint32_t* cur, float* C, uint32_t* ccounts, uint32_t* keys_in,
+                                 uint32_t* vals_in, uint32_t* keys_out, uint32_t* vals_out, uint32_t* offsets,
+                                 void* cub_tmp, size_t cub_bytes, cudaStream_t st);
 // multi-GPU exchange through peer memory: out_sums = sums[0] + sums[1] + ... (device order, so every GPU computes
 // the same bits), out_counts likewise; the pointers may live on other GPUs (peer access enabled by the caller)
 constexpr int kMaxPeers = 32;

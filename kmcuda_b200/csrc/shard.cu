@@ -17,6 +17,8 @@ KMCUDAResult Shard::create(bool with_update) {
   KMB_CU(cudaSetDevice(device), kmcudaNoSuchDevice);
   const char* fe = getenv("KMCUDA_B200_FORCE_EXACT");
   force_exact = fe && fe[0] == '1';
+  const char* su = getenv("KMCUDA_B200_STRICT_UPDATE");
+  strict_update = su && su[0] == '1';
   KMB_CU(csq.alloc(K), kmcudaMemoryAllocationFailure);
   KMB_CU(result.alloc(max_n), kmcudaMemoryAllocationFailure);
   if (with_update) {
@@ -129,6 +131,24 @@ KMCUDAResult Shard::assign(uint32_t n, const float* X, const float* C, uint32_t*
            kmcudaRuntimeError);
     KMB_CU(launch_finalize_assign(n, result, assignments, prev, d_changed, st), kmcudaRuntimeError);
   }
+  return kmcudaSuccess;
+}
+
+KMCUDAResult Shard::update_reference_order(uint32_t n, const float* X, const uint32_t* assignments,
+                                           const uint32_t* prev, float* C, uint32_t* ccounts, cudaStream_t st) {
+  if (n > max_n) return kmcudaInvalidArguments;
+  if (!su_keys_in.get()) {   // first use: event buffers (2 entries per sample)
+    const size_t m = 2 * static_cast<size_t>(max_n);
+    KMB_CU(su_keys_in.alloc(m), kmcudaMemoryAllocationFailure);
+    KMB_CU(su_vals_in.alloc(m), kmcudaMemoryAllocationFailure);
+    KMB_CU(su_keys_out.alloc(m), kmcudaMemoryAllocationFailure);
+    KMB_CU(su_vals_out.alloc(m), kmcudaMemoryAllocationFailure);
+    KMB_CU(su_offsets.alloc(static_cast<size_t>(K) + 2), kmcudaMemoryAllocationFailure);
+    su_cub_bytes = strict_update_cub_bytes(max_n);
+    KMB_CU(su_cub.alloc(su_cub_bytes), kmcudaMemoryAllocationFailure);
+  }
+  KMB_CU(launch_strict_update(metric, X, n, D, K, prev, assignments, C, ccounts, su_keys_in, su_vals_in, su_keys_out,
+                              su_vals_out, su_offsets, su_cub.get(), su_cub_bytes, st), kmcudaRuntimeError);
   return kmcudaSuccess;
 }
 

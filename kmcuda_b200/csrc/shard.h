@@ -114,6 +114,9 @@ class Shard {
                             uint32_t* counts, cudaStream_t st);
   KMCUDAResult finish_update(const float* sums, const uint32_t* counts, float* C, uint32_t* ccounts,
                              cudaStream_t st);
+  // strict parity mode (KMCUDA_B200_STRICT_UPDATE=1): the reference's running-sum update in sample order, in place
+  KMCUDAResult update_reference_order(uint32_t n, const float* X, const uint32_t* assignments, const uint32_t* prev,
+                                      float* C, uint32_t* ccounts, cudaStream_t st);
   // after the stream has been synchronised: kmcudaRuntimeError if the tensor-core pipeline of the last pass
   // reported a timed-out barrier (its results are not valid), kmcudaSuccess otherwise
   KMCUDAResult check_pipeline();
@@ -127,6 +130,10 @@ class Shard {
   bool last_tc = false;
   uint32_t last_rechecked = 0, last_overflowed = 0;
   bool force_exact = false;  // KMCUDA_B200_FORCE_EXACT=1 (debug / parity tests)
+  bool strict_update = false;  // KMCUDA_B200_STRICT_UPDATE=1
+  DevBuf<uint32_t> su_keys_in, su_vals_in, su_keys_out, su_vals_out, su_offsets;
+  DevBuf<char> su_cub;
+  size_t su_cub_bytes = 0;
 
   // scratch
   DevBuf<float> csq;

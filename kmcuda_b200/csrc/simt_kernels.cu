@@ -463,6 +463,107 @@ __global__ void normalize_kernel(const float* __restrict__ sums, const uint32_t*
   ccounts[c] = cnt;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Reference-ORDER centroid update (strict parity mode, KMCUDA_B200_STRICT_UPDATE=1; single GPU).
+// The reference's kmeans_adjust (kmeans.cu:366-429) is a running sum: centroid * old count, then every sample that
+// joined / left the cluster is added / subtracted in SAMPLE ORDER, feature by feature, with ONE compensation term
+// that is carried across features and samples, then the normalisation.  Its result depends on that order in the
+// last ulps, which is what makes whole runs of two implementations drift apart on structureless data.  This path
+// reproduces the order: the (cluster, sample, sign) events of the pass are sorted by cluster (stable: sample order
+// survives) and one thread per centroid replays its events.  The default update (sorted compensated sums, parallel
+// over clusters, features and splits) is ~1e-7 relative away from it and much faster; this one is for bit-identical
+// trajectories (tests, bisecting) and costs O(changed samples per cluster x D) sequential steps per thread.
+// ------------------------------------------------------------------------------------------------
+__global__ void strict_events_kernel(uint32_t n, uint32_t K, const uint32_t* __restrict__ prev,
+                                     const uint32_t* __restrict__ cur, uint32_t* __restrict__ keys,
+                                     uint32_t* __restrict__ vals) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t p = prev[i], c = cur[i];
+  const bool moved = p != c;
+  keys[2 * i] = (moved && p < K) ? p : K;           // key K = "no event" (sorted to the end, never replayed)
+  vals[2 * i] = 2 * i;                              // bit 0: 0 = left the cluster, 1 = joined it
+  keys[2 * i + 1] = (moved && c < K) ? c : K;
+  vals[2 * i + 1] = 2 * i + 1;
+}
+
+template <int METRIC>
+__global__ void __launch_bounds__(32)
+strict_adjust_kernel(const float* __restrict__ X, int D, uint32_t K, const uint32_t* __restrict__ offsets,
+                     const uint32_t* __restrict__ events, float* __restrict__ C, uint32_t* __restrict__ ccounts) {
+  extern __shared__ float srow[];                    // [D][32]: feature-major, one column per thread (no bank conflicts)
+  const uint32_t c = blockIdx.x * 32 + threadIdx.x;
+  if (c >= K) return;
+  float* row = C + static_cast<size_t>(c) * D;
+  float* mine = srow + threadIdx.x;
+  uint32_t cnt = ccounts[c];
+  const float fc = static_cast<float>(cnt);
+  for (int f = 0; f < D; f++) mine[f * 32] = row[f] * fc;
+  float corr = 0.f;
+  const uint32_t beg = offsets[c], end = offsets[c + 1];
+  for (uint32_t e = beg; e < end; e++) {
+    const uint32_t v = events[e];
+    const float fs = (v & 1u) ? 1.f : -1.f;
+    cnt += (v & 1u) ? 1u : 0xFFFFFFFFu;
+    const float* xs = X + static_cast<size_t>(v >> 1) * D;
+    for (int f = 0; f < D; f++) {
+      const float cv = mine[f * 32];
+      const float y = __fmaf_rd(xs[f], fs, corr);
+      const float t = cv + y;
+      corr = y - (t - cv);
+      mine[f * 32] = t;
+    }
+  }
+  if (METRIC == 1) {
+    Kahan k;
+    for (int f = 0; f < D; f++) {
+      const float v = mine[f * 32];
+      k.mac(v, v);
+    }
+    const float scale = __frcp_rn(__fsqrt_rn(k.sum));
+    for (int f = 0; f < D; f++) row[f] = mine[f * 32] * scale;
+  } else {
+    const float scale = __frcp_rn(static_cast<float>(cnt));   // count 0 -> inf -> NaN centroid (kmeans.cu:425-427)
+    for (int f = 0; f < D; f++) row[f] = mine[f * 32] * scale;
+  }
+  ccounts[c] = cnt;
+}
+
+size_t strict_update_cub_bytes(uint32_t n) {
+  size_t bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr,
+                                  (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)(2 * static_cast<size_t>(n)), 0, 32);
+  return bytes;
+}
+
+// keys_in / vals_in / keys_out / vals_out: [2n] each, offsets [K + 2], cub_tmp from strict_update_cub_bytes(n)
+cudaError_t launch_strict_update(int metric, const float* X, uint32_t n, int D, uint32_t K, const uint32_t* prev,
+                                 const uint32_t* cur, float* C, uint32_t* ccounts, uint32_t* keys_in,
+                                 uint32_t* vals_in, uint32_t* keys_out, uint32_t* vals_out, uint32_t* offsets,
+                                 void* cub_tmp, size_t cub_bytes, cudaStream_t st) {
+  if (n == 0) return cudaSuccess;
+  if (static_cast<size_t>(D) * 32 * sizeof(float) > 200 * 1024) return cudaErrorInvalidValue;
+  strict_events_kernel<<<cdiv(n, 256), 256, 0, st>>>(n, K, prev, cur, keys_in, vals_in);
+  int bits = 1;
+  while ((1ull << bits) <= K) bits++;  // keys are in [0, K]
+  cudaError_t e = cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, keys_in, keys_out, vals_in, vals_out,
+                                                  (int)(2 * static_cast<size_t>(n)), 0, bits, st);
+  if (e != cudaSuccess) return e;
+  // offsets[c] = first event of cluster c (binary search in the sorted keys); counts are not needed
+  segment_offsets_kernel<<<cdiv(K + 1, 128), 128, 0, st>>>(keys_out, 2 * n, K, offsets, keys_in /* scratch */);
+  const size_t smem = static_cast<size_t>(D) * 32 * sizeof(float);
+  if (metric == 1) {
+    if ((e = cudaFuncSetAttribute(strict_adjust_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(smem))) != cudaSuccess) return e;
+    strict_adjust_kernel<1><<<cdiv(K, 32), 32, smem, st>>>(X, D, K, offsets, vals_out, C, ccounts);
+  } else {
+    if ((e = cudaFuncSetAttribute(strict_adjust_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(smem))) != cudaSuccess) return e;
+    strict_adjust_kernel<0><<<cdiv(K, 32), 32, smem, st>>>(X, D, K, offsets, vals_out, C, ccounts);
+  }
+  return cudaGetLastError();
+}
+
 // all-reduce of the update's partial sums over peer memory: every GPU gathers and adds all shards' sums itself (K*D*4
 // bytes per peer over NVLink; 16-byte loads, each peer's buffer read exactly once, coalesced)
 __global__ void __launch_bounds__(256)
