@@ -1746,9 +1746,10 @@ yy_own_group_kernel(const float* __restrict__ X, const float* __restrict__ C, ui
 
 // Builds the group-sorted table layout from the centroid -> group map of this run (host vector, G groups; ids >= G
 // mark dead centroids, which get no table row).  Call again whenever the grouping changes.
-cudaError_t tc_yy_layout(TcPlan* p, const uint32_t* host_groups, uint32_t G) {
+void tc_yy_layout_host(const uint32_t* host_groups, uint32_t K, uint32_t G, std::vector<uint32_t>* perm_out,
+                       std::vector<uint32_t>* qgroup_out, std::vector<uint32_t>* goff_out,
+                       std::vector<uint32_t>* gmem_out, int* nt3_out) {
   using namespace tc;
-  const uint32_t K = p->K;
   std::vector<uint32_t> gsz(G, 0);
   for (uint32_t c = 0; c < K; c++)
     if (host_groups[c] < G) gsz[host_groups[c]]++;
@@ -1769,6 +1770,19 @@ cudaError_t tc_yy_layout(TcPlan* p, const uint32_t* host_groups, uint32_t G) {
     for (size_t qd = r / 4; qd < (r + padded) / 4; qd++) qgroup[qd] = g;
     r += padded;
   }
+  *perm_out = std::move(perm);
+  *qgroup_out = std::move(qgroup);
+  *goff_out = std::move(goff);
+  *gmem_out = std::move(gmem);
+  *nt3_out = nt3;
+}
+
+cudaError_t tc_yy_layout(TcPlan* p, const uint32_t* host_groups, uint32_t G) {
+  using namespace tc;
+  std::vector<uint32_t> perm, qgroup, goff, gmem;
+  int nt3 = 0;
+  tc_yy_layout_host(host_groups, p->K, G, &perm, &qgroup, &goff, &gmem, &nt3);
+  const size_t rows_pad = static_cast<size_t>(nt3) * TN;
   cudaError_t e;
   if (nt3 != p->nt3 || !p->table3) {
     cudaFree(p->table3); cudaFree(p->aug_blob3); cudaFree(p->yy_perm); cudaFree(p->yy_qgroup);

@@ -8,6 +8,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <vector>
 
 namespace kmb {
 
@@ -149,6 +150,11 @@ void tc_queues(TcPlan* plan, TcQueues* q);
 // Yinyang bounds refresh on the tensor cores (assign_tc.cu, MODE 3): tc_yy_layout once per grouping (host map
 // centroid -> group), then tc_yy_refresh per refresh; rows left on the overflow list need launch_yy_init_rows
 cudaError_t tc_yy_layout(TcPlan* plan, const uint32_t* host_groups, uint32_t G);
+// the host part of tc_yy_layout (pure function): table row -> centroid (UINT32_MAX = padding), group of every
+// 4-row quad, CSR of the group members, number of 128-row n-tiles
+void tc_yy_layout_host(const uint32_t* host_groups, uint32_t K, uint32_t G, std::vector<uint32_t>* perm,
+                       std::vector<uint32_t>* qgroup, std::vector<uint32_t>* goff, std::vector<uint32_t>* gmem,
+                       int* nt3);
 bool tc_yy_layout_ready(TcPlan* plan, uint32_t G);
 cudaError_t tc_yy_refresh(TcPlan* plan, const float* X, const float* C, const float* csq, uint32_t n,
                           const uint32_t* assign, const uint32_t* groups, uint32_t G, float* bounds, cudaStream_t st);

@@ -307,6 +307,20 @@ int32_t kmcuda_b200_debug_stats(kmcuda_b200_shard* shard, float* out4) {
   return 0;
 }
 
+// host layout of the Yinyang refresh table (assign_tc.cu::tc_yy_layout_host) for tests: perm_out [cap], qgroup_out
+// [cap / 4]; returns the number of 128-row n-tiles, or -1 if cap is too small
+int32_t kmcuda_b200_debug_yy_layout(uint32_t K, uint32_t G, const uint32_t* host_groups, uint32_t cap,
+                                    uint32_t* perm_out, uint32_t* qgroup_out) {
+  if (!host_groups || !perm_out || !qgroup_out) return -1;
+  std::vector<uint32_t> perm, qgroup, goff, gmem;
+  int nt3 = 0;
+  kmb::tc_yy_layout_host(host_groups, K, G, &perm, &qgroup, &goff, &gmem, &nt3);
+  if (perm.size() > cap) return -1;
+  for (size_t i = 0; i < perm.size(); i++) perm_out[i] = perm[i];
+  for (size_t i = 0; i < qgroup.size(); i++) qgroup_out[i] = qgroup[i];
+  return nt3;
+}
+
 // the static (offset, length) split of `amount` rows over `ndev` devices that kmeans_cuda / knn_cuda use
 // (api.cu::split_rows = the rule of the reference's distribute(), private.h:240-273); out: 2 * ndev values
 int32_t kmcuda_b200_debug_split_rows(uint32_t amount, uint32_t row_bytes, uint32_t ndev, uint32_t* out) {

