@@ -20,6 +20,8 @@
 #include <map>
 #include <random>
 #include <string>
+#include <thread>
+#include <atomic>
 #include <utility>
 #include <vector>
 
@@ -995,23 +997,43 @@ KMCUDAResult knn_cuda(uint16_t k, KMCUDADistanceMetric metric, uint32_t samples_
     DevBuf<char> cub;
     DevBuf<unsigned long long> pairs;
     cudaStream_t st = nullptr;
+    cudaEvent_t done = nullptr;
   };
   std::vector<std::unique_ptr<KDev>> kd;
   auto cleanup = [&]() {
     for (size_t i = 0; i < kd.size(); i++) {
       cudaSetDevice(dev_ids[i]);
+      if (kd[i]->done) cudaEventDestroy(kd[i]->done);
       if (kd[i]->st) cudaStreamDestroy(kd[i]->st);
     }
   };
-  // every device gets the whole sample matrix (candidates can live anywhere), its slice of queries
-  for (size_t i = 0; i < dev_ids.size(); i++) {
-    kd.emplace_back(new KDev);
-    KDev& d = *kd.back();
+  // Several GPUs on the tensor-core path: every GPU holds all samples (as in the reference, kmcuda.cc:157-158) and
+  // the cluster-aligned candidate table, and serves an equal share of the query TILES into its own full-size
+  // neighbour array; device 0 merges the arrays over peer memory (element-wise minimum against the 0xFFFFFFFF fill).
+  bool shard_tc = false;
+  {
+    const char* fx0 = getenv("KMCUDA_B200_FORCE_EXACT");
+    shard_tc = dev_ids.size() > 1 && !(fx0 && fx0[0] == '1') && tc_knn_supported(m, k, N, D, K);
+    for (size_t i = 0; i < dev_ids.size() && shard_tc; i++)
+      for (size_t j = 0; j < dev_ids.size() && shard_tc; j++) {
+        int access = 0;
+        if (i != j && (cudaDeviceCanAccessPeer(&access, dev_ids[i], dev_ids[j]) != cudaSuccess || !access)) shard_tc = false;
+      }
+  }
+  bool shard_tc_ok = shard_tc;
+  // every device gets the whole sample matrix (candidates can live anywhere), its slice of queries.  With several
+  // devices on the tensor-core path the per-device pipelines (which synchronise their own stream a few times) run
+  // on one host thread each, so the GPUs work concurrently.
+  for (size_t i = 0; i < dev_ids.size(); i++) kd.emplace_back(new KDev);
+  std::atomic<bool> any_tc_miss{false};
+  auto per_device = [&](size_t i) -> KMCUDAResult {
+    KDev& d = *kd[i];
     const int dev = dev_ids[i];
-    const uint32_t qlen = plan[i].second;
-#define KNN_CU(call, code) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { KMB_INFO("%s:%d -> %s\n", __FILE__, __LINE__, cudaGetErrorString(e__)); cleanup(); return code; } } while (false)
+    const uint32_t qlen = shard_tc ? N : plan[i].second;   // rows of this device's neighbour array
+#define KNN_CU(call, code) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { KMB_INFO("%s:%d -> %s\n", __FILE__, __LINE__, cudaGetErrorString(e__)); return code; } } while (false)
     KNN_CU(cudaSetDevice(dev), kmcudaNoSuchDevice);
     KNN_CU(cudaStreamCreateWithFlags(&d.st, cudaStreamNonBlocking), kmcudaRuntimeError);
+    KNN_CU(cudaEventCreateWithFlags(&d.done, cudaEventDisableTiming), kmcudaRuntimeError);
     const size_t xcount = static_cast<size_t>(N) * D, ccount = static_cast<size_t>(K) * D;
     auto load = [&](DevBuf<float>& dst, const float* src, size_t count) -> cudaError_t {
       cudaError_t e;
@@ -1054,6 +1076,7 @@ KMCUDAResult knn_cuda(uint16_t k, KMCUDADistanceMetric metric, uint32_t samples_
     KNN_CU(d.neigh.alloc(static_cast<size_t>(qlen) * k), kmcudaMemoryAllocationFailure);
     KNN_CU(d.pairs.alloc(1), kmcudaMemoryAllocationFailure);
     KNN_CU(cudaMemsetAsync(d.pairs.get(), 0, sizeof(unsigned long long), d.st), kmcudaRuntimeError);
+    if (shard_tc) KNN_CU(cudaMemsetAsync(d.neigh.get(), 0xff, sizeof(uint32_t) * static_cast<size_t>(qlen) * k, d.st), kmcudaRuntimeError);
     // inverse assignments (reference: host std::sort of (assignment, index) tuples, kmcuda.cc:648-691):
     // stable device radix sort + binary-searched CSR offsets
     if (i == 0) KMB_INFO("initializing the inverse assignments...\n");
@@ -1061,15 +1084,15 @@ KMCUDAResult knn_cuda(uint16_t k, KMCUDADistanceMetric metric, uint32_t samples_
     ws.cub_tmp_bytes = update_cub_bytes(N);
     KNN_CU(d.cub.alloc(ws.cub_tmp_bytes), kmcudaMemoryAllocationFailure);
     ws.cub_tmp = d.cub.get();
-    g_prof.mark("knn: alloc + ingest");
+    if (dev_ids.size() == 1) g_prof.mark("knn: alloc + ingest");
     KNN_CU(launch_knn_inverse(d.assign, N, K, d.iota, d.inv_keys, d.inv, d.off, d.counts, ws, d.st), kmcudaRuntimeError);
     KNN_CU(launch_knn_radii(m, d.X, d.C, N, D, K, d.assign, d.radii, d.st), kmcudaRuntimeError);
     KNN_CU(launch_knn_centroid_distances(m, d.C, K, D, d.cd, d.st), kmcudaRuntimeError);
     KNN_CU(launch_knn_radii_fix(d.off, K, d.radii, d.st), kmcudaRuntimeError);
-    g_prof.mark("knn: inverse, radii, centroid distances");
+    if (dev_ids.size() == 1) g_prof.mark("knn: inverse, radii, centroid distances");
     bool searched = false;
     const char* fx = getenv("KMCUDA_B200_FORCE_EXACT");
-    if (dev_ids.size() == 1 && !(fx && fx[0] == '1') && tc_knn_supported(m, k, N, D, K)) {
+    if ((dev_ids.size() == 1 || shard_tc) && !(fx && fx[0] == '1') && tc_knn_supported(m, k, N, D, K)) {
       // tensor-core candidate search; the rows it cannot serve go through the reference-order search below
       uint32_t nv = 0, tc_err = 0;
       KNN_CU(cudaMemcpyAsync(&nv, d.off.get() + K, sizeof(nv), cudaMemcpyDeviceToHost, d.st), kmcudaMemoryCopyError);
@@ -1081,31 +1104,86 @@ KMCUDAResult knn_cuda(uint16_t k, KMCUDADistanceMetric metric, uint32_t samples_
       cudaError_t te = cudaSuccess;
       if (nv >= 4096)
         te = tc_knn_search(k, d.X, d.C, N, D, K, d.assign, d.inv, d.off, d.cd, d.radii, nv, d.neigh, fb_rows, d_nfb,
-                           d.pairs, &tc_err, d.st);
-      g_prof.mark("knn: tensor-core candidate search");
+                           d.pairs, &tc_err, shard_tc ? static_cast<uint32_t>(i) : 0u,
+                           shard_tc ? static_cast<uint32_t>(dev_ids.size()) : 1u, d.st);
+      if (dev_ids.size() == 1) g_prof.mark("knn: tensor-core candidate search");
       if (nv >= 4096 && te == cudaSuccess && tc_err == 0) {
-        KNN_CU(launch_knn_tail_rows(d.inv, nv, N, fb_rows, d_nfb, d.st), kmcudaRuntimeError);
+        if (i == 0) KNN_CU(launch_knn_tail_rows(d.inv, nv, N, fb_rows, d_nfb, d.st), kmcudaRuntimeError);
         KNN_CU(launch_knn_search(m, k, d.X, d.C, N, D, K, 0, qlen, d.assign, d.inv, d.off, d.cd, d.radii, d.heap,
                                  d.neigh, d.pairs, fb_rows, d_nfb, d.st), kmcudaRuntimeError);
         KNN_CU(cudaStreamSynchronize(d.st), kmcudaRuntimeError);   // fb_rows goes out of scope
         searched = true;
       } else if (te != cudaSuccess || tc_err) {
+        if (shard_tc) {   // the shards cannot be mixed with the exact route: report instead of degrading silently
+          KMB_INFO("tensor-core k-NN pass failed on device %d (%s, 0x%x)\n", dev, cudaGetErrorString(te), tc_err);
+          return kmcudaRuntimeError;
+        }
         KMB_INFO("tensor-core k-NN pass failed (%s, 0x%x): exact search for every query\n", cudaGetErrorString(te), tc_err);
         if (te == cudaErrorMemoryAllocation) cudaGetLastError();
-        else if (te != cudaSuccess) { cleanup(); return kmcudaRuntimeError; }
+        else if (te != cudaSuccess) { return kmcudaRuntimeError; }
         KNN_CU(cudaMemsetAsync(d.pairs.get(), 0, sizeof(unsigned long long), d.st), kmcudaRuntimeError);
       }
     }
-    if (!searched)
-      KNN_CU(launch_knn_search(m, k, d.X, d.C, N, D, K, plan[i].first, qlen, d.assign, d.inv, d.off, d.cd,
-                               d.radii, d.heap, d.neigh, d.pairs, nullptr, nullptr, d.st), kmcudaRuntimeError);
+    if (!searched) {
+      if (shard_tc) {   // nv < 4096: too few valid samples for the tensor-core pass -- device 0 searches everything exactly
+        any_tc_miss = true;
+        if (i == 0)
+          KNN_CU(launch_knn_search(m, k, d.X, d.C, N, D, K, 0, N, d.assign, d.inv, d.off, d.cd, d.radii, d.heap, d.neigh,
+                                   d.pairs, nullptr, nullptr, d.st), kmcudaRuntimeError);
+      } else {
+        KNN_CU(launch_knn_search(m, k, d.X, d.C, N, D, K, plan[i].first, qlen, d.assign, d.inv, d.off, d.cd,
+                                 d.radii, d.heap, d.neigh, d.pairs, nullptr, nullptr, d.st), kmcudaRuntimeError);
+      }
+    }
+    KNN_CU(cudaEventRecord(d.done, d.st), kmcudaRuntimeError);
+    return kmcudaSuccess;
+  };
+#undef KNN_CU
+#define KNN_CU(call, code) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { KMB_INFO("%s:%d -> %s\n", __FILE__, __LINE__, cudaGetErrorString(e__)); cleanup(); return code; } } while (false)
+  {
+    std::vector<KMCUDAResult> res(dev_ids.size(), kmcudaSuccess);
+    if (shard_tc) {
+      std::vector<std::thread> workers;
+      for (size_t i = 0; i < dev_ids.size(); i++) workers.emplace_back([&, i]() { res[i] = per_device(i); });
+      for (auto& w : workers) w.join();
+    } else {
+      for (size_t i = 0; i < dev_ids.size(); i++) {
+        res[i] = per_device(i);
+        if (res[i] != kmcudaSuccess) break;
+      }
+    }
+    for (KMCUDAResult r : res)
+      if (r != kmcudaSuccess) { cleanup(); return r; }
+    if (any_tc_miss) shard_tc_ok = false;
+  }
+  if (shard_tc) {
+    // merge on device 0 (in place): min over the devices' arrays; then one copy-out of all N rows
+    KDev& d0 = *kd[0];
+    KNN_CU(cudaSetDevice(dev_ids[0]), kmcudaRuntimeError);
+    if (shard_tc_ok) {
+      PeerU32 pb;
+      pb.n = static_cast<int>(dev_ids.size());
+      for (size_t i = 0; i < dev_ids.size(); i++) {
+        pb.p[i] = kd[i]->neigh.get();
+        if (i) KNN_CU(cudaStreamWaitEvent(d0.st, kd[i]->done, 0), kmcudaRuntimeError);
+      }
+      KNN_CU(launch_peer_min_u32(pb, static_cast<size_t>(N) * k, d0.neigh.get(), d0.st), kmcudaRuntimeError);
+    }
+    if (device_ptrs < 0)
+      KNN_CU(cudaMemcpyAsync(neighbors, d0.neigh.get(), sizeof(uint32_t) * static_cast<size_t>(N) * k,
+                             cudaMemcpyDeviceToHost, d0.st), kmcudaMemoryCopyError);
+    else
+      KNN_CU(cudaMemcpyPeerAsync(neighbors, device_ptrs, d0.neigh.get(), dev_ids[0],
+                                 sizeof(uint32_t) * static_cast<size_t>(N) * k, d0.st), kmcudaMemoryCopyError);
   }
   for (size_t i = 0; i < dev_ids.size(); i++) {
     KDev& d = *kd[i];
     const int dev = dev_ids[i];
     const uint32_t qoff = plan[i].first, qlen = plan[i].second;
     KNN_CU(cudaSetDevice(dev), kmcudaRuntimeError);
-    if (device_ptrs < 0)
+    if (shard_tc) {
+      // (copy-out was issued on device 0 above)
+    } else if (device_ptrs < 0)
       KNN_CU(cudaMemcpyAsync(neighbors + static_cast<size_t>(qoff) * k, d.neigh.get(),
                              sizeof(uint32_t) * static_cast<size_t>(qlen) * k, cudaMemcpyDeviceToHost, d.st),
              kmcudaMemoryCopyError);

@@ -226,6 +226,7 @@ struct Params {
   uint32_t* knn_flags;           // [stride]
   float* knn_dub;                // [stride] upper bound of the exact distance to the kk-th nearest candidate seen so far
   uint4* knn_entries;            // [stride][KNN_CAP]: (group max bits (g-space), mask, chunk id, margin bits)
+  uint32_t knn_part, knn_nparts; // query-tile shard of this device (0, 1 = everything)
   float* dbg_scores;         // optional [ntiles*128][nt*128] dump of the approximate scores
 };
 
@@ -537,6 +538,14 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
   [[maybe_unused]] const int nt = p.nt;
   const uint32_t n_eff = MODE == 1 ? min(*p.d_nrows, p.n) : p.n;
   const uint32_t ntiles = MODE == 1 ? (n_eff + TM - 1) / TM : (MODE == 2 ? *p.d_ntiles : p.ntiles);
+  // MODE 2 on several GPUs: this device serves the query tiles of part knn_part of knn_nparts (every GPU holds the
+  // whole candidate table; tiles are independent)
+  uint32_t tile_lo = 0, tile_end = ntiles;
+  if (MODE == 2 && p.knn_nparts > 1) {
+    tile_lo = static_cast<uint32_t>(static_cast<uint64_t>(ntiles) * p.knn_part / p.knn_nparts);
+    tile_end = static_cast<uint32_t>(static_cast<uint64_t>(ntiles) * (p.knn_part + 1) / p.knn_nparts);
+  }
+  const uint32_t tile_begin = tile_lo + blockIdx.x;
 
   if (warp == WARP_B_PRODUCER && lane == 0) {
     ptx::prefetch_tmap(&tmap_b);
@@ -581,7 +590,7 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
     // ================================ TMA producer: centroid table + bias blocks ================================
     if (lane == 0) {
       uint32_t bs = 0, bph = 0, ac = 0;      // B ring stage / phase, bias blocks issued
-      for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      for (uint32_t tile = tile_begin; tile < tile_end; tile += gridDim.x) {
         for (BlockIter<MODE> it(p, tile); it.valid(); it.next()) {
           const int n = static_cast<int>(it.cur);
           // the bias block first: it is consumed last, and its buffer was released two n-tiles ago, so the copy is
@@ -609,7 +618,7 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
     // ================================ TMA producer: fp32 sample rows ================================
     if ((MODE == 0 || MODE == 3) && lane == 0) {
       uint32_t xc = 0;
-      for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      for (uint32_t tile = tile_begin; tile < tile_end; tile += gridDim.x) {
         for (int hs = 0; hs < 2 * nkb; hs++, xc++) {
           const int s = xc % X_STAGES;
           const uint32_t ph = (xc / X_STAGES) & 1;
@@ -629,7 +638,7 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
     const uint64_t aug_ad = ptx::make_smem_desc(ptx::smem_u32(smem + L.aug_a), TM * 16, 128, 0);
     const uint32_t augb = ptx::smem_u32(smem + L.aug_b);
     uint32_t bs = 0, bph = 0, ac = 0, si = 0;             // B ring stage / phase; n-tiles; segments (= A conversions) so far
-    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    for (uint32_t tile = tile_begin; tile < tile_end; tile += gridDim.x) {
       if (MODE == 2 && p.knn_nblk[tile] == 0) continue;   // nothing to visit: every role skips the tile
       for (BlockIter<MODE> it(p, tile); it.valid(); it.next(), ac++) {
         const bool first = it.seg_first();
@@ -677,7 +686,7 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
     const int row = q * 32 + lane;          // this thread's sample row within the tile
     const float s = p.stats->scale;
     uint32_t xc = 0, si = 0;
-    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    for (uint32_t tile = tile_begin; tile < tile_end; tile += gridDim.x) {
       if (MODE == 2 && p.knn_nblk[tile] == 0) continue;
       const float* xrow = nullptr;
       if (MODE == 1) {
@@ -797,7 +806,7 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
     // never rises above s^2 * 1 (the accumulator holds s^2 * dot)
     const float cap = p.metric == 1 ? p.stats->scale * p.stats->scale : INFINITY;
     uint32_t ac = 0, ti = 0, si = 0;
-    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    for (uint32_t tile = tile_begin; tile < tile_end; tile += gridDim.x) {
       if (MODE == 2 && p.knn_nblk[tile] == 0) continue;
       const int par = ti & 1;
       float* list_cm = reinterpret_cast<float*>(smem + L.list_cm) + par * LIST_LEN * 256;
@@ -1127,7 +1136,7 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
     const float cap = p.metric == 1 ? p.stats->scale * p.stats->scale : INFINITY;
     const uint32_t force = p.stats->force_exact ? 16u : 0u;
     uint32_t ti = 0, nchanged = 0;
-    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ti++) {
+    for (uint32_t tile = tile_begin; tile < tile_end; tile += gridDim.x, ti++) {
       const int par = ti & 1;
       const float* list_cm = reinterpret_cast<const float*>(smem + L.list_cm) + par * LIST_LEN * 256;
       const uint32_t* list_mask = reinterpret_cast<const uint32_t*>(smem + L.list_mask) + par * LIST_LEN * 256;
@@ -1608,6 +1617,8 @@ static cudaError_t tc_prepare(TcPlan* p, const float* C, const float* csq, uint3
   prm.knn_topk = prm.knn_dub = nullptr;
   prm.knn_cnt = prm.knn_flags = nullptr;
   prm.knn_entries = nullptr;
+  prm.knn_part = 0;
+  prm.knn_nparts = 1;
   prm.dbg_scores = p->dbg_scores;
   *out = prm;
   return cudaGetLastError();
@@ -1942,7 +1953,6 @@ __global__ void tile_fill_kernel(const uint32_t* __restrict__ off, uint32_t K, c
     rcount1[t] = 2;
     nblk1[t] = 2 * nt;
   }
-  if (m) atomicAdd(d_pairs, static_cast<unsigned long long>(m) * m);   // statistics: own-cluster pairs
   if (c == K - 1) *d_ntiles = t0 + nt;
 }
 
@@ -2049,11 +2059,14 @@ range_build_kernel(const uint32_t* __restrict__ d_ntiles, const uint32_t* __rest
                    const float* __restrict__ radii, const float* __restrict__ ysq, const float* __restrict__ dub,
                    uint2* __restrict__ pool, uint32_t pool_cap, uint32_t* __restrict__ pool_used,
                    uint32_t* __restrict__ roff2, uint32_t* __restrict__ rcount2, uint32_t* __restrict__ nblk2,
-                   uint32_t* __restrict__ d_error, unsigned long long* __restrict__ d_pairs) {
+                   uint32_t* __restrict__ d_error, unsigned long long* __restrict__ d_pairs, uint32_t part,
+                   uint32_t nparts) {
   const int lane = threadIdx.x & 31;
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
   const uint32_t T = *d_ntiles;
-  for (uint32_t t = warp; t < T; t += nwarps) {
+  const uint32_t t_lo = static_cast<uint32_t>(static_cast<uint64_t>(T) * part / nparts);
+  const uint32_t t_hi = static_cast<uint32_t>(static_cast<uint64_t>(T) * (part + 1) / nparts);
+  for (uint32_t t = t_lo + warp; t < t_hi; t += nwarps) {
     const uint32_t nr = tile_nrows[t], A = blk_cluster[t];
     // W = max over the tile's queries of d(q, A) + (upper bound of the distance to the k-th neighbour so far);
     // d(q, A) is bounded by the fp32 centred norm (the reference's Kahan value differs by rounding only)
@@ -2068,6 +2081,7 @@ range_build_kernel(const uint32_t* __restrict__ d_ntiles, const uint32_t* __rest
     for (int pass = 0; pass < 2; pass++) {   // pass 0 counts, pass 1 writes
       uint32_t count = 0, blocks = 0, base = 0;
       unsigned long long pairs = 0;
+      if (pass == 0 && lane == 0 && A < K) pairs = static_cast<unsigned long long>(nr) * (off[A + 1] - off[A]);   // own cluster
       if (pass == 1) {
         const uint32_t c0 = rcount2[t];
         if (lane == 0) base = atomicAdd(pool_used, c0);
@@ -2117,11 +2131,14 @@ expand_kernel(const uint32_t* __restrict__ d_ntiles, int kk, uint32_t stride, co
               const uint32_t* __restrict__ cnts, const uint32_t* __restrict__ flags,
               const uint4* __restrict__ entries, const uint32_t* __restrict__ tab2orig, uint32_t max_pairs,
               uint32_t* __restrict__ pair_row, uint32_t* __restrict__ pair_cand, uint32_t* __restrict__ rowq,
-              uint32_t* __restrict__ fb_rows, uint32_t* __restrict__ counters, uint32_t* __restrict__ dbg) {
+              uint32_t* __restrict__ fb_rows, uint32_t* __restrict__ counters, uint32_t* __restrict__ dbg,
+              uint32_t part, uint32_t nparts) {
   const int lane = threadIdx.x & 31;
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-  const uint32_t nrows = *d_ntiles * tc::TM;
-  for (uint32_t row = warp; row < nrows; row += nwarps) {
+  const uint32_t T = *d_ntiles;
+  const uint32_t row_lo = static_cast<uint32_t>(static_cast<uint64_t>(T) * part / nparts) * tc::TM;
+  const uint32_t nrows = static_cast<uint32_t>(static_cast<uint64_t>(T) * (part + 1) / nparts) * tc::TM;
+  for (uint32_t row = row_lo + warp; row < nrows; row += nwarps) {
     const uint32_t self = tab2orig[row];
     if (self == UINT32_MAX) continue;   // padding
     const uint32_t s0 = 2 * row, s1 = 2 * row + 1;
@@ -2260,7 +2277,8 @@ bool tc_knn_supported(int metric, int k, uint32_t N, int D, uint32_t K) {
 cudaError_t tc_knn_search(int k, const float* X, const float* C, uint32_t N, int D, uint32_t K,
                           const uint32_t* assign, const uint32_t* inv, const uint32_t* off, const float* cd,
                           const float* radii, uint32_t nv, uint32_t* neighbors, uint32_t* fb_rows, uint32_t* d_nfb,
-                          unsigned long long* d_pairs, uint32_t* h_error, cudaStream_t st) {
+                          unsigned long long* d_pairs, uint32_t* h_error, uint32_t part, uint32_t nparts,
+                          cudaStream_t st) {
   using namespace tc;
   cudaError_t e = cudaSuccess;
   *h_error = 0;
@@ -2368,17 +2386,19 @@ cudaError_t tc_knn_search(int k, const float* X, const float* C, uint32_t N, int
   prm.dbg_scores = nullptr;
   prm.neg_mu_s = nullptr; prm.assign = prm.prev = prm.d_changed = nullptr;
   prm.yy_qgroup = prm.yy_groups = prm.yy_assign = nullptr; prm.yy_bounds = nullptr; prm.G = 0;
+  prm.knn_part = part; prm.knn_nparts = nparts ? nparts : 1;
   tc_launch_main(2, nkb, grid, smem_bytes, st, tmap, tmap, prm);
   KNN_TRY(cudaGetLastError());
   knn::range_build_kernel<<<num_sms * 4, 256, 0, st>>>(d_ntiles, t_nrows, blk_cluster, blk_first, off, K, cd, radii, ysq,
                                                        dub, pool, pool_cap, pool_used, roff2, rcount2, nblk2, d_err,
-                                                       d_pairs);
+                                                       d_pairs, part, prm.knn_nparts);
   KNN_TRY(cudaGetLastError());
   prm.knn_ranges = pool; prm.knn_roff = roff2; prm.knn_rcount = rcount2; prm.knn_nblk = nblk2; prm.knn_first_pass = 0;
   tc_launch_main(2, nkb, grid, smem_bytes, st, tmap, tmap, prm);
   KNN_TRY(cudaGetLastError());
   knn::expand_kernel<<<num_sms * 8, 256, 0, st>>>(d_ntiles, kk, stride, topk, kcnt, kflags, entries, tab2orig, pair_cap,
-                                                  pair_row, pair_cand, rowq, fb_rows, counters, pool_used + 2);
+                                                  pair_row, pair_cand, rowq, fb_rows, counters, pool_used + 2, part,
+                                                  prm.knn_nparts);
   KNN_TRY(cudaGetLastError());
   recheck_pairs_kernel<0, 1><<<num_sms * 4, 128, 0, st>>>(X, X, nullptr, D, pair_row, pair_cand, counters + CNT_PAIRS,
                                                           pair_cap, N, N, pair_score);

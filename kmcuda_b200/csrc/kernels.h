@@ -163,7 +163,15 @@ bool tc_knn_supported(int metric, int k, uint32_t N, int D, uint32_t K);
 cudaError_t tc_knn_search(int k, const float* X, const float* C, uint32_t N, int D, uint32_t K,
                           const uint32_t* assign, const uint32_t* inv, const uint32_t* off, const float* cd,
                           const float* radii, uint32_t nv, uint32_t* neighbors, uint32_t* fb_rows, uint32_t* d_nfb,
-                          unsigned long long* d_pairs, uint32_t* h_error, cudaStream_t st);
+                          unsigned long long* d_pairs, uint32_t* h_error, uint32_t part, uint32_t nparts,
+                          cudaStream_t st);
+// several GPUs: every device serves part `part` of `nparts` of the query tiles into its own full-size neighbour
+// array (pre-filled with 0xFFFFFFFF); the arrays are merged with an element-wise minimum over peer memory
+struct PeerU32 {
+  int n;
+  const uint32_t* p[kMaxPeers];
+};
+cudaError_t launch_peer_min_u32(const PeerU32& pb, size_t count, uint32_t* out, cudaStream_t st);
 // 0 = clean; 0x1000+site = a pipeline wait timed out at `site` (results of that pass are invalid)
 uint32_t tc_last_error(TcPlan* plan);
 uint32_t tc_last_pairs(TcPlan* plan);

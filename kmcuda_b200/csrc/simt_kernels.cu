@@ -590,6 +590,20 @@ peer_reduce_kernel(const PeerBuffers pb, size_t nvec4, size_t nsums, uint32_t K,
   }
 }
 
+__global__ void peer_min_u32_kernel(const PeerU32 pb, size_t count, uint32_t* __restrict__ out) {
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < count; i += stride) {
+    uint32_t v = pb.p[0][i];
+    for (int d = 1; d < pb.n; d++) v = min(v, pb.p[d][i]);
+    out[i] = v;
+  }
+}
+cudaError_t launch_peer_min_u32(const PeerU32& pb, size_t count, uint32_t* out, cudaStream_t st) {
+  const unsigned grid = static_cast<unsigned>(std::min<size_t>(148 * 8, (count + 255) / 256 + 1));
+  peer_min_u32_kernel<<<grid, 256, 0, st>>>(pb, count, out);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_peer_reduce(const PeerBuffers& pb, uint32_t K, int D, float* out_sums, uint32_t* out_counts,
                                cudaStream_t st) {
   const size_t nsums = static_cast<size_t>(K) * D;
