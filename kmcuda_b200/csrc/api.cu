@@ -407,6 +407,32 @@ KMCUDAResult Job::init_plusplus() {
     if (smoke == smoke) memcpy(hostC.data(), row.data(), sizeof(float) * D);
   } while (smoke != smoke);
   KMB_INFO("performing kmeans++...\n");
+  {
+    const char* hp = getenv("KMCUDA_B200_HOST_PLUSPLUS");   // A/B: the reference-shaped host loop below
+    if (devs.size() == 1 && !(hp && hp[0] == '1')) {
+      // device-resident rounds: no D2H of the distances, no host walk, no H2D of the chosen row; the draws are the
+      // reference's rand() sequence (one per round, kmcuda.cc:296)
+      Dev& d = devs[0];
+      KMB_CU(cudaSetDevice(d.dev), kmcudaRuntimeError);
+      const uint32_t nb = (d.len + 255) / 256;
+      DevBuf<double> bsum, bpre;
+      DevBuf<uint32_t> chosen;
+      KMB_CU(d.dists.alloc(d.len), kmcudaMemoryAllocationFailure);
+      KMB_CU(bsum.alloc(static_cast<size_t>(nb) + 1), kmcudaMemoryAllocationFailure);
+      KMB_CU(bpre.alloc(static_cast<size_t>(nb) + 1), kmcudaMemoryAllocationFailure);
+      KMB_CU(chosen.alloc(K), kmcudaMemoryAllocationFailure);
+      KMB_CU(cudaMemcpyAsync(d.C.get(), hostC.data(), sizeof(float) * D, cudaMemcpyHostToDevice, d.st), kmcudaMemoryCopyError);
+      for (uint32_t i = 1; i < K; i++) {
+        const double choice = ((rand() + .0) / RAND_MAX);
+        KMB_CU(launch_plusplus_round(metric, d.X, d.len, D, d.C.get(), i, choice, d.dists, bsum, bpre, chosen, d.st),
+               kmcudaRuntimeError);
+        if ((i & 255) == 0) KMB_CU(cudaStreamSynchronize(d.st), kmcudaRuntimeError);   // keep the launch queue shallow
+      }
+      KMB_CU(cudaStreamSynchronize(d.st), kmcudaRuntimeError);
+      d.dists.release();
+      return kmcudaSuccess;
+    }
+  }
   for (auto& d : devs) {
     KMB_CU(cudaSetDevice(d.dev), kmcudaRuntimeError);
     KMB_CU(d.dists.alloc(d.len), kmcudaMemoryAllocationFailure);

@@ -97,6 +97,9 @@ cudaError_t launch_afkmc2_min_dist(int metric, const float* X, const float* C, i
                                    const uint32_t* rows, uint32_t m, float* min_dists, cudaStream_t st);
 cudaError_t launch_plusplus_step(int metric, const float* X, uint32_t n, int D, const float* centroid,
                                  int first, float* dists, double* d_sum, cudaStream_t st);
+// device-resident k-means++ round (simt_kernels.cu): bsum / bpre hold ceil(n / 256) + 1 doubles, chosen [K]
+cudaError_t launch_plusplus_round(int metric, const float* X, uint32_t n, int D, float* C, uint32_t i, double choice,
+                                  float* dists, double* bsum, double* bpre, uint32_t* chosen, cudaStream_t st);
 cudaError_t launch_half_to_float(const void* src, float* dst, size_t n, cudaStream_t st);
 cudaError_t launch_float_to_half(const float* src, void* dst, size_t n, cudaStream_t st);
 cudaError_t launch_fill_u32(uint32_t* p, uint32_t v, size_t n, cudaStream_t st);

@@ -701,6 +701,155 @@ cudaError_t launch_plusplus_step(int metric, const float* X, uint32_t n, int D, 
   return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------
+// Device-resident k-means++ (reference kmcuda.cc:262-333 + kmeans.cu:42-67).  The reference runs K - 1 rounds of
+// {distance kernel, D2H of all N distances, sequential CDF walk on the host, H2D of the chosen row}; here a round is
+// two kernels and nothing crosses PCIe: pp_update_kernel refreshes the min-distances and leaves one partial sum per
+// 256 samples, pp_pick_kernel (one CTA) scans the partial sums, resolves the draw to a sample with the reference's
+// walk semantics (including its backward branch, kmcuda.cc:304-320) and copies that sample into the centroid table.
+// The random draws are the reference's: rand() on the host, one per round, uploaded once.
+// ------------------------------------------------------------------------------------------------
+constexpr int kPpBlock = 256;
+
+template <int METRIC>
+__global__ void __launch_bounds__(kPpBlock)
+pp_update_kernel(const float* __restrict__ X, uint32_t n, int D, const float* __restrict__ centroid, int first,
+                 float* __restrict__ dists, double* __restrict__ bsum) {
+  __shared__ double s_part[kPpBlock / 32];
+  const uint32_t i = blockIdx.x * kPpBlock + threadIdx.x;
+  float dist = 0.f;
+  if (i < n) {
+    const float* x = X + static_cast<size_t>(i) * D;
+    if (x[0] == x[0]) dist = distance_exact<METRIC>(x, centroid, D);
+    float prev;
+    if (first || dist < (prev = dists[i])) dists[i] = dist;
+    else dist = prev;
+  }
+  double v = (dist == dist) ? static_cast<double>(dist) : 0.0;
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < kPpBlock / 32; w++) t += s_part[w];
+    bsum[blockIdx.x] = t;            // deterministic (fixed order), unlike an atomic total
+  }
+}
+
+// prefix P(t) = sum of the first t distances, from the scanned block sums + the tail of one block
+__device__ double pp_prefix(const float* __restrict__ dists, const double* __restrict__ bpre, uint32_t t) {
+  const uint32_t b = t / kPpBlock;
+  double p = bpre[b];
+  for (uint32_t u = b * kPpBlock; u < t; u++) {
+    const float d = dists[u];
+    if (d == d) p += static_cast<double>(d);
+  }
+  return p;
+}
+
+__global__ void __launch_bounds__(1024)
+pp_pick_kernel(const float* __restrict__ X, uint32_t n, int D, const float* __restrict__ dists,
+               const double* __restrict__ bsum, double* __restrict__ bpre, uint32_t nb, double choice,
+               float* __restrict__ next_centroid, uint32_t* __restrict__ chosen_out) {
+  __shared__ double s_chunk[1024];
+  __shared__ double s_total;
+  __shared__ uint32_t s_j;
+  // exclusive scan of the block sums into bpre[0 .. nb] (bpre[nb] = total): each thread owns a contiguous chunk
+  const uint32_t per = (nb + 1023) / 1024;
+  const uint32_t lo = min(nb, threadIdx.x * per), hi = min(nb, lo + per);
+  double acc = 0.0;
+  for (uint32_t b = lo; b < hi; b++) acc += bsum[b];
+  s_chunk[threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double run = 0.0;
+    for (int t = 0; t < 1024; t++) {
+      const double c = s_chunk[t];
+      s_chunk[t] = run;
+      run += c;
+    }
+    s_total = run;
+  }
+  __syncthreads();
+  double run = s_chunk[threadIdx.x];
+  for (uint32_t b = lo; b < hi; b++) {
+    bpre[b] = run;
+    run += bsum[b];
+  }
+  if (threadIdx.x == 0) bpre[nb] = s_total;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const double total = bpre[nb];
+    const double cs = choice * total;
+    uint32_t ca = static_cast<uint32_t>(choice * n);
+    uint32_t j;
+    // smallest j >= from with P(j) >= cs (n if none): binary search over the block prefixes, then inside the block
+    auto first_reaching = [&](uint32_t from) -> uint32_t {
+      if (pp_prefix(dists, bpre, from) >= cs) return from;
+      uint32_t blo = from / kPpBlock, bhi = nb;          // invariant: prefix at block start blo < cs <= ... search block
+      while (blo + 1 < bhi) {
+        const uint32_t mid = blo + (bhi - blo) / 2;
+        if (bpre[mid] >= cs) bhi = mid; else blo = mid;
+      }
+      double p = bpre[blo];
+      uint32_t u = blo * kPpBlock;
+      if (u < from) { p = pp_prefix(dists, bpre, from); u = from; }
+      const uint32_t end = min(n, (blo + 1) * kPpBlock);
+      for (; u < end; u++) {
+        const float d = dists[u];
+        if (d == d) p += static_cast<double>(d);
+        if (p >= cs) return u + 1;
+      }
+      // rounding left the crossing in the next block (or nowhere): continue linearly
+      for (; u < n; u++) {
+        const float d = dists[u];
+        if (d == d) p += static_cast<double>(d);
+        if (p >= cs) return u + 1;
+      }
+      return n;
+    };
+    if (ca < 100) {
+      j = first_reaching(0);                                              // kmcuda.cc:298-302
+    } else {
+      ca = min(ca, n - 1);
+      const double s2 = pp_prefix(dists, bpre, ca);
+      if (s2 < cs) {
+        j = first_reaching(ca);                                           // kmcuda.cc:309-313
+      } else {
+        // backward walk (kmcuda.cc:314-320): it subtracts d[ca], d[ca-1], ... from P(ca) until the sum drops below the
+        // draw or j reaches 1, i.e. it stops at the largest t <= ca with P(t) - d[ca] < cs, and picks sample t - 1
+        const float dca = dists[ca];
+        const double lim = cs + ((dca == dca) ? static_cast<double>(dca) : 0.0);
+        uint32_t tlo = 0, thi = ca;                                       // P(tlo) < lim assumed (P(0) = 0), find largest t
+        if (!(0.0 < lim)) { tlo = 0; thi = 0; }
+        while (tlo < thi) {
+          const uint32_t mid = tlo + (thi - tlo + 1) / 2;
+          if (pp_prefix(dists, bpre, mid) < lim) tlo = mid; else thi = mid - 1;
+        }
+        const uint32_t t = max(tlo, 2u);
+        j = t;                                                            // chosen sample t - 1  (j = j_end + 1 = t)
+      }
+    }
+    if (j == 0 || j > n) j = min(max(j, 1u), n);                          // kmcuda.cc:322-327
+    s_j = j - 1;
+    *chosen_out = j - 1;
+  }
+  __syncthreads();
+  const float* src = X + static_cast<size_t>(s_j) * D;
+  for (int f = threadIdx.x; f < D; f += 1024) next_centroid[f] = src[f];
+}
+
+// one k-means++ round on the device: distances to C[i-1], pick sample for C[i]
+cudaError_t launch_plusplus_round(int metric, const float* X, uint32_t n, int D, float* C, uint32_t i, double choice,
+                                  float* dists, double* bsum, double* bpre, uint32_t* chosen, cudaStream_t st) {
+  const uint32_t nb = cdiv(n, kPpBlock);
+  const float* cprev = C + static_cast<size_t>(i - 1) * D;
+  if (metric == 1) pp_update_kernel<1><<<nb, kPpBlock, 0, st>>>(X, n, D, cprev, i == 1, dists, bsum);
+  else pp_update_kernel<0><<<nb, kPpBlock, 0, st>>>(X, n, D, cprev, i == 1, dists, bsum);
+  pp_pick_kernel<<<1, 1024, 0, st>>>(X, n, D, dists, bsum, bpre, nb, choice, C + static_cast<size_t>(i) * D, chosen + i);
+  return cudaGetLastError();
+}
+
 // AFK-MC2 (reference kmeans_afkmc2_min_dist, kmeans.cu:159-176): for every candidate sample the distance to the
 // nearest of the first k centroids.  One thread per (candidate, centroid) pair (the reference walks the k
 // centroids serially per candidate); the minimum is taken on the float bit patterns (distances are >= 0, NaN

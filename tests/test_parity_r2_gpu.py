@@ -455,3 +455,28 @@ def test_strict_update_mode_reproduces_reference_runs_bit_for_bit(ours, ref, mon
         assert lo[:3] == lr[:3] and abs(len(lo) - len(lr)) <= 1
         assert (Ao == Ar).mean() > 0.9995
         assert np.abs(Co - Cr).max() < 1e-5
+
+
+# ------------------------------------------------------------------------------------------- k-means++ on the device
+@pytest.mark.parametrize("metric", ["L2", "cos"])
+def test_device_kmeanspp_picks_the_same_centroids_as_the_host_walk(km, monkeypatch, metric):
+    """k-means++ with the rounds resident on the device (distances, CDF walk and row copy never leave the GPU) picks
+    the same samples as the reference-shaped host loop (kmcuda.cc:262-333: D2H of all distances + sequential walk
+    per round), because both consume the same rand() draws with the same walk semantics.  tolerance=1 returns the
+    initial centroids (the run stops after the first assignment pass)."""
+    rng = np.random.default_rng(40)
+    n, d, k = 30000, 24, 80
+    centers = rng.random((k, d), dtype=np.float32) * 4
+    X = (centers[rng.integers(0, k, n)] + 0.2 * rng.standard_normal((n, d), dtype=np.float32)).astype(np.float32)
+    if metric == "cos":
+        X = _unit(X - X.mean(0))
+    got = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("KMCUDA_B200_HOST_PLUSPLUS", mode)
+        got[mode] = km.kmeans_cuda(X, k, init="k-means++", tolerance=1.0, yinyang_t=0, metric=metric, seed=11, device=1)
+    monkeypatch.delenv("KMCUDA_B200_HOST_PLUSPLUS")
+    np.testing.assert_array_equal(got["0"][0], got["1"][0])
+    assert np.array_equal(got["0"][1], got["1"][1])
+    # every centroid is one of the samples, and they are spread (k-means++): no duplicates
+    cent = got["0"][0]
+    assert len({tuple(np.round(c, 5)) for c in cent}) == k
