@@ -1,7 +1,8 @@
 #!/usr/bin/env python
-"""A/B timing of builds of libKMCUDA.so on the headline shape (run on the B200 box).
+"""A/B timing of builds of libKMCUDA.so on the headline shape (run on the B200 box).  Checker script: it lives
+under tests/ because it loads the reference library through oracle/ (not collected by pytest).
 
-    python tools/ab_kernel.py [name=path/to/libKMCUDA.so ...] [--n 8000000] [--env KEY=VAL,...]
+    python tests/ab_kernel.py [name=path/to/libKMCUDA.so ...] [--n 8000000] [--env KEY=VAL,...]
 
 Every (library, environment) pair runs in its own process: a parity check of one assignment pass against the
 unmodified reference (oracle/_ref) on 100 000 x 256 @ 1024, then CUDA-event timing of the tensor-core kernel and
