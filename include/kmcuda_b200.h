@@ -75,6 +75,11 @@ KMCUDAResult kmcuda_b200_shard_reset(kmcuda_b200_shard *shard, void *stream);
  * kmcudaRuntimeError. */
 uint32_t kmcuda_b200_last_error(kmcuda_b200_shard *shard);
 
+/* kmeans_cuda / knn_cuda keep the device memory of their workspace cached between calls (GB-sized cudaMalloc /
+ * cudaFree pairs cost more than the kernels of a call); KMCUDA_B200_CACHE_MB caps the amount (default 24576, 0 = no
+ * cache).  This returns everything that is cached to the driver. */
+void kmcuda_b200_trim_cache(void);
+
 /* Device-memory helpers for language bindings that hand out raw device pointers (the reference's
  * Python binding calls cudaMalloc / cudaMemcpy directly, src/python.cc:298-313,343-352; a ctypes
  * binding cannot reach the statically linked CUDA runtime, so the library re-exports what it needs).

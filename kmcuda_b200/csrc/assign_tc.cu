@@ -1454,26 +1454,26 @@ bool tc_supported(int metric, uint32_t n, int D, uint32_t K) {
 
 void tc_plan_destroy(TcPlan* p) {
   if (!p) return;
-  cudaFree(p->table);
-  cudaFree(p->aug_blob);
-  cudaFree(p->stats);
-  cudaFree(p->cnorm2);
-  cudaFree(p->musum);
-  cudaFree(p->mu);
-  cudaFree(p->neg_mu_s);
-  cudaFree(p->table3);
-  cudaFree(p->aug_blob3);
-  cudaFree(p->yy_perm);
-  cudaFree(p->yy_qgroup);
-  cudaFree(p->yy_goff);
-  cudaFree(p->yy_gmem);
-  cudaFree(p->pair_row);
-  cudaFree(p->pair_cand);
-  cudaFree(p->pair_score);
-  cudaFree(p->rowq);
-  cudaFree(p->ovf_rows);
-  cudaFree(p->counters);
-  cudaFree(p->dbg_scores);
+  pool_free(p->table);
+  pool_free(p->aug_blob);
+  pool_free(p->stats);
+  pool_free(p->cnorm2);
+  pool_free(p->musum);
+  pool_free(p->mu);
+  pool_free(p->neg_mu_s);
+  pool_free(p->table3);
+  pool_free(p->aug_blob3);
+  pool_free(p->yy_perm);
+  pool_free(p->yy_qgroup);
+  pool_free(p->yy_goff);
+  pool_free(p->yy_gmem);
+  pool_free(p->pair_row);
+  pool_free(p->pair_cand);
+  pool_free(p->pair_score);
+  pool_free(p->rowq);
+  pool_free(p->ovf_rows);
+  pool_free(p->counters);
+  pool_free(p->dbg_scores);
   if (p->h_counters) cudaFreeHost(p->h_counters);
   for (int i = 0; i < TcPlan::kEvRing; i++) {
     if (p->ev0[i]) cudaEventDestroy(p->ev0[i]);
@@ -1499,31 +1499,31 @@ cudaError_t tc_plan_create(TcPlan** out, int metric, uint32_t max_n, int D, uint
   TC_TRY(cudaGetDeviceProperties(&prop, device));
   p->num_sms = prop.multiProcessorCount;
   const size_t rows_pad = static_cast<size_t>(p->nt) * TN;
-  TC_TRY(cudaMalloc(&p->table, rows_pad * p->nkb * KB * sizeof(__half)));
-  TC_TRY(cudaMalloc(&p->aug_blob, static_cast<size_t>(p->nt) * AUG_B_BYTES));
-  TC_TRY(cudaMalloc(&p->stats, sizeof(Stats)));
-  TC_TRY(cudaMalloc(&p->cnorm2, sizeof(float) * K));
-  TC_TRY(cudaMalloc(&p->musum, sizeof(double) * (D + 1)));
-  TC_TRY(cudaMalloc(&p->mu, sizeof(float) * D));
-  TC_TRY(cudaMalloc(&p->neg_mu_s, sizeof(float) * MAX_NKB * KB));
+  TC_TRY(pool_alloc(reinterpret_cast<void**>(&p->table), rows_pad * p->nkb * KB * sizeof(__half)));
+  TC_TRY(pool_alloc(reinterpret_cast<void**>(&p->aug_blob), static_cast<size_t>(p->nt) * AUG_B_BYTES));
+  TC_TRY(pool_alloc(reinterpret_cast<void**>(&p->stats), sizeof(Stats)));
+  TC_TRY(pool_alloc(reinterpret_cast<void**>(&p->cnorm2), sizeof(float) * K));
+  TC_TRY(pool_alloc(reinterpret_cast<void**>(&p->musum), sizeof(double) * (D + 1)));
+  TC_TRY(pool_alloc(reinterpret_cast<void**>(&p->mu), sizeof(float) * D));
+  TC_TRY(pool_alloc(reinterpret_cast<void**>(&p->neg_mu_s), sizeof(float) * MAX_NKB * KB));
   {
     const char* nc = getenv("KMCUDA_B200_NO_CENTER");   // A/B switch: uncentred operands (the round-1 filter)
     p->centred = metric == 0 && !(nc && nc[0] == '1');
     const char* ie = getenv("KMCUDA_B200_INJECT_PIPELINE_ERROR");
     p->inject_error = ie && ie[0] == '1';
   }
-  TC_TRY(cudaMalloc(&p->pair_row, sizeof(uint32_t) * p->max_pairs));
-  TC_TRY(cudaMalloc(&p->pair_cand, sizeof(uint32_t) * p->max_pairs));
-  TC_TRY(cudaMalloc(&p->pair_score, sizeof(float) * p->max_pairs));
-  TC_TRY(cudaMalloc(&p->rowq, sizeof(uint32_t) * 3 * static_cast<size_t>(max_n)));
-  TC_TRY(cudaMalloc(&p->ovf_rows, sizeof(uint32_t) * static_cast<size_t>(max_n)));
-  TC_TRY(cudaMalloc(&p->counters, sizeof(uint32_t) * CNT_N));
+  TC_TRY(pool_alloc(reinterpret_cast<void**>(&p->pair_row), sizeof(uint32_t) * p->max_pairs));
+  TC_TRY(pool_alloc(reinterpret_cast<void**>(&p->pair_cand), sizeof(uint32_t) * p->max_pairs));
+  TC_TRY(pool_alloc(reinterpret_cast<void**>(&p->pair_score), sizeof(float) * p->max_pairs));
+  TC_TRY(pool_alloc(reinterpret_cast<void**>(&p->rowq), sizeof(uint32_t) * 3 * static_cast<size_t>(max_n)));
+  TC_TRY(pool_alloc(reinterpret_cast<void**>(&p->ovf_rows), sizeof(uint32_t) * static_cast<size_t>(max_n)));
+  TC_TRY(pool_alloc(reinterpret_cast<void**>(&p->counters), sizeof(uint32_t) * CNT_N));
   TC_TRY(cudaMallocHost(&p->h_counters, sizeof(uint32_t) * CNT_N));
   memset(p->h_counters, 0, sizeof(uint32_t) * CNT_N);
   const char* dbg = getenv("KMCUDA_B200_DUMP_SCORES");
   if (dbg && dbg[0] == '1') {
     size_t tiles = (static_cast<size_t>(max_n) + TM - 1) / TM;
-    TC_TRY(cudaMalloc(&p->dbg_scores, tiles * TM * rows_pad * sizeof(float)));
+    TC_TRY(pool_alloc(reinterpret_cast<void**>(&p->dbg_scores), tiles * TM * rows_pad * sizeof(float)));
   }
   // tensor map over the fp16 centroid table [rows_pad][nkb*64], box 64 x 256, 128-byte swizzle
   EncodeTiledFn enc = get_encode_fn();
@@ -1796,12 +1796,12 @@ cudaError_t tc_yy_layout(TcPlan* p, const uint32_t* host_groups, uint32_t G) {
   const size_t rows_pad = static_cast<size_t>(nt3) * TN;
   cudaError_t e;
   if (nt3 != p->nt3 || !p->table3) {
-    cudaFree(p->table3); cudaFree(p->aug_blob3); cudaFree(p->yy_perm); cudaFree(p->yy_qgroup);
+    pool_free(p->table3); pool_free(p->aug_blob3); pool_free(p->yy_perm); pool_free(p->yy_qgroup);
     p->table3 = nullptr; p->aug_blob3 = nullptr; p->yy_perm = nullptr; p->yy_qgroup = nullptr;
-    if ((e = cudaMalloc(&p->table3, rows_pad * p->nkb * KB * sizeof(__half))) != cudaSuccess) return e;
-    if ((e = cudaMalloc(&p->aug_blob3, static_cast<size_t>(nt3) * AUG_B_BYTES)) != cudaSuccess) return e;
-    if ((e = cudaMalloc(&p->yy_perm, rows_pad * sizeof(uint32_t))) != cudaSuccess) return e;
-    if ((e = cudaMalloc(&p->yy_qgroup, rows_pad / 4 * sizeof(uint32_t))) != cudaSuccess) return e;
+    if ((e = pool_alloc(reinterpret_cast<void**>(&p->table3), rows_pad * p->nkb * KB * sizeof(__half))) != cudaSuccess) return e;
+    if ((e = pool_alloc(reinterpret_cast<void**>(&p->aug_blob3), static_cast<size_t>(nt3) * AUG_B_BYTES)) != cudaSuccess) return e;
+    if ((e = pool_alloc(reinterpret_cast<void**>(&p->yy_perm), rows_pad * sizeof(uint32_t))) != cudaSuccess) return e;
+    if ((e = pool_alloc(reinterpret_cast<void**>(&p->yy_qgroup), rows_pad / 4 * sizeof(uint32_t))) != cudaSuccess) return e;
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) return cudaErrorNotSupported;
     cuuint64_t gdim[2] = {static_cast<cuuint64_t>(p->nkb * KB), static_cast<cuuint64_t>(rows_pad)};
@@ -1815,10 +1815,10 @@ cudaError_t tc_yy_layout(TcPlan* p, const uint32_t* host_groups, uint32_t G) {
     p->nt3 = nt3;
   }
   if (G != p->G3 || !p->yy_goff) {
-    cudaFree(p->yy_goff); cudaFree(p->yy_gmem);
+    pool_free(p->yy_goff); pool_free(p->yy_gmem);
     p->yy_goff = nullptr; p->yy_gmem = nullptr;
-    if ((e = cudaMalloc(&p->yy_goff, (static_cast<size_t>(G) + 1) * sizeof(uint32_t))) != cudaSuccess) return e;
-    if ((e = cudaMalloc(&p->yy_gmem, gmem.size() * sizeof(uint32_t))) != cudaSuccess) return e;
+    if ((e = pool_alloc(reinterpret_cast<void**>(&p->yy_goff), (static_cast<size_t>(G) + 1) * sizeof(uint32_t))) != cudaSuccess) return e;
+    if ((e = pool_alloc(reinterpret_cast<void**>(&p->yy_gmem), gmem.size() * sizeof(uint32_t))) != cudaSuccess) return e;
     p->G3 = G;
   }
   if ((e = cudaMemcpy(p->yy_perm, perm.data(), perm.size() * 4, cudaMemcpyHostToDevice)) != cudaSuccess) return e;
@@ -2313,7 +2313,7 @@ cudaError_t tc_knn_search(int k, const float* X, const float* C, uint32_t N, int
       *pool_used, *d_err;
   {
     const size_t words = static_cast<size_t>(K) + (K + 1) + 8ull * tmax + 16;
-    KNN_TRY(cudaMalloc(&u32, words * sizeof(uint32_t)));
+    KNN_TRY(pool_alloc(reinterpret_cast<void**>(&u32), words * sizeof(uint32_t)));
     KNN_TRY(cudaMemsetAsync(u32, 0, words * sizeof(uint32_t), st));
     uint32_t* q = u32;
     ntile = q; q += K;
@@ -2323,24 +2323,24 @@ cudaError_t tc_knn_search(int k, const float* X, const float* C, uint32_t N, int
     roff2 = q; q += tmax; rcount2 = q; q += tmax; nblk2 = q; q += tmax;
     d_ntiles = q++; pool_used = q++; d_err = q++;   // pool_used + 2 .. + 9: debug counters of expand_kernel
   }
-  KNN_TRY(cudaMalloc(&table, static_cast<size_t>(rows_max) * nkb * KB * sizeof(__half)));
-  KNN_TRY(cudaMalloc(&blobs, static_cast<size_t>(tmax) * AUG_B_BYTES));
-  KNN_TRY(cudaMalloc(&ysq, sizeof(float) * rows_max));
-  KNN_TRY(cudaMalloc(&yabs, sizeof(float)));
-  KNN_TRY(cudaMalloc(&stats, sizeof(Stats)));
-  KNN_TRY(cudaMalloc(&tab2orig, sizeof(uint32_t) * rows_max));
-  KNN_TRY(cudaMalloc(&topk, sizeof(float) * static_cast<size_t>(kk) * stride));
-  KNN_TRY(cudaMalloc(&dub, sizeof(float) * stride));
-  KNN_TRY(cudaMalloc(&kcnt, sizeof(uint32_t) * stride));
-  KNN_TRY(cudaMalloc(&kflags, sizeof(uint32_t) * stride));
-  KNN_TRY(cudaMalloc(&entries, sizeof(uint4) * static_cast<size_t>(stride) * KNN_CAP));
-  KNN_TRY(cudaMalloc(&ranges1, sizeof(uint2) * 2ull * tmax));
-  KNN_TRY(cudaMalloc(&pool, sizeof(uint2) * pool_cap));
-  KNN_TRY(cudaMalloc(&pair_row, sizeof(uint32_t) * pair_cap));
-  KNN_TRY(cudaMalloc(&pair_cand, sizeof(uint32_t) * pair_cap));
-  KNN_TRY(cudaMalloc(&pair_score, sizeof(float) * pair_cap));
-  KNN_TRY(cudaMalloc(&rowq, sizeof(uint32_t) * 3ull * nv));
-  KNN_TRY(cudaMalloc(&counters, sizeof(uint32_t) * CNT_N));
+  KNN_TRY(pool_alloc(reinterpret_cast<void**>(&table), static_cast<size_t>(rows_max) * nkb * KB * sizeof(__half)));
+  KNN_TRY(pool_alloc(reinterpret_cast<void**>(&blobs), static_cast<size_t>(tmax) * AUG_B_BYTES));
+  KNN_TRY(pool_alloc(reinterpret_cast<void**>(&ysq), sizeof(float) * rows_max));
+  KNN_TRY(pool_alloc(reinterpret_cast<void**>(&yabs), sizeof(float)));
+  KNN_TRY(pool_alloc(reinterpret_cast<void**>(&stats), sizeof(Stats)));
+  KNN_TRY(pool_alloc(reinterpret_cast<void**>(&tab2orig), sizeof(uint32_t) * rows_max));
+  KNN_TRY(pool_alloc(reinterpret_cast<void**>(&topk), sizeof(float) * static_cast<size_t>(kk) * stride));
+  KNN_TRY(pool_alloc(reinterpret_cast<void**>(&dub), sizeof(float) * stride));
+  KNN_TRY(pool_alloc(reinterpret_cast<void**>(&kcnt), sizeof(uint32_t) * stride));
+  KNN_TRY(pool_alloc(reinterpret_cast<void**>(&kflags), sizeof(uint32_t) * stride));
+  KNN_TRY(pool_alloc(reinterpret_cast<void**>(&entries), sizeof(uint4) * static_cast<size_t>(stride) * KNN_CAP));
+  KNN_TRY(pool_alloc(reinterpret_cast<void**>(&ranges1), sizeof(uint2) * 2ull * tmax));
+  KNN_TRY(pool_alloc(reinterpret_cast<void**>(&pool), sizeof(uint2) * pool_cap));
+  KNN_TRY(pool_alloc(reinterpret_cast<void**>(&pair_row), sizeof(uint32_t) * pair_cap));
+  KNN_TRY(pool_alloc(reinterpret_cast<void**>(&pair_cand), sizeof(uint32_t) * pair_cap));
+  KNN_TRY(pool_alloc(reinterpret_cast<void**>(&pair_score), sizeof(float) * pair_cap));
+  KNN_TRY(pool_alloc(reinterpret_cast<void**>(&rowq), sizeof(uint32_t) * 3ull * nv));
+  KNN_TRY(pool_alloc(reinterpret_cast<void**>(&counters), sizeof(uint32_t) * CNT_N));
   KNN_TRY(cudaMemsetAsync(counters, 0, sizeof(uint32_t) * CNT_N, st));
   KNN_TRY(cudaMemsetAsync(stats, 0, sizeof(Stats), st));
   KNN_TRY(cudaMemsetAsync(yabs, 0, sizeof(float), st));
@@ -2352,7 +2352,7 @@ cudaError_t tc_knn_search(int k, const float* X, const float* C, uint32_t N, int
   // cluster-aligned table layout: blocks per cluster, first block of every cluster, table row -> sample
   knn::tile_count_kernel<<<(K + 255) / 256, 256, 0, st>>>(off, K, ntile);
   KNN_TRY(cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, ntile, blk_first, static_cast<int>(K), st));
-  KNN_TRY(cudaMalloc(&cub_tmp, cub_bytes ? cub_bytes : 16));
+  KNN_TRY(pool_alloc(reinterpret_cast<void**>(&cub_tmp), cub_bytes ? cub_bytes : 16));
   KNN_TRY(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, ntile, blk_first, static_cast<int>(K), st));
   knn::tile_fill_kernel<<<(K + 255) / 256, 256, 0, st>>>(off, K, blk_first, t_nrows, blk_cluster, ranges1, roff1, rcount1,
                                                          nblk1, d_ntiles, d_pairs);
@@ -2416,10 +2416,10 @@ cudaError_t tc_knn_search(int k, const float* X, const float* C, uint32_t N, int
             "<k cand %u; candidates seen %u\n", h_cnt[CNT_ROWQ], h_cnt[CNT_PAIRS], h_cnt[CNT_OVF], *h_error, h_dbg[0],
             h_dbg[1], h_dbg[2], h_dbg[3], h_dbg[4], h_dbg[5], h_dbg[6]);
 done:
-  cudaFree(u32); cudaFree(table); cudaFree(blobs); cudaFree(ysq); cudaFree(yabs); cudaFree(stats); cudaFree(tab2orig);
-  cudaFree(topk); cudaFree(dub); cudaFree(kcnt); cudaFree(kflags); cudaFree(entries); cudaFree(ranges1);
-  cudaFree(pool); cudaFree(pair_row); cudaFree(pair_cand); cudaFree(pair_score); cudaFree(rowq); cudaFree(counters);
-  cudaFree(cub_tmp);
+  pool_free(u32); pool_free(table); pool_free(blobs); pool_free(ysq); pool_free(yabs); pool_free(stats); pool_free(tab2orig);
+  pool_free(topk); pool_free(dub); pool_free(kcnt); pool_free(kflags); pool_free(entries); pool_free(ranges1);
+  pool_free(pool); pool_free(pair_row); pool_free(pair_cand); pool_free(pair_score); pool_free(rowq); pool_free(counters);
+  pool_free(cub_tmp);
   return e;
 }
 #undef KNN_TRY

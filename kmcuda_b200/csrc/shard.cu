@@ -2,11 +2,117 @@
 #include "shard.h"
 
 #include <cstdlib>
+#include <map>
+#include <mutex>
 #include <new>
+#include <unordered_map>
 
 #include "kmcuda_b200.h"
 
 namespace kmb {
+
+// ---------------------------------------------------------------------------------------------------
+// device-memory cache (see shard.h)
+// ---------------------------------------------------------------------------------------------------
+namespace {
+struct PoolState {
+  std::mutex mu;
+  std::map<int, std::multimap<size_t, void*>> free_blocks;          // per device: size -> block
+  std::unordered_map<void*, std::pair<int, size_t>> live;           // block -> (device, size)
+  std::map<int, size_t> cached_bytes;
+  size_t cap = 0;
+  bool cap_read = false;
+};
+PoolState& pool_state() {
+  static PoolState st;
+  return st;
+}
+size_t pool_round(size_t bytes) {
+  if (bytes < 512) bytes = 512;
+  const size_t q = bytes >= (1u << 20) ? (2u << 20) : 512;          // 2 MB granules for large blocks
+  return (bytes + q - 1) / q * q;
+}
+}  // namespace
+
+cudaError_t pool_alloc(void** p, size_t bytes) {
+  PoolState& st = pool_state();
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const size_t want = pool_round(bytes);
+  {
+    std::lock_guard<std::mutex> lk(st.mu);
+    if (!st.cap_read) {
+      const char* c = getenv("KMCUDA_B200_CACHE_MB");
+      st.cap = (c ? static_cast<size_t>(strtoull(c, nullptr, 10)) : 24576u) << 20;
+      st.cap_read = true;
+    }
+    auto& fb = st.free_blocks[dev];
+    auto it = fb.lower_bound(want);
+    if (it != fb.end() && it->first <= want + want / 4) {           // close enough in size: reuse
+      *p = it->second;
+      st.live[*p] = {dev, it->first};
+      st.cached_bytes[dev] -= it->first;
+      fb.erase(it);
+      return cudaSuccess;
+    }
+  }
+  e = cudaMalloc(p, want);
+  if (e != cudaSuccess) {                                            // out of memory: give the cache back and retry once
+    cudaGetLastError();
+    pool_trim();
+    e = cudaMalloc(p, want);
+    if (e != cudaSuccess) return e;
+  }
+  std::lock_guard<std::mutex> lk(st.mu);
+  st.live[*p] = {dev, want};
+  return cudaSuccess;
+}
+
+void pool_free(void* p) {
+  if (!p) return;
+  PoolState& st = pool_state();
+  int dev = -1;
+  size_t size = 0;
+  bool keep = false;
+  {
+    std::lock_guard<std::mutex> lk(st.mu);
+    auto it = st.live.find(p);
+    if (it == st.live.end()) {       // not ours (should not happen): plain free
+      cudaFree(p);
+      return;
+    }
+    dev = it->second.first;
+    size = it->second.second;
+    st.live.erase(it);
+    if (st.cap && st.cached_bytes[dev] + size <= st.cap) {
+      st.free_blocks[dev].emplace(size, p);
+      st.cached_bytes[dev] += size;
+      keep = true;
+    }
+  }
+  if (!keep) {
+    int cur = 0;
+    cudaGetDevice(&cur);
+    if (cur != dev) cudaSetDevice(dev);
+    cudaFree(p);
+    if (cur != dev) cudaSetDevice(cur);
+  }
+}
+
+void pool_trim() {
+  PoolState& st = pool_state();
+  std::lock_guard<std::mutex> lk(st.mu);
+  int cur = 0;
+  cudaGetDevice(&cur);
+  for (auto& kv : st.free_blocks) {
+    cudaSetDevice(kv.first);
+    for (auto& b : kv.second) cudaFree(b.second);
+    kv.second.clear();
+    st.cached_bytes[kv.first] = 0;
+  }
+  cudaSetDevice(cur);
+}
 
 Shard::~Shard() {
   cudaSetDevice(device);
@@ -332,6 +438,9 @@ int32_t kmcuda_b200_debug_split_rows(uint32_t amount, uint32_t row_bytes, uint32
   }
   return 0;
 }
+
+// releases the device memory the library keeps cached between calls (see shard.h)
+void kmcuda_b200_trim_cache(void) { kmb::pool_trim(); }
 
 KMCUDAResult kmcuda_b200_device_malloc(int32_t device, uint64_t bytes, void** ptr) {
   if (!ptr) return kmcudaInvalidArguments;

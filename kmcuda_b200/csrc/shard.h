@@ -40,7 +40,7 @@ namespace kmb {
     if (kmb_res__ != kmcudaSuccess) return kmb_res__; \
   } while (false)
 
-// cudaMalloc'ed buffer that frees itself; `borrow` wraps a caller-owned pointer (wrappers.h:16-21)
+// pooled device buffer that frees itself; `borrow` wraps a caller-owned pointer (wrappers.h:16-21)
 template <typename T>
 class DevBuf {
  public:
@@ -65,7 +65,7 @@ class DevBuf {
   cudaError_t alloc(size_t n) {
     release();
     if (n == 0) n = 1;
-    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&p_), n * sizeof(T));
+    cudaError_t e = pool_alloc(reinterpret_cast<void**>(&p_), n * sizeof(T));
     owned_ = (e == cudaSuccess);
     if (!owned_) p_ = nullptr;
     return e;
@@ -76,7 +76,7 @@ class DevBuf {
     owned_ = false;
   }
   void release() {
-    if (owned_ && p_) cudaFree(p_);
+    if (owned_ && p_) pool_free(p_);
     p_ = nullptr;
     owned_ = false;
   }
