@@ -820,11 +820,24 @@ pp_pick_kernel(const float* __restrict__ X, uint32_t n, int D, const float* __re
         // draw or j reaches 1, i.e. it stops at the largest t <= ca with P(t) - d[ca] < cs, and picks sample t - 1
         const float dca = dists[ca];
         const double lim = cs + ((dca == dca) ? static_cast<double>(dca) : 0.0);
-        uint32_t tlo = 0, thi = ca;                                       // P(tlo) < lim assumed (P(0) = 0), find largest t
-        if (!(0.0 < lim)) { tlo = 0; thi = 0; }
-        while (tlo < thi) {
-          const uint32_t mid = tlo + (thi - tlo + 1) / 2;
-          if (pp_prefix(dists, bpre, mid) < lim) tlo = mid; else thi = mid - 1;
+        // largest t <= ca with P(t) < lim: the block by binary search over the block prefixes (P at block starts),
+        // then a scan inside that block
+        uint32_t tlo = 0;
+        if (0.0 < lim) {
+          uint32_t blo = 0, bhi = ca / kPpBlock;                          // bpre[blo] < lim holds for blo = 0
+          while (blo < bhi) {
+            const uint32_t mid = blo + (bhi - blo + 1) / 2;
+            if (bpre[mid] < lim) blo = mid; else bhi = mid - 1;
+          }
+          double pcur = bpre[blo];
+          tlo = blo * kPpBlock;
+          while (tlo < ca) {
+            const float d = dists[tlo];
+            const double pn = pcur + ((d == d) ? static_cast<double>(d) : 0.0);
+            if (!(pn < lim)) break;
+            pcur = pn;
+            tlo++;
+          }
         }
         const uint32_t t = max(tlo, 2u);
         j = t;                                                            // chosen sample t - 1  (j = j_end + 1 = t)
