@@ -1433,16 +1433,17 @@ static cudaError_t tc_set_smem_attr_one(int bytes) {
   if (e != cudaSuccess) return e;
   return cudaFuncSetAttribute(tc::tc_assign_kernel<NKB, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
 }
-static cudaError_t tc_set_smem_attr(int bytes) {
-  cudaError_t e;
-  if ((e = tc_set_smem_attr_one<1>(bytes)) != cudaSuccess) return e;
-  if ((e = tc_set_smem_attr_one<2>(bytes)) != cudaSuccess) return e;
-  if ((e = tc_set_smem_attr_one<3>(bytes)) != cudaSuccess) return e;
-  if ((e = tc_set_smem_attr_one<4>(bytes)) != cudaSuccess) return e;
-  if ((e = tc_set_smem_attr_one<5>(bytes)) != cudaSuccess) return e;
-  if ((e = tc_set_smem_attr_one<6>(bytes)) != cudaSuccess) return e;
-  if ((e = tc_set_smem_attr_one<7>(bytes)) != cudaSuccess) return e;
-  return tc_set_smem_attr_one<8>(bytes);
+static cudaError_t tc_set_smem_attr(int bytes, int nkb) {   // only the instantiation this shape launches
+  switch (nkb) {
+    case 1: return tc_set_smem_attr_one<1>(bytes);
+    case 2: return tc_set_smem_attr_one<2>(bytes);
+    case 3: return tc_set_smem_attr_one<3>(bytes);
+    case 4: return tc_set_smem_attr_one<4>(bytes);
+    case 5: return tc_set_smem_attr_one<5>(bytes);
+    case 6: return tc_set_smem_attr_one<6>(bytes);
+    case 7: return tc_set_smem_attr_one<7>(bytes);
+    default: return tc_set_smem_attr_one<8>(bytes);
+  }
 }
 
 bool tc_supported(int metric, uint32_t n, int D, uint32_t K) {
@@ -1541,7 +1542,7 @@ cudaError_t tc_plan_create(TcPlan** out, int metric, uint32_t max_n, int D, uint
     TC_TRY(cudaEventCreate(&p->ev1[i]));
   }
   p->smem_bytes = smem_layout().total + 1024;
-  TC_TRY(tc_set_smem_attr(static_cast<int>(p->smem_bytes)));
+  TC_TRY(tc_set_smem_attr(static_cast<int>(p->smem_bytes), p->nkb));
 #undef TC_TRY
   *out = p;
   return cudaSuccess;
@@ -2348,7 +2349,7 @@ cudaError_t tc_knn_search(int k, const float* X, const float* C, uint32_t N, int
   KNN_TRY(cudaMemsetAsync(kcnt, 0, sizeof(uint32_t) * stride, st));
   KNN_TRY(cudaMemsetAsync(kflags, 0, sizeof(uint32_t) * stride, st));
   KNN_TRY(cudaMemsetAsync(tab2orig, 0xff, sizeof(uint32_t) * rows_max, st));
-  KNN_TRY(tc_set_smem_attr(static_cast<int>(smem_bytes)));
+  KNN_TRY(tc_set_smem_attr(static_cast<int>(smem_bytes), nkb));
   // cluster-aligned table layout: blocks per cluster, first block of every cluster, table row -> sample
   knn::tile_count_kernel<<<(K + 255) / 256, 256, 0, st>>>(off, K, ntile);
   KNN_TRY(cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, ntile, blk_first, static_cast<int>(K), st));
