@@ -1382,6 +1382,8 @@ struct TcPlan {
   static constexpr int kEvRing = 64;
   cudaEvent_t ev0[kEvRing] = {}, ev1[kEvRing] = {};
   uint64_t passes = 0;
+  bool capturing = false;          // the pass is being captured into a CUDA graph (Shard::assign): events are recorded as
+  int graph_slot = -1;             // external event nodes into one fixed slot, which every replay of the graph refreshes
 };
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -1655,9 +1657,16 @@ cudaError_t tc_assign(TcPlan* p, const float* X, const float* C, const float* cs
   prm.d_changed = d_changed;
   const unsigned grid = min(static_cast<uint32_t>(p->num_sms), prm.ntiles);
   const int slot = static_cast<int>(p->passes % TcPlan::kEvRing);
-  cudaEventRecord(p->ev0[slot], st);
+  if (p->capturing) {
+    p->graph_slot = slot;
+    cudaEventRecordWithFlags(p->ev0[slot], st, cudaEventRecordExternal);
+  } else {
+    p->graph_slot = -1;
+    cudaEventRecord(p->ev0[slot], st);
+  }
   tc_launch_main(0, p->nkb, grid, p->smem_bytes, st, p->tmap, tmap_x, prm);
-  cudaEventRecord(p->ev1[slot], st);
+  if (p->capturing) cudaEventRecordWithFlags(p->ev1[slot], st, cudaEventRecordExternal);
+  else cudaEventRecord(p->ev1[slot], st);
   p->passes++;
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   // exact re-check of the multi-candidate rows, then the rows that need the full exact pass
@@ -1889,6 +1898,7 @@ void tc_last_stats(TcPlan* p, uint32_t* n_recheck, uint32_t* n_overflow) {
 }
 
 uint32_t tc_last_error(TcPlan* p) { return p->h_counters[tc::CNT_ERR]; }
+void tc_set_capture(TcPlan* p, bool on) { p->capturing = on; }
 uint32_t tc_last_pairs(TcPlan* p) { return p->h_counters[tc::CNT_PAIRS]; }
 
 // device time (ms) of the main kernel in the most recent passes, oldest first; call after a sync
@@ -1896,7 +1906,8 @@ int tc_kernel_times(TcPlan* p, float* ms_out, int max_out) {
   const uint64_t have = p->passes < static_cast<uint64_t>(TcPlan::kEvRing) ? p->passes : TcPlan::kEvRing;
   const int n = static_cast<int>(have < static_cast<uint64_t>(max_out) ? have : max_out);
   for (int i = 0; i < n; i++) {
-    const int slot = static_cast<int>((p->passes - n + i) % TcPlan::kEvRing);
+    // graph replays refresh the one slot that was captured; otherwise the ring holds one pair per pass
+    const int slot = p->graph_slot >= 0 ? p->graph_slot : static_cast<int>((p->passes - n + i) % TcPlan::kEvRing);
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, p->ev0[slot], p->ev1[slot]) != cudaSuccess) ms = -1.f;
     ms_out[i] = ms;

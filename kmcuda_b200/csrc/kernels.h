@@ -187,6 +187,7 @@ cudaError_t launch_peer_min_u32(const PeerU32& pb, size_t count, uint32_t* out, 
 // 0 = clean; 0x1000+site = a pipeline wait timed out at `site` (results of that pass are invalid)
 uint32_t tc_last_error(TcPlan* plan);
 uint32_t tc_last_pairs(TcPlan* plan);
+void tc_set_capture(TcPlan* plan, bool on);   // the next tc_assign is recorded into a CUDA graph (stream capture)
 int tc_kernel_times(TcPlan* plan, float* ms_out, int max_out);
 // diagnostics (KMCUDA_B200_DUMP_SCORES=1): approximate scores [tiles*128][nt*256], prep statistics
 const float* tc_debug_scores(TcPlan* plan, size_t* row_stride);

@@ -116,6 +116,7 @@ void pool_trim() {
 
 Shard::~Shard() {
   cudaSetDevice(device);
+  if (assign_graph) cudaGraphExecDestroy(assign_graph);
   if (tc) tc_plan_destroy(tc);
 }
 
@@ -125,6 +126,8 @@ KMCUDAResult Shard::create(bool with_update) {
   force_exact = fe && fe[0] == '1';
   const char* su = getenv("KMCUDA_B200_STRICT_UPDATE");
   strict_update = su && su[0] == '1';
+  const char* ug = getenv("KMCUDA_B200_GRAPH");
+  use_graph = ug && ug[0] == '1';
   KMB_CU(csq.alloc(K), kmcudaMemoryAllocationFailure);
   KMB_CU(result.alloc(max_n), kmcudaMemoryAllocationFailure);
   if (with_update) {
@@ -227,8 +230,35 @@ KMCUDAResult Shard::yy_step(uint32_t n, const float* X, const float* C, uint32_t
 KMCUDAResult Shard::assign(uint32_t n, const float* X, const float* C, uint32_t* assignments,
                            uint32_t* prev, uint32_t* d_changed, cudaStream_t st) {
   if (n > max_n) return kmcudaInvalidArguments;
-  KMB_CU(launch_csqr(metric, C, K, D, csq, st), kmcudaRuntimeError);
+  if (!(tc && n > 0 && use_graph)) KMB_CU(launch_csqr(metric, C, K, D, csq, st), kmcudaRuntimeError);
   last_tc = false;
+  if (tc && n > 0 && use_graph) {
+    GraphKey key;
+    key.X = X; key.C = C; key.a = assignments; key.prev = prev; key.ch = d_changed; key.n = n; key.st = st;
+    if (!(assign_graph && key == graph_key)) {
+      if (assign_graph) { cudaGraphExecDestroy(assign_graph); assign_graph = nullptr; }
+      cudaGraph_t g = nullptr;
+      KMB_CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal), kmcudaRuntimeError);
+      tc_set_capture(tc, true);
+      cudaError_t e1 = launch_csqr(metric, C, K, D, csq, st);
+      cudaError_t e2 = e1 == cudaSuccess ? tc_assign(tc, X, C, csq, n, result, assignments, prev, d_changed, st) : e1;
+      tc_set_capture(tc, false);
+      cudaError_t e3 = cudaStreamEndCapture(st, &g);
+      if (e2 != cudaSuccess || e3 != cudaSuccess || !g) {
+        if (g) cudaGraphDestroy(g);
+        cudaGetLastError();
+        KMB_INFO("CUDA graph capture of the assignment pass failed (%s / %s)\n", cudaGetErrorString(e2), cudaGetErrorString(e3));
+        return kmcudaRuntimeError;
+      }
+      cudaError_t e4 = cudaGraphInstantiate(&assign_graph, g, 0);
+      cudaGraphDestroy(g);
+      KMB_CU(e4, kmcudaRuntimeError);
+      graph_key = key;
+    }
+    KMB_CU(cudaGraphLaunch(assign_graph, st), kmcudaRuntimeError);
+    last_tc = true;
+    return kmcudaSuccess;
+  }
   if (tc && n > 0) {
     KMB_CU(tc_assign(tc, X, C, csq, n, result, assignments, prev, d_changed, st), kmcudaRuntimeError);
     last_tc = true;

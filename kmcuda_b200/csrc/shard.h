@@ -130,6 +130,22 @@ class Shard {
   bool last_tc = false;
   uint32_t last_rechecked = 0, last_overflowed = 0;
   bool force_exact = false;  // KMCUDA_B200_FORCE_EXACT=1 (debug / parity tests)
+  // KMCUDA_B200_GRAPH=1: the ~13 launches of an assignment pass are captured once per (buffers, n, stream) and replayed
+  // as ONE CUDA graph launch (iterative runs call assign() with the same buffers; the centroids change in place)
+  bool use_graph = false;
+  cudaGraphExec_t assign_graph = nullptr;
+  struct GraphKey {
+    const float* X = nullptr;
+    const float* C = nullptr;
+    uint32_t* a = nullptr;
+    uint32_t* prev = nullptr;
+    uint32_t* ch = nullptr;
+    uint32_t n = 0;
+    cudaStream_t st = nullptr;
+    bool operator==(const GraphKey& o) const {
+      return X == o.X && C == o.C && a == o.a && prev == o.prev && ch == o.ch && n == o.n && st == o.st;
+    }
+  } graph_key;
   bool strict_update = false;  // KMCUDA_B200_STRICT_UPDATE=1
   DevBuf<uint32_t> su_keys_in, su_vals_in, su_keys_out, su_vals_out, su_offsets;
   DevBuf<char> su_cub;
