@@ -1019,6 +1019,7 @@ KMCUDAResult knn_cuda(uint16_t k, KMCUDADistanceMetric metric, uint32_t samples_
   g_prof.begin(dev_ids);
   struct KDev {
     DevBuf<float> X, C, cd, radii, heap;
+    DevBuf<float> cd_l2, radii_l2;   // angular metric on the tensor-core route: its cluster pruning works in L2
     DevBuf<uint32_t> assign, inv_keys, iota, inv, off, counts, neigh;
     DevBuf<char> cub;
     DevBuf<unsigned long long> pairs;
@@ -1039,7 +1040,7 @@ KMCUDAResult knn_cuda(uint16_t k, KMCUDADistanceMetric metric, uint32_t samples_
   bool shard_tc = false;
   {
     const char* fx0 = getenv("KMCUDA_B200_FORCE_EXACT");
-    shard_tc = dev_ids.size() > 1 && !(fx0 && fx0[0] == '1') && tc_knn_supported(m, k, N, D, K);
+    shard_tc = dev_ids.size() > 1 && m == 0 && !(fx0 && fx0[0] == '1') && tc_knn_supported(m, k, N, D, K);
     for (size_t i = 0; i < dev_ids.size() && shard_tc; i++)
       for (size_t j = 0; j < dev_ids.size() && shard_tc; j++) {
         int access = 0;
@@ -1128,8 +1129,18 @@ KMCUDAResult knn_cuda(uint16_t k, KMCUDADistanceMetric metric, uint32_t samples_
       KNN_CU(d_nfb.alloc(1), kmcudaMemoryAllocationFailure);
       KNN_CU(cudaMemsetAsync(d_nfb.get(), 0, sizeof(uint32_t), d.st), kmcudaRuntimeError);
       cudaError_t te = cudaSuccess;
+      const float *tcd = d.cd, *tradii = d.radii;
+      if (m == 1 && nv >= 4096) {
+        KNN_CU(d.cd_l2.alloc(static_cast<size_t>(K) * K), kmcudaMemoryAllocationFailure);
+        KNN_CU(d.radii_l2.alloc(K), kmcudaMemoryAllocationFailure);
+        KNN_CU(launch_knn_radii(0, d.X, d.C, N, D, K, d.assign, d.radii_l2, d.st), kmcudaRuntimeError);
+        KNN_CU(launch_knn_centroid_distances(0, d.C, K, D, d.cd_l2, d.st), kmcudaRuntimeError);
+        KNN_CU(launch_knn_radii_fix(d.off, K, d.radii_l2, d.st), kmcudaRuntimeError);
+        tcd = d.cd_l2;
+        tradii = d.radii_l2;
+      }
       if (nv >= 4096)
-        te = tc_knn_search(k, d.X, d.C, N, D, K, d.assign, d.inv, d.off, d.cd, d.radii, nv, d.neigh, fb_rows, d_nfb,
+        te = tc_knn_search(m, k, d.X, d.C, N, D, K, d.assign, d.inv, d.off, tcd, tradii, nv, d.neigh, fb_rows, d_nfb,
                            d.pairs, &tc_err, shard_tc ? static_cast<uint32_t>(i) : 0u,
                            shard_tc ? static_cast<uint32_t>(dev_ids.size()) : 1u, d.st);
       if (dev_ids.size() == 1) g_prof.mark("knn: tensor-core candidate search");

@@ -112,6 +112,7 @@ struct Stats {       // written by the centroid prep kernels, read by the main k
   uint32_t force_exact; // cosine only: a centroid with an infinite element / norm can still win -> no filtering
   float yabs;           // k-NN: max over samples of s * (|y| + |c(y)|): bounds the rounding of the centring y - c
   float mun;            // s * ||mu|| (upper bound): mu = centring vector of the assignment filter (0 when not centred)
+  float knn_extra;      // k-NN, angular metric served through the L2 pass: s^2 * max |1 - ||y||^2| (see tc_knn_search)
 };
 
 struct SmemLayout {  // byte offsets from the 1024-aligned dynamic smem base
@@ -802,6 +803,7 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
     const int slot = h * TM + row;             // 0..255
     const float cmax = p.stats->cmax, dcmax = p.stats->dcmax;
     const float mun = MODE == 2 ? 0.f : p.stats->mun;
+    const float knn_extra = MODE == 2 ? p.stats->knn_extra : 0.f;
     // cosine: every dot >= 1 is clamped to angle 0 by the reference, so all of them tie -> the threshold
     // never rises above s^2 * 1 (the accumulator holds s^2 * dot)
     const float cap = p.metric == 1 ? p.stats->scale * p.stats->scale : INFINITY;
@@ -891,6 +893,7 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
             E += 1.2e-7f * (__fsqrt_ru(norms[3 * TM + row]) * cmax + p.stats->yabs * xn) + 4.8e-7f * (goff + xn * cmax);
           }
           margin = 2.f * E * 1.001f + 1e-30f;
+          if (MODE == 2) margin += knn_extra;
           if (!(margin < 1.0e30f)) flags |= 1u;                            // NaN / Inf somewhere in the row
           if (MODE == 2) {
             mmax = fmaxf(mmax, margin);
@@ -1982,7 +1985,7 @@ __global__ void layout_kernel(const uint32_t* __restrict__ inv, const uint32_t* 
 __global__ void prep_norms_kernel(const float* __restrict__ X, const float* __restrict__ C, int D,
                                   const uint32_t* __restrict__ tab2orig, const uint32_t* __restrict__ blk_cluster,
                                   const uint32_t* __restrict__ d_ntiles, float* __restrict__ ysq,
-                                  float* __restrict__ yabs_max) {
+                                  float* __restrict__ yabs_max, int angular) {
   const uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= *d_ntiles * tc::TM) return;
@@ -2007,6 +2010,13 @@ __global__ void prep_norms_kernel(const float* __restrict__ X, const float* __re
     ysq[row] = a;
     if (r == r && r < 3.0e38f) atomicMax(reinterpret_cast<uint32_t*>(yabs_max), __float_as_uint(__fsqrt_ru(r)));
   }
+  if (angular) {   // deviation of the sample from unit length (yabs_max[1]); NaN / Inf rows count as "far off"
+    float xx = 0.f;
+    for (int f = lane; f < D; f += 32) xx = fmaf(x[f], x[f], xx);
+    for (int o = 16; o > 0; o >>= 1) xx += __shfl_xor_sync(0xffffffffu, xx, o);
+    const float dev = fabsf(xx - 1.f) + 4.0e-6f * (1.f + xx);    // + the fp32 rounding of the sum itself
+    if (lane == 0) atomicMax(reinterpret_cast<uint32_t*>(yabs_max + 1), (dev == dev) ? __float_as_uint(dev) : 0x7f800000u);
+  }
 }
 
 // one warp per table row: fp16(s (y - c)), rounding residual, bias -(s^2 |y - c|^2 / 2) in three fp16 terms;
@@ -2015,14 +2025,26 @@ __global__ void prep_table_kernel(const float* __restrict__ X, const float* __re
                                   const uint32_t* __restrict__ tab2orig, const uint32_t* __restrict__ blk_cluster,
                                   const uint32_t* __restrict__ d_ntiles, const float* __restrict__ ysq,
                                   __half* __restrict__ table, __half* __restrict__ aug_blob,
-                                  tc::Stats* __restrict__ st, const float* __restrict__ yabs_max) {
+                                  tc::Stats* __restrict__ st, const float* __restrict__ yabs_max, int angular,
+                                  uint32_t* __restrict__ d_error) {
   using namespace tc;
   const uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= *d_ntiles * TM) return;
   const int Dp = nkb * KB;
   const float s = st->scale;
-  if (row == 0 && lane == 0) st->yabs = *yabs_max * s * 1.0001f;
+  if (row == 0 && lane == 0) {
+    st->yabs = *yabs_max * s * 1.0001f;
+    st->knn_extra = 0.f;
+    if (angular) {
+      // angular neighbours through the L2 pass: for |1 - |y|^2| <= eps the true top-k by dot product lie within
+      // s^2 * eps of the (k+1)-th best L2 score (x.y = (|x|^2 + |y|^2 - d^2) / 2), so the margin grows by that much;
+      // samples far from unit length make the equivalence useless -> the caller runs the exact search instead
+      const float eps = yabs_max[1];
+      if (!(eps <= 1.0e-2f)) *d_error = 2u;
+      st->knn_extra = (s * s) * eps * 1.01f;
+    }
+  }
   const uint32_t sidx = tab2orig[row];
   bool finite = sidx != UINT32_MAX;
   const float* x = X + static_cast<size_t>(finite ? sidx : 0) * D;
@@ -2274,7 +2296,7 @@ select_kernel(int k, const uint32_t* __restrict__ rowq, const uint32_t* __restri
 }  // namespace knn
 
 bool tc_knn_supported(int metric, int k, uint32_t N, int D, uint32_t K) {
-  if (metric != 0) return false;                                   // angular k-NN: SIMT path
+  // (the angular metric is served through the L2 pass when the samples have unit length, see tc_knn_search)
   if (k + 1 > tc::KNN_MAX_KK) return false;
   if (D < 4 || D % 4 != 0 || D > tc::MAX_NKB * tc::KB) return false;
   if (N < 4096 || N > (1u << 30)) return false;                    // tiny inputs: not worth the set-up
@@ -2286,7 +2308,7 @@ bool tc_knn_supported(int metric, int k, uint32_t N, int D, uint32_t K) {
 
 // neighbors: device array [N][k] indexed by the original sample index (this build shards k-NN queries only on the
 // SIMT path).  Rows the filter cannot serve are appended to fb_rows / d_nfb for the caller's exact search.
-cudaError_t tc_knn_search(int k, const float* X, const float* C, uint32_t N, int D, uint32_t K,
+cudaError_t tc_knn_search(int metric, int k, const float* X, const float* C, uint32_t N, int D, uint32_t K,
                           const uint32_t* assign, const uint32_t* inv, const uint32_t* off, const float* cd,
                           const float* radii, uint32_t nv, uint32_t* neighbors, uint32_t* fb_rows, uint32_t* d_nfb,
                           unsigned long long* d_pairs, uint32_t* h_error, uint32_t part, uint32_t nparts,
@@ -2338,7 +2360,7 @@ cudaError_t tc_knn_search(int k, const float* X, const float* C, uint32_t N, int
   KNN_TRY(pool_alloc(reinterpret_cast<void**>(&table), static_cast<size_t>(rows_max) * nkb * KB * sizeof(__half)));
   KNN_TRY(pool_alloc(reinterpret_cast<void**>(&blobs), static_cast<size_t>(tmax) * AUG_B_BYTES));
   KNN_TRY(pool_alloc(reinterpret_cast<void**>(&ysq), sizeof(float) * rows_max));
-  KNN_TRY(pool_alloc(reinterpret_cast<void**>(&yabs), sizeof(float)));
+  KNN_TRY(pool_alloc(reinterpret_cast<void**>(&yabs), 2 * sizeof(float)));
   KNN_TRY(pool_alloc(reinterpret_cast<void**>(&stats), sizeof(Stats)));
   KNN_TRY(pool_alloc(reinterpret_cast<void**>(&tab2orig), sizeof(uint32_t) * rows_max));
   KNN_TRY(pool_alloc(reinterpret_cast<void**>(&topk), sizeof(float) * static_cast<size_t>(kk) * stride));
@@ -2355,7 +2377,7 @@ cudaError_t tc_knn_search(int k, const float* X, const float* C, uint32_t N, int
   KNN_TRY(pool_alloc(reinterpret_cast<void**>(&counters), sizeof(uint32_t) * CNT_N));
   KNN_TRY(cudaMemsetAsync(counters, 0, sizeof(uint32_t) * CNT_N, st));
   KNN_TRY(cudaMemsetAsync(stats, 0, sizeof(Stats), st));
-  KNN_TRY(cudaMemsetAsync(yabs, 0, sizeof(float), st));
+  KNN_TRY(cudaMemsetAsync(yabs, 0, 2 * sizeof(float), st));
   KNN_TRY(cudaMemsetAsync(ysq, 0, sizeof(float) * rows_max, st));   // rows past the last block stay 0 for the max
   KNN_TRY(cudaMemsetAsync(kcnt, 0, sizeof(uint32_t) * stride, st));
   KNN_TRY(cudaMemsetAsync(kflags, 0, sizeof(uint32_t) * stride, st));
@@ -2371,11 +2393,11 @@ cudaError_t tc_knn_search(int k, const float* X, const float* C, uint32_t N, int
   KNN_TRY(cudaMemcpyAsync(blk_first + K, d_ntiles, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
   knn::layout_kernel<<<(nv + 255) / 256, 256, 0, st>>>(inv, assign, off, blk_first, nv, tab2orig);
   // fp16 table of the centred samples + bias blobs + statistics
-  knn::prep_norms_kernel<<<(rows_max / 8) + 1, 256, 0, st>>>(X, C, D, tab2orig, blk_cluster, d_ntiles, ysq, yabs);
+  knn::prep_norms_kernel<<<(rows_max / 8) + 1, 256, 0, st>>>(X, C, D, tab2orig, blk_cluster, d_ntiles, ysq, yabs, metric);
   tc_prep_stats_kernel<<<8, 256, 0, st>>>(ysq, rows_max, stats);
   tc_prep_scale_kernel<<<1, 1, 0, st>>>(stats, nullptr, 0, 0, nullptr);
   knn::prep_table_kernel<<<(rows_max / 8) + 1, 256, 0, st>>>(X, C, D, nkb, tab2orig, blk_cluster, d_ntiles, ysq, table,
-                                                             blobs, stats, yabs);
+                                                             blobs, stats, yabs, metric, d_err);
   KNN_TRY(cudaGetLastError());
   {
     cuuint64_t gdim[2] = {static_cast<cuuint64_t>(nkb * KB), static_cast<cuuint64_t>(rows_max)};
@@ -2412,8 +2434,13 @@ cudaError_t tc_knn_search(int k, const float* X, const float* C, uint32_t N, int
                                                   pair_row, pair_cand, rowq, fb_rows, counters, pool_used + 2, part,
                                                   prm.knn_nparts);
   KNN_TRY(cudaGetLastError());
-  recheck_pairs_kernel<0, 1><<<num_sms * 4, 128, 0, st>>>(X, X, nullptr, D, pair_row, pair_cand, counters + CNT_PAIRS,
-                                                          pair_cap, N, N, pair_score);
+  // the exact distance of every candidate pair in the CALLER's metric (angular: acos of the Kahan dot product)
+  if (metric == 1)
+    recheck_pairs_kernel<1, 1><<<num_sms * 4, 128, 0, st>>>(X, X, nullptr, D, pair_row, pair_cand, counters + CNT_PAIRS,
+                                                            pair_cap, N, N, pair_score);
+  else
+    recheck_pairs_kernel<0, 1><<<num_sms * 4, 128, 0, st>>>(X, X, nullptr, D, pair_row, pair_cand, counters + CNT_PAIRS,
+                                                            pair_cap, N, N, pair_score);
   knn::select_kernel<<<num_sms * 8, 256, 0, st>>>(k, rowq, counters, pair_cand, pair_score, 0u, neighbors);
   KNN_TRY(cudaGetLastError());
   KNN_TRY(cudaMemcpyAsync(h_cnt, counters, sizeof(uint32_t) * CNT_N, cudaMemcpyDeviceToHost, st));

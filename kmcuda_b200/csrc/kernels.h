@@ -172,7 +172,10 @@ cudaError_t tc_yy_refresh(TcPlan* plan, const float* X, const float* C, const fl
                           const uint32_t* assign, const uint32_t* groups, uint32_t G, float* bounds, cudaStream_t st);
 // k-NN candidate search on the tensor cores (assign_tc.cu); see the comment there
 bool tc_knn_supported(int metric, int k, uint32_t N, int D, uint32_t K);
-cudaError_t tc_knn_search(int k, const float* X, const float* C, uint32_t N, int D, uint32_t K,
+// metric 1 (angular): candidates come from the L2 pass (cd / radii must then be the L2 quantities), the margin is
+// widened by the samples' deviation from unit length, exact distances and the selection use the angular metric; if the
+// samples are not unit vectors (deviation > 1e-2) *h_error is set and the caller has to run the exact search
+cudaError_t tc_knn_search(int metric, int k, const float* X, const float* C, uint32_t N, int D, uint32_t K,
                           const uint32_t* assign, const uint32_t* inv, const uint32_t* off, const float* cd,
                           const float* radii, uint32_t nv, uint32_t* neighbors, uint32_t* fb_rows, uint32_t* d_nfb,
                           unsigned long long* d_pairs, uint32_t* h_error, uint32_t part, uint32_t nparts,
