@@ -79,6 +79,12 @@ constexpr int LIST_LEN = 8;             // chunk entries per epilogue thread
 #ifndef KMB_ROLE_ORDER
 #define KMB_ROLE_ORDER 1
 #endif
+// Knock-out builds (timing experiments only, results are garbage): 1 = epilogue does not read the accumulators,
+// 2 = no MMA is issued, 3 = converters do no work (no LDS / math / tcgen05.st), 5 = the B / bias copies are not issued,
+// 6 = the X copies are not issued.  Which of them shortens the kernel says what bounds it.
+#ifndef KMB_KO
+#define KMB_KO 0
+#endif
 #if KMB_ROLE_ORDER == 1
 constexpr int FIRST_EMIT_WARP = 0;      // 4 emitter warps (merge + global emission)
 constexpr int FIRST_CONV_WARP = 4;      // 4 converter warps, warp % 4 = TMEM lane quarter
@@ -600,16 +606,24 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
           const int as = ac & 1;
           const uint32_t aph = (ac >> 1) & 1;
           TC_WAIT(BAR_AUG_EMPTY + as, aph ^ 1, 2);
+#if KMB_KO == 5
+          ptx::mbar_arrive(&bars[BAR_AUG_FULL + as]);
+#else
           ptx::mbar_arrive_expect_tx(&bars[BAR_AUG_FULL + as], AUG_B_BYTES);
           ptx::bulk_load(smem + L.aug_b + as * AUG_B_BYTES,
                          reinterpret_cast<const uint8_t*>(p.aug_blob) + static_cast<size_t>(n) * AUG_B_BYTES,
                          AUG_B_BYTES, &bars[BAR_AUG_FULL + as]);
+#endif
           ac++;
 #pragma unroll
           for (int kb = 0; kb < NKB; kb++) {
             TC_WAIT(BAR_B_EMPTY + bs, bph ^ 1, 1);
+#if KMB_KO == 5
+            ptx::mbar_arrive(&bars[BAR_B_FULL + bs]);
+#else
             ptx::mbar_arrive_expect_tx(&bars[BAR_B_FULL + bs], B_KB_BYTES);
             ptx::tma_load_2d(smem + L.b + bs * B_STAGE_BYTES, &tmap_b, kb * KB, n * TN, &bars[BAR_B_FULL + bs]);
+#endif
             if (++bs == B_STAGES) { bs = 0; bph ^= 1; }
           }
         }
@@ -624,9 +638,13 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
           const int s = xc % X_STAGES;
           const uint32_t ph = (xc / X_STAGES) & 1;
           TC_WAIT(BAR_X_EMPTY + s, ph ^ 1, 9);
+#if KMB_KO == 6
+          ptx::mbar_arrive(&bars[BAR_X_FULL + s]);
+#else
           ptx::mbar_arrive_expect_tx(&bars[BAR_X_FULL + s], X_STAGE_BYTES);
           ptx::tma_load_2d(smem + L.x + s * X_STAGE_BYTES, &tmap_x, hs * 32, static_cast<int>(tile * TM),
                            &bars[BAR_X_FULL + s]);
+#endif
         }
       }
     }
@@ -658,10 +676,14 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
           if (ptx::elect_one()) {
             const uint64_t bd0 = ptx::make_smem_desc(b_base + bs * B_STAGE_BYTES, 16, 1024, 2);
             const uint32_t at = a_tmem + kb * 32;
+#if KMB_KO != 2
             ptx::umma_f16_ts(d_tmem, at, bd0, idesc, kb ? 1u : 0u);
             ptx::umma_f16_ts(d_tmem, at + 8, bd0 + 2, idesc, 1u);     // +32 bytes along K = +2 in the address field
             ptx::umma_f16_ts(d_tmem, at + 16, bd0 + 4, idesc, 1u);
             ptx::umma_f16_ts(d_tmem, at + 24, bd0 + 6, idesc, 1u);
+#else
+            (void)bd0; (void)at;
+#endif
             ptx::umma_commit(&bars[BAR_B_EMPTY + bs]);
           }
           __syncwarp();
@@ -672,7 +694,11 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
         ptx::tc_fence_after();
         if (ptx::elect_one()) {
           const uint64_t bd = ptx::make_smem_desc(augb + buf * AUG_B_BYTES, TN * 16, 128, 0);
+#if KMB_KO != 2
           ptx::umma_f16(d_tmem, aug_ad, bd, idesc, 1u);
+#else
+          (void)bd;
+#endif
           ptx::umma_commit(&bars[BAR_AUG_EMPTY + buf]);
           ptx::umma_commit(&bars[BAR_ACC_FULL + buf]);
           if (it.seg_last()) ptx::umma_commit(&bars[BAR_A_FREE + abuf]);  // every MMA reading this A buffer is done
@@ -725,7 +751,7 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
             }
             const uint8_t* xs = smem + L.x + st * X_STAGE_BYTES + row * 128;
 #pragma unroll
-            for (int c = 0; c < 8; c++) {
+            for (int c = 0; c < (KMB_KO == 3 ? 0 : 8); c++) {
               float4 v = (MODE == 0 || MODE == 3) ? *reinterpret_cast<const float4*>(xs + ((c ^ (row & 7)) << 4)) : gv[c];
               float4 m4 = make_float4(0.f, 0.f, 0.f, 0.f);
               if (MODE == 2) {
@@ -769,8 +795,12 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
               if (lane == 0) ptx::mbar_arrive(&bars[BAR_X_EMPTY + st]);
             }
           }
+#if KMB_KO != 3
           ptx::tmem_st_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + TMEM_A0 + abuf * 128 + kb * 32, pk);
           ptx::tmem_st_wait();
+#else
+          (void)pk;
+#endif
           if (kb == nkb - 1) {
             float* norms = reinterpret_cast<float*>(smem + L.norms) + (si & 3) * 4 * TM;
             float nxl, nxh, ndl, ndh;
@@ -866,8 +896,15 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
         // both 32-column chunks of this warp are fetched up front so that their dependency chains interleave
         uint32_t r0[32], r1[32];
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + TMEM_ACC0 + buf * TN + h * 64;
+#if KMB_KO != 1
         ptx::tmem_ld_32x32(taddr, r0);
         ptx::tmem_ld_32x32(taddr + 32, r1);
+#else
+        for (int jj = 0; jj < 32; jj++) {   // stand-in values: strictly decreasing, 64 apart -> one candidate per row
+          r0[jj] = __float_as_uint(-64.f * static_cast<float>(n * 128 + h * 64 + jj + 1));
+          r1[jj] = __float_as_uint(-64.f * static_cast<float>(n * 128 + h * 64 + 32 + jj + 1));
+        }
+#endif
         if (it.seg_first()) {
           const float* norms = reinterpret_cast<const float*>(smem + L.norms) + (si & 3) * 4 * TM;
           // rigorous bound on |acc - (s^2 x.c - s^2||c||^2/2)| (see header): Cauchy-Schwarz on the
@@ -879,8 +916,17 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
           // reference Kahan/rd rounding + bias split + fp32 centring of both operands: the reference works on the
           // UNCENTRED vectors, whose norms are bounded by the centred ones + ||mu||
           const float xu = xn + mun, cu = cmax + mun;
-          E += 2.0e-6f * (cu * cu + xu * cu);
-          if (MODE >= 1) E += 2.0e-6f * xu * xu;                           // true distances: rounding of sum (x-c)^2
+          if (MODE == 0) {
+            // the reference ranks with fma_rd(-2, Kahan dot, csq): |error| <= 1.2e-7 cu^2 + 2.4e-7 xu cu in score units
+            // (2^-23 per directed rounding, Kahan sums to ~1 ulp); 2.5x - 5x of that is allowed for
+            E += 6.0e-7f * (cu * cu + xu * cu);
+          } else if (MODE == 2) {
+            E += 2.0e-6f * (cu * cu + xu * cu) + 2.0e-6f * xu * xu;
+          } else {
+            // MODE 1 / 3 decide on TRUE distances sqrt(Kahan sum (x - c)^2): their rounding is relative to |x - c|^2 <=
+            // (|x^| + |c^|)^2 (the subtraction cancels the common offset exactly), plus the fp32 centring of both operands
+            E += 2.0e-6f * (xn + cmax) * (xn + cmax) + 2.4e-7f * (xn * cmax + cmax * cmax);
+          }
           if (MODE == 3) {
             xa2lo = norms[2 * TM + row] * (1.f - 1.0e-4f);                 // lower bound of |s (x - mu)|^2 (fp32 summation error)
             // scores this low are not separable from the padding sentinel (-65504): such rows take the exact pass
