@@ -85,13 +85,22 @@ constexpr int LIST_LEN = 8;             // chunk entries per epilogue thread
 #ifndef KMB_KO
 #define KMB_KO 0
 #endif
+// MMA issuer warps.  ncu (profiles/r02_tc_assign_v5_*): with ONE issuer the converter warps wait 62 % and the epilogue
+// warps 41 % of their time for the MMA warp, whose own samples are spread over its control code (barrier probes at ~100
+// cycles each, branches, instruction fetches): 6 waits + 17 MMAs + 6 commits per n-tile take ~2200 cycles to issue
+// against 1088 cycles of tensor work, so the tensor pipe idles 42 %.  Two issuers take alternate n-tiles (one per
+// accumulator buffer): their waits overlap.
+#ifndef KMB_MMA_WARPS
+#define KMB_MMA_WARPS 2
+#endif
+constexpr int N_MMA_WARPS = KMB_MMA_WARPS;
 #if KMB_ROLE_ORDER == 1
 constexpr int FIRST_EMIT_WARP = 0;      // 4 emitter warps (merge + global emission)
 constexpr int FIRST_CONV_WARP = 4;      // 4 converter warps, warp % 4 = TMEM lane quarter
 constexpr int FIRST_EPI_WARP = 8;       // 8 epilogue warps
-constexpr int WARP_B_PRODUCER = 16, WARP_X_PRODUCER = 17, WARP_MMA = 19;
+constexpr int WARP_B_PRODUCER = 16, WARP_X_PRODUCER = 17, WARP_MMA = 19, WARP_MMA2 = 18;
 #else
-constexpr int WARP_B_PRODUCER = 0, WARP_MMA = 1, WARP_X_PRODUCER = 2;
+constexpr int WARP_B_PRODUCER = 0, WARP_MMA = 1, WARP_X_PRODUCER = 2, WARP_MMA2 = 3;
 constexpr int FIRST_CONV_WARP = 4;
 constexpr int FIRST_EPI_WARP = 8;
 constexpr int FIRST_EMIT_WARP = 16;
@@ -570,7 +579,7 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
       ptx::mbar_init(&bars[BAR_AUG_EMPTY + s], 1);
       ptx::mbar_init(&bars[BAR_ACC_FULL + s], 1);
       ptx::mbar_init(&bars[BAR_ACC_EMPTY + s], N_EPI_WARPS);
-      ptx::mbar_init(&bars[BAR_A_FREE + s], 1);
+      ptx::mbar_init(&bars[BAR_A_FREE + s], N_MMA_WARPS);
       ptx::mbar_init(&bars[BAR_EMIT_FULL + s], N_EPI_WARPS);
       ptx::mbar_init(&bars[BAR_EMIT_EMPTY + s], N_EMIT_WARPS);
       for (int kb = 0; kb < MAX_NKB; kb++) ptx::mbar_init(&bars[BAR_A_FULL + s * MAX_NKB + kb], N_CONV_WARPS);
@@ -648,63 +657,85 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
         }
       }
     }
-  } else if (warp == WARP_MMA) {
-    // ================================ MMA issuer ================================
-    // The whole warp runs the (warp-uniform) control flow so that addresses and descriptors stay in
-    // uniform registers; one elected lane issues the tcgen05 instructions.
+  } else if (warp == WARP_MMA || (N_MMA_WARPS == 2 && warp == WARP_MMA2)) {
+    // ================================ MMA issuers ================================
+    // Every issuer warp runs the same (warp-uniform) control flow over all n-tiles, so that the ring / buffer
+    // counters stay in step, but issues only the n-tiles whose accumulator buffer it owns (n-tile counter & 1 == me).
+    // One elected lane issues the tcgen05 instructions.
+    const uint32_t me = (warp == WARP_MMA) ? 0u : 1u;
     const uint32_t idesc = ptx::make_idesc_f16(TM, TN);
     const uint32_t b_base = ptx::smem_u32(smem + L.b);
     const uint64_t aug_ad = ptx::make_smem_desc(ptx::smem_u32(smem + L.aug_a), TM * 16, 128, 0);
     const uint32_t augb = ptx::smem_u32(smem + L.aug_b);
     uint32_t bs = 0, bph = 0, ac = 0, si = 0;             // B ring stage / phase; n-tiles; segments (= A conversions) so far
+    uint32_t a_ready_si = 0xFFFFFFFFu;                    // segment whose A operand this warp has already waited for
+    bool issued = false;                                  // this warp has MMAs in flight that read the current A buffer
     for (uint32_t tile = tile_begin; tile < tile_end; tile += gridDim.x) {
       if (MODE == 2 && p.knn_nblk[tile] == 0) continue;   // nothing to visit: every role skips the tile
       for (BlockIter<MODE> it(p, tile); it.valid(); it.next(), ac++) {
-        const bool first = it.seg_first();
+        const bool mine = N_MMA_WARPS == 1 || (ac & 1u) == me;
         const int abuf = si % NBUF;
         const uint32_t a_par = (si / NBUF) & 1;
         const uint32_t a_tmem = tmem_base + TMEM_A0 + abuf * 128;
         const int buf = ac & 1;
         const uint32_t aph = (ac >> 1) & 1;
-        TC_WAIT(BAR_ACC_EMPTY + buf, aph ^ 1, 3);
-        const uint32_t d_tmem = tmem_base + TMEM_ACC0 + buf * TN;
+        if (mine) {
+          const bool need_a = a_ready_si != si;           // first n-tile of this segment that THIS warp multiplies
+          a_ready_si = si;
+          TC_WAIT(BAR_ACC_EMPTY + buf, aph ^ 1, 3);
+          const uint32_t d_tmem = tmem_base + TMEM_ACC0 + buf * TN;
+          uint32_t s_ = bs, ph_ = bph;
 #pragma unroll
-        for (int kb = 0; kb < NKB; kb++) {
-          if (first) TC_WAIT(BAR_A_FULL + abuf * MAX_NKB + kb, a_par, 4);
-          TC_WAIT(BAR_B_FULL + bs, bph, 5);
+          for (int kb = 0; kb < NKB; kb++) {
+            if (need_a) TC_WAIT(BAR_A_FULL + abuf * MAX_NKB + kb, a_par, 4);
+            TC_WAIT(BAR_B_FULL + s_, ph_, 5);
+            ptx::tc_fence_after();
+            if (ptx::elect_one()) {
+              const uint64_t bd0 = ptx::make_smem_desc(b_base + s_ * B_STAGE_BYTES, 16, 1024, 2);
+              const uint32_t at = a_tmem + kb * 32;
+#if KMB_KO != 2
+              ptx::umma_f16_ts(d_tmem, at, bd0, idesc, kb ? 1u : 0u);
+              ptx::umma_f16_ts(d_tmem, at + 8, bd0 + 2, idesc, 1u);     // +32 bytes along K = +2 in the address field
+              ptx::umma_f16_ts(d_tmem, at + 16, bd0 + 4, idesc, 1u);
+              ptx::umma_f16_ts(d_tmem, at + 24, bd0 + 6, idesc, 1u);
+#else
+              (void)bd0; (void)at;
+#endif
+              ptx::umma_commit(&bars[BAR_B_EMPTY + s_]);
+            }
+            __syncwarp();
+            if (++s_ == B_STAGES) { s_ = 0; ph_ ^= 1; }
+          }
+          // bias step: acc += ones(128x16) * bias(128x16)^T  (both operands no-swizzle K-major smem blocks)
+          TC_WAIT(BAR_AUG_FULL + buf, aph, 6);
           ptx::tc_fence_after();
           if (ptx::elect_one()) {
-            const uint64_t bd0 = ptx::make_smem_desc(b_base + bs * B_STAGE_BYTES, 16, 1024, 2);
-            const uint32_t at = a_tmem + kb * 32;
+            const uint64_t bd = ptx::make_smem_desc(augb + buf * AUG_B_BYTES, TN * 16, 128, 0);
 #if KMB_KO != 2
-            ptx::umma_f16_ts(d_tmem, at, bd0, idesc, kb ? 1u : 0u);
-            ptx::umma_f16_ts(d_tmem, at + 8, bd0 + 2, idesc, 1u);     // +32 bytes along K = +2 in the address field
-            ptx::umma_f16_ts(d_tmem, at + 16, bd0 + 4, idesc, 1u);
-            ptx::umma_f16_ts(d_tmem, at + 24, bd0 + 6, idesc, 1u);
+            ptx::umma_f16(d_tmem, aug_ad, bd, idesc, 1u);
 #else
-            (void)bd0; (void)at;
+            (void)bd;
 #endif
-            ptx::umma_commit(&bars[BAR_B_EMPTY + bs]);
+            ptx::umma_commit(&bars[BAR_AUG_EMPTY + buf]);
+            ptx::umma_commit(&bars[BAR_ACC_FULL + buf]);
           }
           __syncwarp();
-          if (++bs == B_STAGES) { bs = 0; bph ^= 1; }
+          issued = true;
         }
-        // bias step: acc += ones(128x16) * bias(128x16)^T  (both operands no-swizzle K-major smem blocks)
-        TC_WAIT(BAR_AUG_FULL + buf, aph, 6);
-        ptx::tc_fence_after();
-        if (ptx::elect_one()) {
-          const uint64_t bd = ptx::make_smem_desc(augb + buf * AUG_B_BYTES, TN * 16, 128, 0);
-#if KMB_KO != 2
-          ptx::umma_f16(d_tmem, aug_ad, bd, idesc, 1u);
-#else
-          (void)bd;
-#endif
-          ptx::umma_commit(&bars[BAR_AUG_EMPTY + buf]);
-          ptx::umma_commit(&bars[BAR_ACC_FULL + buf]);
-          if (it.seg_last()) ptx::umma_commit(&bars[BAR_A_FREE + abuf]);  // every MMA reading this A buffer is done
+        // the B ring advances by one n-tile for every issuer
+        bs += NKB;
+        while (bs >= static_cast<uint32_t>(B_STAGES)) { bs -= B_STAGES; bph ^= 1; }
+        if (it.seg_last()) {
+          // the A buffer of this segment is free once BOTH issuers' MMAs on it have retired: a commit tracks only the
+          // issuing thread's own MMAs, so every issuer arrives (a plain arrive if it multiplied nothing here)
+          if (ptx::elect_one()) {
+            if (issued) ptx::umma_commit(&bars[BAR_A_FREE + abuf]);
+            else ptx::mbar_arrive(&bars[BAR_A_FREE + abuf]);
+          }
+          __syncwarp();
+          issued = false;
+          si++;
         }
-        __syncwarp();
-        if (it.seg_last()) si++;
       }
     }
   } else if (warp >= FIRST_CONV_WARP && warp < FIRST_CONV_WARP + N_CONV_WARPS) {

@@ -230,9 +230,9 @@ KMCUDAResult Shard::yy_step(uint32_t n, const float* X, const float* C, uint32_t
 KMCUDAResult Shard::assign(uint32_t n, const float* X, const float* C, uint32_t* assignments,
                            uint32_t* prev, uint32_t* d_changed, cudaStream_t st) {
   if (n > max_n) return kmcudaInvalidArguments;
-  if (!(tc && n > 0 && use_graph)) KMB_CU(launch_csqr(metric, C, K, D, csq, st), kmcudaRuntimeError);
+  if (!(tc && n > 0 && use_graph && st != nullptr)) KMB_CU(launch_csqr(metric, C, K, D, csq, st), kmcudaRuntimeError);
   last_tc = false;
-  if (tc && n > 0 && use_graph) {
+  if (tc && n > 0 && use_graph && st != nullptr) {   // (the legacy default stream cannot be captured)
     GraphKey key;
     key.X = X; key.C = C; key.a = assignments; key.prev = prev; key.ch = d_changed; key.n = n; key.st = st;
     if (!(assign_graph && key == graph_key)) {
