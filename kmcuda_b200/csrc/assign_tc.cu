@@ -81,7 +81,7 @@ constexpr int LIST_LEN = 8;             // chunk entries per epilogue thread
 #endif
 // Knock-out builds (timing experiments only, results are garbage): 1 = epilogue does not read the accumulators,
 // 2 = no MMA is issued, 3 = converters do no work (no LDS / math / tcgen05.st), 5 = the B / bias copies are not issued,
-// 6 = the X copies are not issued.  Which of them shortens the kernel says what bounds it.
+// 6 = the X copies are not issued, 7 = the epilogue loads the accumulators but skips the ALU work on them.  Which of them shortens the kernel says what bounds it.
 #ifndef KMB_KO
 #define KMB_KO 0
 #endif
@@ -433,6 +433,16 @@ __device__ __forceinline__ void note_timeout(uint32_t* counters, int where) {
 #define TC_WAIT(bar, parity, site) \
   do { if (!ptx::mbar_wait(&bars[bar], (parity), p.counters + CNT_ERR)) note_timeout(p.counters, site); } while (0)
 
+#ifndef KMB_MMA_SPIN
+#define KMB_MMA_SPIN 0
+#endif
+#if KMB_MMA_SPIN
+#define TC_WAIT_MMA(bar, parity, site) \
+  do { if (!ptx::mbar_wait_spin(&bars[bar], (parity), p.counters + CNT_ERR)) note_timeout(p.counters, site); } while (0)
+#else
+#define TC_WAIT_MMA TC_WAIT
+#endif
+
 // the reference's bookkeeping for one decided row (kmeans.cu:356-363); returns 1 if the assignment changed
 __device__ __forceinline__ uint32_t commit_assignment(uint32_t* __restrict__ assign, uint32_t* __restrict__ prev,
                                                       uint64_t row, uint32_t winner) {
@@ -682,13 +692,13 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
         if (mine) {
           const bool need_a = a_ready_si != si;           // first n-tile of this segment that THIS warp multiplies
           a_ready_si = si;
-          TC_WAIT(BAR_ACC_EMPTY + buf, aph ^ 1, 3);
+          TC_WAIT_MMA(BAR_ACC_EMPTY + buf, aph ^ 1, 3);
           const uint32_t d_tmem = tmem_base + TMEM_ACC0 + buf * TN;
           uint32_t s_ = bs, ph_ = bph;
 #pragma unroll
           for (int kb = 0; kb < NKB; kb++) {
-            if (need_a) TC_WAIT(BAR_A_FULL + abuf * MAX_NKB + kb, a_par, 4);
-            TC_WAIT(BAR_B_FULL + s_, ph_, 5);
+            if (need_a) TC_WAIT_MMA(BAR_A_FULL + abuf * MAX_NKB + kb, a_par, 4);
+            TC_WAIT_MMA(BAR_B_FULL + s_, ph_, 5);
             ptx::tc_fence_after();
             if (ptx::elect_one()) {
               const uint64_t bd0 = ptx::make_smem_desc(b_base + s_ * B_STAGE_BYTES, 16, 1024, 2);
@@ -707,7 +717,7 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
             if (++s_ == B_STAGES) { s_ = 0; ph_ ^= 1; }
           }
           // bias step: acc += ones(128x16) * bias(128x16)^T  (both operands no-swizzle K-major smem blocks)
-          TC_WAIT(BAR_AUG_FULL + buf, aph, 6);
+          TC_WAIT_MMA(BAR_AUG_FULL + buf, aph, 6);
           ptx::tc_fence_after();
           if (ptx::elect_one()) {
             const uint64_t bd = ptx::make_smem_desc(augb + buf * AUG_B_BYTES, TN * 16, 128, 0);
@@ -1053,6 +1063,16 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
         // chunk maxima with three-input maxima (FMNMX3): 16 instructions per 32 columns
         float t0[8], t1[8];      // MODE 2 only: maxima of the 4-column groups
         float cm0, cm1;
+#if KMB_KO == 7
+        if (MODE == 0) {   // timing build: the accumulators are loaded, the ALU work on them is skipped
+          uint32_t x0 = 0, x1 = 0;
+#pragma unroll
+          for (int jj = 0; jj < 32; jj += 8) { x0 ^= r0[jj]; x1 ^= r1[jj]; }
+          M = fmaxf(M, __uint_as_float(x0 & x1 & 0x3fffffffu));
+          if (it.seg_last()) si++;
+          continue;
+        }
+#endif
         if (MODE == 2) {
 #pragma unroll
           for (int i = 0; i < 8; i++) {

@@ -98,6 +98,16 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, volati
   return mbar_wait_slow(addr, parity, err);
 }
 
+// The MMA issuer's wait: plain polling (no suspend hint).  The issuer is the one warp whose wake-up latency is paid by
+// the tensor pipe; a sleeping wait hands the issue slot to the other warps but resumes late.
+__device__ __forceinline__ bool mbar_wait_spin(uint64_t* bar, uint32_t parity, volatile uint32_t* err) {
+  const uint32_t addr = smem_u32(bar);
+#pragma unroll 1
+  for (int i = 0; i < 4096; i++)
+    if (mbar_try_wait_nohint(addr, parity)) return true;
+  return mbar_wait_slow(addr, parity, err);
+}
+
 // ---------------------------------------------------------------------------- packed fp32 pairs (sm_100: FADD2 / FMUL2 / FFMA2)
 // One instruction, two IEEE fp32 operations (same rounding as the scalar forms).  Used where every lane walks a
 // whole row: halves the issue slots of the converter and of the epilogue's threshold compare.
