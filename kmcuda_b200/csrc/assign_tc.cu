@@ -85,13 +85,11 @@ constexpr int LIST_LEN = 8;             // chunk entries per epilogue thread
 #ifndef KMB_KO
 #define KMB_KO 0
 #endif
-// MMA issuer warps.  ncu (profiles/r02_tc_assign_v5_*): with ONE issuer the converter warps wait 62 % and the epilogue
-// warps 41 % of their time for the MMA warp, whose own samples are spread over its control code (barrier probes at ~100
-// cycles each, branches, instruction fetches): 6 waits + 17 MMAs + 6 commits per n-tile take ~2200 cycles to issue
-// against 1088 cycles of tensor work, so the tensor pipe idles 42 %.  Two issuers take alternate n-tiles (one per
-// accumulator buffer): their waits overlap.
+// MMA issuer warps: ONE.  (Round 2 measured a second issuer taking alternate n-tiles: it helped the whole-warp
+// elect-per-K-block issue loop, 5.05 -> 4.40 ms, and hurts the lean single-thread loop, 3.88 -> 4.29 ms: with two n-tiles
+// in flight the 5-stage B ring, 1.25 n-tiles deep, becomes the limit.)  KMB_MMA_WARPS=2 keeps the variant buildable.
 #ifndef KMB_MMA_WARPS
-#define KMB_MMA_WARPS 2
+#define KMB_MMA_WARPS 1
 #endif
 constexpr int N_MMA_WARPS = KMB_MMA_WARPS;
 #if KMB_ROLE_ORDER == 1
@@ -427,18 +425,13 @@ __global__ void tc_prep_table_kernel(int metric, const float* __restrict__ C, co
 // ---------------------------------------------------------------------------------------------------
 // the main kernel
 // ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void note_timeout(uint32_t* counters, int where) {
-  atomicMax(&counters[CNT_ERR], 0x1000u + where);
-}
-#define TC_WAIT(bar, parity, site) \
-  do { if (!ptx::mbar_wait(&bars[bar], (parity), p.counters + CNT_ERR)) note_timeout(p.counters, site); } while (0)
-
+// bars_u32 = shared-space address of bars[0] (computed once per thread)
+#define TC_WAIT(bar, parity, site) ptx::mbar_wait(bars_u32 + 8u * static_cast<uint32_t>(bar), (parity), p.counters + CNT_ERR, site)
 #ifndef KMB_MMA_SPIN
 #define KMB_MMA_SPIN 0
 #endif
 #if KMB_MMA_SPIN
-#define TC_WAIT_MMA(bar, parity, site) \
-  do { if (!ptx::mbar_wait_spin(&bars[bar], (parity), p.counters + CNT_ERR)) note_timeout(p.counters, site); } while (0)
+#define TC_WAIT_MMA(bar, parity, site) ptx::mbar_wait_spin(bars_u32 + 8u * static_cast<uint32_t>(bar), (parity), p.counters + CNT_ERR, site)
 #else
 #define TC_WAIT_MMA TC_WAIT
 #endif
@@ -557,6 +550,7 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   const SmemLayout L = smem_layout();
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
+  const uint32_t bars_u32 = ptx::smem_u32(bars);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L.tmem_slot);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int nkb = NKB;
@@ -668,83 +662,73 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
       }
     }
   } else if (warp == WARP_MMA || (N_MMA_WARPS == 2 && warp == WARP_MMA2)) {
-    // ================================ MMA issuers ================================
-    // Every issuer warp runs the same (warp-uniform) control flow over all n-tiles, so that the ring / buffer
-    // counters stay in step, but issues only the n-tiles whose accumulator buffer it owns (n-tile counter & 1 == me).
-    // One elected lane issues the tcgen05 instructions.
-    const uint32_t me = (warp == WARP_MMA) ? 0u : 1u;
-    const uint32_t idesc = ptx::make_idesc_f16(TM, TN);
-    const uint32_t b_base = ptx::smem_u32(smem + L.b);
-    const uint64_t aug_ad = ptx::make_smem_desc(ptx::smem_u32(smem + L.aug_a), TM * 16, 128, 0);
-    const uint32_t augb = ptx::smem_u32(smem + L.aug_b);
-    uint32_t bs = 0, bph = 0, ac = 0, si = 0;             // B ring stage / phase; n-tiles; segments (= A conversions) so far
-    uint32_t a_ready_si = 0xFFFFFFFFu;                    // segment whose A operand this warp has already waited for
-    bool issued = false;                                  // this warp has MMAs in flight that read the current A buffer
-    for (uint32_t tile = tile_begin; tile < tile_end; tile += gridDim.x) {
-      if (MODE == 2 && p.knn_nblk[tile] == 0) continue;   // nothing to visit: every role skips the tile
-      for (BlockIter<MODE> it(p, tile); it.valid(); it.next(), ac++) {
-        const bool mine = N_MMA_WARPS == 1 || (ac & 1u) == me;
-        const int abuf = si % NBUF;
-        const uint32_t a_par = (si / NBUF) & 1;
-        const uint32_t a_tmem = tmem_base + TMEM_A0 + abuf * 128;
-        const int buf = ac & 1;
-        const uint32_t aph = (ac >> 1) & 1;
-        if (mine) {
-          const bool need_a = a_ready_si != si;           // first n-tile of this segment that THIS warp multiplies
-          a_ready_si = si;
-          TC_WAIT_MMA(BAR_ACC_EMPTY + buf, aph ^ 1, 3);
-          const uint32_t d_tmem = tmem_base + TMEM_ACC0 + buf * TN;
-          uint32_t s_ = bs, ph_ = bph;
+    // ================================ MMA issuer(s) ================================
+    // ONE thread per issuer warp runs the whole role (tcgen05.mma / commit are single-thread instructions): no
+    // election, no reconvergence points, no warp-wide barrier probes.  ncu of the previous version (whole warp +
+    // elect per K-block, profiles/r02_tc_assign_v6_*): ~330 SASS instructions per n-tile at ~6 cycles each = ~2000
+    // cycles to issue 1088 cycles of tensor work -- the issuer, not the tensor pipe, paced the kernel.  Descriptors are
+    // built once; a K-block is one asm statement (4 MMAs + commit).
+    // With two issuers every issuer walks all n-tiles (so the ring / buffer counters stay in step) but issues only
+    // the n-tiles whose accumulator buffer it owns (n-tile counter & 1 == me).
+    if (ptx::elect_one()) {   // (elect.sync, not `lane == 0`: ptxas then keeps the operands in uniform registers instead of
+                              // wrapping every tcgen05 instruction in a per-lane R2UR.BROADCAST loop)
+      const uint32_t me = (warp == WARP_MMA) ? 0u : 1u;
+      const uint32_t idesc = ptx::make_idesc_f16(TM, TN);
+      const uint64_t bdesc0 = ptx::make_smem_desc(ptx::smem_u32(smem + L.b), 16, 1024, 2);
+      const uint64_t aug_ad = ptx::make_smem_desc(ptx::smem_u32(smem + L.aug_a), TM * 16, 128, 0);
+      const uint64_t aug_bd0 = ptx::make_smem_desc(ptx::smem_u32(smem + L.aug_b), TN * 16, 128, 0);
+      uint32_t bs = 0, bph = 0, ac = 0, si = 0;             // B ring stage / phase; n-tiles; segments (= A conversions) so far
+      uint32_t a_ready_si = 0xFFFFFFFFu;                    // segment whose A operand this issuer has already waited for
+      bool issued = false;                                  // this issuer has MMAs in flight that read the current A buffer
+      for (uint32_t tile = tile_begin; tile < tile_end; tile += gridDim.x) {
+        if (MODE == 2 && p.knn_nblk[tile] == 0) continue;   // nothing to visit: every role skips the tile
+        for (BlockIter<MODE> it(p, tile); it.valid(); it.next(), ac++) {
+          const bool mine = N_MMA_WARPS == 1 || (ac & 1u) == me;
+          const uint32_t abuf = si % NBUF;
+          const uint32_t a_par = (si / NBUF) & 1;
+          const uint32_t buf = ac & 1;
+          const uint32_t aph = (ac >> 1) & 1;
+          if (mine) {
+            const bool need_a = a_ready_si != si;           // first n-tile of this segment that THIS issuer multiplies
+            a_ready_si = si;
+            const uint32_t a_tmem = tmem_base + TMEM_A0 + abuf * 128;
+            const uint32_t d_tmem = tmem_base + TMEM_ACC0 + buf * TN;
+            TC_WAIT_MMA(BAR_ACC_EMPTY + buf, aph ^ 1, 3);
+            uint32_t s_ = bs, ph_ = bph;
 #pragma unroll
-          for (int kb = 0; kb < NKB; kb++) {
-            if (need_a) TC_WAIT_MMA(BAR_A_FULL + abuf * MAX_NKB + kb, a_par, 4);
-            TC_WAIT_MMA(BAR_B_FULL + s_, ph_, 5);
-            ptx::tc_fence_after();
-            if (ptx::elect_one()) {
-              const uint64_t bd0 = ptx::make_smem_desc(b_base + s_ * B_STAGE_BYTES, 16, 1024, 2);
-              const uint32_t at = a_tmem + kb * 32;
+            for (int kb = 0; kb < NKB; kb++) {
+              if (need_a) TC_WAIT_MMA(BAR_A_FULL + abuf * MAX_NKB + kb, a_par, 4);
+              TC_WAIT_MMA(BAR_B_FULL + s_, ph_, 5);
+              ptx::tc_fence_after();
 #if KMB_KO != 2
-              ptx::umma_f16_ts(d_tmem, at, bd0, idesc, kb ? 1u : 0u);
-              ptx::umma_f16_ts(d_tmem, at + 8, bd0 + 2, idesc, 1u);     // +32 bytes along K = +2 in the address field
-              ptx::umma_f16_ts(d_tmem, at + 16, bd0 + 4, idesc, 1u);
-              ptx::umma_f16_ts(d_tmem, at + 24, bd0 + 6, idesc, 1u);
+              ptx::umma_f16_ts_kblock(d_tmem, a_tmem + kb * 32, bdesc0 + s_ * (B_STAGE_BYTES >> 4), idesc, kb ? 1u : 0u,
+                                      bars_u32 + 8u * (BAR_B_EMPTY + s_));
 #else
-              (void)bd0; (void)at;
+              ptx::umma_commit_u32(bars_u32 + 8u * (BAR_B_EMPTY + s_));
 #endif
-              ptx::umma_commit(&bars[BAR_B_EMPTY + s_]);
+              if (++s_ == B_STAGES) { s_ = 0; ph_ ^= 1; }
             }
-            __syncwarp();
-            if (++s_ == B_STAGES) { s_ = 0; ph_ ^= 1; }
-          }
-          // bias step: acc += ones(128x16) * bias(128x16)^T  (both operands no-swizzle K-major smem blocks)
-          TC_WAIT_MMA(BAR_AUG_FULL + buf, aph, 6);
-          ptx::tc_fence_after();
-          if (ptx::elect_one()) {
-            const uint64_t bd = ptx::make_smem_desc(augb + buf * AUG_B_BYTES, TN * 16, 128, 0);
+            // bias step: acc += ones(128x16) * bias(128x16)^T  (both operands no-swizzle K-major smem blocks)
+            TC_WAIT_MMA(BAR_AUG_FULL + buf, aph, 6);
+            ptx::tc_fence_after();
 #if KMB_KO != 2
-            ptx::umma_f16(d_tmem, aug_ad, bd, idesc, 1u);
-#else
-            (void)bd;
+            ptx::umma_f16(d_tmem, aug_ad, aug_bd0 + buf * (AUG_B_BYTES >> 4), idesc, 1u);
 #endif
-            ptx::umma_commit(&bars[BAR_AUG_EMPTY + buf]);
-            ptx::umma_commit(&bars[BAR_ACC_FULL + buf]);
+            ptx::umma_commit_u32(bars_u32 + 8u * (BAR_AUG_EMPTY + buf));
+            ptx::umma_commit_u32(bars_u32 + 8u * (BAR_ACC_FULL + buf));
+            issued = true;
           }
-          __syncwarp();
-          issued = true;
-        }
-        // the B ring advances by one n-tile for every issuer
-        bs += NKB;
-        while (bs >= static_cast<uint32_t>(B_STAGES)) { bs -= B_STAGES; bph ^= 1; }
-        if (it.seg_last()) {
-          // the A buffer of this segment is free once BOTH issuers' MMAs on it have retired: a commit tracks only the
-          // issuing thread's own MMAs, so every issuer arrives (a plain arrive if it multiplied nothing here)
-          if (ptx::elect_one()) {
-            if (issued) ptx::umma_commit(&bars[BAR_A_FREE + abuf]);
-            else ptx::mbar_arrive(&bars[BAR_A_FREE + abuf]);
+          // the B ring advances by one n-tile for every issuer
+          bs += NKB;
+          while (bs >= static_cast<uint32_t>(B_STAGES)) { bs -= B_STAGES; bph ^= 1; }
+          if (it.seg_last()) {
+            // the A buffer of this segment is free once BOTH issuers' MMAs on it have retired: a commit tracks only the
+            // issuing thread's own MMAs, so every issuer arrives (a plain arrive if it multiplied nothing here)
+            if (issued) ptx::umma_commit_u32(bars_u32 + 8u * (BAR_A_FREE + abuf));
+            else ptx::mbar_arrive_u32(bars_u32 + 8u * (BAR_A_FREE + abuf));
+            issued = false;
+            si++;
           }
-          __syncwarp();
-          issued = false;
-          si++;
         }
       }
     }

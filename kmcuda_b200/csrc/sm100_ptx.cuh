@@ -70,42 +70,59 @@ __device__ __forceinline__ bool mbar_try_wait_nohint(uint32_t addr, uint32_t par
       : "memory");
   return done != 0;
 }
-__device__ __noinline__ bool mbar_wait_slow(uint32_t addr, uint32_t parity, volatile uint32_t* err) {
-  long long t0 = clock64();
-  for (uint32_t spin = 1;; spin++) {
-#if KMB_WAIT_HINT_NS > 0
-    if (mbar_try_wait(addr, parity, 20000u)) return true;
-    if ((spin & 15) == 0) {
-#else
-    if (mbar_try_wait_nohint(addr, parity)) return true;
-    if ((spin & 1023) == 0) {
+// Out-of-line remainder of every wait: a TIGHT polling loop (round 2's first version re-checked the error word and
+// the clock in the loop body: ncu counted 0.9 G warp instructions per pass -- a third of everything the kernel issued --
+// in that loop, because a hinted try_wait returns on every update of the barrier, not only when the phase flips).
+// `site` names the waiting role; after ~2 s (or as soon as another thread has reported an error) the wait gives up and
+// reports 0x1000 + site in *err: a stuck pipeline must not hang the GPU box.
+#ifndef KMB_SLOW_HINT_NS
+#define KMB_SLOW_HINT_NS 20000
 #endif
-      if (*err) return false;
-      if (clock64() - t0 > 4000000000ll) return false;
+__device__ __noinline__ void mbar_wait_slow(uint32_t addr, uint32_t parity, uint32_t* err, uint32_t site) {
+  const long long t0 = clock64();
+  for (;;) {
+    uint32_t done;
+    // 4096 probes in a loop of 6 SASS instructions (probe, predicated sleep + re-check, counter, compare, branch)
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t.reg .b32 c;\n\t"
+        "mov.u32 c, 0;\n"
+        "KMB_WAIT_LOOP_%=:\n\t"
+#if KMB_WAIT_HINT_NS > 0
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+#else
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+#endif
+        "@p bra KMB_WAIT_DONE_%=;\n\t"
+        "add.u32 c, c, 1;\n\t"
+        "setp.lt.u32 q, c, 4096;\n\t"
+        "@q bra KMB_WAIT_LOOP_%=;\n"
+        "KMB_WAIT_DONE_%=:\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity), "r"(static_cast<uint32_t>(KMB_SLOW_HINT_NS))
+        : "memory");
+    if (done) return;
+    if (*reinterpret_cast<volatile uint32_t*>(err) || clock64() - t0 > 4000000000ll) {
+      atomicMax(err, 0x1000u + site);
+      return;
     }
   }
 }
-__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, volatile uint32_t* err) {
-  const uint32_t addr = smem_u32(bar);
+// The inline part: one probe (with the suspend hint it may sleep up to the hint while the phase has not flipped).
+__device__ __forceinline__ void mbar_wait(uint32_t addr, uint32_t parity, uint32_t* err, uint32_t site) {
 #if KMB_WAIT_HINT_NS > 0
-  if (mbar_try_wait(addr, parity, KMB_WAIT_HINT_NS)) return true;    // common case: one probe (it may sleep up to the hint)
-  if (mbar_try_wait(addr, parity, 20000u)) return true;
+  if (!mbar_try_wait(addr, parity, KMB_WAIT_HINT_NS)) mbar_wait_slow(addr, parity, err, site);
 #else
+  if (!mbar_try_wait_nohint(addr, parity)) mbar_wait_slow(addr, parity, err, site);
+#endif
+}
+// The MMA issuer's wait: plain polling first (no suspend: the issuer is the one warp whose wake-up latency is paid by
+// the tensor pipe).
+__device__ __forceinline__ void mbar_wait_spin(uint32_t addr, uint32_t parity, uint32_t* err, uint32_t site) {
 #pragma unroll 1
   for (int i = 0; i < 64; i++)
-    if (mbar_try_wait_nohint(addr, parity)) return true;
-#endif
-  return mbar_wait_slow(addr, parity, err);
-}
-
-// The MMA issuer's wait: plain polling (no suspend hint).  The issuer is the one warp whose wake-up latency is paid by
-// the tensor pipe; a sleeping wait hands the issue slot to the other warps but resumes late.
-__device__ __forceinline__ bool mbar_wait_spin(uint64_t* bar, uint32_t parity, volatile uint32_t* err) {
-  const uint32_t addr = smem_u32(bar);
-#pragma unroll 1
-  for (int i = 0; i < 4096; i++)
-    if (mbar_try_wait_nohint(addr, parity)) return true;
-  return mbar_wait_slow(addr, parity, err);
+    if (mbar_try_wait_nohint(addr, parity)) return;
+  mbar_wait_slow(addr, parity, err, site);
 }
 
 // ---------------------------------------------------------------------------- packed fp32 pairs (sm_100: FADD2 / FMUL2 / FFMA2)
@@ -205,6 +222,31 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, ui
       "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
       ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+// One K-block of the TS form in a single statement: four K=16 steps (A: +8 TMEM columns per step; B: +32 bytes along K
+// inside the 128-byte swizzle atom = +2 in the descriptor's address field), then a commit that arrives on `bar_u32`
+// (shared-space address) when they have retired.  Keeping it one asm block keeps the issue sequence dense.
+__device__ __forceinline__ void umma_f16_ts_kblock(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
+                                                   uint32_t accumulate_first, uint32_t bar_u32) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t.reg .b64 d1, d2, d3;\n\t.reg .b32 a1, a2, a3;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.eq.b32 q, 0, 0;\n\t"
+      "add.u64 d1, %2, 2;\n\tadd.u64 d2, %2, 4;\n\tadd.u64 d3, %2, 6;\n\t"
+      "add.u32 a1, %1, 8;\n\tadd.u32 a2, %1, 16;\n\tadd.u32 a3, %1, 24;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [a1], d1, %3, q;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [a2], d2, %3, q;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [a3], d3, %3, q;\n\t"
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%5];\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate_first), "r"(bar_u32)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_u32(uint32_t bar_u32) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_u32) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_u32(uint32_t bar_u32) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_u32) : "memory");
 }
 // arrive on an mbarrier when all previously issued tcgen05.mma of this thread have completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
