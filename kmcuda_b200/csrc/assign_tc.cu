@@ -67,6 +67,8 @@ constexpr int X_STAGES = 4;             // fp32 sample stages: 32 features x 128
 constexpr int B_STAGES = KMB_B_STAGES;  // fp16 centroid stages of ONE K-block (64 features x 128 rows = 16 KiB): a stage is
                                         // refilled as soon as its 4 MMAs retire; 4 stages x 256 MMA cycles in flight cover
                                         // the L2 round trip (round 1: 2 stages of 32 KiB left the MMA warp waiting)
+constexpr int B_STAGES_PAIR = 8;        // CTA-pair mode (cta_group::2): every CTA stages HALF a centroid tile per K-block, 8 KiB
+constexpr int B_STAGES_MAX = B_STAGES > B_STAGES_PAIR ? B_STAGES : B_STAGES_PAIR;
 constexpr int X_STAGE_BYTES = TM * 128;
 constexpr int B_KB_BYTES = TN * 128;     // one K-block of the centroid tile: 16 KiB
 constexpr int B_STAGE_BYTES = B_KB_BYTES;
@@ -158,9 +160,9 @@ static_assert(4 * LIST_ARRAY + 2 * 5 * 256 * 4 >= 48 * 256 * 4, "k-NN scratch ov
 enum {
   BAR_X_FULL = 0,                         // [X_STAGES]
   BAR_X_EMPTY = BAR_X_FULL + X_STAGES,    // [X_STAGES]
-  BAR_B_FULL = BAR_X_EMPTY + X_STAGES,    // [B_STAGES]
-  BAR_B_EMPTY = BAR_B_FULL + B_STAGES,    // [B_STAGES]
-  BAR_AUG_FULL = BAR_B_EMPTY + B_STAGES,  // [2]
+  BAR_B_FULL = BAR_X_EMPTY + X_STAGES,    // [B_STAGES_MAX]
+  BAR_B_EMPTY = BAR_B_FULL + B_STAGES_MAX,    // [B_STAGES_MAX]
+  BAR_AUG_FULL = BAR_B_EMPTY + B_STAGES_MAX,  // [2]
   BAR_AUG_EMPTY = BAR_AUG_FULL + 2,       // [2]
   BAR_A_FULL = BAR_AUG_EMPTY + 2,         // [2][MAX_NKB]
   BAR_A_FREE = BAR_A_FULL + 2 * MAX_NKB,  // [2]
@@ -170,7 +172,7 @@ enum {
   BAR_EMIT_EMPTY = BAR_EMIT_FULL + 2,     // [2]
   BAR_COUNT = BAR_EMIT_EMPTY + 2
 };
-static_assert(BAR_COUNT <= 64, "barrier array too small");
+static_assert(BAR_COUNT <= 63, "barrier array too small");   // slot 63 is the CTA's "a wait has given up" flag
 
 struct Params {
   uint32_t n;
@@ -348,7 +350,7 @@ __global__ void tc_prep_table_kernel(int metric, const float* __restrict__ C, co
                                      uint32_t K, int D, int nkb, int nt, __half* __restrict__ table,
                                      __half* __restrict__ aug_blob, Stats* __restrict__ st,
                                      const uint32_t* __restrict__ gather, const float* __restrict__ mu,
-                                     int by_source) {
+                                     int by_source, int pair_blob = 0) {
   // by_source (Yinyang refresh layout): table row r holds centroid gather[r] (UINT32_MAX = padding) and csq[] is
   // indexed by the centroid; otherwise csq[] is indexed by the table row and rows >= K are padding
   const uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -418,7 +420,11 @@ __global__ void tc_prep_table_kernel(int metric, const float* __restrict__ C, co
     __half* blob = aug_blob + static_cast<size_t>(t) * (AUG_B_BYTES / 2);
     for (int k = 0; k < 16; k++) {
       int j = k >> 3, e = k & 7;
-      blob[(j * (TN * 16) + (r >> 3) * 128 + (r & 7) * 16) / 2 + e] = k < 3 ? b[k] : __float2half_rn(0.f);
+      // CTA-pair mode: the block is two 2 KiB pieces (rows 0-63 for the leader CTA, 64-127 for its peer), each in the
+      // layout of a 64-row operand (K halves 64 * 16 bytes apart)
+      const uint32_t off = pair_blob ? (r >> 6) * 2048u + j * 1024u + ((r & 63u) >> 3) * 128u + (r & 7u) * 16u
+                                     : j * (TN * 16) + (r >> 3) * 128 + (r & 7) * 16;
+      blob[off / 2 + e] = k < 3 ? b[k] : __float2half_rn(0.f);
     }
   }
 }
@@ -427,12 +433,14 @@ __global__ void tc_prep_table_kernel(int metric, const float* __restrict__ C, co
 // the main kernel
 // ---------------------------------------------------------------------------------------------------
 // bars_u32 = shared-space address of bars[0] (computed once per thread)
-#define TC_WAIT(bar, parity, site) ptx::mbar_wait(bars_u32 + 8u * static_cast<uint32_t>(bar), (parity), p.counters + CNT_ERR, site)
+#define TC_WAIT(bar, parity, site) \
+  ptx::mbar_wait(bars_u32 + 8u * static_cast<uint32_t>(bar), (parity), p.counters + CNT_ERR, site, bars_u32 + 8u * 63u)
 #ifndef KMB_MMA_SPIN
 #define KMB_MMA_SPIN 0
 #endif
 #if KMB_MMA_SPIN
-#define TC_WAIT_MMA(bar, parity, site) ptx::mbar_wait_spin(bars_u32 + 8u * static_cast<uint32_t>(bar), (parity), p.counters + CNT_ERR, site)
+#define TC_WAIT_MMA(bar, parity, site) \
+  ptx::mbar_wait_spin(bars_u32 + 8u * static_cast<uint32_t>(bar), (parity), p.counters + CNT_ERR, site, bars_u32 + 8u * 63u)
 #else
 #define TC_WAIT_MMA TC_WAIT
 #endif
@@ -540,11 +548,24 @@ __device__ __noinline__ uint32_t knn_append(uint4* ent, uint32_t cnt, float kth,
   return cnt + 1;
 }
 
-template <int NKB, int MODE>   // NKB: K-blocks of 64 features (compile-time: the MMA issue loop must be branch- and
-                               // address-arithmetic-free); MODE 0 = Lloyd assignment, 1 = Yinyang local step (see Params)
+// NKB: K-blocks of 64 features (compile-time: the MMA issue loop must be branch- and address-arithmetic-free); MODE 0 =
+// Lloyd assignment, 1 = Yinyang local step, 2 = k-NN, 3 = Yinyang bounds refresh (see Params).
+// CG = 2 (MODE 0 only): the kernel runs as clusters of two CTAs (the two SMs of a TPC) and the MMAs are
+// tcgen05.mma.cta_group::2 with M = 256: every CTA converts, keeps and post-processes its own 128 sample rows exactly
+// as with CG = 1, but stages only HALF of every centroid tile (64 of the 128 rows) in its shared memory; the leader CTA
+// (cluster rank 0) issues the MMAs for both and its commits arrive on the barriers of both CTAs.  What it buys: the
+// centroid table is streamed L2 -> shared memory once per PAIR of sample tiles (36 GB -> 18 GB per pass at 8M x 256 @
+// 1024) and the tensor cores' shared-memory reads per SM halve -- the kernel runs against the board's power limit, and
+// that traffic is energy.
+template <int NKB, int MODE, int CG = 1>
 __global__ void __launch_bounds__(N_THREADS, 1)
 tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_x,
-                 const Params p) {
+                 const __grid_constant__ CUtensorMap tmap_aug, const Params p) {
+  static_assert(CG == 1 || MODE == 0, "CTA pairs are built for the Lloyd assignment pass only");
+  constexpr bool PAIR = CG == 2;
+  constexpr int BST = PAIR ? B_STAGES_PAIR : B_STAGES;                 // B ring depth
+  constexpr uint32_t BSTAGE = PAIR ? B_KB_BYTES / 2 : B_STAGE_BYTES;   // bytes per B stage in this CTA
+  const uint32_t cta_rank = PAIR ? ptx::cluster_ctarank() : 0u;
   // 1024-byte alignment (128B-swizzle atoms) by an OFFSET into the shared array: the pointer keeps its shared address
   // space, so every access below is LDS / STS.  (Round 1 aligned through uintptr_t; the compiler then treated
   // `smem` as a generic pointer: all shared traffic went through generic LD / ST and the aligned base was
@@ -579,16 +600,21 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
     tile_lo = static_cast<uint32_t>(static_cast<uint64_t>(ntiles) * p.knn_part / p.knn_nparts);
     tile_end = static_cast<uint32_t>(static_cast<uint64_t>(ntiles) * (p.knn_part + 1) / p.knn_nparts);
   }
+  // CTA pairs: consecutive tiles go to the two CTAs of a cluster (gridDim.x is even, cluster rank = blockIdx.x & 1); both
+  // CTAs must make the same number of trips, so an odd tile count is rounded up (the phantom tile's rows are out of
+  // range: TMA fills zeros, nothing is emitted)
+  if (PAIR) tile_end = (tile_end + 1u) & ~1u;
   const uint32_t tile_begin = tile_lo + blockIdx.x;
 
   if (warp == WARP_B_PRODUCER && lane == 0) {
+    bars[63] = 0ull;   // "a wait has given up" flag (mbar_wait_slow)
     ptx::prefetch_tmap(&tmap_b);
     ptx::prefetch_tmap(&tmap_x);
     for (int s = 0; s < X_STAGES; s++) {
       ptx::mbar_init(&bars[BAR_X_FULL + s], 1);
       ptx::mbar_init(&bars[BAR_X_EMPTY + s], N_CONV_WARPS);
     }
-    for (int s = 0; s < B_STAGES; s++) {
+    for (int s = 0; s < BST; s++) {
       ptx::mbar_init(&bars[BAR_B_FULL + s], 1);
       ptx::mbar_init(&bars[BAR_B_EMPTY + s], 1);
     }
@@ -596,15 +622,18 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
       ptx::mbar_init(&bars[BAR_AUG_FULL + s], 1);
       ptx::mbar_init(&bars[BAR_AUG_EMPTY + s], 1);
       ptx::mbar_init(&bars[BAR_ACC_FULL + s], 1);
-      ptx::mbar_init(&bars[BAR_ACC_EMPTY + s], N_EPI_WARPS);
+      ptx::mbar_init(&bars[BAR_ACC_EMPTY + s], N_EPI_WARPS * CG);   // pair: the leader's barrier counts both CTAs' warps
       ptx::mbar_init(&bars[BAR_A_FREE + s], N_MMA_WARPS);
       ptx::mbar_init(&bars[BAR_EMIT_FULL + s], N_EPI_WARPS);
       ptx::mbar_init(&bars[BAR_EMIT_EMPTY + s], N_EMIT_WARPS);
-      for (int kb = 0; kb < MAX_NKB; kb++) ptx::mbar_init(&bars[BAR_A_FULL + s * MAX_NKB + kb], N_CONV_WARPS);
+      for (int kb = 0; kb < MAX_NKB; kb++) ptx::mbar_init(&bars[BAR_A_FULL + s * MAX_NKB + kb], N_CONV_WARPS * CG);
     }
     ptx::fence_mbar_init();
   }
-  if (warp == WARP_MMA) ptx::tmem_alloc(tmem_slot, TMEM_COLS);
+  if (warp == WARP_MMA) {
+    if (PAIR) ptx::tmem_alloc_pair(tmem_slot, TMEM_COLS);   // the same warp of both CTAs
+    else ptx::tmem_alloc(tmem_slot, TMEM_COLS);
+  }
   // constant A-side bias block: ones in the first three K positions of every row
   for (int i = threadIdx.x; i < TM * 16; i += N_THREADS) {
     int r = i >> 4, k = i & 15;
@@ -617,8 +646,11 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
   ptx::fence_proxy_async_smem();
   ptx::tc_fence_before();
   __syncthreads();
+  if (PAIR) ptx::cluster_sync_all();   // the peer's barriers are initialised before anything arrives on them
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // pair mode: arrivals that the LEADER's MMA thread waits for go to the leader's copy of the barrier
+  auto leader_bar = [&](int bar) -> uint32_t { return ptx::mapa_u32(bars_u32 + 8u * static_cast<uint32_t>(bar), 0u); };
 
   if (warp == WARP_B_PRODUCER) {
     // ================================ TMA producer: centroid table + bias blocks ================================
@@ -633,6 +665,12 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
           const int as = ac & 1;
           const uint32_t aph = (ac >> 1) & 1;
           TC_WAIT(BAR_AUG_EMPTY + as, aph ^ 1, 2);
+          if (PAIR) {
+            // this CTA's half of the bias block (2 KiB, rows rank*64 ..) ; the leader's barrier counts both halves
+            if (cta_rank == 0) ptx::mbar_arrive_expect_tx(&bars[BAR_AUG_FULL + as], AUG_B_BYTES);
+            ptx::tma_load_2d_pair(ptx::smem_u32(smem + L.aug_b + as * AUG_B_BYTES), &tmap_aug, 0,
+                                  (n * 2 + static_cast<int>(cta_rank)) * 2, leader_bar(BAR_AUG_FULL + as));
+          } else {
 #if KMB_KO == 5
           ptx::mbar_arrive(&bars[BAR_AUG_FULL + as]);
 #else
@@ -641,17 +679,24 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
                          reinterpret_cast<const uint8_t*>(p.aug_blob) + static_cast<size_t>(n) * AUG_B_BYTES,
                          AUG_B_BYTES, &bars[BAR_AUG_FULL + as]);
 #endif
+          }
           ac++;
 #pragma unroll
           for (int kb = 0; kb < NKB; kb++) {
             TC_WAIT(BAR_B_EMPTY + bs, bph ^ 1, 1);
+            if (PAIR) {
+              if (cta_rank == 0) ptx::mbar_arrive_expect_tx(&bars[BAR_B_FULL + bs], B_KB_BYTES);   // both halves
+              ptx::tma_load_2d_pair(ptx::smem_u32(smem + L.b + bs * BSTAGE), &tmap_b, kb * KB,
+                                    n * TN + static_cast<int>(cta_rank) * (TN / 2), leader_bar(BAR_B_FULL + bs));
+            } else {
 #if KMB_KO == 5
             ptx::mbar_arrive(&bars[BAR_B_FULL + bs]);
 #else
             ptx::mbar_arrive_expect_tx(&bars[BAR_B_FULL + bs], B_KB_BYTES);
             ptx::tma_load_2d(smem + L.b + bs * B_STAGE_BYTES, &tmap_b, kb * KB, n * TN, &bars[BAR_B_FULL + bs]);
 #endif
-            if (++bs == B_STAGES) { bs = 0; bph ^= 1; }
+            }
+            if (++bs == BST) { bs = 0; bph ^= 1; }
           }
         }
       }
@@ -684,13 +729,19 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
     // built once; a K-block is one asm statement (4 MMAs + commit).
     // With two issuers every issuer walks all n-tiles (so the ring / buffer counters stay in step) but issues only
     // the n-tiles whose accumulator buffer it owns (n-tile counter & 1 == me).
-    if (ptx::elect_one()) {   // (elect.sync, not `lane == 0`: ptxas then keeps the operands in uniform registers instead of
-                              // wrapping every tcgen05 instruction in a per-lane R2UR.BROADCAST loop)
+    // CTA pairs: only the leader issues (M = 256 covers both CTAs' rows); its commits are multicast to both CTAs.
+    if ((!PAIR || cta_rank == 0) && ptx::elect_one()) {   // (elect.sync, not `lane == 0`: ptxas then keeps the operands in
+                              // uniform registers instead of wrapping every tcgen05 instruction in a per-lane R2UR.BROADCAST loop)
       const uint32_t me = (warp == WARP_MMA) ? 0u : 1u;
-      const uint32_t idesc = ptx::make_idesc_f16(TM, TN);
+      const uint32_t idesc = ptx::make_idesc_f16(TM * CG, TN);
       const uint64_t bdesc0 = ptx::make_smem_desc(ptx::smem_u32(smem + L.b), 16, 1024, 2);
       const uint64_t aug_ad = ptx::make_smem_desc(ptx::smem_u32(smem + L.aug_a), TM * 16, 128, 0);
-      const uint64_t aug_bd0 = ptx::make_smem_desc(ptx::smem_u32(smem + L.aug_b), TN * 16, 128, 0);
+      // B-side bias block: (TN / CG) rows x 16 K in this CTA; the second K half lies rows * 16 bytes further
+      const uint64_t aug_bd0 = ptx::make_smem_desc(ptx::smem_u32(smem + L.aug_b), (TN / CG) * 16, 128, 0);
+      auto commit = [&](int bar) {
+        if (PAIR) ptx::umma_commit_pair(bars_u32 + 8u * static_cast<uint32_t>(bar));
+        else ptx::umma_commit_u32(bars_u32 + 8u * static_cast<uint32_t>(bar));
+      };
       uint32_t bs = 0, bph = 0, ac = 0, si = 0;             // B ring stage / phase; n-tiles; segments (= A conversions) so far
       uint32_t a_ready_si = 0xFFFFFFFFu;                    // segment whose A operand this issuer has already waited for
       bool issued = false;                                  // this issuer has MMAs in flight that read the current A buffer
@@ -715,30 +766,35 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
               TC_WAIT_MMA(BAR_B_FULL + s_, ph_, 5);
               ptx::tc_fence_after();
 #if KMB_KO != 2
-              ptx::umma_f16_ts_kblock(d_tmem, a_tmem + kb * 32, bdesc0 + s_ * (B_STAGE_BYTES >> 4), idesc, kb ? 1u : 0u,
-                                      bars_u32 + 8u * (BAR_B_EMPTY + s_));
+              if (PAIR)
+                ptx::umma_f16_ts_kblock_pair(d_tmem, a_tmem + kb * 32, bdesc0 + s_ * (BSTAGE >> 4), idesc, kb ? 1u : 0u,
+                                             bars_u32 + 8u * (BAR_B_EMPTY + s_));
+              else
+                ptx::umma_f16_ts_kblock(d_tmem, a_tmem + kb * 32, bdesc0 + s_ * (BSTAGE >> 4), idesc, kb ? 1u : 0u,
+                                        bars_u32 + 8u * (BAR_B_EMPTY + s_));
 #else
-              ptx::umma_commit_u32(bars_u32 + 8u * (BAR_B_EMPTY + s_));
+              commit(BAR_B_EMPTY + s_);
 #endif
-              if (++s_ == B_STAGES) { s_ = 0; ph_ ^= 1; }
+              if (++s_ == BST) { s_ = 0; ph_ ^= 1; }
             }
             // bias step: acc += ones(128x16) * bias(128x16)^T  (both operands no-swizzle K-major smem blocks)
             TC_WAIT_MMA(BAR_AUG_FULL + buf, aph, 6);
             ptx::tc_fence_after();
 #if KMB_KO != 2
-            ptx::umma_f16(d_tmem, aug_ad, aug_bd0 + buf * (AUG_B_BYTES >> 4), idesc, 1u);
+            if (PAIR) ptx::umma_f16_pair(d_tmem, aug_ad, aug_bd0 + buf * (AUG_B_BYTES >> 4), idesc, 1u);
+            else ptx::umma_f16(d_tmem, aug_ad, aug_bd0 + buf * (AUG_B_BYTES >> 4), idesc, 1u);
 #endif
-            ptx::umma_commit_u32(bars_u32 + 8u * (BAR_AUG_EMPTY + buf));
-            ptx::umma_commit_u32(bars_u32 + 8u * (BAR_ACC_FULL + buf));
+            commit(BAR_AUG_EMPTY + buf);
+            commit(BAR_ACC_FULL + buf);
             issued = true;
           }
           // the B ring advances by one n-tile for every issuer
           bs += NKB;
-          while (bs >= static_cast<uint32_t>(B_STAGES)) { bs -= B_STAGES; bph ^= 1; }
+          while (bs >= static_cast<uint32_t>(BST)) { bs -= BST; bph ^= 1; }
           if (it.seg_last()) {
             // the A buffer of this segment is free once BOTH issuers' MMAs on it have retired: a commit tracks only the
             // issuing thread's own MMAs, so every issuer arrives (a plain arrive if it multiplied nothing here)
-            if (issued) ptx::umma_commit_u32(bars_u32 + 8u * (BAR_A_FREE + abuf));
+            if (issued) commit(BAR_A_FREE + abuf);
             else ptx::mbar_arrive_u32(bars_u32 + 8u * (BAR_A_FREE + abuf));
             issued = false;
             si++;
@@ -856,7 +912,10 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
           }
           ptx::tc_fence_before();
           __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(&bars[BAR_A_FULL + abuf * MAX_NKB + kb]);
+          if (lane == 0) {
+            if (PAIR) ptx::mbar_arrive_cluster(leader_bar(BAR_A_FULL + abuf * MAX_NKB + kb));
+            else ptx::mbar_arrive(&bars[BAR_A_FULL + abuf * MAX_NKB + kb]);
+          }
         }
       }
     }
@@ -1005,7 +1064,10 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
         // the accumulator values are in registers: hand the TMEM buffer back to the MMA warp right away
         ptx::tc_fence_before();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&bars[BAR_ACC_EMPTY + buf]);
+        if (lane == 0) {
+          if (PAIR) ptx::mbar_arrive_cluster(leader_bar(BAR_ACC_EMPTY + buf));
+          else ptx::mbar_arrive(&bars[BAR_ACC_EMPTY + buf]);
+        }
 #ifdef KMB_DEBUG_SCORES   // bring-up builds only: 64 stores per n-tile bloat the hot loop's instruction footprint
         if (MODE == 0 && p.dbg_scores) {
           const uint64_t grow = static_cast<uint64_t>(tile) * TM + row;
@@ -1333,9 +1395,11 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
   // teardown
   ptx::tc_fence_before();
   __syncthreads();
+  if (PAIR) ptx::cluster_sync_all();   // no CTA leaves while its peer may still arrive on its barriers / use the pair's TMEM
   if (warp == WARP_MMA) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+    if (PAIR) ptx::tmem_dealloc_pair(tmem_base, TMEM_COLS);
+    else ptx::tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
@@ -1474,6 +1538,11 @@ struct TcPlan {
   float* pair_score = nullptr;
   uint32_t* h_counters = nullptr;  // pinned
   CUtensorMap tmap;     // fp16 centroid table
+  // CTA-pair mode of the Lloyd pass (cta_group::2, see tc_assign_kernel): half-tile boxes of the table, the bias blocks
+  // as 2 KiB pieces per (n-tile, CTA rank), number of CTA pairs that can be resident at once
+  bool pair = false;
+  int pair_clusters = 0;
+  CUtensorMap tmap_pair, tmap_aug;
   int num_sms = 148;
   size_t smem_bytes = 0;
   float* dbg_scores = nullptr;
@@ -1506,15 +1575,15 @@ template <int MODE>
 static void tc_launch_mode(int nkb, unsigned grid, size_t smem, cudaStream_t st, const CUtensorMap& tb,
                            const CUtensorMap& tx, const tc::Params& prm) {
   using namespace tc;
-  switch (nkb) {
-    case 1: tc_assign_kernel<1, MODE><<<grid, N_THREADS, smem, st>>>(tb, tx, prm); break;
-    case 2: tc_assign_kernel<2, MODE><<<grid, N_THREADS, smem, st>>>(tb, tx, prm); break;
-    case 3: tc_assign_kernel<3, MODE><<<grid, N_THREADS, smem, st>>>(tb, tx, prm); break;
-    case 4: tc_assign_kernel<4, MODE><<<grid, N_THREADS, smem, st>>>(tb, tx, prm); break;
-    case 5: tc_assign_kernel<5, MODE><<<grid, N_THREADS, smem, st>>>(tb, tx, prm); break;
-    case 6: tc_assign_kernel<6, MODE><<<grid, N_THREADS, smem, st>>>(tb, tx, prm); break;
-    case 7: tc_assign_kernel<7, MODE><<<grid, N_THREADS, smem, st>>>(tb, tx, prm); break;
-    default: tc_assign_kernel<8, MODE><<<grid, N_THREADS, smem, st>>>(tb, tx, prm); break;
+  switch (nkb) {   // (the third tensor map is only read in CTA-pair mode)
+    case 1: tc_assign_kernel<1, MODE><<<grid, N_THREADS, smem, st>>>(tb, tx, tb, prm); break;
+    case 2: tc_assign_kernel<2, MODE><<<grid, N_THREADS, smem, st>>>(tb, tx, tb, prm); break;
+    case 3: tc_assign_kernel<3, MODE><<<grid, N_THREADS, smem, st>>>(tb, tx, tb, prm); break;
+    case 4: tc_assign_kernel<4, MODE><<<grid, N_THREADS, smem, st>>>(tb, tx, tb, prm); break;
+    case 5: tc_assign_kernel<5, MODE><<<grid, N_THREADS, smem, st>>>(tb, tx, tb, prm); break;
+    case 6: tc_assign_kernel<6, MODE><<<grid, N_THREADS, smem, st>>>(tb, tx, tb, prm); break;
+    case 7: tc_assign_kernel<7, MODE><<<grid, N_THREADS, smem, st>>>(tb, tx, tb, prm); break;
+    default: tc_assign_kernel<8, MODE><<<grid, N_THREADS, smem, st>>>(tb, tx, tb, prm); break;
   }
 }
 static void tc_launch_main(int mode, int nkb, unsigned grid, size_t smem, cudaStream_t st, const CUtensorMap& tb,
@@ -1523,6 +1592,74 @@ static void tc_launch_main(int mode, int nkb, unsigned grid, size_t smem, cudaSt
   else if (mode == 2) tc_launch_mode<2>(nkb, grid, smem, st, tb, tx, prm);
   else if (mode == 1) tc_launch_mode<1>(nkb, grid, smem, st, tb, tx, prm);
   else tc_launch_mode<0>(nkb, grid, smem, st, tb, tx, prm);
+}
+// CTA-pair launch of the Lloyd pass: clusters of 2 CTAs
+template <int NKB>
+static cudaError_t tc_launch_pair_one(unsigned grid, size_t smem, cudaStream_t st, const CUtensorMap& tb,
+                                      const CUtensorMap& tx, const CUtensorMap& ta, const tc::Params& prm) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(tc::N_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, tc::tc_assign_kernel<NKB, 0, 2>, tb, tx, ta, prm);
+}
+static cudaError_t tc_launch_pair(int nkb, unsigned grid, size_t smem, cudaStream_t st, const CUtensorMap& tb,
+                                  const CUtensorMap& tx, const CUtensorMap& ta, const tc::Params& prm) {
+  switch (nkb) {
+    case 1: return tc_launch_pair_one<1>(grid, smem, st, tb, tx, ta, prm);
+    case 2: return tc_launch_pair_one<2>(grid, smem, st, tb, tx, ta, prm);
+    case 3: return tc_launch_pair_one<3>(grid, smem, st, tb, tx, ta, prm);
+    case 4: return tc_launch_pair_one<4>(grid, smem, st, tb, tx, ta, prm);
+    case 5: return tc_launch_pair_one<5>(grid, smem, st, tb, tx, ta, prm);
+    case 6: return tc_launch_pair_one<6>(grid, smem, st, tb, tx, ta, prm);
+    case 7: return tc_launch_pair_one<7>(grid, smem, st, tb, tx, ta, prm);
+    default: return tc_launch_pair_one<8>(grid, smem, st, tb, tx, ta, prm);
+  }
+}
+template <int NKB>
+static int tc_pair_clusters_one(int bytes) {
+  // how many CTA pairs fit on the device at once (0: pair mode unavailable)
+  if (cudaFuncSetAttribute(tc::tc_assign_kernel<NKB, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2);
+  cfg.blockDim = dim3(tc::N_THREADS);
+  cfg.dynamicSmemBytes = bytes;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, tc::tc_assign_kernel<NKB, 0, 2>, &cfg) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+static int tc_pair_clusters(int bytes, int nkb) {
+  switch (nkb) {
+    case 1: return tc_pair_clusters_one<1>(bytes);
+    case 2: return tc_pair_clusters_one<2>(bytes);
+    case 3: return tc_pair_clusters_one<3>(bytes);
+    case 4: return tc_pair_clusters_one<4>(bytes);
+    case 5: return tc_pair_clusters_one<5>(bytes);
+    case 6: return tc_pair_clusters_one<6>(bytes);
+    case 7: return tc_pair_clusters_one<7>(bytes);
+    default: return tc_pair_clusters_one<8>(bytes);
+  }
 }
 template <int NKB>
 static cudaError_t tc_set_smem_attr_one(int bytes) {
@@ -1644,6 +1781,29 @@ cudaError_t tc_plan_create(TcPlan** out, int metric, uint32_t max_n, int D, uint
   }
   p->smem_bytes = smem_layout().total + 1024;
   TC_TRY(tc_set_smem_attr(static_cast<int>(p->smem_bytes), p->nkb));
+  {
+    // CTA-pair mode (KMCUDA_B200_PAIR=0 switches it off): half-tile boxes of the table, the bias blocks as a
+    // [nt * 4][256 words] matrix whose rows (t, rank, K half) are the 1 KiB halves of the 2 KiB pieces
+    const char* pe = getenv("KMCUDA_B200_PAIR");
+    bool want = !(pe && pe[0] == '0');
+    if (want) {
+      cuuint32_t boxp[2] = {KB, TN / 2};
+      CUresult c1 = enc(&p->tmap_pair, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, p->table, gdim, gstride, boxp, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      cuuint64_t gdima[2] = {256, static_cast<cuuint64_t>(p->nt) * 4};
+      cuuint64_t gstridea[1] = {1024};
+      cuuint32_t boxa[2] = {256, 2};
+      CUresult c2 = enc(&p->tmap_aug, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, p->aug_blob, gdima, gstridea, boxa, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (c1 == CUDA_SUCCESS && c2 == CUDA_SUCCESS) {
+        p->pair_clusters = tc_pair_clusters(static_cast<int>(p->smem_bytes), p->nkb);
+        // only worth it when (nearly) every SM finds a partner
+        p->pair = p->pair_clusters * 2 >= p->num_sms - 4;
+      }
+    }
+  }
 #undef TC_TRY
   *out = p;
   return cudaSuccess;
@@ -1651,7 +1811,7 @@ cudaError_t tc_plan_create(TcPlan** out, int metric, uint32_t max_n, int D, uint
 
 // counters reset + centroid preparation (scale, fp16 table, bias blobs) + the parameter block shared by both modes
 static cudaError_t tc_prepare(TcPlan* p, const float* C, const float* csq, uint32_t n, tc::Params* out,
-                              cudaStream_t st, bool yy_layout = false) {
+                              cudaStream_t st, bool yy_layout = false, bool pair_blob = false) {
   using namespace tc;
   cudaError_t e;
   if ((e = cudaMemsetAsync(p->counters, 0, sizeof(uint32_t) * CNT_N, st)) != cudaSuccess) return e;
@@ -1676,7 +1836,7 @@ static cudaError_t tc_prepare(TcPlan* p, const float* C, const float* csq, uint3
   const uint32_t rows_pad = static_cast<uint32_t>(p->nt) * TN;
   if (!yy_layout)
     tc_prep_table_kernel<<<(rows_pad * 32 + 255) / 256, 256, 0, st>>>(p->metric, C, nsq, p->K, p->D, p->nkb, p->nt, p->table,
-                                                                      p->aug_blob, p->stats, nullptr, mu, 0);
+                                                                      p->aug_blob, p->stats, nullptr, mu, 0, pair_blob ? 1 : 0);
   else
     tc_prep_table_kernel<<<(static_cast<uint32_t>(p->nt3) * TN * 32 + 255) / 256, 256, 0, st>>>(
         p->metric, C, nsq, p->K, p->D, p->nkb, p->nt3, p->table3, p->aug_blob3, p->stats, p->yy_perm, mu, 1);
@@ -1749,12 +1909,15 @@ cudaError_t tc_assign(TcPlan* p, const float* X, const float* C, const float* cs
     if (cr != CUDA_SUCCESS) return cudaErrorInvalidValue;
   }
   Params prm;
-  if ((e = tc_prepare(p, C, csq, n, &prm, st)) != cudaSuccess) return e;
+  // CTA pairs pay off once every pair has several tile pairs to stream the table for
+  const bool pair = p->pair && (n + TM - 1) / TM >= 4u * static_cast<uint32_t>(p->num_sms);
+  if ((e = tc_prepare(p, C, csq, n, &prm, st, false, pair)) != cudaSuccess) return e;
   prm.result = result;
   prm.assign = assign;      // non-null: the pass's bookkeeping (prev / assign / changed counter) is fused
   prm.prev = prev;
   prm.d_changed = d_changed;
-  const unsigned grid = min(static_cast<uint32_t>(p->num_sms), prm.ntiles);
+  unsigned grid = min(static_cast<uint32_t>(p->num_sms), prm.ntiles);
+  if (pair) grid = min(static_cast<uint32_t>(p->pair_clusters) * 2u, (prm.ntiles + 1u) & ~1u);
   const int slot = static_cast<int>(p->passes % TcPlan::kEvRing);
   if (p->capturing) {
     p->graph_slot = slot;
@@ -1763,7 +1926,11 @@ cudaError_t tc_assign(TcPlan* p, const float* X, const float* C, const float* cs
     p->graph_slot = -1;
     cudaEventRecord(p->ev0[slot], st);
   }
-  tc_launch_main(0, p->nkb, grid, p->smem_bytes, st, p->tmap, tmap_x, prm);
+  if (pair) {
+    if ((e = tc_launch_pair(p->nkb, grid, p->smem_bytes, st, p->tmap_pair, tmap_x, p->tmap_aug, prm)) != cudaSuccess) return e;
+  } else {
+    tc_launch_main(0, p->nkb, grid, p->smem_bytes, st, p->tmap, tmap_x, prm);
+  }
   if (p->capturing) cudaEventRecordWithFlags(p->ev1[slot], st, cudaEventRecordExternal);
   else cudaEventRecord(p->ev1[slot], st);
   p->passes++;

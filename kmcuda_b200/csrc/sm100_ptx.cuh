@@ -78,11 +78,16 @@ __device__ __forceinline__ bool mbar_try_wait_nohint(uint32_t addr, uint32_t par
 #ifndef KMB_SLOW_HINT_NS
 #define KMB_SLOW_HINT_NS 20000
 #endif
-__device__ __noinline__ void mbar_wait_slow(uint32_t addr, uint32_t parity, uint32_t* err, uint32_t site) {
+__device__ __noinline__ void mbar_wait_slow(uint32_t addr, uint32_t parity, uint32_t* err, uint32_t site, uint32_t flag_u32) {
+  // flag_u32: a word of this CTA's shared memory that is set once any wait of the CTA has given up; from then on every
+  // wait returns at once, so a broken pipeline drains in milliseconds instead of timing out wait by wait
+  uint32_t dead;
+  asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(dead) : "r"(flag_u32));
+  if (dead) return;
   const long long t0 = clock64();
   for (;;) {
     uint32_t done;
-    // 4096 probes in a loop of 6 SASS instructions (probe, predicated sleep + re-check, counter, compare, branch)
+    // 1024 probes in a loop of 7 SASS instructions (probe, predicated sleep + re-check, counter, compare, branch)
     asm volatile(
         "{\n\t.reg .pred p, q;\n\t.reg .b32 c;\n\t"
         "mov.u32 c, 0;\n"
@@ -94,7 +99,7 @@ __device__ __noinline__ void mbar_wait_slow(uint32_t addr, uint32_t parity, uint
 #endif
         "@p bra KMB_WAIT_DONE_%=;\n\t"
         "add.u32 c, c, 1;\n\t"
-        "setp.lt.u32 q, c, 4096;\n\t"
+        "setp.lt.u32 q, c, 1024;\n\t"
         "@q bra KMB_WAIT_LOOP_%=;\n"
         "KMB_WAIT_DONE_%=:\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
@@ -102,27 +107,30 @@ __device__ __noinline__ void mbar_wait_slow(uint32_t addr, uint32_t parity, uint
         : "r"(addr), "r"(parity), "r"(static_cast<uint32_t>(KMB_SLOW_HINT_NS))
         : "memory");
     if (done) return;
-    if (*reinterpret_cast<volatile uint32_t*>(err) || clock64() - t0 > 4000000000ll) {
-      atomicMax(err, 0x1000u + site);
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(dead) : "r"(flag_u32));
+    const bool lost = dead || *reinterpret_cast<volatile uint32_t*>(err);
+    if (lost || clock64() - t0 > 4000000000ll) {
+      if (!lost) atomicMax(err, 0x1000u + site);
+      asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(flag_u32), "r"(1u) : "memory");
       return;
     }
   }
 }
 // The inline part: one probe (with the suspend hint it may sleep up to the hint while the phase has not flipped).
-__device__ __forceinline__ void mbar_wait(uint32_t addr, uint32_t parity, uint32_t* err, uint32_t site) {
+__device__ __forceinline__ void mbar_wait(uint32_t addr, uint32_t parity, uint32_t* err, uint32_t site, uint32_t flag_u32) {
 #if KMB_WAIT_HINT_NS > 0
-  if (!mbar_try_wait(addr, parity, KMB_WAIT_HINT_NS)) mbar_wait_slow(addr, parity, err, site);
+  if (!mbar_try_wait(addr, parity, KMB_WAIT_HINT_NS)) mbar_wait_slow(addr, parity, err, site, flag_u32);
 #else
-  if (!mbar_try_wait_nohint(addr, parity)) mbar_wait_slow(addr, parity, err, site);
+  if (!mbar_try_wait_nohint(addr, parity)) mbar_wait_slow(addr, parity, err, site, flag_u32);
 #endif
 }
 // The MMA issuer's wait: plain polling first (no suspend: the issuer is the one warp whose wake-up latency is paid by
 // the tensor pipe).
-__device__ __forceinline__ void mbar_wait_spin(uint32_t addr, uint32_t parity, uint32_t* err, uint32_t site) {
+__device__ __forceinline__ void mbar_wait_spin(uint32_t addr, uint32_t parity, uint32_t* err, uint32_t site, uint32_t flag_u32) {
 #pragma unroll 1
   for (int i = 0; i < 64; i++)
     if (mbar_try_wait_nohint(addr, parity)) return;
-  mbar_wait_slow(addr, parity, err, site);
+  mbar_wait_slow(addr, parity, err, site, flag_u32);
 }
 
 // ---------------------------------------------------------------------------- packed fp32 pairs (sm_100: FADD2 / FMUL2 / FFMA2)
@@ -280,6 +288,84 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------- CTA pairs (cta_group::2)
+// Two CTAs of one cluster (the two SMs of a TPC) run ONE tcgen05.mma of M = 256: each CTA holds its 128 rows of A and
+// of the accumulator in its own tensor memory and HALF of the B tile (N / 2 rows) in its own shared memory; the
+// leader CTA (cluster rank 0) issues the instruction for both.  Per SM this halves the B traffic: L2 -> shared memory
+// copies, shared-memory writes and the tensor core's shared-memory reads.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `local_u32` (a shared::cta address of this CTA's layout) inside CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_u32, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_u32), "r"(rank));
+  return r;
+}
+// Arrive on a barrier of another CTA of the cluster.  RELAXED: what the waiter (the leader's MMA thread) consumes was
+// produced through tensor memory and is ordered by tcgen05.wait::ld / wait::st + tcgen05.fence::before_thread_sync; a
+// .release at cluster scope compiles to a cluster-wide memory barrier in front of every arrive (ncu of the first
+// CTA-pair build: half of the epilogue warps' time was that barrier).
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// 2-D tiled load into THIS CTA's shared memory whose completion bytes are counted on the barrier at `leader_bar_u32`
+// (a shared::cluster address inside the leader CTA)
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst_u32, const void* tmap, int c0, int c1, uint32_t leader_bar_u32) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst_u32), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(leader_bar_u32), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_dst, uint32_t ncols) {  // the same warp of BOTH CTAs
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// commit of the leader's MMAs: arrives on the barrier at the same shared-memory offset in BOTH CTAs
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar_u32) {
+  asm volatile(
+      "{\n\t.reg .b16 m;\n\tmov.b16 m, 3;\n\t"
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], m;\n\t}"
+      ::"r"(bar_u32)
+      : "memory");
+}
+// one K-block (TS form) for the pair: 4 x (M = 256, N = 128, K = 16), then the multicast commit
+__device__ __forceinline__ void umma_f16_ts_kblock_pair(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
+                                                        uint32_t accumulate_first, uint32_t bar_u32) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t.reg .b64 d1, d2, d3;\n\t.reg .b32 a1, a2, a3;\n\t.reg .b16 m;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.eq.b32 q, 0, 0;\n\t"
+      "mov.b16 m, 3;\n\t"
+      "add.u64 d1, %2, 2;\n\tadd.u64 d2, %2, 4;\n\tadd.u64 d3, %2, 6;\n\t"
+      "add.u32 a1, %1, 8;\n\tadd.u32 a2, %1, 16;\n\tadd.u32 a3, %1, 24;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [a1], d1, %3, q;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [a2], d2, %3, q;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [a3], d3, %3, q;\n\t"
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%5], m;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate_first), "r"(bar_u32)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 
 // ---------------------------------------------------------------------------- descriptors
 // shared-memory matrix descriptor (PTX ISA, tcgen05 "matrix descriptor"):

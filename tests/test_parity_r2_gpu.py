@@ -502,3 +502,23 @@ def test_cuda_graph_replay_of_the_assignment_pass(ours, monkeypatch):
     monkeypatch.delenv("KMCUDA_B200_GRAPH")
     assert np.array_equal(runs["0"][1], runs["1"][1])
     np.testing.assert_array_equal(runs["0"][0], runs["1"][0])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [75776 + 3 * 128 + 17, 75776 + 4 * 128])
+def test_cta_pair_pass_equals_single_cta_pass_and_reference(ours, ref, monkeypatch, n):
+    """The Lloyd pass runs as clusters of two CTAs (tcgen05.mma.cta_group::2, M = 256) once there are enough sample
+    tiles; an odd tile count leaves a phantom tile in the last pair.  Both launch modes must give the reference's
+    assignments (reference src/kmeans.cu:293-364)."""
+    rng = np.random.default_rng(4242)
+    d, k = 256, 1000          # K % 128 != 0: padded table rows in the last n-tile of both CTAs' halves
+    X = rng.random((n, d), dtype=np.float32)
+    C = X[rng.choice(n, k, replace=False)].copy()
+    _, a_ref = c_kmeans(ref, X, C, 1.0, 0.0)
+    got = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("KMCUDA_B200_PAIR", mode)
+        _, a = c_kmeans(ours, X, C, 1.0, 0.0)
+        got[mode] = a
+        assert np.array_equal(a, a_ref), "pair=%s: %d assignments differ from the reference" % (mode, int((a != a_ref).sum()))
+    assert np.array_equal(got["1"], got["0"])
