@@ -67,7 +67,10 @@ constexpr int X_STAGES = 4;             // fp32 sample stages: 32 features x 128
 constexpr int B_STAGES = KMB_B_STAGES;  // fp16 centroid stages of ONE K-block (64 features x 128 rows = 16 KiB): a stage is
                                         // refilled as soon as its 4 MMAs retire; 4 stages x 256 MMA cycles in flight cover
                                         // the L2 round trip (round 1: 2 stages of 32 KiB left the MMA warp waiting)
-constexpr int B_STAGES_PAIR = 8;        // CTA-pair mode (cta_group::2): every CTA stages HALF a centroid tile per K-block, 8 KiB
+#ifndef KMB_B_STAGES_PAIR
+#define KMB_B_STAGES_PAIR 8
+#endif
+constexpr int B_STAGES_PAIR = KMB_B_STAGES_PAIR;        // CTA-pair mode (cta_group::2): every CTA stages HALF a centroid tile per K-block, 8 KiB
 constexpr int B_STAGES_MAX = B_STAGES > B_STAGES_PAIR ? B_STAGES : B_STAGES_PAIR;
 constexpr int X_STAGE_BYTES = TM * 128;
 constexpr int B_KB_BYTES = TN * 128;     // one K-block of the centroid tile: 16 KiB
@@ -1415,12 +1418,15 @@ recheck_pairs_kernel(const float* __restrict__ X, const float* __restrict__ C,
                      const uint32_t* __restrict__ pair_cand, const uint32_t* __restrict__ d_npairs,
                      uint32_t max_pairs, uint32_t n, uint32_t K, float* __restrict__ pair_score) {
   // 128 (row, candidate) pairs per CTA; features stream through shared memory 32 at a time.
-  // Staging: every thread issues 16 independent 16-byte loads per chunk (8 lanes cover one 128-byte
-  // row segment), so the kernel runs at memory throughput rather than at load latency.
+  // Staging: every thread issues 16 independent 16-byte loads per chunk (8 lanes cover one 128-byte row segment).  The
+  // loads of chunk i+1 are issued BEFORE the sequential Kahan loop of chunk i (32 features x a 4-instruction dependent
+  // chain per pair), so the global-memory latency of a chunk hides behind the previous chunk's arithmetic (round 2:
+  // load -> store -> compute ran back to back, 233 us for 0.92 M pairs at the headline shape).
   __shared__ float sX[32 * 129];     // [feature][pair]   (+1 padding: conflict-free both ways)
   __shared__ float sC[128 * 33];     // [pair][feature]
   __shared__ uint32_t s_row[128], s_cand[128];
   const uint32_t np = min(*d_npairs, max_pairs);
+  const int nchunks = (D + 31) / 32;
   for (uint32_t tile0 = blockIdx.x * 128; tile0 < np; tile0 += gridDim.x * 128) {
     const uint32_t pidx = tile0 + threadIdx.x;
     const bool active = pidx < np;
@@ -1428,11 +1434,11 @@ recheck_pairs_kernel(const float* __restrict__ X, const float* __restrict__ C,
     // (slots past the last complete row group may hold stale data: stay in bounds)
     s_row[threadIdx.x] = active ? min(pair_row[pidx], n - 1) : 0;
     s_cand[threadIdx.x] = active ? min(pair_cand[pidx], K - 1) : 0;
+    __syncthreads();
     Kahan k;
-    for (int f0 = 0; f0 < D; f0 += 32) {
+    float4 v[16];
+    auto load_chunk = [&](int f0) {
       const int fl = min(32, D - f0);
-      __syncthreads();
-      float4 v[16];
 #pragma unroll
       for (int i = 0; i < 16; i++) {
         const int idx = i * 128 + threadIdx.x;  // [which(1)][pair(7)][quad(3)]
@@ -1440,6 +1446,11 @@ recheck_pairs_kernel(const float* __restrict__ X, const float* __restrict__ C,
         const float* src = which ? C + static_cast<size_t>(s_cand[e]) * D : X + static_cast<size_t>(s_row[e]) * D;
         v[i] = (q * 4 < fl) ? *reinterpret_cast<const float4*>(src + f0 + q * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
+    };
+    load_chunk(0);
+    for (int ch = 0; ch < nchunks; ch++) {
+      const int fl = min(32, D - ch * 32);
+      __syncthreads();                      // the previous chunk has been consumed
 #pragma unroll
       for (int i = 0; i < 16; i++) {
         const int idx = i * 128 + threadIdx.x;
@@ -1453,6 +1464,7 @@ recheck_pairs_kernel(const float* __restrict__ X, const float* __restrict__ C,
         }
       }
       __syncthreads();
+      if (ch + 1 < nchunks) load_chunk((ch + 1) * 32);   // in flight during the loop below
       if (active)
         for (int f = 0; f < fl; f++) {
           if (MODE == 1 && METRIC == 0) k.sqdiff(sX[f * 129 + threadIdx.x], sC[threadIdx.x * 33 + f]);
