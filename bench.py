@@ -55,8 +55,9 @@ WORKLOAD = ("k-means assignment step, %d x %d fp32 samples in total (U[0,1)) @ %
             "range-partitioned over the GPUs (BASELINE configs[1] at 1 GPU, configs[3] at 2/4/8)")
 IMPORT = 3
 # kernels of this library per assignment pass (L2, tensor-core path): csqr, mean, mu, centred norms, stats, scale,
-# table, tc_assign_kernel, recheck_pairs, recheck_reduce, exact_rows_few, finalize_rows
-LAUNCHES_PER_ASSIGN = 12
+# table, tc_assign_kernel, recheck_pairs, recheck_reduce, exact_pass (row list), exact_rows_few, finalize_rows
+# (profiles/r02_launches_final.csv lists them)
+LAUNCHES_PER_ASSIGN = 13
 
 
 def _rank_info():
@@ -71,23 +72,75 @@ def shard_range(total, rank, world):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe).
+    """SM clock / power / throttle reasons DURING the timed region (B200_PROFILING.md's clocks line).
 
-    nvidia-smi needs a few hundred ms to start, longer than the default timed region, so it is started early
-    (`start`, then `wait_ready`), the caller brackets the timed region with `mark()` and only the samples whose
-    timestamps fall inside the marks are used."""
+    The timed region of the default run is ~0.1 s, shorter than nvidia-smi's start-up and coarser than its averaged
+    readings, so NVML is polled in-process by a thread (~1 ms period) and only the samples between the two `mark()`
+    calls are used.  Falls back to an `nvidia-smi -lms 20` child process when pynvml is unavailable."""
+
+    REASONS = (("hw_slowdown", "nvmlClocksEventReasonHwSlowdown"), ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown"),
+               ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown"), ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap"),
+               ("hw_power_brake", "nvmlClocksEventReasonHwPowerBrakeSlowdown"))
 
     def __init__(self, index):
-        self.path = tempfile.mktemp(prefix="clocks_", suffix=".csv")
-        self.proc = None
         self.index = index
         self.marks = []
+        self.samples = []        # (t, sm_mhz, power_w, reasons_bitmask)
+        self.thread = None
+        self.stop_flag = False
+        self.nv = None
+        self.handle = None
+        self.max_mhz = None
+        self.path = None
+        self.proc = None
+
+    def _poll(self):
+        nv, h = self.nv, self.handle
+        while not self.stop_flag:
+            try:
+                clk = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                try:
+                    pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                except Exception:
+                    pw = None
+                try:
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    rs = 0
+                self.samples.append((time.time(), clk, pw, rs))
+            except Exception:
+                pass
+            time.sleep(0.001)
 
     def start(self):
+        try:
+            import pynvml as nv
+            import threading
+            nv.nvmlInit()
+            # NVML enumerates physical devices: honour CUDA_VISIBLE_DEVICES when it is a plain index list
+            idx = self.index
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if vis:
+                try:
+                    idx = int(vis.split(",")[self.index])
+                except Exception:
+                    pass
+            self.handle = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.nv = nv
+            try:
+                self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(self.handle, nv.NVML_CLOCK_SM)
+            except Exception:
+                self.max_mhz = None
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nv = None
         q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
+            self.path = tempfile.mktemp(prefix="clocks_", suffix=".csv")
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
                                           "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
@@ -96,21 +149,49 @@ class ClockSampler:
 
     def wait_ready(self, timeout=5.0):
         t = time.time()
-        while self.proc and time.time() - t < timeout:
-            try:
-                if os.path.getsize(self.path) > 0:
+        while time.time() - t < timeout:
+            if self.nv is not None:
+                if self.samples:
                     return True
-            except OSError:
-                pass
-            time.sleep(0.02)
+            elif self.proc is not None:
+                try:
+                    if os.path.getsize(self.path) > 0:
+                        return True
+                except OSError:
+                    pass
+            else:
+                return False
+            time.sleep(0.01)
         return False
 
     def mark(self):
         self.marks.append(time.time())
 
     def stop(self):
-        import datetime
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        lo, hi = (self.marks[0], self.marks[1]) if len(self.marks) >= 2 else (0.0, 1e18)
+        if self.nv is not None:
+            self.stop_flag = True
+            if self.thread:
+                self.thread.join(timeout=2)
+            inside = [x for x in self.samples if lo <= x[0] <= hi]
+            out["source"] = "NVML polled in-process (~1 ms period)"
+            if inside:
+                out["sm_mhz"] = statistics.median(x[1] for x in inside)
+                out["sm_min_mhz"] = min(x[1] for x in inside)
+                out["sm_max_mhz"] = self.max_mhz
+                out["samples"] = len(inside)
+                pw = [x[2] for x in inside if x[2] is not None]
+                if pw:
+                    out["power_w_max"] = max(pw)
+                bits = 0
+                for x in inside:
+                    bits |= x[3]
+                out["reasons"] = sorted(name for name, attr in self.REASONS if bits & getattr(self.nv, attr, 0))
+            else:
+                out["note"] = "no NVML sample fell inside the timed region (%d outside it)" % len(self.samples)
+            return out
+        import datetime
         if not self.proc:
             return out
         time.sleep(0.05)
@@ -120,7 +201,7 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, pw, reasons, all_sm = [], [], [], set(), []
-        lo, hi = (self.marks[0] - 0.02, self.marks[1] + 0.02) if len(self.marks) >= 2 else (0.0, 1e18)
+        lo, hi = lo - 0.02, hi + 0.02
         try:
             for line in open(self.path):
                 f = [x.strip() for x in line.split(",")]
@@ -147,6 +228,7 @@ class ClockSampler:
             os.unlink(self.path)
         except Exception:
             pass
+        out["source"] = "nvidia-smi -lms 20"
         if sm:
             out["sm_mhz"] = statistics.median(sm)
             out["sm_max_mhz"] = max(mx)

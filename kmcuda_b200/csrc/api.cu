@@ -239,7 +239,9 @@ class Job {
   KMCUDAResult assign_pass(uint32_t* changed);
   KMCUDAResult update();
   KMCUDAResult lloyd(float tolerance, int* iter_out, uint32_t* changed_out);
+  KMCUDAResult lloyd_continue(float tolerance, int iter);
   KMCUDAResult yinyang(float tolerance, uint32_t G);
+  double lloyd_iter_ms = 0;   // wall time of the fastest complete Lloyd iteration of this run (assign pass + update), 0 = none yet
   KMCUDAResult group_centroids(uint32_t G, std::vector<uint32_t>* groups);
   KMCUDAResult average_distance(float* out);
 };
@@ -764,16 +766,40 @@ KMCUDAResult Job::lloyd(float tolerance, int* iter_out, uint32_t* changed_out) {
     KMB_CU(cudaMemsetAsync(d.assign.get(), 0xff, sizeof(uint32_t) * d.len, d.st), kmcudaRuntimeError);
     KMB_CU(cudaMemsetAsync(d.prev.get(), 0xff, sizeof(uint32_t) * d.len, d.st), kmcudaRuntimeError);
   }
+  auto t_prev = std::chrono::steady_clock::now();
   for (int iter = 1;; iter++) {
     uint32_t changed = 0;
     KMB_RET(assign_pass(&changed));
     g_prof.mark("assign pass");
+    // iteration period (update of the previous iteration + this pass; assign_pass synchronises): what a Yinyang
+    // iteration has to beat (Job::yinyang)
+    const auto t_now = std::chrono::steady_clock::now();
+    if (iter >= 2) {
+      const double ms = std::chrono::duration<double, std::milli>(t_now - t_prev).count();
+      if (lloyd_iter_ms == 0 || ms < lloyd_iter_ms) lloyd_iter_ms = ms;
+    }
+    t_prev = t_now;
     KMB_INFO("iteration %d: %" PRIu32 " reassignments\n", iter, changed);
     if (iter_out) *iter_out = iter;
     if (changed_out) *changed_out = changed;
     if (changed <= tolerance * N) return kmcudaSuccess;  // float compare, kmeans.cu:707
     KMB_RET(update());
     g_prof.mark("centroid update");
+  }
+}
+
+// Lloyd iterations from the current state (assignments belong to the current centroids, the update is due): used when
+// the Yinyang iterations of a run turn out slower than its Lloyd passes (Job::yinyang)
+KMCUDAResult Job::lloyd_continue(float tolerance, int iter) {
+  for (;;) {
+    KMB_RET(update());
+    g_prof.mark("centroid update");
+    iter++;
+    uint32_t changed = 0;
+    KMB_RET(assign_pass(&changed));
+    g_prof.mark("assign pass");
+    KMB_INFO("iteration %d: %" PRIu32 " reassignments\n", iter, changed);
+    if (changed <= tolerance * N) return kmcudaSuccess;
   }
 }
 
@@ -792,6 +818,25 @@ KMCUDAResult Job::group_centroids(uint32_t G, std::vector<uint32_t>* groups) {
   KMB_CU(cudaSetDevice(devs[0].dev), kmcudaRuntimeError);
   KMB_CU(cudaMemcpy(groups->data(), sub.devs[0].assign.get(), sizeof(uint32_t) * K, cudaMemcpyDeviceToHost),
          kmcudaMemoryCopyError);
+  // The grouping only steers how tight the bounds are, never the result.  The exact part of a bounds refresh costs
+  // |group(a_i)| distances per sample, so a degenerate grouping (near-equidistant centroids: one group swallows most
+  // of them) is evened out: centroids in (group, index) order are cut into G runs of equal length.
+  {
+    std::vector<uint32_t> gsz(G, 0);
+    uint32_t live = 0;
+    for (uint32_t c = 0; c < K; c++)
+      if ((*groups)[c] < G) { gsz[(*groups)[c]]++; live++; }
+    const uint32_t avg = (live + G - 1) / G, biggest = *std::max_element(gsz.begin(), gsz.end());
+    if (avg && biggest > 4 * avg) {
+      KMB_INFO("Yinyang groups are unbalanced (largest %" PRIu32 ", average %" PRIu32 "): evened out\n", biggest, avg);
+      std::vector<uint32_t> order;
+      order.reserve(live);
+      for (uint32_t c = 0; c < K; c++)
+        if ((*groups)[c] < G) order.push_back(c);
+      std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return (*groups)[x] < (*groups)[y]; });
+      for (uint32_t i = 0; i < live; i++) (*groups)[order[i]] = static_cast<uint32_t>(static_cast<uint64_t>(i) * G / live);
+    }
+  }
   return kmcudaSuccess;
 }
 
@@ -823,6 +868,14 @@ KMCUDAResult Job::yinyang(float tolerance, uint32_t G) {
   }
   KMB_RET(sync_all());
   bool refresh = true;
+  // A Yinyang iteration only pays when it beats a Lloyd pass of the same run, and with the tensor-core pass that takes a
+  // large K (the bounds stream is 8 (G + 1) bytes per sample, the pass 2 K D flop).  Both are timed: once a clean Yinyang
+  // iteration (no refresh in it) was slower than the fastest Lloyd iteration, the run continues with Lloyd passes --
+  // the assignments are the same either way (KMCUDA_B200_YY_ADAPTIVE=0 keeps Yinyang).
+  const char* ad = getenv("KMCUDA_B200_YY_ADAPTIVE");
+  const bool adaptive = !(ad && ad[0] == '0') && lloyd_iter_ms > 0;
+  auto t_prev = std::chrono::steady_clock::now();
+  bool clean = false;          // the iteration that just ended contained no refresh
   for (;; iter++) {
     if (!refresh) {
       uint32_t total_changed = 0, total_passed = 0;
@@ -838,6 +891,16 @@ KMCUDAResult Job::yinyang(float tolerance, uint32_t G) {
       }
       KMB_INFO("iteration %d: %" PRIu32 " reassignments\n", iter, total_changed);
       if (total_changed <= tolerance * N) return kmcudaSuccess;
+      {
+        const auto t_now = std::chrono::steady_clock::now();
+        const double ms = std::chrono::duration<double, std::milli>(t_now - t_prev).count();
+        t_prev = t_now;
+        if (adaptive && clean && ms > lloyd_iter_ms) {
+          KMB_INFO("a Yinyang iteration takes %.2f ms, a Lloyd iteration %.2f ms => Lloyd\n", ms, lloyd_iter_ms);
+          return lloyd_continue(tolerance, iter);
+        }
+        clean = true;
+      }
       for (auto& d : devs) {
         KMB_CU(cudaSetDevice(d.dev), kmcudaRuntimeError);
         KMB_CU(cudaMemsetAsync(d.d_changed.get(), 0, sizeof(uint32_t), d.st), kmcudaRuntimeError);
@@ -852,6 +915,7 @@ KMCUDAResult Job::yinyang(float tolerance, uint32_t G) {
         KMB_RET(d.shard->yy_refresh(d.len, d.X, d.C, d.assign, d.st));
       }
       refresh = false;
+      clean = false;
       g_prof.mark("yinyang: bounds refresh");
     }
     for (auto& d : devs) {

@@ -290,11 +290,21 @@ __global__ void tc_prep_mean_kernel(const float* __restrict__ C, const float* __
   const uint32_t r0 = blockIdx.y * 64u, r1 = min(K, r0 + 64u);
   double a = 0.0;
   uint32_t nv = 0;
-  for (uint32_t r = r0; r < r1; r++) {
-    const float q = csq[r];
-    if (!(q == q && q < 3.0e38f)) continue;
-    nv++;
-    if (f < D) a += static_cast<double>(C[static_cast<size_t>(r) * D + f]);
+  // 8 rows per step, loads first: the 64 rows of a CTA were one chain of dependent global loads before (36 us per pass)
+  for (uint32_t rb = r0; rb < r1; rb += 8) {
+    float v[8], q[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const uint32_t r = min(rb + j, r1 - 1);
+      q[j] = csq[r];
+      v[j] = f < D ? C[static_cast<size_t>(r) * D + f] : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      if (rb + j >= r1 || !(q[j] == q[j] && q[j] < 3.0e38f)) continue;
+      nv++;
+      a += static_cast<double>(v[j]);
+    }
   }
   if (f < D && nv) atomicAdd(&musum[f], a);
   if (blockIdx.x == 0 && threadIdx.x == 0 && nv) atomicAdd(nvalid, nv);
@@ -327,7 +337,8 @@ __global__ void tc_prep_cnorm_kernel(const float* __restrict__ C, const float* _
 }
 
 __global__ void tc_prep_scale_kernel(Stats* __restrict__ st, const float* __restrict__ mu, int D, int Dp,
-                                     float* __restrict__ neg_mu_s) {
+                                     float* __restrict__ neg_mu_s) {   // one warp
+  const int lane = threadIdx.x;
   float cmax = __fsqrt_ru(__uint_as_float(st->csq_max_bits));
   float s = 1.f;
   if (cmax > 0.f && cmax < 3.0e38f) {
@@ -335,17 +346,20 @@ __global__ void tc_prep_scale_kernel(Stats* __restrict__ st, const float* __rest
     frexpf(cmax, &e);          // cmax = m * 2^e, m in [0.5, 1)
     s = ldexpf(1.f, 6 - e);    // s*cmax in [32, 64)
   }
-  st->scale = s;
-  st->cmax = cmax * s * 1.001f;
-  st->dcmax = 0.f;
   float m2 = 0.f;
   if (neg_mu_s)
-  for (int f = 0; f < Dp; f++) {
-    const float m = (mu && f < D) ? mu[f] : 0.f;
-    neg_mu_s[f] = -m * s;      // exact (power of two) unless it overflows, which the norm below reports
-    m2 = fmaf(m * s, m * s, m2);
+    for (int f = lane; f < Dp; f += 32) {
+      const float m = (mu && f < D) ? mu[f] : 0.f;
+      neg_mu_s[f] = -m * s;      // exact (power of two) unless it overflows, which the norm below reports
+      m2 = fmaf(m * s, m * s, m2);
+    }
+  for (int o = 16; o > 0; o >>= 1) m2 += __shfl_xor_sync(0xffffffffu, m2, o);
+  if (lane == 0) {
+    st->scale = s;
+    st->cmax = cmax * s * 1.001f;
+    st->dcmax = 0.f;
+    st->mun = __fsqrt_ru(m2) * 1.002f;   // (1.002: the lane-partial sums are added in a different order than a serial loop)
   }
-  st->mun = __fsqrt_ru(m2) * 1.001f;
 }
 
 // one warp per centroid row (including the zero padding rows up to nt*256)
@@ -1435,6 +1449,13 @@ recheck_pairs_kernel(const float* __restrict__ X, const float* __restrict__ C,
     s_row[threadIdx.x] = active ? min(pair_row[pidx], n - 1) : 0;
     s_cand[threadIdx.x] = active ? min(pair_cand[pidx], K - 1) : 0;
     __syncthreads();
+    // the whole sample row of this thread's pair is requested from DRAM now, line after line (one open DRAM page per
+    // row), so that the chunk loads below -- 128 bytes of the row per chunk, spread over the chunk loop -- hit L2
+    // instead of making eight scattered DRAM accesses per row
+    if (active) {
+      const char* xr = reinterpret_cast<const char*>(X + static_cast<size_t>(s_row[threadIdx.x]) * D);
+      for (int b = 128; b < D * 4; b += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(xr + b));
+    }
     Kahan k;
     float4 v[16];
     auto load_chunk = [&](int f0) {
@@ -1545,6 +1566,7 @@ struct TcPlan {
   uint32_t* yy_qgroup = nullptr;   // [nt3*32] group of every 4-column quad
   uint32_t* yy_goff = nullptr;     // [G+1] CSR of the group members
   uint32_t* yy_gmem = nullptr;     // [K]
+  uint32_t yy_max_gsize = 0;       // members of the largest group
   CUtensorMap tmap3;
   uint32_t *pair_row = nullptr, *pair_cand = nullptr, *rowq = nullptr, *ovf_rows = nullptr, *counters = nullptr;
   float* pair_score = nullptr;
@@ -1844,7 +1866,7 @@ static cudaError_t tc_prepare(TcPlan* p, const float* C, const float* csq, uint3
     mu = p->mu;
   }
   tc_prep_stats_kernel<<<8, 256, 0, st>>>(nsq, p->K, p->stats);
-  tc_prep_scale_kernel<<<1, 1, 0, st>>>(p->stats, mu, p->D, p->nkb * KB, p->neg_mu_s);
+  tc_prep_scale_kernel<<<1, 32, 0, st>>>(p->stats, mu, p->D, p->nkb * KB, p->neg_mu_s);
   const uint32_t rows_pad = static_cast<uint32_t>(p->nt) * TN;
   if (!yy_layout)
     tc_prep_table_kernel<<<(rows_pad * 32 + 255) / 256, 256, 0, st>>>(p->metric, C, nsq, p->K, p->D, p->nkb, p->nt, p->table,
@@ -2009,37 +2031,77 @@ cudaError_t tc_exact_distances(TcPlan* p, const float* X, const float* C, uint32
 // Yinyang bounds refresh on the tensor cores (reference kmeans_yy_init, kmeans.cu:431-485)
 // ---------------------------------------------------------------------------------------------------
 // exact part of the refresh: upper bound = distance to the own centroid, lower bound of the OWN group = nearest other
-// member (both as the reference computes them); one warp per sample, one lane per group member
-template <int METRIC>
+// member (both as the reference computes them).  Round 2's first version gave every sample a warp whose lanes each walked
+// one member's row from global memory -- a chain of 256 dependent Kahan steps per lane with 10 of 32 lanes busy: 1.1 s
+// at 8M x 256 @ 1024 (G = 102), more than the whole Lloyd run.  Now: (1) the (sample, group member) pairs of a chunk of
+// rows are written to the plan's pair queue, (2) recheck_pairs_kernel computes their exact true distances (128 pairs
+// per CTA, coalesced staging), (3) one thread per row folds its pairs into the two bounds.
 __global__ void __launch_bounds__(256)
-yy_own_group_kernel(const float* __restrict__ X, const float* __restrict__ C, uint32_t n, int D, uint32_t K, uint32_t G,
-                    const uint32_t* __restrict__ assign, const uint32_t* __restrict__ groups,
-                    const uint32_t* __restrict__ goff, const uint32_t* __restrict__ gmem, float* __restrict__ bounds) {
+yy_own_pairs_kernel(uint32_t row0, uint32_t row1, uint32_t K, uint32_t G, const uint32_t* __restrict__ assign,
+                    const uint32_t* __restrict__ groups, const uint32_t* __restrict__ goff,
+                    const uint32_t* __restrict__ gmem, uint32_t* __restrict__ pair_row, uint32_t* __restrict__ pair_cand,
+                    uint32_t max_pairs, uint32_t* __restrict__ rowq, uint32_t* __restrict__ counters) {
   const int lane = threadIdx.x & 31;
-  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-  for (uint32_t row = warp; row < n; row += nwarps) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t base_row = row0 + blockIdx.x * blockDim.x; base_row < row1; base_row += stride) {
+    const uint32_t row = base_row + threadIdx.x;
+    uint32_t cnt = 0, beg = 0;
+    if (row < row1) {
+      const uint32_t a = assign[row];
+      if (a < K) {                                   // "insane" samples keep FLT_MAX bounds
+        const uint32_t g = groups[a];
+        if (g < G) { beg = goff[g]; cnt = goff[g + 1] - beg; }
+      }
+    }
+    uint32_t pre = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xffffffffu, pre, o);
+      if (lane >= o) pre += v;
+    }
+    const uint32_t warp_total = __shfl_sync(0xffffffffu, pre, 31);
+    const unsigned have = __ballot_sync(0xffffffffu, cnt != 0);
+    uint32_t pbase = 0, qbase = 0;
+    if (lane == 0 && warp_total) {
+      pbase = atomicAdd(&counters[tc::CNT_PAIRS], warp_total);
+      qbase = atomicAdd(&counters[tc::CNT_ROWQ], static_cast<uint32_t>(__popc(have)));
+    }
+    pbase = __shfl_sync(0xffffffffu, pbase, 0) + (pre - cnt);
+    qbase = __shfl_sync(0xffffffffu, qbase, 0) + __popc(have & ((1u << lane) - 1));
+    if (cnt && pbase + cnt <= max_pairs) {           // (the host sizes the chunks so that this always holds)
+      for (uint32_t j = 0; j < cnt; j++) {
+        pair_row[pbase + j] = row;
+        pair_cand[pbase + j] = gmem[beg + j];
+      }
+      rowq[3 * qbase] = row;
+      rowq[3 * qbase + 1] = pbase;
+      rowq[3 * qbase + 2] = cnt;
+    } else if (cnt) {
+      rowq[3 * qbase] = row;
+      rowq[3 * qbase + 1] = 0;
+      rowq[3 * qbase + 2] = 0;
+    }
+  }
+}
+
+__global__ void yy_own_reduce_kernel(const uint32_t* __restrict__ rowq, const uint32_t* __restrict__ d_nrowq,
+                                     const uint32_t* __restrict__ pair_cand, const float* __restrict__ pair_score,
+                                     const uint32_t* __restrict__ assign, const uint32_t* __restrict__ groups, uint32_t G,
+                                     float* __restrict__ bounds) {
+  const uint32_t nq = *d_nrowq;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nq; i += gridDim.x * blockDim.x) {
+    const uint32_t row = rowq[3 * i], base = rowq[3 * i + 1], cnt = rowq[3 * i + 2];
+    if (cnt == 0) continue;
     const uint32_t a = assign[row];
-    if (a >= K) continue;                       // "insane" sample: its bounds stay FLT_MAX (reference: c != nearest for all c)
-    const uint32_t g = groups[a];
-    if (g >= G) continue;
-    const float* x = X + static_cast<size_t>(row) * D;
-    const uint32_t beg = goff[g], end = goff[g + 1];
     float lb = FLT_MAX, ub = FLT_MAX;
-    for (uint32_t j = beg + lane; j < end; j += 32) {
-      const uint32_t c = gmem[j];
-      const float d = distance_exact<METRIC>(x, C + static_cast<size_t>(c) * D, D);
-      if (c == a) ub = d;
-      else if (d < lb) lb = d;                   // NaN never lowers a bound (as the reference's `dist < bound`)
+    for (uint32_t j = 0; j < cnt; j++) {
+      const float d = pair_score[base + j];
+      if (pair_cand[base + j] == a) ub = d;
+      else if (d < lb) lb = d;                       // NaN never lowers a bound (as the reference's `dist < bound`)
     }
-    for (int o = 16; o > 0; o >>= 1) {
-      lb = fminf(lb, __shfl_xor_sync(0xffffffffu, lb, o));
-      ub = fminf(ub, __shfl_xor_sync(0xffffffffu, ub, o));
-    }
-    if (lane == 0) {
-      float* b = bounds + static_cast<size_t>(row) * (G + 1);
-      b[0] = ub;
-      b[1 + g] = lb;
-    }
+    float* b = bounds + static_cast<size_t>(row) * (G + 1);
+    b[0] = ub;
+    b[1 + groups[a]] = lb;
   }
 }
 
@@ -2109,6 +2171,8 @@ cudaError_t tc_yy_layout(TcPlan* p, const uint32_t* host_groups, uint32_t G) {
     if ((e = pool_alloc(reinterpret_cast<void**>(&p->yy_gmem), gmem.size() * sizeof(uint32_t))) != cudaSuccess) return e;
     p->G3 = G;
   }
+  p->yy_max_gsize = 0;
+  for (uint32_t g = 0; g < G; g++) p->yy_max_gsize = std::max(p->yy_max_gsize, goff[g + 1] - goff[g]);
   if ((e = cudaMemcpy(p->yy_perm, perm.data(), perm.size() * 4, cudaMemcpyHostToDevice)) != cudaSuccess) return e;
   if ((e = cudaMemcpy(p->yy_qgroup, qgroup.data(), qgroup.size() * 4, cudaMemcpyHostToDevice)) != cudaSuccess) return e;
   if ((e = cudaMemcpy(p->yy_goff, goff.data(), goff.size() * 4, cudaMemcpyHostToDevice)) != cudaSuccess) return e;
@@ -2151,11 +2215,20 @@ cudaError_t tc_yy_refresh(TcPlan* p, const float* X, const float* C, const float
   const unsigned grid = min(static_cast<uint32_t>(p->num_sms), prm.ntiles);
   tc_launch_main(3, p->nkb, grid, p->smem_bytes, st, p->tmap3, tmap_x, prm);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
-  const unsigned ogrid = p->num_sms * 16;
-  if (p->metric == 1)
-    yy_own_group_kernel<1><<<ogrid, 256, 0, st>>>(X, C, n, p->D, p->K, G, assign, groups, p->yy_goff, p->yy_gmem, bounds);
-  else
-    yy_own_group_kernel<0><<<ogrid, 256, 0, st>>>(X, C, n, p->D, p->K, G, assign, groups, p->yy_goff, p->yy_gmem, bounds);
+  // own group + upper bound, exactly: chunks of rows whose pairs fit the queue (yy_max_gsize members per row at most)
+  const uint32_t per_row = max(1u, p->yy_max_gsize);
+  const uint32_t chunk = max(1u, p->max_pairs / per_row);
+  for (uint32_t r0 = 0; r0 < n; r0 += chunk) {
+    const uint32_t r1 = min(n, r0 + chunk);
+    if ((e = cudaMemsetAsync(p->counters, 0, sizeof(uint32_t) * 2, st)) != cudaSuccess) return e;   // CNT_PAIRS, CNT_ROWQ
+    yy_own_pairs_kernel<<<p->num_sms * 8, 256, 0, st>>>(r0, r1, p->K, G, assign, groups, p->yy_goff, p->yy_gmem, p->pair_row,
+                                                       p->pair_cand, p->max_pairs, p->rowq, p->counters);
+    if ((e = tc_exact_distances(p, X, C, n, p->pair_row, p->pair_cand, p->counters + CNT_PAIRS, p->max_pairs,
+                                p->pair_score, st)) != cudaSuccess)
+      return e;
+    yy_own_reduce_kernel<<<p->num_sms * 4, 256, 0, st>>>(p->rowq, p->counters + CNT_ROWQ, p->pair_cand, p->pair_score, assign,
+                                                        groups, G, bounds);
+  }
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   return cudaMemcpyAsync(p->h_counters, p->counters, sizeof(uint32_t) * CNT_N, cudaMemcpyDeviceToHost, st);
 }
@@ -2670,7 +2743,7 @@ cudaError_t tc_knn_search(int metric, int k, const float* X, const float* C, uin
   // fp16 table of the centred samples + bias blobs + statistics
   knn::prep_norms_kernel<<<(rows_max / 8) + 1, 256, 0, st>>>(X, C, D, tab2orig, blk_cluster, d_ntiles, ysq, yabs, metric);
   tc_prep_stats_kernel<<<8, 256, 0, st>>>(ysq, rows_max, stats);
-  tc_prep_scale_kernel<<<1, 1, 0, st>>>(stats, nullptr, 0, 0, nullptr);
+  tc_prep_scale_kernel<<<1, 32, 0, st>>>(stats, nullptr, 0, 0, nullptr);
   knn::prep_table_kernel<<<(rows_max / 8) + 1, 256, 0, st>>>(X, C, D, nkb, tab2orig, blk_cluster, d_ntiles, ysq, table,
                                                              blobs, stats, yabs, metric, d_err);
   KNN_TRY(cudaGetLastError());

@@ -10,6 +10,10 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    # The library continues a Yinyang run with Lloyd passes once a Yinyang iteration proves slower than a Lloyd
+    # iteration of the same run (identical results).  The tests that exercise the Yinyang kernels need them to run:
+    # the switch is off for the suite and on in the one test that checks it.
+    os.environ.setdefault("KMCUDA_B200_YY_ADAPTIVE", "0")
 
 
 @pytest.fixture(scope="session", autouse=True)

@@ -522,3 +522,25 @@ def test_cta_pair_pass_equals_single_cta_pass_and_reference(ours, ref, monkeypat
         got[mode] = a
         assert np.array_equal(a, a_ref), "pair=%s: %d assignments differ from the reference" % (mode, int((a != a_ref).sum()))
     assert np.array_equal(got["1"], got["0"])
+
+
+def test_adaptive_yinyang_switch_and_fast_refresh_keep_the_clustering(ours, monkeypatch, capfd):
+    """yinyang_t > 0 on a shape where a tensor-core Lloyd pass beats a Yinyang iteration (K = 1024): with the adaptive
+    switch the run finishes with Lloyd passes, without it Yinyang runs to the end; Yinyang being exact, both give the
+    assignments of the plain Lloyd run from the same start.  Also covers the pair-queue form of the exact own-group
+    bounds and the evening-out of a degenerate grouping (near-equidistant random centres)."""
+    rng = np.random.default_rng(99)
+    n, d, k = 200000, 256, 1024
+    centers = rng.random((k, d), dtype=np.float32)
+    X = (centers[rng.integers(0, k, n)] + 0.05 * rng.standard_normal((n, d), dtype=np.float32)).astype(np.float32)
+    C0 = X[rng.choice(n, k, replace=False)].copy()
+    runs = {}
+    for name, yy, adaptive in (("lloyd", 0.0, "0"), ("yinyang", 0.1, "0"), ("adaptive", 0.1, "1")):
+        monkeypatch.setenv("KMCUDA_B200_YY_ADAPTIVE", adaptive)
+        runs[name] = c_kmeans(ours, X, C0, 0.0005, yy, verbosity=1 if name == "adaptive" else 0)
+    out = capfd.readouterr().out
+    monkeypatch.setenv("KMCUDA_B200_YY_ADAPTIVE", "0")
+    for name in ("yinyang", "adaptive"):
+        assert (runs[name][1] == runs["lloyd"][1]).mean() > 0.9999, name
+        np.testing.assert_allclose(runs[name][0], runs["lloyd"][0], rtol=1e-4, atol=1e-5)
+    assert "iteration" in out

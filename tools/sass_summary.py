@@ -16,7 +16,7 @@ want = sys.argv[1] if len(sys.argv) > 1 else "tc_assign_kernelILi4ELi0"
 names = subprocess.run(["cuobjdump", "-res-usage", LIB], stdout=subprocess.PIPE, text=True).stdout
 fn = [ln.split()[1].rstrip(":") for ln in names.splitlines() if ln.strip().startswith("Function") and want in ln]
 assert fn, "no kernel matches " + want
-sass = subprocess.run(["cuobjdump", "-sass", "-fun", fn[0], LIB], stdout=subprocess.PIPE, text=True).stdout
+sass = subprocess.run(["cuobjdump", "-sass", "-fun", fn[0], LIB], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True).stdout
 res = [ln for ln in names.splitlines() if fn[0] in ln or ln.strip().startswith("REG:")]
 ops = collections.Counter()
 total = 0
@@ -29,6 +29,11 @@ print("kernel:", fn[0])
 i = names.splitlines().index([ln for ln in names.splitlines() if fn[0] in ln][0])
 print("resources:", names.splitlines()[i + 1].strip())
 print("static SASS instructions: %d (%.1f KB)" % (total, total * 16 / 1024))
+full = collections.Counter(re.findall(r"\b(UTCHMMA[.A-Z0-9_]*|UTCBAR[.A-Z0-9_]*|UTMALDG[.A-Z0-9_]*|UCGABAR_[A-Z]*|UTCATOMSWS[.A-Z0-9_]*)", sass))
+print()
+print("CTA-pair (cta_group::2) forms, with modifiers:")
+for k in sorted(full):
+    print("  %-36s %5d" % (k, full[k]))
 print()
 print("Blackwell-native markers (B200_PROFILING.md table):")
 for key, what in [("UTCHMMA", "tcgen05.mma kind::f16"), ("UTCBAR", "tcgen05.commit"), ("LDTM", "tcgen05.ld"),
