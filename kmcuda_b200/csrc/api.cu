@@ -18,6 +18,7 @@
 #include <memory>
 #include <chrono>
 #include <map>
+#include <mutex>
 #include <random>
 #include <string>
 #include <thread>
@@ -203,6 +204,85 @@ struct PhaseProfile {
 };
 static PhaseProfile g_prof;   // the library is not re-entrant (kmcuda.h:25-26), one profile is enough
 
+// ------------------------------------------------------------------------------------------------
+// Ingest of PAGEABLE host memory (the reference: one pageable cudaMemcpy of the whole matrix to every
+// GPU, kmcuda.cc:139-170).  A pageable cudaMemcpyAsync is staged by the driver through one small pinned buffer by one
+// thread: ~11 GB/s on this box, 0.72 s of a 1.2 s C2 run.  Here a few host threads copy interleaved 16 MB chunks into
+// their own pinned staging buffers (kept for the life of the process) and enqueue the DMA on their own streams, so the
+// page-touching memcpy of one chunk overlaps the DMA of the others.  Pinned or registered sources, small copies and
+// KMCUDA_B200_INGEST_THREADS=1 take the plain cudaMemcpyAsync.
+// ------------------------------------------------------------------------------------------------
+struct IngestLane {
+  int dev = -1;
+  cudaStream_t st = nullptr;
+  void* buf[2] = {nullptr, nullptr};
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+};
+static constexpr size_t kIngestChunk = 16u << 20;
+static std::vector<IngestLane>& ingest_lanes() {
+  static std::vector<IngestLane> lanes;
+  return lanes;
+}
+static bool ingest_lane_ready(IngestLane& l, int dev) {
+  if (l.dev == dev && l.st) return true;
+  if (cudaSetDevice(dev) != cudaSuccess) return false;
+  if (l.st) {   // the lane belonged to another device: rebuild its stream and events there
+    cudaStreamDestroy(l.st);
+    for (int i = 0; i < 2; i++) cudaEventDestroy(l.ev[i]);
+    l.st = nullptr;
+  }
+  if (cudaStreamCreateWithFlags(&l.st, cudaStreamNonBlocking) != cudaSuccess) { l.st = nullptr; return false; }
+  for (int i = 0; i < 2; i++) {
+    if (!l.buf[i] && cudaHostAlloc(&l.buf[i], kIngestChunk, cudaHostAllocPortable) != cudaSuccess) { l.buf[i] = nullptr; return false; }
+    if (cudaEventCreateWithFlags(&l.ev[i], cudaEventDisableTiming) != cudaSuccess) return false;
+  }
+  l.dev = dev;
+  return true;
+}
+// copies `bytes` from host `src` to device `dst` (current device `dev`); returns when the data is on the device or
+// enqueued on `st` (plain path); cudaSuccess or the first error
+static cudaError_t host_to_device(void* dst, const void* src, size_t bytes, int dev, cudaStream_t st) {
+  int nthreads = 6;
+  if (const char* e = getenv("KMCUDA_B200_INGEST_THREADS")) nthreads = std::max(1, std::min(16, atoi(e)));
+  bool pageable = false;
+  if (bytes >= (256u << 20) && nthreads > 1) {   // (below that the one-time cost of the pinned staging buffers, ~50 ms, is not earned back)
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, src) == cudaSuccess) pageable = at.type == cudaMemoryTypeUnregistered;
+    else cudaGetLastError();
+  }
+  if (!pageable) return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st);
+  static std::mutex mu;                       // knn_cuda drives several devices from concurrent host threads: the lanes
+  std::lock_guard<std::mutex> lock(mu);       // (staging buffers) are shared, one staged copy at a time
+  auto& lanes = ingest_lanes();
+  if (static_cast<int>(lanes.size()) < nthreads) lanes.resize(nthreads);
+  for (int t = 0; t < nthreads; t++)
+    if (!ingest_lane_ready(lanes[t], dev)) {
+      cudaGetLastError();
+      return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st);
+    }
+  const size_t nchunks = (bytes + kIngestChunk - 1) / kIngestChunk;
+  std::vector<cudaError_t> err(nthreads, cudaSuccess);
+  std::vector<std::thread> workers;
+  for (int t = 0; t < nthreads; t++)
+    workers.emplace_back([&, t]() {
+      IngestLane& l = lanes[t];
+      if ((err[t] = cudaSetDevice(dev)) != cudaSuccess) return;
+      int slot = 0;
+      for (size_t c = t; c < nchunks; c += nthreads, slot ^= 1) {
+        const size_t off = c * kIngestChunk, len = std::min(kIngestChunk, bytes - off);
+        if ((err[t] = cudaEventSynchronize(l.ev[slot])) != cudaSuccess) return;   // the DMA that last read this buffer
+        memcpy(l.buf[slot], static_cast<const char*>(src) + off, len);
+        if ((err[t] = cudaMemcpyAsync(static_cast<char*>(dst) + off, l.buf[slot], len, cudaMemcpyHostToDevice, l.st)) != cudaSuccess) return;
+        if ((err[t] = cudaEventRecord(l.ev[slot], l.st)) != cudaSuccess) return;
+      }
+      err[t] = cudaStreamSynchronize(l.st);
+    });
+  for (auto& w : workers) w.join();
+  for (int t = 0; t < nthreads; t++)
+    if (err[t] != cudaSuccess) return err[t];
+  return cudaSuccess;
+}
+
 class Job {
  public:
   Job(int metric, uint32_t N, int D, uint32_t K, int verbosity)
@@ -335,7 +415,7 @@ KMCUDAResult Job::ingest(const float* samples, int device_ptrs, bool fp16x2) {
     const char* src = reinterpret_cast<const char*>(samples) + static_cast<size_t>(d.off) * D * elem;
     if (!fp16x2) {
       if (device_ptrs < 0) {
-        KMB_CU(cudaMemcpyAsync(d.X.get(), src, count * 4, cudaMemcpyHostToDevice, d.st), kmcudaMemoryCopyError);
+        KMB_CU(host_to_device(d.X.get(), src, count * 4, d.dev, d.st), kmcudaMemoryCopyError);
       } else if (device_ptrs == d.dev) {
         d.X.borrow(const_cast<float*>(reinterpret_cast<const float*>(src)));  // work in place, read-only
       } else {
@@ -347,7 +427,7 @@ KMCUDAResult Job::ingest(const float* samples, int device_ptrs, bool fp16x2) {
       if (!(device_ptrs >= 0 && device_ptrs == d.dev)) {
         KMB_CU(tmp.alloc(count * 2), kmcudaMemoryAllocationFailure);
         if (device_ptrs < 0)
-          KMB_CU(cudaMemcpyAsync(tmp.get(), src, count * 2, cudaMemcpyHostToDevice, d.st), kmcudaMemoryCopyError);
+          KMB_CU(host_to_device(tmp.get(), src, count * 2, d.dev, d.st), kmcudaMemoryCopyError);
         else
           KMB_CU(cudaMemcpyPeerAsync(tmp.get(), d.dev, src, device_ptrs, count * 2, d.st), kmcudaMemoryCopyError);
         hsrc = tmp.get();
@@ -1131,7 +1211,7 @@ KMCUDAResult knn_cuda(uint16_t k, KMCUDADistanceMetric metric, uint32_t samples_
       if (!fp16x2) {
         if (device_ptrs >= 0 && device_ptrs == dev) { dst.borrow(const_cast<float*>(src)); return cudaSuccess; }
         if ((e = dst.alloc(count)) != cudaSuccess) return e;
-        if (device_ptrs < 0) return cudaMemcpyAsync(dst.get(), src, count * 4, cudaMemcpyHostToDevice, d.st);
+        if (device_ptrs < 0) return host_to_device(dst.get(), src, count * 4, dev, d.st);
         return cudaMemcpyPeerAsync(dst.get(), dev, src, device_ptrs, count * 4, d.st);
       }
       if ((e = dst.alloc(count)) != cudaSuccess) return e;
@@ -1139,7 +1219,7 @@ KMCUDAResult knn_cuda(uint16_t k, KMCUDADistanceMetric metric, uint32_t samples_
       const void* hsrc = src;
       if (!(device_ptrs >= 0 && device_ptrs == dev)) {
         if ((e = tmp.alloc(count * 2)) != cudaSuccess) return e;
-        e = device_ptrs < 0 ? cudaMemcpyAsync(tmp.get(), src, count * 2, cudaMemcpyHostToDevice, d.st)
+        e = device_ptrs < 0 ? host_to_device(tmp.get(), src, count * 2, dev, d.st)
                             : cudaMemcpyPeerAsync(tmp.get(), dev, src, device_ptrs, count * 2, d.st);
         if (e != cudaSuccess) return e;
         hsrc = tmp.get();

@@ -544,3 +544,18 @@ def test_adaptive_yinyang_switch_and_fast_refresh_keep_the_clustering(ours, monk
         assert (runs[name][1] == runs["lloyd"][1]).mean() > 0.9999, name
         np.testing.assert_allclose(runs[name][0], runs["lloyd"][0], rtol=1e-4, atol=1e-5)
     assert "iteration" in out
+
+
+def test_staged_pageable_ingest_delivers_the_same_bytes(ours, monkeypatch):
+    """host buffers >= 256 MB that are not pinned are copied by several host threads through pinned staging buffers
+    (api.cu::host_to_device); the result must be the one of the plain cudaMemcpy (ragged last chunk included)"""
+    rng = np.random.default_rng(5)
+    n, d, k = 280001, 260, 300           # 291 MB (staged from 256 MB upwards), not a multiple of the 16 MB chunk
+    X = rng.random((n, d), dtype=np.float32)
+    C0 = X[rng.choice(n, k, replace=False)].copy()
+    out = {}
+    for threads in ("6", "1"):
+        monkeypatch.setenv("KMCUDA_B200_INGEST_THREADS", threads)
+        out[threads] = c_kmeans(ours, X, C0, 0.01, 0.0)
+    assert np.array_equal(out["6"][1], out["1"][1])
+    assert np.array_equal(out["6"][0], out["1"][0])
