@@ -39,11 +39,14 @@ csqr_kernel(const float* __restrict__ C, uint32_t K, int D, float* __restrict__ 
   Kahan k;
   for (int f0 = 0; f0 < D; f0 += 32) {
     const int fl = min(32, D - f0);
-#pragma unroll 8
-    for (int r = 0; r < 32; r++) {
+    float v[32];
+#pragma unroll
+    for (int r = 0; r < 32; r++) {   // all 32 row segments in flight at once
       const uint32_t c = min(c0 + r, K - 1);
-      tile[r * 33 + lane] = lane < fl ? C[static_cast<size_t>(c) * D + f0 + lane] : 0.f;
+      v[r] = lane < fl ? C[static_cast<size_t>(c) * D + f0 + lane] : 0.f;
     }
+#pragma unroll
+    for (int r = 0; r < 32; r++) tile[r * 33 + lane] = v[r];
     __syncwarp();
     for (int f = 0; f < fl; f++) {
       const float v = tile[lane * 33 + f];
