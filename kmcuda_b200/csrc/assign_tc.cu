@@ -17,7 +17,9 @@
 //   MMA thread      : tcgen05.mma kind::f16, A from TMEM, B from shared memory, M=128 N=128 K=16,
 //                     fp32 accumulators double-buffered in TMEM (2 x 128 columns); one extra K=16
 //                     step (A and B from shared memory) adds -||c||^2/2 as three fp16 terms against
-//                     constant ones, so acc = x.c - ||c||^2/2
+//                     constant ones, so acc = x.c - ||c||^2/2.  The Lloyd pass on large inputs runs as
+//                     clusters of two CTAs: one tcgen05.mma.cta_group::2 of M=256 per K step, issued by
+//                     the leader CTA, every CTA staging half of each centroid tile (template parameter CG)
 //   epilogue warps  : tcgen05.ld 32 columns at a time; running row maximum M; every column whose
 //                     value is within `margin` of M is recorded (bit mask per 32-column chunk);
 //                     margin is a rigorous bound on |approx - exact| derived from the actual
