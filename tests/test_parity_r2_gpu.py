@@ -493,15 +493,16 @@ def test_cuda_graph_replay_of_the_assignment_pass(ours, monkeypatch):
     """KMCUDA_B200_GRAPH=1: the launches of an assignment pass are captured once and replayed as one CUDA graph per
     iteration; a whole Lloyd run must not change"""
     rng = np.random.default_rng(61)
-    X = rng.random((70000, 128), dtype=np.float32)
-    C0 = X[rng.choice(len(X), 300, replace=False)].copy()
-    runs = {}
-    for mode in ("0", "1"):
-        monkeypatch.setenv("KMCUDA_B200_GRAPH", mode)
-        runs[mode] = c_kmeans(ours, X, C0, 0.005, 0.0)
-    monkeypatch.delenv("KMCUDA_B200_GRAPH")
-    assert np.array_equal(runs["0"][1], runs["1"][1])
-    np.testing.assert_array_equal(runs["0"][0], runs["1"][0])
+    for n in (70000, 90000):             # single CTAs / CTA pairs (cluster launch inside the captured graph)
+        X = rng.random((n, 128), dtype=np.float32)
+        C0 = X[rng.choice(len(X), 300, replace=False)].copy()
+        runs = {}
+        for mode in ("0", "1"):
+            monkeypatch.setenv("KMCUDA_B200_GRAPH", mode)
+            runs[mode] = c_kmeans(ours, X, C0, 0.005, 0.0)
+        monkeypatch.delenv("KMCUDA_B200_GRAPH")
+        assert np.array_equal(runs["0"][1], runs["1"][1])
+        np.testing.assert_array_equal(runs["0"][0], runs["1"][0])
 
 
 @pytest.mark.gpu
