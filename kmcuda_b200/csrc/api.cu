@@ -345,8 +345,10 @@ KMCUDAResult Job::setup(const std::vector<int>& dev_ids, bool alloc_samples) {
     KMB_CU(d.counts.alloc(K), kmcudaMemoryAllocationFailure);
     KMB_CU(d.d_changed.alloc(1), kmcudaMemoryAllocationFailure);
     KMB_CU(d.d_dsum.alloc(1), kmcudaMemoryAllocationFailure);
+    g_prof.mark("setup: stream + job buffers");
     d.shard.reset(new Shard(metric, d.dev, d.len, D, K, verbosity));
     KMB_RET(d.shard->create(true));
+    g_prof.mark("setup: shard workspace + tensor-core plan");
   }
   if (devs.size() > 1) {
     // Exchange step of the centroid update.  Preferred: every GPU reads its peers' partial sums straight from
@@ -1092,7 +1094,7 @@ KMCUDAResult kmeans_cuda(KMCUDAInitMethod init, const void* init_params, float t
   g_prof.begin(dev_ids);
   Job job(m, samples_size, D, clusters_size, verbosity);
   KMB_RET(job.setup(dev_ids, true));
-  g_prof.mark("setup (alloc, plans, nccl)");
+  g_prof.mark("setup: exchange (peer / nccl)");
   KMB_RET(job.ingest(samples, device_ptrs, fp16x2 != 0));
   g_prof.mark("ingest (H2D / peer copy)");
   if (verbosity > 1) KMB_RET(print_memory_stats(dev_ids));

@@ -47,6 +47,9 @@
 #include <cstdio>
 #include <algorithm>
 #include <cstring>
+#include <map>
+#include <mutex>
+#include <tuple>
 #include <vector>
 
 #include <cub/cub.cuh>
@@ -95,6 +98,9 @@ constexpr int LIST_LEN = 5;             // entries per epilogue thread: one per 
 // MMA issuer warps: ONE.  (Round 2 measured a second issuer taking alternate n-tiles: it helped the whole-warp
 // elect-per-K-block issue loop, 5.05 -> 4.40 ms, and hurts the lean single-thread loop, 3.88 -> 4.29 ms: with two n-tiles
 // in flight the 5-stage B ring, 1.25 n-tiles deep, becomes the limit.)  KMB_MMA_WARPS=2 keeps the variant buildable.
+#ifndef KMB_PREP_FUSED
+#define KMB_PREP_FUSED 1   // 1: centroid preparation as one launch (tc_prep_fused_kernel), 0: the chain of small kernels
+#endif
 #ifndef KMB_MMA_WARPS
 #define KMB_MMA_WARPS 1
 #endif
@@ -364,20 +370,16 @@ __global__ void tc_prep_scale_kernel(Stats* __restrict__ st, const float* __rest
   }
 }
 
-// one warp per centroid row (including the zero padding rows up to nt*256)
-__global__ void tc_prep_table_kernel(int metric, const float* __restrict__ C, const float* __restrict__ csq,
-                                     uint32_t K, int D, int nkb, int nt, __half* __restrict__ table,
-                                     __half* __restrict__ aug_blob, Stats* __restrict__ st,
-                                     const uint32_t* __restrict__ gather, const float* __restrict__ mu,
-                                     int by_source, int pair_blob = 0) {
+// one table row (a centroid, or a zero padding row up to nt*TN) by one warp; s = Stats::scale; csq / mu may have been
+// written earlier in the SAME launch by other CTAs (fused preparation), hence no __restrict__ / read-only loads on them
+__device__ __forceinline__ void prep_table_row(uint32_t row, int lane, float s, int metric, const float* __restrict__ C,
+                                               const float* csq, uint32_t K, int D, int nkb, __half* __restrict__ table,
+                                               __half* __restrict__ aug_blob, Stats* st,
+                                               const uint32_t* __restrict__ gather, const float* mu, int by_source,
+                                               int pair_blob) {
   // by_source (Yinyang refresh layout): table row r holds centroid gather[r] (UINT32_MAX = padding) and csq[] is
   // indexed by the centroid; otherwise csq[] is indexed by the table row and rows >= K are padding
-  const uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  const uint32_t rows_pad = static_cast<uint32_t>(nt) * TN;
-  if (row >= rows_pad) return;
   const int Dp = nkb * KB;
-  const float s = st->scale;
   uint32_t src = row;
   bool finite = row < K;
   if (by_source) {
@@ -390,7 +392,7 @@ __global__ void tc_prep_table_kernel(int metric, const float* __restrict__ C, co
   const uint32_t qrow = by_source ? src : row;
   const float* Crow = C + static_cast<size_t>(src) * D;
   if (finite) {
-    float q = csq[qrow];
+    float q = __ldcg(csq + qrow);
     finite = (q == q) && q < 3.0e38f;
     for (int f = lane; f < D; f += 32) {
       float v = Crow[f];
@@ -423,7 +425,7 @@ __global__ void tc_prep_table_kernel(int metric, const float* __restrict__ C, co
     // bias: three fp16 terms of -(s^2 ||c - mu||^2 / 2); invalid / padded centroids get -65504
     __half b[3];
     if (finite) {
-      float h = metric == 1 ? 0.f : -0.5f * ((s * csq[qrow]) * s);   // s = 2^k: exact; this order cannot overflow for tiny data
+      float h = metric == 1 ? 0.f : -0.5f * ((s * __ldcg(csq + qrow)) * s);   // s = 2^k: exact; this order cannot overflow for tiny data
       b[0] = __float2half_rn(h);
       float r1 = h - __half2float(b[0]);
       b[1] = __float2half_rn(r1);
@@ -446,6 +448,233 @@ __global__ void tc_prep_table_kernel(int metric, const float* __restrict__ C, co
       blob[off / 2 + e] = k < 3 ? b[k] : __float2half_rn(0.f);
     }
   }
+}
+
+// one warp per centroid row (including the zero padding rows up to nt*256)
+__global__ void tc_prep_table_kernel(int metric, const float* __restrict__ C, const float* __restrict__ csq,
+                                     uint32_t K, int D, int nkb, int nt, __half* __restrict__ table,
+                                     __half* __restrict__ aug_blob, Stats* __restrict__ st,
+                                     const uint32_t* __restrict__ gather, const float* __restrict__ mu,
+                                     int by_source, int pair_blob = 0) {
+  const uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= static_cast<uint32_t>(nt) * TN) return;
+  prep_table_row(row, lane, st->scale, metric, C, csq, K, D, nkb, table, aug_blob, st, gather, mu, by_source, pair_blob);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// The whole centroid preparation of one pass as ONE launch (Lloyd / Yinyang tables; the k-NN tables have their own
+// chain).  The chain above is ten stream operations (three memsets, ||c||^2, mean, mu, centred norms, maximum, scale,
+// table) of 3-12 us each on a 1 MB centroid matrix: ~0.05 ms of dependent launches per pass, 1 % of the step of an
+// 8M-row shard and 8 % of the step of a 1M-row shard (8 GPUs).  Here the same arithmetic (the device bodies are shared
+// with the chain, which stays as the KMB_PREP_FUSED=0 build) runs as four phases of one small grid separated by a
+// sense-reversing grid barrier; every CTA is resident (grid <= number of SMs, 256 threads, 34 KB static shared memory),
+// so the barrier cannot deadlock.  Values produced by other CTAs in an earlier phase are read with ld.global.cg.
+// ---------------------------------------------------------------------------------------------------
+struct PrepArgs {
+  int metric, centred, D, nkb, by_source, pair_blob;
+  uint32_t K, rows_pad;
+  const float* C;
+  float* csq;            // reference-order ||c||^2 (L2) / 1 (cosine); written here when compute_csq
+  int compute_csq;
+  float* cnorm2;         // L2 centred: ||c - mu||^2; cosine: upper bound of ||c||^2
+  double* musum;         // [D] + valid-row count
+  float* mu;             // [D]
+  float* neg_mu_s;       // [nkb * KB]
+  Stats* stats;
+  uint32_t* counters;    // CNT_N words, zeroed here
+  __half* table;
+  __half* aug_blob;
+  const uint32_t* gather;
+  unsigned* barrier;     // {arrivals, generation}
+};
+
+__device__ __forceinline__ void prep_grid_barrier(unsigned* bar, unsigned nblocks) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    volatile unsigned* gen = bar + 1;
+    const unsigned g = *gen;          // cannot advance before this CTA has arrived
+    __threadfence();
+    if (atomicAdd(bar, 1u) == nblocks - 1u) {
+      atomicExch(bar, 0u);
+      __threadfence();
+      atomicAdd(bar + 1, 1u);
+    } else {
+      while (*gen == g) __nanosleep(32);
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256)
+tc_prep_fused_kernel(const PrepArgs a) {
+  __shared__ float s_tile[8][32 * 33];   // ||c||^2: one 32 x 32 staging tile per warp
+  __shared__ float s_mu[MAX_NKB * KB];
+  __shared__ float s_scale;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t gw = blockIdx.x * 8u + warp, nw = gridDim.x * 8u;
+  const uint32_t gt = blockIdx.x * 256u + tid, nthr = gridDim.x * 256u;
+  const int D = a.D;
+  const uint32_t K = a.K;
+
+  // ---- phase 0: zero the pass counters / statistics / column sums; ||c||^2 in the reference's order
+  if (gt < CNT_N) a.counters[gt] = 0u;
+  if (gt < sizeof(Stats) / 4) reinterpret_cast<uint32_t*>(a.stats)[gt] = 0u;
+  if (a.centred)
+    for (uint32_t i = gt; i < static_cast<uint32_t>(D) + 1u; i += nthr) a.musum[i] = 0.0;
+  if (a.compute_csq) {
+    float* tile = s_tile[warp];
+    for (uint32_t c0 = gw * 32u; c0 < K; c0 += nw * 32u) {
+      if (a.metric == 1) {
+        if (c0 + lane < K) a.csq[c0 + lane] = 1.f;
+        continue;
+      }
+      kmb::Kahan k;
+      for (int f0 = 0; f0 < D; f0 += 32) {
+        const int fl = min(32, D - f0);
+        float v[32];
+#pragma unroll
+        for (int r = 0; r < 32; r++) {
+          const uint32_t c = min(c0 + r, K - 1);
+          v[r] = lane < fl ? a.C[static_cast<size_t>(c) * D + f0 + lane] : 0.f;
+        }
+#pragma unroll
+        for (int r = 0; r < 32; r++) tile[r * 33 + lane] = v[r];
+        __syncwarp();
+        for (int f = 0; f < fl; f++) {
+          const float x = tile[lane * 33 + f];
+          k.mac(x, x);
+        }
+        __syncwarp();
+      }
+      if (c0 + lane < K) a.csq[c0 + lane] = k.sum;
+    }
+  }
+  prep_grid_barrier(a.barrier, gridDim.x);
+
+  const float* nsq = a.csq;
+  if (a.metric == 1) {
+    // ---- cosine: upper bound of ||c||^2 per centroid + its maximum (tc_prep_norms_kernel, tc_prep_stats_kernel)
+    uint32_t best = 0;
+    for (uint32_t row = gw; row < K; row += nw) {
+      const float* src = a.C + static_cast<size_t>(row) * D;
+      float acc = 0.f;
+      for (int f = lane; f < D; f += 32) {
+        float v = src[f];
+        acc = fmaf(v, v, acc);
+      }
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      const float v = acc * 1.0001f;
+      if (lane == 0) a.cnorm2[row] = v;
+      if (v == v && v < 3.0e38f) best = max(best, __float_as_uint(fmaxf(v, 0.f)));
+    }
+    if (lane == 0 && best) atomicMax(&a.stats->csq_max_bits, best);
+    nsq = a.cnorm2;
+    prep_grid_barrier(a.barrier, gridDim.x);
+  } else if (a.centred) {
+    // ---- phase 1: column sums of the valid centroids (tc_prep_mean_kernel: 128 features x 64 rows per half CTA)
+    {
+      const int fb = (D + 127) / 128;
+      const uint32_t nvb = static_cast<uint32_t>(fb) * ((K + 63u) / 64u);
+      const int ht = tid & 127;
+      for (uint32_t vb = blockIdx.x * 2u + (tid >> 7); vb < nvb; vb += gridDim.x * 2u) {
+        const int f = static_cast<int>(vb % fb) * 128 + ht;
+        const uint32_t r0 = (vb / fb) * 64u, r1 = min(K, r0 + 64u);
+        double acc = 0.0;
+        uint32_t nv = 0;
+        for (uint32_t rb = r0; rb < r1; rb += 8) {
+          float v[8], q[8];
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            const uint32_t r = min(rb + j, r1 - 1);
+            q[j] = __ldcg(a.csq + r);
+            v[j] = f < D ? a.C[static_cast<size_t>(r) * D + f] : 0.f;
+          }
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            if (rb + j >= r1 || !(q[j] == q[j] && q[j] < 3.0e38f)) continue;
+            nv++;
+            acc += static_cast<double>(v[j]);
+          }
+        }
+        if (f < D && nv) atomicAdd(&a.musum[f], acc);
+        if (vb % fb == 0 && ht == 0 && nv) atomicAdd(reinterpret_cast<uint32_t*>(a.musum + D), nv);
+      }
+    }
+    prep_grid_barrier(a.barrier, gridDim.x);
+    // ---- phase 2: mu (every CTA keeps its own copy), ||c - mu||^2 per centroid, its maximum
+    {
+      const uint32_t nv = __ldcg(reinterpret_cast<const uint32_t*>(a.musum + D));
+      for (int f = tid; f < D; f += 256) {
+        const float m = nv ? static_cast<float>(__ldcg(a.musum + f) / nv) : 0.f;
+        const float mm = (fabsf(m) < 3.0e38f) ? m : 0.f;
+        s_mu[f] = mm;
+        if (blockIdx.x == 0) a.mu[f] = mm;
+      }
+      __syncthreads();
+      uint32_t best = 0;
+      for (uint32_t row = gw; row < K; row += nw) {
+        const float* src = a.C + static_cast<size_t>(row) * D;
+        double acc = 0.0;
+        for (int f = lane; f < D; f += 32) {
+          const float v = src[f] - s_mu[f];
+          acc += static_cast<double>(v) * v;
+        }
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        const float q = __ldcg(a.csq + row);
+        const float v = (q == q && q < 3.0e38f) ? static_cast<float>(acc) : q;   // dead centroids stay dead
+        if (lane == 0) a.cnorm2[row] = v;
+        if (v == v && v < 3.0e38f) best = max(best, __float_as_uint(fmaxf(v, 0.f)));
+      }
+      if (lane == 0 && best) atomicMax(&a.stats->csq_max_bits, best);
+    }
+    nsq = a.cnorm2;
+    prep_grid_barrier(a.barrier, gridDim.x);
+  } else {
+    // ---- uncentred L2 (A/B switch): maximum of ||c||^2
+    uint32_t best = 0;
+    for (uint32_t c = gt; c < K; c += nthr) {
+      const float v = __ldcg(a.csq + c);
+      if (v == v && v < 3.0e38f) best = max(best, __float_as_uint(fmaxf(v, 0.f)));
+    }
+    for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
+    if (lane == 0 && best) atomicMax(&a.stats->csq_max_bits, best);
+    prep_grid_barrier(a.barrier, gridDim.x);
+  }
+
+  // ---- phase 3: scale (every CTA derives it; CTA 0 publishes Stats and -mu*s), then the fp16 table + bias blocks
+  const bool have_mu = a.metric == 0 && a.centred;
+  if (warp == 0) {
+    float cmax = __fsqrt_ru(__uint_as_float(__ldcg(&a.stats->csq_max_bits)));
+    float s = 1.f;
+    if (cmax > 0.f && cmax < 3.0e38f) {
+      int e;
+      frexpf(cmax, &e);
+      s = ldexpf(1.f, 6 - e);
+    }
+    if (lane == 0) s_scale = s;
+    if (blockIdx.x == 0) {
+      const int Dp = a.nkb * KB;
+      float m2 = 0.f;
+      for (int f = lane; f < Dp; f += 32) {
+        const float m = (have_mu && f < D) ? s_mu[f] : 0.f;
+        a.neg_mu_s[f] = -m * s;
+        m2 = fmaf(m * s, m * s, m2);
+      }
+      for (int o = 16; o > 0; o >>= 1) m2 += __shfl_xor_sync(0xffffffffu, m2, o);
+      if (lane == 0) {
+        a.stats->scale = s;
+        a.stats->cmax = cmax * s * 1.001f;
+        a.stats->mun = __fsqrt_ru(m2) * 1.002f;
+      }
+    }
+  }
+  __syncthreads();
+  const float s = s_scale;
+  for (uint32_t row = gw; row < a.rows_pad; row += nw)
+    prep_table_row(row, lane, s, a.metric, a.C, nsq, K, D, a.nkb, a.table, a.aug_blob, a.stats, a.gather,
+                   have_mu ? s_mu : nullptr, a.by_source, a.pair_blob);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -1573,6 +1802,7 @@ struct TcPlan {
   uint32_t *pair_row = nullptr, *pair_cand = nullptr, *rowq = nullptr, *ovf_rows = nullptr, *counters = nullptr;
   float* pair_score = nullptr;
   uint32_t* h_counters = nullptr;  // pinned
+  unsigned* prep_barrier = nullptr;   // {arrivals, generation} of tc_prep_fused_kernel's grid barrier (zero between launches)
   CUtensorMap tmap;     // fp16 centroid table
   // CTA-pair mode of the Lloyd pass (cta_group::2, see tc_assign_kernel): half-tile boxes of the table, the bias blocks
   // as 2 KiB pieces per (n-tile, CTA rank), number of CTA pairs that can be resident at once
@@ -1685,7 +1915,7 @@ static int tc_pair_clusters_one(int bytes) {
   }
   return n;
 }
-static int tc_pair_clusters(int bytes, int nkb) {
+static int tc_pair_clusters_query(int bytes, int nkb) {
   switch (nkb) {
     case 1: return tc_pair_clusters_one<1>(bytes);
     case 2: return tc_pair_clusters_one<2>(bytes);
@@ -1697,6 +1927,45 @@ static int tc_pair_clusters(int bytes, int nkb) {
     default: return tc_pair_clusters_one<8>(bytes);
   }
 }
+// (cudaOccupancyMaxActiveClusters and the pinned allocation below are milliseconds each: a plan is created by every
+// kmeans_cuda call, so their results are kept per process)
+static int tc_pair_clusters(int bytes, int nkb) {
+  static std::mutex mu;
+  static std::map<std::tuple<int, int, int>, int> cache;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lk(mu);
+  auto key = std::make_tuple(dev, bytes, nkb);
+  auto it = cache.find(key);
+  if (it != cache.end()) return it->second;
+  const int n = tc_pair_clusters_query(bytes, nkb);
+  cache[key] = n;
+  return n;
+}
+static std::mutex g_pinned_mu;
+static std::vector<uint32_t*> g_pinned_free;   // CNT_N-word pinned blocks of destroyed plans
+static uint32_t* pinned_counters_alloc() {
+  {
+    std::lock_guard<std::mutex> lk(g_pinned_mu);
+    if (!g_pinned_free.empty()) {
+      uint32_t* p = g_pinned_free.back();
+      g_pinned_free.pop_back();
+      return p;
+    }
+  }
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, sizeof(uint32_t) * tc::CNT_N, cudaHostAllocPortable) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return static_cast<uint32_t*>(p);
+}
+static void pinned_counters_free(uint32_t* p) {
+  if (!p) return;
+  std::lock_guard<std::mutex> lk(g_pinned_mu);
+  g_pinned_free.push_back(p);
+}
+
 template <int NKB>
 static cudaError_t tc_set_smem_attr_one(int bytes) {
   cudaError_t e = cudaFuncSetAttribute(tc::tc_assign_kernel<NKB, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
@@ -1748,8 +2017,9 @@ void tc_plan_destroy(TcPlan* p) {
   pool_free(p->rowq);
   pool_free(p->ovf_rows);
   pool_free(p->counters);
+  pool_free(p->prep_barrier);
   pool_free(p->dbg_scores);
-  if (p->h_counters) cudaFreeHost(p->h_counters);
+  pinned_counters_free(p->h_counters);
   for (int i = 0; i < TcPlan::kEvRing; i++) {
     if (p->ev0[i]) cudaEventDestroy(p->ev0[i]);
     if (p->ev1[i]) cudaEventDestroy(p->ev1[i]);
@@ -1770,9 +2040,7 @@ cudaError_t tc_plan_create(TcPlan** out, int metric, uint32_t max_n, int D, uint
   p->max_pairs = max_n < (1u << 28) ? 10 * max_n + 1024 : 0xFFFFFFF0u;   // Lloyd needs ~0.4 n, the Yinyang top-2 mode up to ~7 n
   cudaError_t e;
 #define TC_TRY(x) do { e = (x); if (e != cudaSuccess) { tc_plan_destroy(p); return e; } } while (0)
-  cudaDeviceProp prop;
-  TC_TRY(cudaGetDeviceProperties(&prop, device));
-  p->num_sms = prop.multiProcessorCount;
+  TC_TRY(cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, device));
   const size_t rows_pad = static_cast<size_t>(p->nt) * TN;
   TC_TRY(pool_alloc(reinterpret_cast<void**>(&p->table), rows_pad * p->nkb * KB * sizeof(__half)));
   TC_TRY(pool_alloc(reinterpret_cast<void**>(&p->aug_blob), static_cast<size_t>(p->nt) * AUG_B_BYTES));
@@ -1793,7 +2061,10 @@ cudaError_t tc_plan_create(TcPlan** out, int metric, uint32_t max_n, int D, uint
   TC_TRY(pool_alloc(reinterpret_cast<void**>(&p->rowq), sizeof(uint32_t) * 3 * static_cast<size_t>(max_n)));
   TC_TRY(pool_alloc(reinterpret_cast<void**>(&p->ovf_rows), sizeof(uint32_t) * static_cast<size_t>(max_n)));
   TC_TRY(pool_alloc(reinterpret_cast<void**>(&p->counters), sizeof(uint32_t) * CNT_N));
-  TC_TRY(cudaMallocHost(&p->h_counters, sizeof(uint32_t) * CNT_N));
+  TC_TRY(pool_alloc(reinterpret_cast<void**>(&p->prep_barrier), sizeof(unsigned) * 2));
+  TC_TRY(cudaMemset(p->prep_barrier, 0, sizeof(unsigned) * 2));
+  p->h_counters = pinned_counters_alloc();
+  if (!p->h_counters) { tc_plan_destroy(p); return cudaErrorMemoryAllocation; }
   memset(p->h_counters, 0, sizeof(uint32_t) * CNT_N);
   const char* dbg = getenv("KMCUDA_B200_DUMP_SCORES");
   if (dbg && dbg[0] == '1') {
@@ -1847,9 +2118,40 @@ cudaError_t tc_plan_create(TcPlan** out, int metric, uint32_t max_n, int D, uint
 
 // counters reset + centroid preparation (scale, fp16 table, bias blobs) + the parameter block shared by both modes
 static cudaError_t tc_prepare(TcPlan* p, const float* C, const float* csq, uint32_t n, tc::Params* out,
-                              cudaStream_t st, bool yy_layout = false, bool pair_blob = false) {
+                              cudaStream_t st, bool yy_layout = false, bool pair_blob = false, bool compute_csq = false) {
   using namespace tc;
   cudaError_t e;
+#if KMB_PREP_FUSED
+  {
+    PrepArgs a;
+    a.metric = p->metric;
+    a.centred = p->centred ? 1 : 0;
+    a.D = p->D;
+    a.nkb = p->nkb;
+    a.by_source = yy_layout ? 1 : 0;
+    a.pair_blob = pair_blob ? 1 : 0;
+    a.K = p->K;
+    a.rows_pad = static_cast<uint32_t>(yy_layout ? p->nt3 : p->nt) * TN;
+    a.C = C;
+    a.csq = const_cast<float*>(csq);
+    a.compute_csq = compute_csq ? 1 : 0;
+    a.cnorm2 = p->cnorm2;
+    a.musum = p->musum;
+    a.mu = p->mu;
+    a.neg_mu_s = p->neg_mu_s;
+    a.stats = p->stats;
+    a.counters = p->counters;
+    a.table = yy_layout ? p->table3 : p->table;
+    a.aug_blob = yy_layout ? p->aug_blob3 : p->aug_blob;
+    a.gather = yy_layout ? p->yy_perm : nullptr;
+    a.barrier = p->prep_barrier;
+    // two table rows per warp: enough CTAs to hide the latency of the row reads, few enough for a cheap barrier
+    const unsigned grid = std::min<unsigned>(static_cast<unsigned>(p->num_sms), std::max(1u, (a.rows_pad + 15u) / 16u));
+    tc_prep_fused_kernel<<<grid, 256, 0, st>>>(a);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  }
+#else
+  if (compute_csq && (e = kmb::launch_csqr(p->metric, C, p->K, p->D, const_cast<float*>(csq), st)) != cudaSuccess) return e;
   if ((e = cudaMemsetAsync(p->counters, 0, sizeof(uint32_t) * CNT_N, st)) != cudaSuccess) return e;
   if ((e = cudaMemsetAsync(p->stats, 0, sizeof(Stats), st)) != cudaSuccess) return e;
   const float* nsq = csq;
@@ -1876,6 +2178,7 @@ static cudaError_t tc_prepare(TcPlan* p, const float* C, const float* csq, uint3
   else
     tc_prep_table_kernel<<<(static_cast<uint32_t>(p->nt3) * TN * 32 + 255) / 256, 256, 0, st>>>(
         p->metric, C, nsq, p->K, p->D, p->nkb, p->nt3, p->table3, p->aug_blob3, p->stats, p->yy_perm, mu, 1);
+#endif
   Params prm;
   prm.n = n;
   prm.D = p->D;
@@ -1923,7 +2226,8 @@ static cudaError_t tc_prepare(TcPlan* p, const float* C, const float* csq, uint3
 }
 
 cudaError_t tc_assign(TcPlan* p, const float* X, const float* C, const float* csq, uint32_t n,
-                      uint32_t* result, uint32_t* assign, uint32_t* prev, uint32_t* d_changed, cudaStream_t st) {
+                      uint32_t* result, uint32_t* assign, uint32_t* prev, uint32_t* d_changed, cudaStream_t st,
+                      bool compute_csq) {
   using namespace tc;
   if (n > p->max_n) return cudaErrorInvalidValue;
   // TMA needs 16-byte aligned rows; the re-check kernels read both matrices with 16-byte vector loads
@@ -1947,7 +2251,7 @@ cudaError_t tc_assign(TcPlan* p, const float* X, const float* C, const float* cs
   Params prm;
   // CTA pairs pay off once every pair has several tile pairs to stream the table for
   const bool pair = p->pair && (n + TM - 1) / TM >= 4u * static_cast<uint32_t>(p->num_sms);
-  if ((e = tc_prepare(p, C, csq, n, &prm, st, false, pair)) != cudaSuccess) return e;
+  if ((e = tc_prepare(p, C, csq, n, &prm, st, false, pair, compute_csq)) != cudaSuccess) return e;
   prm.result = result;
   prm.assign = assign;      // non-null: the pass's bookkeeping (prev / assign / changed counter) is fused
   prm.prev = prev;

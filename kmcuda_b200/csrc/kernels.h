@@ -40,11 +40,12 @@ cudaError_t launch_finalize_assign(uint32_t n, const uint32_t* result, uint32_t*
 struct UpdateWorkspace {
   uint32_t *keys_in = nullptr, *keys_out = nullptr, *vals_in = nullptr, *vals_out = nullptr;
   uint32_t* offsets = nullptr;   // [K+1]
-  float* partial = nullptr;      // [K][kSplits][D]
+  float* partial = nullptr;      // [update_partial_rows(max_n, K)][D]: one row per (chunk, cluster) run
   void* cub_tmp = nullptr;
   size_t cub_tmp_bytes = 0;
 };
-constexpr int kUpdateSplits = 8;
+constexpr uint32_t kSumChunk = 512;   // sorted positions per CTA of the member-sum kernel
+size_t update_partial_rows(uint32_t n, uint32_t K);
 size_t update_cub_bytes(uint32_t n);
 // sums[K][D] (fp32) and counts[K] (uint32) of this shard's samples
 cudaError_t launch_partial_sums(const float* X, uint32_t n, int D, uint32_t K, const uint32_t* assign,
@@ -140,8 +141,11 @@ void tc_plan_destroy(TcPlan* plan);
 // one full assignment pass.  assign == nullptr: result[i] as launch_assign_exact would produce it.  Otherwise the
 // pass's bookkeeping (launch_finalize_assign) is fused: prev[i] = assign[i], assign[i] = winner, *d_changed +=
 // changes; result[] is then scratch for the few rows that take the exact full pass.
+// compute_csq: csq[] (the caller's buffer, K floats) is filled by the pass's own preparation launch (what launch_csqr
+// would write) instead of being read as an input.
 cudaError_t tc_assign(TcPlan* plan, const float* X, const float* C, const float* csq, uint32_t n,
-                      uint32_t* result, uint32_t* assign, uint32_t* prev, uint32_t* d_changed, cudaStream_t st);
+                      uint32_t* result, uint32_t* assign, uint32_t* prev, uint32_t* d_changed, cudaStream_t st,
+                      bool compute_csq = false);
 // statistics of the last pass (for logging / bench): queue length and overflow rows
 void tc_last_stats(TcPlan* plan, uint32_t* n_recheck, uint32_t* n_overflow);
 // Yinyang local step (assign_tc.cu): candidate pairs with exact true distances for the listed rows

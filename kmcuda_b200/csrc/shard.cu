@@ -135,7 +135,7 @@ KMCUDAResult Shard::create(bool with_update) {
     KMB_CU(ws_vals_in.alloc(max_n), kmcudaMemoryAllocationFailure);
     KMB_CU(ws_vals_out.alloc(max_n), kmcudaMemoryAllocationFailure);
     KMB_CU(ws_offsets.alloc(static_cast<size_t>(K) + 1), kmcudaMemoryAllocationFailure);
-    KMB_CU(ws_partial.alloc(static_cast<size_t>(K) * kUpdateSplits * D), kmcudaMemoryAllocationFailure);
+    KMB_CU(ws_partial.alloc(update_partial_rows(max_n, K) * D), kmcudaMemoryAllocationFailure);
     ws.cub_tmp_bytes = update_cub_bytes(max_n);
     KMB_CU(ws_cub.alloc(ws.cub_tmp_bytes), kmcudaMemoryAllocationFailure);
     ws.keys_out = ws_keys_out;
@@ -230,7 +230,8 @@ KMCUDAResult Shard::yy_step(uint32_t n, const float* X, const float* C, uint32_t
 KMCUDAResult Shard::assign(uint32_t n, const float* X, const float* C, uint32_t* assignments,
                            uint32_t* prev, uint32_t* d_changed, cudaStream_t st) {
   if (n > max_n) return kmcudaInvalidArguments;
-  if (!(tc && n > 0 && use_graph && st != nullptr)) KMB_CU(launch_csqr(metric, C, K, D, csq, st), kmcudaRuntimeError);
+  // (the tensor-core pass computes ||c||^2 in its own preparation launch)
+  if (!(tc && n > 0)) KMB_CU(launch_csqr(metric, C, K, D, csq, st), kmcudaRuntimeError);
   last_tc = false;
   if (tc && n > 0 && use_graph && st != nullptr) {   // (the legacy default stream cannot be captured)
     GraphKey key;
@@ -240,8 +241,7 @@ KMCUDAResult Shard::assign(uint32_t n, const float* X, const float* C, uint32_t*
       cudaGraph_t g = nullptr;
       KMB_CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal), kmcudaRuntimeError);
       tc_set_capture(tc, true);
-      cudaError_t e1 = launch_csqr(metric, C, K, D, csq, st);
-      cudaError_t e2 = e1 == cudaSuccess ? tc_assign(tc, X, C, csq, n, result, assignments, prev, d_changed, st) : e1;
+      cudaError_t e2 = tc_assign(tc, X, C, csq, n, result, assignments, prev, d_changed, st, true);
       tc_set_capture(tc, false);
       cudaError_t e3 = cudaStreamEndCapture(st, &g);
       if (e2 != cudaSuccess || e3 != cudaSuccess || !g) {
@@ -260,7 +260,7 @@ KMCUDAResult Shard::assign(uint32_t n, const float* X, const float* C, uint32_t*
     return kmcudaSuccess;
   }
   if (tc && n > 0) {
-    KMB_CU(tc_assign(tc, X, C, csq, n, result, assignments, prev, d_changed, st), kmcudaRuntimeError);
+    KMB_CU(tc_assign(tc, X, C, csq, n, result, assignments, prev, d_changed, st, true), kmcudaRuntimeError);
     last_tc = true;
   } else {
     KMB_CU(launch_assign_exact(metric, X, C, csq, n, D, K, nullptr, nullptr, result, st),

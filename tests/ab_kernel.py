@@ -61,6 +61,17 @@ def child():
     e1.record()
     torch.cuda.synchronize()
     kt = sh.kernel_times(steps)
+    sums = torch.zeros((K, D), dtype=torch.float32, device="cuda")
+    counts = torch.zeros(K, dtype=torch.int32, device="cuda")
+    sh.partial_sums(X, a, sums, counts)
+    u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    u0.record()
+    for _ in range(5):
+        sh.partial_sums(X, a, sums, counts)
+    u1.record()
+    torch.cuda.synchronize()
+    out["partial_sums_ms"] = u0.elapsed_time(u1) / 5
+    out["sums_checksum"] = float(sums.double().sum().item())
     tc, rq, ov = sh.last_pass_info()
     out.update({"n": n, "step_ms": e0.elapsed_time(e1) / steps, "kernel_ms": sum(kt) / len(kt), "kernel_ms_min": min(kt),
                 "tc": tc, "rechecked": rq, "overflowed": ov, "err": hex(sh.last_error()),

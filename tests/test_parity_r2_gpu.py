@@ -560,3 +560,39 @@ def test_staged_pageable_ingest_delivers_the_same_bytes(ours, monkeypatch):
         out[threads] = c_kmeans(ours, X, C0, 0.01, 0.0)
     assert np.array_equal(out["6"][1], out["1"][1])
     assert np.array_equal(out["6"][0], out["1"][0])
+
+
+@pytest.mark.parametrize("D,K", [(256, 1024), (96, 37), (480, 300)])
+def test_member_sums_with_skewed_empty_and_unassigned_clusters(km, D, K):
+    """The member-sum kernel walks fixed chunks of the cluster-sorted order (simt_kernels.cu::cluster_sums_kernel):
+    one giant cluster spanning hundreds of chunks, clusters smaller than the unroll depth, empty clusters, runs that
+    end exactly on a chunk boundary and rows with the "unassigned" key K must all give the fp64 sums to fp32
+    accuracy and the exact counts (reference semantics: kmeans.cu:366-429 sums the members of every cluster)."""
+    import torch
+    from kmcuda_b200.shard import Shard
+    rng = np.random.default_rng(D * 1000 + K)
+    n = 300000
+    X = (rng.standard_normal((n, D)) * 3 + 1).astype(np.float32)
+    a = np.empty(n, np.int64)
+    a[:150000] = 5                                     # giant cluster
+    a[150000:150512] = 7                               # exactly one chunk's worth
+    a[150512:150515] = 9                               # below the unroll depth
+    a[150515:200000] = rng.integers(10, K // 2, 49485)
+    a[200000:299000] = rng.integers(K // 2 + 3, K, 99000)   # K//2 .. K//2+2 stay empty
+    a[299000:] = K                                     # unassigned
+    a = a[rng.permutation(n)]
+    sh = Shard(n, D, K)
+    sums = torch.full((K, D), 7.0, device="cuda")
+    counts = torch.full((K,), 7, dtype=torch.int32, device="cuda")
+    sh.partial_sums(torch.from_numpy(X).cuda(), torch.from_numpy(a.astype(np.int32)).cuda(), sums, counts)
+    torch.cuda.synchronize()
+    exp = np.zeros((K, D), np.float64)
+    valid = a < K
+    np.add.at(exp, a[valid], X[valid].astype(np.float64))
+    cnt = np.bincount(a[valid], minlength=K)
+    assert np.array_equal(counts.cpu().numpy(), cnt)
+    got = sums.cpu().numpy().astype(np.float64)
+    scale = np.zeros((K, D), np.float64)
+    np.add.at(scale, a[valid], np.abs(X[valid]).astype(np.float64))
+    assert np.all(np.abs(got - exp) <= 4e-7 * scale + 1e-30), float(np.max(np.abs(got - exp) / (scale + 1e-30)))
+    assert np.all(got[cnt == 0] == 0)
