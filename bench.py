@@ -54,10 +54,10 @@ N_POINTS, D, K = 8000000, 256, 1024
 WORKLOAD = ("k-means assignment step, %d x %d fp32 samples in total (U[0,1)) @ %d clusters (rows of the samples), "
             "range-partitioned over the GPUs (BASELINE configs[1] at 1 GPU, configs[3] at 2/4/8)")
 IMPORT = 3
-# kernels of this library per assignment pass (L2, tensor-core path): csqr, mean, mu, centred norms, stats, scale,
-# table, tc_assign_kernel, recheck_pairs, recheck_reduce, exact_pass (row list), exact_rows_few, finalize_rows
-# (profiles/r02_launches_final.csv lists them)
-LAUNCHES_PER_ASSIGN = 13
+# kernels of this library per assignment pass (L2, tensor-core path): tc_prep_fused_kernel (||c||^2, mean, centred
+# norms, scale, fp16 table in one launch), tc_assign_kernel, recheck_pairs, recheck_reduce, exact_rows_few, exact_pass
+# (row list), finalize_rows (profiles/r02_launches_final.csv lists them)
+LAUNCHES_PER_ASSIGN = 7
 
 
 def _rank_info():
@@ -457,32 +457,67 @@ def run_ours(args):
     iters = max(3, min(args.steps, 10))
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(iters)]
 
-    def iteration(evs=None):
+    # the exchange step two ways when there are peers: summed over peer memory in rank order by one kernel per GPU
+    # (kmcuda_b200.shard.PeerExchange, csrc/exchange.cu: CUDA IPC mappings over NVLink / NVSwitch), and the
+    # communicator's all-reduce (two NCCL collectives: fp32 sums, integer counts)
+    ex, ex_note = None, "none (1 GPU)"
+    if world > 1 and os.environ.get("KMCUDA_B200_EXCHANGE", "") != "nccl":
+        try:
+            from kmcuda_b200.shard import PeerExchange
+            ex = PeerExchange(K, D)
+        except Exception as e:  # no peer access / IPC refused: the communicator's all-reduce is the exchange
+            ex, ex_note = None, "peer-memory exchange unavailable: %s" % str(e)[:120]
+
+    def iteration(evs=None, peer=False):
         if evs: evs[0].record()
         sh.assign(X, C, a, prev, changed)
         if evs: evs[1].record()
-        sh.partial_sums(X, a, sums, counts)
-        if evs: evs[2].record()
-        if world > 1:
-            dist.all_reduce(sums, op=dist.ReduceOp.SUM)
-            dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+        if peer:
+            ps, pc = ex.buffers()
+            sh.partial_sums_into(X, a, ps, pc)
+            if evs: evs[2].record()
+            ex.reduce(sums, counts)
+        else:
+            sh.partial_sums(X, a, sums, counts)
+            if evs: evs[2].record()
+            if world > 1:
+                dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+                dist.all_reduce(counts, op=dist.ReduceOp.SUM)
         if evs: evs[3].record()
         sh.finish_update(sums, counts, C, ccounts)
         if evs: evs[4].record()
 
-    C.copy_(C0)
-    sh.reset()
-    for _ in range(2):
-        iteration()
-    barrier()
-    for i in range(iters):
-        iteration(ev[i])
-    barrier()
-    phase_names = ["assign", "partial_sums", "allreduce", "normalise"]
-    phases = {}
-    for j, name in enumerate(phase_names):
-        phases[name] = max_over_ranks(sum(ev[i][j].elapsed_time(ev[i][j + 1]) for i in range(iters)) / iters)
-    it_ms = max_over_ranks(ev[0][0].elapsed_time(ev[iters - 1][4]) / iters)
+    def time_iterations(peer):
+        C.copy_(C0)
+        sh.reset()
+        for _ in range(2):
+            iteration(None, peer)
+        barrier()
+        for i in range(iters):
+            iteration(ev[i], peer)
+        barrier()
+        ph = {}
+        for j, name in enumerate(["assign", "partial_sums", "exchange", "normalise"]):
+            ph[name] = max_over_ranks(sum(ev[i][j].elapsed_time(ev[i][j + 1]) for i in range(iters)) / iters)
+        ms = max_over_ranks(ev[0][0].elapsed_time(ev[iters - 1][4]) / iters)
+        return ms, ph
+
+    it_ms, phases = time_iterations(False)
+    it_collective = "torch.distributed NCCL all_reduce x2" if world > 1 else "none (1 GPU)"
+    it_other = None
+    if ex is not None:
+        nccl_ms, nccl_phases = it_ms, phases
+        it_ms, phases = time_iterations(True)
+        torch.cuda.synchronize()
+        if ex.error() != 0:
+            raise RuntimeError("peer-memory exchange timed out")
+        it_collective = ("peer memory: every GPU reads its peers' partial sums over NVLink / NVSwitch (CUDA IPC) and adds "
+                         "them in rank order, one kernel per iteration")
+        it_other = {"collective": "torch.distributed NCCL all_reduce x2", "value": total / (nccl_ms * 1e-3), "unit": UNIT,
+                    "ms": nccl_ms, "phase_ms": nccl_phases}
+        ex.close()
+    elif world > 1:
+        it_collective += " (%s)" % ex_note
     C.copy_(C0)
 
     # ---- end to end through the reference-facing C ABI with host buffers (pinned), rank-local shard
@@ -515,14 +550,14 @@ def run_ours(args):
             "dtype": "f16 tensor-core filter (f32 accumulate) + f32 exact re-check", "data": "synthetic",
             "config": {"workload": WORKLOAD % (total, D, K),
                        "parallelism": "%d rows per GPU x %d GPUs (one process per GPU); the assignment step needs no "
-                                      "collective, the centroid update one NCCL all-reduce (see `iteration`)" % (n, world),
+                                      "collective, the centroid update one exchange of the partial sums (see `iteration`)" % (n, world),
                        "l2": "inputs (%.2f GB per GPU) larger than L2, no flush needed" % (n * D * 4 / 1e9),
                        "rows_rechecked_exactly": rechecked, "rows_full_exact_fallback": overflowed},
             "step_tflops": 2.0 * total * K * D / (ms_per_step * 1e-3) / 1e12 / world,
-            "iteration": {"what": "full Lloyd iteration: assign + partial sums + all-reduce(K*D f32 + K i32) + normalise",
+            "iteration": {"what": "full Lloyd iteration: assign + partial sums + exchange (sum over GPUs of K*D f32 + K i32) + normalise",
                           "value": total / (it_ms * 1e-3), "unit": UNIT, "ms": it_ms, "iterations": iters,
                           "phase_ms": phases, "allreduce_bytes": K * D * 4 + K * 4,
-                          "collective": "torch.distributed NCCL all_reduce x2" if world > 1 else "none (1 GPU)"},
+                          "collective": it_collective, "same_iteration_over_nccl": it_other},
             "e2e": {"value": total / e2e_dt, "unit": UNIT, "h2d_bytes_per_step": n * D * 4 + K * D * 4,
                     "d2h_bytes_per_step": n * 4 + K * D * 4, "steps": e2e_steps,
                     "call": "kmeans_cuda(init=import, tolerance=1.0, yinyang_t=0) with pinned host buffers, one call "

@@ -66,6 +66,29 @@ KMCUDAResult kmcuda_b200_finish_update(kmcuda_b200_shard *shard, const float *su
                                        const uint32_t *counts, float *centroids, uint32_t *ccounts,
                                        void *stream);
 
+/* ---- exchange step of the centroid update for one process per GPU, over peer memory (CUDA IPC; csrc/exchange.cu) ----
+ * Replaces the caller's all-reduce between kmcuda_b200_partial_sums() and kmcuda_b200_finish_update() when all ranks
+ * sit on GPUs of one node with peer access (NVLink / NVSwitch): every rank reads its peers' partial sums straight from
+ * their HBM and adds them in rank order (bit-identical totals on all ranks), one kernel per iteration.  The reference's
+ * counterpart is the cudaMemcpyPeerAsync exchange of src/kmeans.cu:980-990,1014-1024 (single process).
+ *
+ *   create   (every rank; fills handle_out with kmcuda_b200_exchange_handle_bytes() bytes)
+ *   all-gather the handles with the caller's communicator (rank-major), then connect
+ *   per iteration: buffers -> kmcuda_b200_partial_sums() into them -> reduce -> kmcuda_b200_finish_update() on the totals
+ *   destroy  after a barrier of the ranks
+ */
+typedef struct kmcuda_b200_exchange kmcuda_b200_exchange;
+uint32_t kmcuda_b200_exchange_handle_bytes(void);
+KMCUDAResult kmcuda_b200_exchange_create(kmcuda_b200_exchange **exchange, uint32_t clusters_size,
+                                         uint16_t features_size, int32_t rank, int32_t world, void *handle_out);
+KMCUDAResult kmcuda_b200_exchange_connect(kmcuda_b200_exchange *exchange, const void *all_handles);
+KMCUDAResult kmcuda_b200_exchange_buffers(kmcuda_b200_exchange *exchange, float **sums, uint32_t **counts);
+KMCUDAResult kmcuda_b200_exchange_reduce(kmcuda_b200_exchange *exchange, float *total_sums,
+                                         uint32_t *total_counts, void *stream);
+/* 0 = clean; non-zero = a peer never arrived within ~20 s (valid after the stream was synchronised) */
+uint32_t kmcuda_b200_exchange_error(kmcuda_b200_exchange *exchange);
+void kmcuda_b200_exchange_destroy(kmcuda_b200_exchange *exchange);
+
 /* Start of a new clustering run on a reused handle: forgets the cached member sums (see above). */
 KMCUDAResult kmcuda_b200_shard_reset(kmcuda_b200_shard *shard, void *stream);
 

@@ -31,10 +31,12 @@ def allreduce_scalar(value, device):
     return int(t.item())
 
 
-def sharded_lloyd(backend, X, C, total_samples, tolerance=0.01, max_iter=0, log=None):
+def sharded_lloyd(backend, X, C, total_samples, tolerance=0.01, max_iter=0, log=None, exchange=None):
     """Lloyd's algorithm on this rank's shard X ([n_local][D]) starting from centroids C ([K][D],
     identical on every rank; updated in place).  Stop rule of the reference (kmeans.cu:707):
-    reassignments <= tolerance * total_samples.  Returns (assignments, iterations)."""
+    reassignments <= tolerance * total_samples.  Returns (assignments, iterations).
+    exchange: a `kmcuda_b200.shard.PeerExchange` (ranks on one node with peer access): the partial sums are summed
+    over peer memory in rank order instead of by the communicator's all-reduce."""
     n, K = X.shape[0], C.shape[0]
     dev = X.device
     assign = torch.full((n,), -1, dtype=torch.int32, device=dev)
@@ -59,7 +61,10 @@ def sharded_lloyd(backend, X, C, total_samples, tolerance=0.01, max_iter=0, log=
             break
         if max_iter and it >= max_iter:
             break
-        backend.partial_sums(X, assign, sums, counts)
-        allreduce_update(sums, counts)
+        if exchange is not None:
+            exchange.update(backend, X, assign, sums, counts)
+        else:
+            backend.partial_sums(X, assign, sums, counts)
+            allreduce_update(sums, counts)
         backend.finish_update(sums, counts, C, ccounts)
     return assign, it

@@ -42,6 +42,24 @@ _lib.kmcuda_b200_debug_stats.restype = ctypes.c_int32
 _lib.kmcuda_b200_debug_stats.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
 
 
+_lib.kmcuda_b200_exchange_handle_bytes.restype = ctypes.c_uint32
+_lib.kmcuda_b200_exchange_handle_bytes.argtypes = []
+_lib.kmcuda_b200_exchange_create.restype = ctypes.c_int
+_lib.kmcuda_b200_exchange_create.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_uint32, ctypes.c_uint16,
+                                             ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p]
+_lib.kmcuda_b200_exchange_connect.restype = ctypes.c_int
+_lib.kmcuda_b200_exchange_connect.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+_lib.kmcuda_b200_exchange_buffers.restype = ctypes.c_int
+_lib.kmcuda_b200_exchange_buffers.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p),
+                                              ctypes.POINTER(ctypes.c_void_p)]
+_lib.kmcuda_b200_exchange_reduce.restype = ctypes.c_int
+_lib.kmcuda_b200_exchange_reduce.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+_lib.kmcuda_b200_exchange_error.restype = ctypes.c_uint32
+_lib.kmcuda_b200_exchange_error.argtypes = [ctypes.c_void_p]
+_lib.kmcuda_b200_exchange_destroy.restype = None
+_lib.kmcuda_b200_exchange_destroy.argtypes = [ctypes.c_void_p]
+
+
 def _stream_ptr():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -106,6 +124,12 @@ class Shard:
                                                  _ptr(counts, torch.int32), _stream_ptr()),
                    "kmcuda_b200_partial_sums")
 
+    def partial_sums_into(self, X, assignments, sums_ptr, counts_ptr):
+        """partial_sums() into raw device pointers (the buffers of a PeerExchange)"""
+        _raise_for(_lib.kmcuda_b200_partial_sums(self._h, X.shape[0], _ptr(X, torch.float32),
+                                                 _ptr(assignments, torch.int32), sums_ptr, counts_ptr, _stream_ptr()),
+                   "kmcuda_b200_partial_sums")
+
     def finish_update(self, sums, counts, C, ccounts):
         _raise_for(_lib.kmcuda_b200_finish_update(self._h, _ptr(sums, torch.float32), _ptr(counts, torch.int32),
                                                   _ptr(C, torch.float32), _ptr(ccounts, torch.int32),
@@ -152,3 +176,74 @@ def assign_once(X, C, metric="L2", assignments=None):
     if err:
         raise RuntimeError("tensor-core pipeline error 0x%x" % err)
     return a, prev, int(changed.item()), info
+
+
+class PeerExchange:
+    """Exchange step of the centroid update over peer memory (include/kmcuda_b200.h, csrc/exchange.cu) for one process
+    per GPU on one node: replaces the all-reduce between `Shard.partial_sums` and `Shard.finish_update`.
+
+        ex = PeerExchange(K, D)                      # collective: every rank of the default process group
+        ex.update(shard, X, assignments, sums, counts)   # sums / counts = totals over all ranks, same bits everywhere
+        shard.finish_update(sums, counts, C, ccounts)
+        ex.close()                                   # collective
+
+    Raises RuntimeError when the handles cannot be mapped (no peer access, different nodes): fall back to
+    `torch.distributed.all_reduce` then."""
+
+    def __init__(self, clusters, features, group=None):
+        import torch.distributed as dist
+        self._dist, self._group = dist, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.K, self.D = int(clusters), int(features)
+        hb = int(_lib.kmcuda_b200_exchange_handle_bytes())
+        mine = (ctypes.c_ubyte * hb)()
+        h = ctypes.c_void_p()
+        rc = _lib.kmcuda_b200_exchange_create(ctypes.byref(h), self.K, self.D, self.rank, self.world, mine)
+        # every rank takes part in the gather, also one whose creation failed (no rank may be left waiting)
+        mine_t = torch.tensor(list(bytes(mine)) + [rc], dtype=torch.uint8, device="cuda")
+        allh = [torch.empty_like(mine_t) for _ in range(self.world)]
+        dist.all_gather(allh, mine_t, group=group)
+        blobs = [bytes(t.cpu().numpy().tobytes()) for t in allh]
+        self._h = h if rc == 0 else None
+        ok = all(b[hb] == 0 for b in blobs)
+        if ok:
+            flat = b"".join(b[:hb] for b in blobs)
+            buf = (ctypes.c_ubyte * len(flat)).from_buffer_copy(flat)
+            rc = _lib.kmcuda_b200_exchange_connect(self._h, buf)
+            ok = rc == 0
+        flag = torch.tensor([0 if ok else 1], dtype=torch.int32, device="cuda")
+        dist.all_reduce(flag, group=group)
+        if int(flag.item()) != 0:
+            self.close(collective=False)
+            raise RuntimeError("peer-memory exchange unavailable (CUDA IPC handles could not be created / mapped)")
+
+    def update(self, shard, X, assignments, total_sums, total_counts):
+        """this rank's partial sums -> totals over all ranks, enqueued on the current stream (no host sync)"""
+        ps, pc = ctypes.c_void_p(), ctypes.c_void_p()
+        _raise_for(_lib.kmcuda_b200_exchange_buffers(self._h, ctypes.byref(ps), ctypes.byref(pc)),
+                   "kmcuda_b200_exchange_buffers")
+        shard.partial_sums_into(X, assignments, ps, pc)
+        self.reduce(total_sums, total_counts)
+
+    def buffers(self):
+        ps, pc = ctypes.c_void_p(), ctypes.c_void_p()
+        _raise_for(_lib.kmcuda_b200_exchange_buffers(self._h, ctypes.byref(ps), ctypes.byref(pc)),
+                   "kmcuda_b200_exchange_buffers")
+        return ps, pc
+
+    def reduce(self, total_sums, total_counts):
+        _raise_for(_lib.kmcuda_b200_exchange_reduce(self._h, _ptr(total_sums, torch.float32),
+                                                    _ptr(total_counts, torch.int32), _stream_ptr()),
+                   "kmcuda_b200_exchange_reduce")
+
+    def error(self):
+        """0 = every exchange so far completed (synchronise the stream first)"""
+        return int(_lib.kmcuda_b200_exchange_error(self._h))
+
+    def close(self, collective=True):
+        if getattr(self, "_h", None):
+            if collective:
+                torch.cuda.synchronize()
+                self._dist.barrier(group=self._group)   # no peer may still be reading this rank's block
+            _lib.kmcuda_b200_exchange_destroy(self._h)
+            self._h = None

@@ -596,3 +596,15 @@ def test_member_sums_with_skewed_empty_and_unassigned_clusters(km, D, K):
     np.add.at(scale, a[valid], np.abs(X[valid]).astype(np.float64))
     assert np.all(np.abs(got - exp) <= 4e-7 * scale + 1e-30), float(np.max(np.abs(got - exp) / (scale + 1e-30)))
     assert np.all(got[cnt == 0] == 0)
+
+
+def test_multi_gpu_peer_memory_exchange_one_process_per_gpu():
+    """the CUDA-IPC exchange of the centroid update (csrc/exchange.cu) under torchrun: tests/_peer_exchange_worker.py"""
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    world = min(_ngpu(), 4)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+                        "--master-addr", "127.0.0.1", "--master-port", "29541",
+                        os.path.join(HERE, "_peer_exchange_worker.py")],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert "PEER_EXCHANGE_OK" in r.stdout, r.stdout[-3000:]
