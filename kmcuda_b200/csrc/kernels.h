@@ -44,7 +44,10 @@ struct UpdateWorkspace {
   void* cub_tmp = nullptr;
   size_t cub_tmp_bytes = 0;
 };
-constexpr uint32_t kSumChunk = 512;   // sorted positions per CTA of the member-sum kernel
+#ifndef KMB_SUM_CHUNK
+#define KMB_SUM_CHUNK 512
+#endif
+constexpr uint32_t kSumChunk = KMB_SUM_CHUNK;   // sorted positions per CTA of the member-sum kernel
 size_t update_partial_rows(uint32_t n, uint32_t K);
 size_t update_cub_bytes(uint32_t n);
 // sums[K][D] (fp32) and counts[K] (uint32) of this shard's samples

@@ -87,7 +87,9 @@ def main():
     torch.cuda.synchronize()
     assert it1 == it2, (it1, it2)
     assert float((a1 != a2).float().mean()) < 1e-4
-    rel = ((C1 - C2).abs() / C2.abs().amax(1, keepdim=True)).max()
+    live = torch.isfinite(C2).all(1)             # (a cluster that lost all members has no centroid in either run)
+    assert torch.equal(live, torch.isfinite(C1).all(1)) and int(live.sum()) > K // 2
+    rel = ((C1[live] - C2[live]).abs() / C2[live].abs().amax(1, keepdim=True)).max()
     assert float(rel) < 1e-5, float(rel)
     ex.close()
     dist.barrier()

@@ -71,6 +71,14 @@ def child():
     u1.record()
     torch.cuda.synchronize()
     out["partial_sums_ms"] = u0.elapsed_time(u1) / 5
+    ab = torch.randint(0, K, (n,), generator=g, device="cuda", dtype=torch.int32)   # balanced clusters
+    sh.partial_sums(X, ab, sums, counts)
+    u0.record()
+    for _ in range(5):
+        sh.partial_sums(X, ab, sums, counts)
+    u1.record()
+    torch.cuda.synchronize()
+    out["partial_sums_balanced_ms"] = u0.elapsed_time(u1) / 5
     out["sums_checksum"] = float(sums.double().sum().item())
     tc, rq, ov = sh.last_pass_info()
     out.update({"n": n, "step_ms": e0.elapsed_time(e1) / steps, "kernel_ms": sum(kt) / len(kt), "kernel_ms_min": min(kt),

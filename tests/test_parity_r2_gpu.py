@@ -575,9 +575,9 @@ def test_member_sums_with_skewed_empty_and_unassigned_clusters(km, D, K):
     X = (rng.standard_normal((n, D)) * 3 + 1).astype(np.float32)
     a = np.empty(n, np.int64)
     a[:150000] = 5                                     # giant cluster
-    a[150000:150512] = 7                               # exactly one chunk's worth
-    a[150512:150515] = 9                               # below the unroll depth
-    a[150515:200000] = rng.integers(10, K // 2, 49485)
+    a[150000:151024] = 7                               # exactly one chunk's worth
+    a[151024:151027] = 9                               # below the unroll depth
+    a[151027:200000] = rng.integers(10, K // 2, 48973)
     a[200000:299000] = rng.integers(K // 2 + 3, K, 99000)   # K//2 .. K//2+2 stay empty
     a[299000:] = K                                     # unassigned
     a = a[rng.permutation(n)]
