@@ -488,33 +488,53 @@ def run_ours(args):
         if evs: evs[4].record()
 
     def time_iterations(peer):
+        """(ms per iteration, phase ms, failed).  Every rank runs the same sequence of collectives whatever happens
+        inside the loop (a timed-out peer exchange raises on some ranks only)."""
+        failed = 0
         C.copy_(C0)
         sh.reset()
-        for _ in range(2):
-            iteration(None, peer)
+        try:
+            for _ in range(2):
+                iteration(None, peer)
+        except Exception as e:
+            sys.stderr.write("iteration leg failed on rank %d: %s\n" % (rank, str(e)[:200]))
+            failed = 1
         barrier()
-        for i in range(iters):
-            iteration(ev[i], peer)
+        if not failed:
+            try:
+                for i in range(iters):
+                    iteration(ev[i], peer)
+            except Exception as e:
+                sys.stderr.write("iteration leg failed on rank %d: %s\n" % (rank, str(e)[:200]))
+                failed = 1
         barrier()
+        if peer and not failed and ex.error() != 0:
+            failed = 1
         ph = {}
         for j, name in enumerate(["assign", "partial_sums", "exchange", "normalise"]):
-            ph[name] = max_over_ranks(sum(ev[i][j].elapsed_time(ev[i][j + 1]) for i in range(iters)) / iters)
-        ms = max_over_ranks(ev[0][0].elapsed_time(ev[iters - 1][4]) / iters)
-        return ms, ph
+            v = 0.0 if failed else sum(ev[i][j].elapsed_time(ev[i][j + 1]) for i in range(iters)) / iters
+            ph[name] = max_over_ranks(v)
+        ms = max_over_ranks(0.0 if failed else ev[0][0].elapsed_time(ev[iters - 1][4]) / iters)
+        return ms, ph, failed
 
-    it_ms, phases = time_iterations(False)
+    it_ms, phases, nccl_failed = time_iterations(False)
+    if nccl_failed:
+        raise RuntimeError("the Lloyd iteration leg failed")
     it_collective = "torch.distributed NCCL all_reduce x2" if world > 1 else "none (1 GPU)"
     it_other = None
     if ex is not None:
         nccl_ms, nccl_phases = it_ms, phases
-        it_ms, phases = time_iterations(True)
-        torch.cuda.synchronize()
-        if ex.error() != 0:
-            raise RuntimeError("peer-memory exchange timed out")
-        it_collective = ("peer memory: every GPU reads its peers' partial sums over NVLink / NVSwitch (CUDA IPC) and adds "
-                         "them in rank order, one kernel per iteration")
-        it_other = {"collective": "torch.distributed NCCL all_reduce x2", "value": total / (nccl_ms * 1e-3), "unit": UNIT,
-                    "ms": nccl_ms, "phase_ms": nccl_phases}
+        peer_ms, peer_phases, failed = time_iterations(True)
+        bad = torch.tensor([failed], dtype=torch.int32, device="cuda")
+        dist.all_reduce(bad, op=dist.ReduceOp.MAX)     # every rank takes the same branch
+        if int(bad.item()) == 0:
+            it_ms, phases = peer_ms, peer_phases
+            it_collective = ("peer memory: every GPU reads its peers' partial sums over NVLink / NVSwitch (CUDA IPC) and "
+                             "adds them in rank order, one kernel per iteration")
+            it_other = {"collective": "torch.distributed NCCL all_reduce x2", "value": total / (nccl_ms * 1e-3),
+                        "unit": UNIT, "ms": nccl_ms, "phase_ms": nccl_phases}
+        else:
+            it_collective += " (the peer-memory exchange timed out on some rank: not reported)"
         ex.close()
     elif world > 1:
         it_collective += " (%s)" % ex_note

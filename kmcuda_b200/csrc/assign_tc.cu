@@ -530,18 +530,26 @@ tc_prep_fused_kernel(const PrepArgs a) {
         if (c0 + lane < K) a.csq[c0 + lane] = 1.f;
         continue;
       }
+      // lane r walks row c0 + r in feature order (the reference's sequential Kahan sum); 32 features x 32 rows are
+      // staged through shared memory with coalesced loads (lane = feature), and the loads of the NEXT 32 features are
+      // in flight during the walk -- this phase is the longest of the launch (a 256-step dependent chain per row)
       kmb::Kahan k;
-      for (int f0 = 0; f0 < D; f0 += 32) {
+      float v[32];
+      auto load32 = [&](int f0) {
         const int fl = min(32, D - f0);
-        float v[32];
 #pragma unroll
         for (int r = 0; r < 32; r++) {
           const uint32_t c = min(c0 + r, K - 1);
           v[r] = lane < fl ? a.C[static_cast<size_t>(c) * D + f0 + lane] : 0.f;
         }
+      };
+      load32(0);
+      for (int f0 = 0; f0 < D; f0 += 32) {
+        const int fl = min(32, D - f0);
 #pragma unroll
         for (int r = 0; r < 32; r++) tile[r * 33 + lane] = v[r];
         __syncwarp();
+        if (f0 + 32 < D) load32(f0 + 32);
         for (int f = 0; f < fl; f++) {
           const float x = tile[lane * 33 + f];
           k.mac(x, x);
@@ -573,14 +581,14 @@ tc_prep_fused_kernel(const PrepArgs a) {
     nsq = a.cnorm2;
     prep_grid_barrier(a.barrier, gridDim.x);
   } else if (a.centred) {
-    // ---- phase 1: column sums of the valid centroids (tc_prep_mean_kernel: 128 features x 64 rows per half CTA)
+    // ---- phase 1: column sums of the valid centroids (as tc_prep_mean_kernel: 128 features per half CTA)
     {
       const int fb = (D + 127) / 128;
-      const uint32_t nvb = static_cast<uint32_t>(fb) * ((K + 63u) / 64u);
+      const uint32_t nvb = static_cast<uint32_t>(fb) * ((K + 15u) / 16u);   // 16 rows per half CTA: two load groups deep
       const int ht = tid & 127;
       for (uint32_t vb = blockIdx.x * 2u + (tid >> 7); vb < nvb; vb += gridDim.x * 2u) {
         const int f = static_cast<int>(vb % fb) * 128 + ht;
-        const uint32_t r0 = (vb / fb) * 64u, r1 = min(K, r0 + 64u);
+        const uint32_t r0 = (vb / fb) * 16u, r1 = min(K, r0 + 16u);
         double acc = 0.0;
         uint32_t nv = 0;
         for (uint32_t rb = r0; rb < r1; rb += 8) {
@@ -2145,8 +2153,8 @@ static cudaError_t tc_prepare(TcPlan* p, const float* C, const float* csq, uint3
     a.aug_blob = yy_layout ? p->aug_blob3 : p->aug_blob;
     a.gather = yy_layout ? p->yy_perm : nullptr;
     a.barrier = p->prep_barrier;
-    // two table rows per warp: enough CTAs to hide the latency of the row reads, few enough for a cheap barrier
-    const unsigned grid = std::min<unsigned>(static_cast<unsigned>(p->num_sms), std::max(1u, (a.rows_pad + 15u) / 16u));
+    // one table row per warp up to the number of SMs (every CTA must be resident for the grid barrier)
+    const unsigned grid = std::min<unsigned>(static_cast<unsigned>(p->num_sms), std::max(1u, (a.rows_pad + 7u) / 8u));
     tc_prep_fused_kernel<<<grid, 256, 0, st>>>(a);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
   }

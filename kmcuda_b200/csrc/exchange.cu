@@ -63,8 +63,10 @@ __device__ __forceinline__ uint32_t ld_sys_u(const uint32_t* p) {
 __global__ void __launch_bounds__(256)
 exchange_reduce_kernel(const ExchangePeers pp, size_t off_sums, size_t off_counts, size_t off_flags, uint32_t iter,
                        size_t nvec4, size_t nsums, uint32_t K, float* __restrict__ out_sums,
-                       uint32_t* __restrict__ out_counts, uint32_t* __restrict__ err) {
+                       uint32_t* __restrict__ out_counts, uint32_t* err) {
   __shared__ int s_fail;
+  // an earlier exchange of this handle timed out: the ranks are out of step for good, do not wait another 20 s per launch
+  if (ld_acquire_sys(err) != 0u) return;
   if (threadIdx.x == 0) s_fail = 0;
   // (the partial sums were written by earlier kernels of this stream: complete and visible before this kernel started)
   if (blockIdx.x == 0 && threadIdx.x < pp.n)

@@ -43,6 +43,7 @@ struct UpdateWorkspace {
   float* partial = nullptr;      // [update_partial_rows(max_n, K)][D]: one row per (chunk, cluster) run
   void* cub_tmp = nullptr;
   size_t cub_tmp_bytes = 0;
+  uint32_t iota_n = 0;           // vals_in[0 .. iota_n) already holds the identity permutation
 };
 #ifndef KMB_SUM_CHUNK
 #define KMB_SUM_CHUNK 512

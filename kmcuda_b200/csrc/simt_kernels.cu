@@ -346,26 +346,42 @@ __global__ void iota_kernel(uint32_t* p, uint32_t n) {
   if (i < n) p[i] = i;
 }
 
+// first position of the sorted keys[0..n) whose key is >= c, by one warp: 32 probes per step (a 33-ary search, 4 steps +
+// a final window at n = 8M; one thread per cluster doing a binary search was a chain of 23 dependent DRAM reads, 27 us)
+__device__ __forceinline__ uint32_t warp_lower_bound(const uint32_t* __restrict__ keys, uint32_t n, uint32_t c, int lane) {
+  uint32_t lo = 0, hi = n;     // every position < lo has key < c; position hi has key >= c (or hi == n)
+  while (hi - lo > 32) {
+    const uint64_t s = hi - lo;
+    const uint32_t q = lo + static_cast<uint32_t>((static_cast<uint64_t>(lane + 1) * s) / 33);   // lo < q < hi, increasing in lane
+    const unsigned m = __ballot_sync(0xffffffffu, keys[q] >= c);
+    const int t = m ? __ffs(m) - 1 : 32;
+    const uint32_t q_prev = __shfl_sync(0xffffffffu, q, t > 0 ? t - 1 : 0);
+    const uint32_t q_t = __shfl_sync(0xffffffffu, q, t < 32 ? t : 31);
+    if (t < 32) hi = q_t;
+    if (t > 0) lo = q_prev + 1;
+  }
+  const uint32_t p = lo + lane;
+  const unsigned m = __ballot_sync(0xffffffffu, p < hi && keys[p] >= c);
+  return m ? lo + (__ffs(m) - 1) : hi;
+}
+
 __global__ void segment_offsets_kernel(const uint32_t* __restrict__ keys, uint32_t n, uint32_t K,
                                        uint32_t* __restrict__ offsets, uint32_t* __restrict__ counts) {
-  uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // one warp per cluster (and one for the end marker K)
+  const int lane = threadIdx.x & 31;
   if (c > K) return;
-  uint32_t lo = 0, hi = n;  // first position with key >= c
-  while (lo < hi) {
-    uint32_t mid = lo + (hi - lo) / 2;
-    if (keys[mid] < c) lo = mid + 1;
-    else hi = mid;
-  }
-  offsets[c] = lo;
+  const uint32_t lo = warp_lower_bound(keys, n, c, lane);
+  if (lane == 0) offsets[c] = lo;
   if (c < K) {
-    uint32_t lo2 = lo, hi2 = n;  // first position with key >= c+1
-    while (lo2 < hi2) {
-      uint32_t mid = lo2 + (hi2 - lo2) / 2;
-      if (keys[mid] < c + 1) lo2 = mid + 1;
-      else hi2 = mid;
-    }
-    counts[c] = lo2 - lo;
+    const uint32_t lo2 = warp_lower_bound(keys, n, c + 1, lane);
+    if (lane == 0) counts[c] = lo2 - lo;
   }
+}
+
+// (the only way this kernel is launched: its grid is one WARP per cluster plus one for the end marker)
+static void launch_segment_offsets(const uint32_t* keys, uint32_t n, uint32_t K, uint32_t* offsets, uint32_t* counts,
+                                   cudaStream_t st) {
+  segment_offsets_kernel<<<cdiv((static_cast<size_t>(K) + 1) * 32, 128), 128, 0, st>>>(keys, n, K, offsets, counts);
 }
 
 #ifndef KMB_UPDATE_UNROLL
@@ -496,14 +512,17 @@ cudaError_t launch_partial_sums(const float* X, uint32_t n, int D, uint32_t K, c
     cudaMemsetAsync(counts, 0, sizeof(uint32_t) * K, st);
     return cudaGetLastError();
   }
-  iota_kernel<<<cdiv(n, 256), 256, 0, st>>>(ws.vals_in, n);
+  if (ws.iota_n < n) {   // the identity permutation is an input the sort never modifies: written once per workspace
+    iota_kernel<<<cdiv(n, 256), 256, 0, st>>>(ws.vals_in, n);
+    ws.iota_n = n;
+  }
   int bits = 1;
   while ((1ull << bits) <= K) bits++;  // keys are in [0, K] (K = "insane")
   size_t bytes = ws.cub_tmp_bytes;
   cudaError_t e = cub::DeviceRadixSort::SortPairs(ws.cub_tmp, bytes, assign, ws.keys_out, ws.vals_in,
                                                   ws.vals_out, (int)n, 0, bits, st);
   if (e != cudaSuccess) return e;
-  segment_offsets_kernel<<<cdiv(K + 1, 128), 128, 0, st>>>(ws.keys_out, n, K, ws.offsets, counts);
+  launch_segment_offsets(ws.keys_out, n, K, ws.offsets, counts, st);
   if (D % 4 == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0) {
     const int threads = std::min(256, (D / 4 + 31) / 32 * 32);
     cluster_sums_kernel<4><<<cdiv(n, kSumChunk), threads, 0, st>>>(X, D, ws.keys_out, ws.vals_out, ws.offsets, K, ws.partial);
@@ -524,7 +543,7 @@ cudaError_t launch_knn_inverse(const uint32_t* assign, uint32_t n, uint32_t K, u
   cudaError_t e = cub::DeviceRadixSort::SortPairs(ws.cub_tmp, bytes, assign, keys_out, iota, inv, (int)n, 0,
                                                   bits, st);
   if (e != cudaSuccess) return e;
-  segment_offsets_kernel<<<cdiv(K + 1, 128), 128, 0, st>>>(keys_out, n, K, off, counts);
+  launch_segment_offsets(keys_out, n, K, off, counts, st);
   return cudaGetLastError();
 }
 
@@ -651,7 +670,7 @@ cudaError_t launch_strict_update(int metric, const float* X, uint32_t n, int D, 
                                                   (int)(2 * static_cast<size_t>(n)), 0, bits, st);
   if (e != cudaSuccess) return e;
   // offsets[c] = first event of cluster c (binary search in the sorted keys); counts are not needed
-  segment_offsets_kernel<<<cdiv(K + 1, 128), 128, 0, st>>>(keys_out, 2 * n, K, offsets, keys_in /* scratch */);
+  launch_segment_offsets(keys_out, 2 * n, K, offsets, keys_in /* scratch */, st);
   const size_t smem = static_cast<size_t>(D) * 32 * sizeof(float);
   if (metric == 1) {
     if ((e = cudaFuncSetAttribute(strict_adjust_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -714,10 +733,22 @@ cudaError_t launch_peer_reduce(const PeerBuffers& pb, uint32_t K, int D, float* 
   return cudaGetLastError();
 }
 
+// L2: element-wise (the same two operations per element as normalize_kernel<0>, one thread per element instead of one
+// thread walking a whole centroid with strided accesses: 24 us -> a few us at 1024 x 256)
+__global__ void normalize_l2_kernel(const float* __restrict__ sums, const uint32_t* __restrict__ counts, uint32_t K, int D,
+                                    float* __restrict__ C, uint32_t* __restrict__ ccounts) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<size_t>(K) * D) return;
+  const uint32_t c = i / D;
+  const uint32_t cnt = counts[c];
+  C[i] = sums[i] * __frcp_rn(static_cast<float>(cnt));
+  if (i - static_cast<size_t>(c) * D == 0) ccounts[c] = cnt;
+}
+
 cudaError_t launch_normalize(int metric, const float* sums, const uint32_t* counts, uint32_t K, int D,
                              float* C, uint32_t* ccounts, float* prev_sums, cudaStream_t st) {
   if (metric == 1) normalize_kernel<1><<<cdiv(K, 64), 64, 0, st>>>(sums, counts, K, D, C, ccounts, prev_sums);
-  else normalize_kernel<0><<<cdiv(K, 64), 64, 0, st>>>(sums, counts, K, D, C, ccounts, prev_sums);
+  else normalize_l2_kernel<<<cdiv(static_cast<size_t>(K) * D, 256), 256, 0, st>>>(sums, counts, K, D, C, ccounts);
   return cudaGetLastError();
 }
 

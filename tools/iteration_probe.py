@@ -28,3 +28,19 @@ for it in range(3):
     sh.finish_update(sums, counts, C, cc)
     torch.cuda.synchronize()
     print("iteration %d: %d reassignments, pipeline error 0x%x" % (it + 1, int(ch.item()), sh.last_error()), flush=True)
+
+# phase times of 10 more iterations (CUDA events)
+ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(10)]
+for e in ev:
+    e[0].record()
+    sh.assign(X, C, a, prev, ch)
+    e[1].record()
+    sh.partial_sums(X, a, sums, counts)
+    e[2].record()
+    sh.finish_update(sums, counts, C, cc)
+    e[3].record()
+torch.cuda.synchronize()
+ph = [sum(e[j].elapsed_time(e[j + 1]) for e in ev) / len(ev) for j in range(3)]
+print("ITER lib=%s n=%d assign %.4f ms, member sums %.4f ms, normalise %.4f ms, iteration %.4f ms" % (
+    os.environ.get("KMCUDA_B200_LIB", "product").split("/")[-2:][0], n, ph[0], ph[1], ph[2],
+    ev[0][0].elapsed_time(ev[-1][3]) / len(ev)), flush=True)
