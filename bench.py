@@ -56,7 +56,7 @@ WORKLOAD = ("k-means assignment step, %d x %d fp32 samples in total (U[0,1)) @ %
 IMPORT = 3
 # kernels of this library per assignment pass (L2, tensor-core path): tc_prep_fused_kernel (||c||^2, mean, centred
 # norms, scale, fp16 table in one launch), tc_assign_kernel, recheck_pairs, recheck_reduce, exact_rows_few, exact_pass
-# (row list), finalize_rows (profiles/r02_launches_final.csv lists them)
+# (row list), finalize_rows (profiles/r02_launches_iteration.csv lists them, next to the update's kernels)
 LAUNCHES_PER_ASSIGN = 7
 
 
