@@ -16,6 +16,17 @@ def pytest_configure(config):
     os.environ.setdefault("KMCUDA_B200_YY_ADAPTIVE", "0")
 
 
+def pytest_collection_modifyitems(config, items):
+    # A GPU test that hangs (a kernel waiting on something that never comes) must end the run loudly, not sit there until
+    # the caller's limit: with pytest-timeout present every GPU test gets 7 minutes (the slowest takes ~20 s), enforced by
+    # the watchdog thread (a signal cannot interrupt a thread blocked inside cudaStreamSynchronize).
+    if not config.pluginmanager.hasplugin("timeout"):
+        return
+    for item in items:
+        if item.get_closest_marker("gpu") and not item.get_closest_marker("timeout"):
+            item.add_marker(pytest.mark.timeout(420, method="thread"))
+
+
 @pytest.fixture(scope="session", autouse=True)
 def _built():
     """The product library and the C oracle must exist before any test imports them."""
