@@ -2071,6 +2071,7 @@ cudaError_t tc_plan_create(TcPlan** out, int metric, uint32_t max_n, int D, uint
   TC_TRY(pool_alloc(reinterpret_cast<void**>(&p->counters), sizeof(uint32_t) * CNT_N));
   TC_TRY(pool_alloc(reinterpret_cast<void**>(&p->prep_barrier), sizeof(unsigned) * 2));
   TC_TRY(cudaMemset(p->prep_barrier, 0, sizeof(unsigned) * 2));
+  TC_TRY(cudaStreamSynchronize(nullptr));   // the passes run on non-blocking streams, which do not order against this memset
   p->h_counters = pinned_counters_alloc();
   if (!p->h_counters) { tc_plan_destroy(p); return cudaErrorMemoryAllocation; }
   memset(p->h_counters, 0, sizeof(uint32_t) * CNT_N);
