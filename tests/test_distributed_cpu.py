@@ -36,7 +36,20 @@ class NumpyBackend:
         ccounts.copy_(counts)
 
 
-def _worker(rank, world, port, X, C0, out):
+class AllReduceExchange:
+    """stand-in with the interface of kmcuda_b200.shard.PeerExchange (update = partial sums + sum over the ranks)"""
+
+    def __init__(self):
+        self.calls = 0
+
+    def update(self, backend, X, assign, sums, counts):
+        self.calls += 1
+        backend.partial_sums(X, assign, sums, counts)
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+
+
+def _worker(rank, world, port, X, C0, out, use_exchange=False):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -45,13 +58,17 @@ def _worker(rank, world, port, X, C0, out):
     n = X.shape[0]
     lo, hi = rank * n // world, (rank + 1) * n // world
     C = C0.clone()
-    assign, iters = sharded_lloyd(NumpyBackend(), X[lo:hi].contiguous(), C, total_samples=n, tolerance=0.0)
+    ex = AllReduceExchange() if use_exchange else None
+    assign, iters = sharded_lloyd(NumpyBackend(), X[lo:hi].contiguous(), C, total_samples=n, tolerance=0.0, exchange=ex)
+    assert ex is None or ex.calls == iters - 1        # one exchange per centroid update
     out[rank] = (assign.numpy().copy(), C.numpy().copy(), iters)
     dist.barrier()
     dist.destroy_process_group()
 
 
-def test_sharded_lloyd_two_ranks_equals_single_rank():
+@pytest.mark.parametrize("use_exchange", [False, True])
+def test_sharded_lloyd_two_ranks_equals_single_rank(use_exchange):
+    """use_exchange: the update's sums go through the `exchange=` route of sharded_lloyd (on GPUs: PeerExchange)"""
     pytest.importorskip("kmcuda_b200")
     rng = np.random.default_rng(0)
     centers = rng.random((6, 8)) * 10
@@ -59,7 +76,7 @@ def test_sharded_lloyd_two_ranks_equals_single_rank():
     C0 = X[torch.from_numpy(rng.choice(3000, 6, replace=False))].clone()
     mgr = mp.Manager()
     out = mgr.dict()
-    mp.spawn(_worker, args=(2, 29533, X, C0, out), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, 29533 + int(use_exchange), X, C0, out, use_exchange), nprocs=2, join=True)
     a = np.concatenate([out[0][0], out[1][0]])
     # single "rank" reference of the same driver
     sys.path.insert(0, ROOT)
