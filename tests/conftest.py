@@ -24,7 +24,7 @@ def pytest_collection_modifyitems(config, items):
         return
     for item in items:
         if item.get_closest_marker("gpu") and not item.get_closest_marker("timeout"):
-            item.add_marker(pytest.mark.timeout(420, method="thread"))
+            item.add_marker(pytest.mark.timeout(int(os.environ.get("KMB_TEST_TIMEOUT", "420")), method="thread"))
 
 
 @pytest.fixture(scope="session", autouse=True)
