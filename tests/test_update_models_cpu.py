@@ -147,3 +147,24 @@ def test_double_buffered_exchange_never_reads_an_overwritten_buffer(world, seed)
             if it > T:
                 done += 1
         state[r] = (it, ms)
+
+
+# ------------------------------------------------------------------------------------ 4. one launch site per grid contract
+def test_warp_per_cluster_kernel_is_launched_through_its_helper_only():
+    """`segment_offsets_kernel` needs one WARP per cluster.  A launch site that kept the old one-thread-per-cluster grid
+    left most offsets unwritten and hung the strict update (round 2); every caller must go through
+    `launch_segment_offsets`."""
+    import os
+    import re
+    csrc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "kmcuda_b200", "csrc")
+    sites = []
+    for name in sorted(os.listdir(csrc)):
+        if name.endswith((".cu", ".cuh", ".h")):
+            text = open(os.path.join(csrc, name)).read()
+            sites += [(name, m.start()) for m in re.finditer(r"segment_offsets_kernel\s*<<<", text)]
+    assert len(sites) == 1 and sites[0][0] == "simt_kernels.cu", sites
+    text = open(os.path.join(csrc, "simt_kernels.cu")).read()
+    helper = text.index("static void launch_segment_offsets(")
+    assert helper < sites[0][1] < text.index("}", sites[0][1]) and text.count("launch_segment_offsets(") >= 4
+    launch = text[sites[0][1]:text.index(";", sites[0][1])]
+    assert "* 32" in launch.replace("*32", "* 32")           # (K + 1) warps
