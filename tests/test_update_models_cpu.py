@@ -10,6 +10,9 @@ step, so an indexing mistake in the kernel's logic shows up here.
 3. `exchange.cu`: partial sums double-buffered by iteration parity with a "partial sums complete" flag per (rank, peer)
    and NO "reads complete" flag.  Under arbitrary interleavings of the ranks no rank ever reads a buffer that a peer has
    already overwritten for a later iteration.
+4. One launch site for the warp-per-cluster kernel (source lint).
+5. `assign_tc.cu::prep_grid_barrier`: the sense-reversing grid barrier of the one-launch preparation separates the phases,
+   never deadlocks and leaves its two words reusable by the next launch / graph replay.
 """
 import numpy as np
 import pytest
@@ -168,3 +171,59 @@ def test_warp_per_cluster_kernel_is_launched_through_its_helper_only():
     assert helper < sites[0][1] < text.index("}", sites[0][1]) and text.count("launch_segment_offsets(") >= 4
     launch = text[sites[0][1]:text.index(";", sites[0][1])]
     assert "* 32" in launch.replace("*32", "* 32")           # (K + 1) warps
+
+
+# ------------------------------------------------------------------------------------ 5. the preparation's grid barrier
+@pytest.mark.parametrize("nblocks", [1, 2, 16, 148])
+@pytest.mark.parametrize("seed", range(3))
+def test_sense_reversing_grid_barrier_separates_phases_and_returns_to_zero(nblocks, seed):
+    """assign_tc.cu::prep_grid_barrier, thread 0 of every CTA: g = gen; if atomicAdd(count, 1) == nblocks - 1 then
+    count = 0, gen += 1 else spin until gen != g.  Three barriers per launch, several launches in a row (a CUDA-graph
+    replay reuses the two words without any host-side reset): under arbitrary interleavings no CTA enters phase p + 1
+    before every CTA has finished phase p, nobody deadlocks, and the words are back to (0, launches * 3)."""
+    rng = np.random.default_rng(seed * 1000 + nblocks)
+    count, gen = 0, 0
+    launches, barriers = 3, 3
+    total_phases = launches * (barriers + 1)
+    # per CTA: phase index, micro-state: 0 = working in phase, 1 = read gen, 2 = arrived (spinning), 3 = past barrier
+    phase = [0] * nblocks
+    st = [0] * nblocks
+    seen_gen = [0] * nblocks
+    finished_phase = [0] * nblocks             # number of phases whose work is complete
+    guard = 0
+    while min(phase) < total_phases - 1 or any(s != 0 for s in st) or min(finished_phase) < total_phases:
+        guard += 1
+        assert guard < 4 * 10 ** 6, "deadlock"
+        b = int(rng.integers(0, nblocks))
+        if phase[b] == total_phases - 1 and st[b] == 0 and finished_phase[b] == total_phases:
+            continue
+        if st[b] == 0:                          # do the phase's work
+            if finished_phase[b] == phase[b]:
+                # entering / working in phase[b]: every CTA must have finished all earlier phases of this launch
+                launch_first = (phase[b] // (barriers + 1)) * (barriers + 1)
+                assert all(fp >= phase[b] or phase[b] == launch_first for fp in finished_phase), (phase, finished_phase)
+                finished_phase[b] += 1
+            if (phase[b] + 1) % (barriers + 1) == 0:
+                # last phase of a launch: no barrier, the next launch starts when ALL CTAs are done (stream order)
+                if phase[b] < total_phases - 1 and min(finished_phase) >= phase[b] + 1:
+                    phase[b] += 1
+                continue
+            st[b] = 1
+        elif st[b] == 1:
+            seen_gen[b] = gen
+            st[b] = 2
+        elif st[b] == 2:
+            count += 1
+            if count == nblocks:
+                count = 0
+                gen += 1
+                st[b] = 3
+            else:
+                st[b] = 4
+        elif st[b] == 4:
+            if gen != seen_gen[b]:
+                st[b] = 3
+        elif st[b] == 3:
+            phase[b] += 1
+            st[b] = 0
+    assert count == 0 and gen == launches * barriers
